@@ -1,0 +1,105 @@
+"""ctypes binding of libdiffroll_b200.so (include/diffroll_b200.h).
+
+There is no CPU fallback: if the shared library is missing or fails to load,
+every entry point raises.  Build it with ``python -m diffroll_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdiffroll_b200.so")
+
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+BRANCH_COND_UNCOND, BRANCH_COND, BRANCH_UNCOND, BRANCH_COND_ZEROSPEC = 0, 1, 2, 3
+UPD_X0, UPD_X0_FINAL, UPD_EPS_DDPM, UPD_EPS_DDIM, UPD_EPS_FINAL, UPD_NONE = range(6)
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+EXPORTS = [
+    "drb_version", "drb_last_error", "drb_plan_workspace_bytes", "drb_plan_create", "drb_plan_destroy",
+    "drb_plan_set_branches", "drb_time_tables", "drb_mel_forward", "drb_in_proj", "drb_resblock_forward",
+    "drb_head_posterior_step", "drb_sample_step", "drb_sample_loop", "drb_launch_count", "drb_plan_buffer",
+]
+
+
+class DrbConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "frames", "pitches", "wave_len", "residual_channels", "residual_layers", "kernel_size",
+        "dilation_base", "dilation_bound", "n_mels", "n_fft", "hop_length", "timesteps", "precision",
+        "branches", "reserved")]
+
+
+_FP = C.c_void_p  # device pointers travel as integers
+_FPP = C.POINTER(C.c_void_p)
+
+
+class DrbWeights(C.Structure):
+    _fields_ = [
+        ("input_projection_w", _FP), ("input_projection_b", _FP),
+        ("emb_projection1_w", _FP), ("emb_projection1_b", _FP),
+        ("emb_projection2_w", _FP), ("emb_projection2_b", _FP),
+        ("dilated_conv_w", _FPP), ("dilated_conv_b", _FPP),
+        ("diffusion_projection_w", _FPP), ("diffusion_projection_b", _FPP),
+        ("conditioner_projection_w", _FPP), ("conditioner_projection_b", _FPP),
+        ("output_projection_w", _FPP), ("output_projection_b", _FPP),
+        ("skip_projection_w", _FP), ("skip_projection_b", _FP),
+        ("head_projection_w", _FP), ("head_projection_b", _FP),
+        ("stft_window", _FP), ("mel_fb", _FP),
+    ]
+
+
+class DrbUpdate(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("has_noise", C.c_int32), ("s", C.c_float * 5), ("w", C.c_float)]
+
+
+class DrbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DrbError(f"{LIB_PATH} is missing: run `python -m diffroll_b200.build` "
+                       "(there is no CPU or PyTorch fallback for the sampling path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.drb_version.restype = C.c_int
+    lib.drb_last_error.restype = C.c_char_p
+    lib.drb_plan_workspace_bytes.restype = C.c_size_t
+    lib.drb_plan_workspace_bytes.argtypes = [C.POINTER(DrbConfig)]
+    lib.drb_plan_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DrbConfig), C.POINTER(DrbWeights),
+                                    C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.drb_plan_destroy.argtypes = [C.c_void_p]
+    lib.drb_plan_set_branches.argtypes = [C.c_void_p, C.c_int32]
+    lib.drb_time_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.drb_mel_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p]
+    lib.drb_in_proj.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.drb_resblock_forward.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.drb_head_posterior_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(DrbUpdate), C.c_void_p]
+    lib.drb_sample_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.POINTER(DrbUpdate), C.c_void_p]
+    lib.drb_sample_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(DrbUpdate), C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p]
+    lib.drb_launch_count.restype = C.c_int64
+    lib.drb_launch_count.argtypes = [C.c_int32]
+    lib.drb_plan_buffer.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("drb_version",):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().drb_last_error()
+        raise DrbError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,65 @@
+"""Build libdiffroll_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m diffroll_b200.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdiffroll_b200.so")
+SOURCES = ["api.cu", "simt_kernels.cu", "mel.cu", "umma_gemm.cu"]
+HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "diffroll_b200.h")]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+               "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed on {src} ---\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(f"--- {src} ---\n{out}\n")
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [nvcc, "-arch=sm_100a", "-shared", "-o", LIB] + objs + ["-L" + cuda_lib, "-lcufft", "-Xlinker", "-rpath," + cuda_lib]
+    subprocess.check_call(link)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

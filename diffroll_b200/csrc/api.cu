@@ -1,0 +1,383 @@
+// C ABI of libdiffroll_b200.so: plan construction (weight repack, TMA descriptors, cuFFT plan) and the
+// per-step entry points.  See include/diffroll_b200.h for the contract and the reference lines replaced.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace drb {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Layout {  // byte offsets into the workspace
+  size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel;
+  size_t wd32, wc32, ybuf, z32;                        // fp32 path
+  size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol;  // tensor path
+  size_t total;
+  int NBcap, Mp, KC;
+};
+
+static bool cfg_ok(const drb_config& c) {
+  if (c.batch <= 0 || c.frames <= 0 || c.pitches <= 0 || c.pitches % 4 || c.wave_len <= 0) return false;
+  if (c.residual_channels <= 0 || c.residual_channels % 256) return false;
+  if (c.residual_layers <= 0 || c.kernel_size <= 0 || !(c.kernel_size & 1)) return false;
+  if (c.dilation_base <= 0 || c.dilation_bound <= 0 || c.n_mels <= 0 || c.n_fft <= 0 || c.hop_length <= 0) return false;
+  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 2 || c.branches < 0 || c.branches > 3) return false;
+  if (c.wave_len / c.hop_length + 1 < c.frames) return false;
+  if (c.wave_len <= c.n_fft / 2) return false;  // reflect padding needs pad < length
+  return true;
+}
+
+static Layout make_layout(const drb_config& c) {
+  Layout l; memset(&l, 0, sizeof(l));
+  const size_t B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size;
+  l.NBcap = (c.branches == DRB_BRANCH_COND_UNCOND || c.branches == DRB_BRANCH_COND_ZEROSPEC) ? 2 * c.batch : c.batch;
+  l.Mp = (c.n_mels + 63) / 64 * 64;
+  l.KC = (int)(k * C);
+  const size_t NB = l.NBcap, Mp = l.Mp, rows = NB * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes); return r; };
+  l.dtab = take(L * c.timesteps * C * 4);
+  l.emb1 = take((size_t)c.timesteps * 512 * 4);
+  l.emb2 = take((size_t)c.timesteps * 512 * 4);
+  l.x32 = take(rows * C * 4);
+  l.skip = take(rows * C * 4);
+  l.hbuf = take(rows * C * 4);
+  l.spec32 = take(B * T * Mp * 4);
+  l.bias = take(L * 4 * 2 * C * 4);
+  l.wtmp = take(2 * C * k * C * 4);
+  l.mel = take(mel_workspace_bytes(c));
+  if (c.precision == DRB_PREC_FP32) {
+    l.wd32 = take(L * 2 * C * k * C * 4);
+    l.wc32 = take(L * 2 * C * Mp * 4);
+    l.ybuf = take(rows * 2 * C * 4);
+    l.z32 = take(rows * C * 4);
+  } else {
+    l.xh = take(rows * C * 2); l.xl = take(rows * C * 2);
+    l.zh = take(rows * C * 2); l.zl = take(rows * C * 2);
+    l.sh = take(B * T * Mp * 2); l.sl = take(B * T * Mp * 2);
+    l.wdh = take(L * 2 * C * k * C * 2); l.wdl = take(L * 2 * C * k * C * 2);
+    l.wch = take(L * 2 * C * Mp * 2); l.wcl = take(L * 2 * C * Mp * 2);
+    l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
+  }
+  l.total = off;
+  return l;
+}
+
+}  // namespace drb
+
+using namespace drb;
+
+struct drb_plan {
+  drb_config cfg;
+  Layout lay;
+  char* ws;
+  int NB, n_cond;      // active branches
+  bool zero_spec;      // second branch = conditional forward on an all-zero spectrogram (cfdg_ddim_x0)
+  bool tables_ready, spec_ready;
+  std::vector<int> dil;
+  // weight pointers used in place (caller keeps them alive)
+  const float *in_w, *in_b, *e1w, *e1b, *e2w, *e2b, *skw, *skb, *hdw, *hdb;
+  std::vector<const float*> dpw, dpb, wo32, bo;
+  MelPlan* mel;
+  UmmaMaps maps;
+  std::vector<UmmaLayer> layers;
+  template <class Tp> Tp* at(size_t off) const { return reinterpret_cast<Tp*>(ws + off); }
+  float* bias_ptr(int layer, int which) const {  // which: 0 cond-interleaved, 1 unc-interleaved, 2 cond-natural, 3 unc-natural
+    return at<float>(lay.bias) + ((size_t)layer * 4 + which) * 2 * cfg.residual_channels;
+  }
+  const float* dvec(int layer, int t) const {
+    return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
+  }
+};
+
+extern "C" {
+
+int drb_version(void) { return DRB_VERSION; }
+const char* drb_last_error(void) { return g_err; }
+int64_t drb_launch_count(int32_t reset) { int64_t v = g_launches; if (reset) g_launches = 0; return v; }
+
+size_t drb_plan_workspace_bytes(const drb_config* cfg) {
+  if (!cfg || !cfg_ok(*cfg)) { set_error("invalid drb_config"); return 0; }
+  return make_layout(*cfg).total;
+}
+
+int drb_plan_set_branches(drb_plan* p, int32_t branches) {
+  if (!p) return DRB_E_INVALID;
+  const int B = p->cfg.batch;
+  int NB, nc;
+  if (branches == DRB_BRANCH_COND_UNCOND) { NB = 2 * B; nc = B; }
+  else if (branches == DRB_BRANCH_COND) { NB = B; nc = B; }
+  else if (branches == DRB_BRANCH_UNCOND) { NB = B; nc = 0; }
+  else if (branches == DRB_BRANCH_COND_ZEROSPEC) { NB = 2 * B; nc = B; }
+  else { set_error("bad branches %d", branches); return DRB_E_INVALID; }
+  if (NB > p->lay.NBcap) { set_error("plan was created for a single branch"); return DRB_E_INVALID; }
+  p->NB = NB; p->n_cond = nc; p->zero_spec = branches == DRB_BRANCH_COND_ZEROSPEC;
+  return 0;
+}
+
+int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w, void* workspace, size_t ws_bytes,
+                    void* stream) {
+  if (!out || !cfg || !w || !workspace) { set_error("null argument"); return DRB_E_INVALID; }
+  if (!cfg_ok(*cfg)) { set_error("invalid drb_config"); return DRB_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  Layout lay = make_layout(*cfg);
+  if (ws_bytes < lay.total || ((uintptr_t)workspace & 255)) {
+    set_error("workspace: need %zu bytes 256-aligned, got %zu", lay.total, ws_bytes);
+    return DRB_E_WORKSPACE;
+  }
+  drb_plan* p = new drb_plan();
+  p->cfg = *cfg; p->lay = lay; p->ws = (char*)workspace; p->mel = nullptr;
+  p->tables_ready = false; p->spec_ready = false;
+  const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
+  p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
+  p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
+  p->skw = w->skip_projection_w; p->skb = w->skip_projection_b; p->hdw = w->head_projection_w; p->hdb = w->head_projection_b;
+  int rc = drb_plan_set_branches(p, cfg->branches);
+  if (rc) { delete p; return rc; }
+#define PLAN_TRY(expr) do { int _r = (expr); if (_r) { drb_plan_destroy(p); return _r; } } while (0)
+  const bool tensor = cfg->precision != DRB_PREC_FP32;
+  if (tensor) PLAN_TRY(umma_init());
+  PLAN_TRY(mel_create(&p->mel, *cfg, w->stft_window, w->mel_fb, p->ws + lay.mel, mel_workspace_bytes(*cfg), s));
+  for (int i = 0; i < L; ++i) {
+    int e = i % cfg->dilation_bound, d = 1;
+    for (int j = 0; j < e; ++j) d *= cfg->dilation_base;  // dilation_base**(i % dilation_bound)  model/diffwave.py:624
+    p->dil.push_back(d);
+    p->dpw.push_back(w->diffusion_projection_w[i]); p->dpb.push_back(w->diffusion_projection_b[i]);
+    p->wo32.push_back(w->output_projection_w[i]); p->bo.push_back(w->output_projection_b[i]);
+    PLAN_TRY(launch_bias1(w->dilated_conv_b[i], w->conditioner_projection_b[i], w->conditioner_projection_w[i],
+                          p->bias_ptr(i, 0), p->bias_ptr(i, 1), p->bias_ptr(i, 2), p->bias_ptr(i, 3), C, cfg->n_mels, s));
+    float* tmp = p->at<float>(lay.wtmp);
+    if (!tensor) {
+      PLAN_TRY(launch_repack_conv_fp32(w->dilated_conv_w[i], p->at<float>(lay.wd32) + (size_t)i * 2 * C * k * C, 2 * C, C, k, s));
+      PLAN_TRY(launch_pad_rows(w->conditioner_projection_w[i], p->at<float>(lay.wc32) + (size_t)i * 2 * C * Mp, 2 * C,
+                               cfg->n_mels, Mp, s));
+    } else {
+      PLAN_TRY(launch_repack_conv_fp32(w->dilated_conv_w[i], tmp, 2 * C, C, k, s));
+      __nv_bfloat16* wdh = p->at<__nv_bfloat16>(lay.wdh) + (size_t)i * 2 * C * k * C;
+      __nv_bfloat16* wdl = p->at<__nv_bfloat16>(lay.wdl) + (size_t)i * 2 * C * k * C;
+      PLAN_TRY(launch_repack_split(tmp, wdh, wdl, 2 * C, k * C, k * C, C, s));
+      __nv_bfloat16* wch = p->at<__nv_bfloat16>(lay.wch) + (size_t)i * 2 * C * Mp;
+      __nv_bfloat16* wcl = p->at<__nv_bfloat16>(lay.wcl) + (size_t)i * 2 * C * Mp;
+      PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], wch, wcl, 2 * C, cfg->n_mels, Mp, C, s));
+      __nv_bfloat16* woh = p->at<__nv_bfloat16>(lay.woh) + (size_t)i * 2 * C * C;
+      __nv_bfloat16* wol = p->at<__nv_bfloat16>(lay.wol) + (size_t)i * 2 * C * C;
+      PLAN_TRY(launch_repack_split(w->output_projection_w[i], woh, wol, 2 * C, C, C, 0, s));
+      UmmaLayer ul;
+      PLAN_TRY(make_tmap_2d(&ul.wd_h, wdh, 2 * C, (uint64_t)k * C, 256, 64));
+      PLAN_TRY(make_tmap_2d(&ul.wd_l, wdl, 2 * C, (uint64_t)k * C, 256, 64));
+      PLAN_TRY(make_tmap_2d(&ul.wc_h, wch, 2 * C, Mp, 256, 64));
+      PLAN_TRY(make_tmap_2d(&ul.wc_l, wcl, 2 * C, Mp, 256, 64));
+      PLAN_TRY(make_tmap_2d(&ul.wo_h, woh, 2 * C, C, 256, 64));
+      PLAN_TRY(make_tmap_2d(&ul.wo_l, wol, 2 * C, C, 256, 64));
+      p->layers.push_back(ul);
+    }
+  }
+  if (tensor) {
+    const uint64_t NBc = lay.NBcap;
+    PLAN_TRY(make_tmap_3d(&p->maps.xh, p->ws + lay.xh, NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.xl, p->ws + lay.xl, NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.sl, p->ws + lay.sl, cfg->batch, T, Mp, 128, 64));
+  }
+#undef PLAN_TRY
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { set_error("plan_create sync: %s", cudaGetErrorString(e)); drb_plan_destroy(p); return (int)e; }
+  *out = p;
+  return 0;
+}
+
+int drb_plan_destroy(drb_plan* p) {
+  if (!p) return 0;
+  mel_destroy(p->mel);
+  delete p;
+  return 0;
+}
+
+int drb_time_tables(drb_plan* p, const float* emb_table, void* stream) {
+  if (!p || !emb_table) return DRB_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int TS = p->cfg.timesteps, C = p->cfg.residual_channels;
+  SimtGemm g;
+  g.A = emb_table; g.lda = 128; g.T = TS; g.Ck = 128; g.W = p->e1w; g.ldw = 128; g.bias = p->e1b; g.act = 2;
+  g.C = p->at<float>(p->lay.emb1); g.ldc = 512; g.M = TS; g.N = 512;
+  int r = launch_simt_gemm(g, s); if (r) return r;
+  g.A = p->at<float>(p->lay.emb1); g.lda = 512; g.Ck = 512; g.W = p->e2w; g.ldw = 512; g.bias = p->e2b;
+  g.C = p->at<float>(p->lay.emb2);
+  r = launch_simt_gemm(g, s); if (r) return r;
+  for (int i = 0; i < p->cfg.residual_layers; ++i) {
+    g.A = p->at<float>(p->lay.emb2); g.W = p->dpw[i]; g.bias = p->dpb[i]; g.act = 0;
+    g.C = p->at<float>(p->lay.dtab) + (size_t)i * TS * C; g.ldc = C; g.N = C;
+    r = launch_simt_gemm(g, s); if (r) return r;
+  }
+  p->tables_ready = true;
+  return 0;
+}
+
+int drb_mel_forward(drb_plan* p, const float* waveform, float* spec_out, int32_t it0, int32_t it1, int32_t if0,
+                    int32_t if1, void* stream) {
+  if (!p || !waveform) return DRB_E_INVALID;
+  const bool tensor = p->cfg.precision != DRB_PREC_FP32;
+  int r = mel_forward(p->mel, waveform, spec_out, p->at<float>(p->lay.spec32),
+                      tensor ? p->at<__nv_bfloat16>(p->lay.sh) : nullptr, tensor ? p->at<__nv_bfloat16>(p->lay.sl) : nullptr,
+                      p->lay.Mp, p->cfg.frames, it0, it1, if0, if1, (cudaStream_t)stream);
+  if (r == 0) p->spec_ready = true;
+  return r;
+}
+
+int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
+  if (!p || !x_t || t_index < 0 || t_index >= p->cfg.timesteps) { set_error("in_proj: bad argument"); return DRB_E_INVALID; }
+  if (!p->tables_ready) { set_error("drb_time_tables has not been called"); return DRB_E_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = p->cfg.batch, T = p->cfg.frames, C = p->cfg.residual_channels, F = p->cfg.pitches;
+  SimtGemm g;  // relu(input_projection(x_t))   model/diffwave.py:667-668 ; x_t [B,1,T,88] is already [B*T][88]
+  g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = p->in_w; g.ldw = F; g.bias = p->in_b; g.act = 1;
+  g.C = p->at<float>(p->lay.x32); g.ldc = C; g.M = B * T; g.N = C;
+  int r = launch_simt_gemm(g, s); if (r) return r;
+  const bool tensor = p->cfg.precision != DRB_PREC_FP32;
+  return launch_prep_xin(p->at<float>(p->lay.x32), tensor ? p->at<__nv_bfloat16>(p->lay.xh) : nullptr,
+                         tensor ? p->at<__nv_bfloat16>(p->lay.xl) : nullptr, p->dvec(0, t_index), B * T, C, p->NB / B,
+                         tensor ? 1 : 0, s);
+}
+
+int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stream) {
+  if (!p || layer < 0 || layer >= p->cfg.residual_layers || t_index < 0 || t_index >= p->cfg.timesteps) {
+    set_error("resblock: bad argument"); return DRB_E_INVALID;
+  }
+  if (!p->tables_ready) { set_error("drb_time_tables has not been called"); return DRB_E_STATE; }
+  if (p->n_cond > 0 && !p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const drb_config& c = p->cfg;
+  const int B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size, Mp = p->lay.Mp;
+  const int NB = p->NB, nc = p->n_cond;
+  const int first = layer == 0, do_res = layer < L - 1;
+  int r;
+  if (c.precision == DRB_PREC_FP32) {
+    float* x32 = p->at<float>(p->lay.x32); float* y = p->at<float>(p->lay.ybuf); float* z = p->at<float>(p->lay.z32);
+    SimtGemm g;  // dilated_conv(x + d)   model/diffwave.py:138-139
+    g.lda = C; g.T = T; g.taps = k; g.dil = p->dil[layer]; g.Ck = C; g.addvec = p->dvec(layer, t_index);
+    g.W = p->at<float>(p->lay.wd32) + (size_t)layer * 2 * C * k * C; g.ldw = k * C; g.ldc = 2 * C; g.N = 2 * C;
+    if (nc > 0) {
+      g.A = x32; g.C = y; g.M = nc * T; g.bias = p->bias_ptr(layer, 2);
+      r = launch_simt_gemm(g, s); if (r) return r;
+      SimtGemm q;  // + conditioner_projection(spec)   model/diffwave.py:143-144
+      q.A = p->at<float>(p->lay.spec32); q.lda = Mp; q.T = T; q.Ck = Mp;
+      q.W = p->at<float>(p->lay.wc32) + (size_t)layer * 2 * C * Mp; q.ldw = Mp; q.accumulate = 1;
+      q.C = y; q.ldc = 2 * C; q.M = nc * T; q.N = 2 * C;
+      r = launch_simt_gemm(q, s); if (r) return r;
+    }
+    if (NB > nc) {
+      g.A = x32 + (size_t)nc * T * C; g.C = y + (size_t)nc * T * 2 * C; g.M = (NB - nc) * T; g.bias = p->bias_ptr(layer, p->zero_spec ? 2 : 3);
+      r = launch_simt_gemm(g, s); if (r) return r;
+    }
+    r = launch_gate(y, z, NB * T, C, s); if (r) return r;
+    SimtGemm o;  // output_projection(z)   model/diffwave.py:149
+    o.A = z; o.lda = C; o.T = T; o.Ck = C; o.W = p->wo32[layer]; o.ldw = C; o.bias = p->bo[layer];
+    o.C = y; o.ldc = 2 * C; o.M = NB * T; o.N = 2 * C;
+    r = launch_simt_gemm(o, s); if (r) return r;
+    return launch_res_skip(y, x32, p->at<float>(p->lay.skip), NB * T, C, first, do_res, s);
+  }
+  UmmaGate ug;
+  ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
+  ug.three = c.precision == DRB_PREC_BF16X3;
+  ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
+  ug.zh = p->at<__nv_bfloat16>(p->lay.zh); ug.zl = p->at<__nv_bfloat16>(p->lay.zl);
+  r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;
+  UmmaOut uo;
+  uo.NB = NB; uo.T = T; uo.C = C; uo.three = ug.three; uo.first = first; uo.do_res = do_res; uo.bias_o = p->bo[layer];
+  uo.x32 = p->at<float>(p->lay.x32); uo.skip = p->at<float>(p->lay.skip);
+  uo.dnext = do_res ? p->dvec(layer + 1, t_index) : nullptr;
+  uo.xh = p->at<__nv_bfloat16>(p->lay.xh); uo.xl = p->at<__nv_bfloat16>(p->lay.xl);
+  return launch_umma_out(p->maps, p->layers[layer], uo, s);
+}
+
+int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, float* x_prev, float* net_out,
+                            const drb_update* upd, void* stream) {
+  if (!p || !x_prev || !upd) { set_error("head: null argument"); return DRB_E_INVALID; }
+  if (upd->has_noise && !noise) { set_error("head: has_noise without a noise pointer"); return DRB_E_INVALID; }
+  const bool needs_x = !(upd->mode == DRB_UPD_X0_FINAL || upd->mode == DRB_UPD_NONE);
+  if (needs_x && !x_t) { set_error("head: update mode %d needs x_t", upd->mode); return DRB_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const drb_config& c = p->cfg;
+  const int B = c.batch, T = c.frames, C = c.residual_channels, F = c.pitches;
+  float* h = p->at<float>(p->lay.hbuf);
+  SimtGemm g;  // relu(skip_projection(skip / sqrt(L)))   model/diffwave.py:682-684
+  g.A = p->at<float>(p->lay.skip); g.lda = C; g.T = T; g.Ck = C; g.a_div = sqrtf((float)c.residual_layers);
+  g.W = p->skw; g.ldw = C; g.bias = p->skb; g.act = 1; g.C = h; g.ldc = C; g.M = p->NB * T; g.N = C;
+  int r = launch_simt_gemm(g, s); if (r) return r;
+  SimtGemm o;  // output_projection + guidance combine + posterior update
+  o.A = h; o.lda = C; o.T = T; o.Ck = C; o.W = p->hdw; o.ldw = C; o.bias = p->hdb;
+  if (p->NB == 2 * B) {  // (1+w)*x0_c - w*x0_u, applied to the (linear) head's input   task/diffusion.py:1009
+    o.A2 = h + (size_t)B * T * C; o.alpha = 1.f + upd->w; o.beta = -upd->w;
+  }
+  o.C = x_prev; o.ldc = F; o.M = B * T; o.N = F; o.upd = upd; o.x_t = x_t; o.noise = noise; o.net_out = net_out;
+  return launch_simt_gemm(o, s);
+}
+
+int drb_sample_step(drb_plan* p, const float* x_t, const float* noise, float* x_prev, int32_t t_index,
+                    const drb_update* upd, void* stream) {
+  int r = drb_in_proj(p, x_t, t_index, stream); if (r) return r;
+  for (int l = 0; l < p->cfg.residual_layers; ++l) { r = drb_resblock_forward(p, l, t_index, stream); if (r) return r; }
+  return drb_head_posterior_step(p, x_t, noise, x_prev, nullptr, upd, stream);
+}
+
+int drb_sample_loop(drb_plan* p, float* x, const float* noise, const drb_update* updates_host, int32_t t_start,
+                    int32_t t_stop, float* trajectory, void* stream) {
+  if (!p || !x || !updates_host || t_start <= t_stop || t_stop < 0 || t_start > p->cfg.timesteps) {
+    set_error("sample_loop: bad argument"); return DRB_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)p->cfg.batch * p->cfg.frames * p->cfg.pitches;
+  size_t j = 0;
+  for (int t = t_start - 1, i = 0; t >= t_stop; --t, ++i) {
+    const drb_update* u = &updates_host[i];
+    const float* nz = nullptr;
+    if (u->has_noise) { if (!noise) { set_error("sample_loop: noise missing"); return DRB_E_INVALID; } nz = noise + (j++) * n; }
+    int r = drb_sample_step(p, x, nz, x, t, u, stream); if (r) return r;
+    if (trajectory) DRB_CUDA(cudaMemcpyAsync(trajectory + (size_t)i * n, x, n * sizeof(float), cudaMemcpyDefault, s));
+  }
+  return 0;
+}
+
+int drb_plan_buffer(drb_plan* p, const char* name, void** ptr, size_t* bytes) {
+  if (!p || !name || !ptr) return DRB_E_INVALID;
+  const drb_config& c = p->cfg;
+  const size_t rows = (size_t)p->lay.NBcap * c.frames, C = c.residual_channels;
+  const bool tensor = c.precision != DRB_PREC_FP32;
+  std::string n(name);
+  size_t off = 0, sz = 0; bool ok = true;
+  if (n == "x32") { off = p->lay.x32; sz = rows * C * 4; }
+  else if (n == "skip") { off = p->lay.skip; sz = rows * C * 4; }
+  else if (n == "h") { off = p->lay.hbuf; sz = rows * C * 4; }
+  else if (n == "dtab") { off = p->lay.dtab; sz = (size_t)c.residual_layers * c.timesteps * C * 4; }
+  else if (n == "spec32") { off = p->lay.spec32; sz = (size_t)c.batch * c.frames * p->lay.Mp * 4; }
+  else if (n == "y" && !tensor) { off = p->lay.ybuf; sz = rows * 2 * C * 4; }
+  else if (n == "z32" && !tensor) { off = p->lay.z32; sz = rows * C * 4; }
+  else if (n == "xh" && tensor) { off = p->lay.xh; sz = rows * C * 2; }
+  else if (n == "xl" && tensor) { off = p->lay.xl; sz = rows * C * 2; }
+  else if (n == "zh" && tensor) { off = p->lay.zh; sz = rows * C * 2; }
+  else if (n == "zl" && tensor) { off = p->lay.zl; sz = rows * C * 2; }
+  else if (n == "logmel") { *ptr = mel_logmel_ptr(p->mel, bytes); return 0; }
+  else ok = false;
+  if (!ok) { set_error("unknown buffer '%s'", name); return DRB_E_INVALID; }
+  *ptr = p->ws + off; if (bytes) *bytes = sz;
+  return 0;
+}
+
+}  // extern "C"

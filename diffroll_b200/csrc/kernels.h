@@ -1,0 +1,101 @@
+// Host-side launchers shared between the translation units of libdiffroll_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include "../../include/diffroll_b200.h"
+
+namespace drb {
+
+// ------------------------------- fp32 CUDA-core GEMM (simt_kernels.cu) -------------------------
+// C[m][n] = epi( sum_k Aeff[m][k] * W[n][k] + bias[n] ),  m in [0,M), n in [0,N)
+//   Aeff[m][k]: k = tap*Ck + c;  row m = seg*T + t;  source row t' = t + (tap - taps/2)*dil
+//               Aeff = (alpha*A[(seg*T+t')*lda + c] + beta*A2[...]) / a_div + addvec[c]   if 0<=t'<T else 0
+struct SimtGemm {
+  const float* A = nullptr;
+  const float* A2 = nullptr;  // optional second source (guidance combine), same indexing
+  float alpha = 1.f, beta = 0.f, a_div = 1.f;  // Aeff = (alpha*A + beta*A2) / a_div + addvec
+  const float* addvec = nullptr;  // [Ck], optional
+  int lda = 0;
+  int T = 1;  // rows per segment (conv boundary)
+  int taps = 1, dil = 1, Ck = 0;
+  const float* W = nullptr;
+  int ldw = 0;
+  const float* bias = nullptr;
+  int act = 0;         // 0 none, 1 relu, 2 silu
+  int accumulate = 0;  // C += ...
+  float* C = nullptr;
+  int ldc = 0;
+  int M = 0, N = 0;
+  // optional fused posterior update (out = upd(net, x_t, noise)); net written to net_out if non-null
+  const drb_update* upd = nullptr;  // host pointer, copied by value
+  const float* x_t = nullptr;
+  const float* noise = nullptr;
+  float* net_out = nullptr;
+};
+int launch_simt_gemm(const SimtGemm& g, cudaStream_t s);
+
+// elementwise (simt_kernels.cu)
+int launch_gate(const float* y, float* z, int M, int C, cudaStream_t s);  // z = sigmoid(y[:, :C]) * tanh(y[:, C:])
+int launch_res_skip(const float* o, float* x, float* skip, int M, int C, int first, int do_res, cudaStream_t s);
+// x32 rows [0,Mb) hold relu(in_proj); duplicate them `copies` times (branches) and emit bf16 hi/lo of x + d
+int launch_prep_xin(float* x32, __nv_bfloat16* xh, __nv_bfloat16* xl, const float* dvec, int Mb, int C, int copies,
+                    int write_split, cudaStream_t s);
+int launch_split_rows(const float* src, __nv_bfloat16* h, __nv_bfloat16* l, const float* addvec, int M, int C,
+                      cudaStream_t s);
+// weight repacks
+int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cudaStream_t s);  // [OC][C][k] -> [OC][k][C]
+// [OC=2C][Kin] fp32 (k index already tap-major) -> bf16 hi/lo rows permuted into 256-wide gate/filter blocks, K padded to Kp
+int launch_repack_split(const float* w, __nv_bfloat16* h, __nv_bfloat16* l, int OC, int Kin, int Kp, int interleave_C,
+                        cudaStream_t s);
+int launch_pad_rows(const float* src, float* dst, int rows, int Kin, int Kp, cudaStream_t s);
+// bias1[n'] (interleaved) = bd[n] + bc[n] (- sum_k Wc[n][k] if uncond)
+int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_cond, float* out_unc,
+                 float* out_cond_nat, float* out_unc_nat, int C, int n_mels, cudaStream_t s);
+int launch_fill(float* p, float v, size_t n, cudaStream_t s);
+
+// ------------------------------- mel front-end (mel.cu) ----------------------------------------
+struct MelPlan;
+size_t mel_workspace_bytes(const drb_config& c);
+int mel_create(MelPlan** mp, const drb_config& c, const float* window, const float* fb, void* ws, size_t ws_bytes,
+               cudaStream_t s);
+void mel_destroy(MelPlan* mp);
+// logmel -> normalised -> masked.  spec_out [B][n_mels][T] fp32 (nullable), spec32 [B][T][Mp] fp32 zero-padded,
+// spec_h/spec_l [B][T][Mp] bf16 (nullable)
+int mel_forward(MelPlan* mp, const float* waveform, float* spec_out, float* spec32, __nv_bfloat16* spec_h,
+                __nv_bfloat16* spec_l, int Mp, int T, int it0, int it1, int if0, int if1, cudaStream_t s);
+float* mel_logmel_ptr(MelPlan* mp, size_t* bytes);
+
+// ------------------------------- tcgen05 GEMMs (umma_gemm.cu) ----------------------------------
+struct UmmaLayer {
+  CUtensorMap wd_h, wd_l;  // [2C rows (interleaved)][k*C] bf16
+  CUtensorMap wc_h, wc_l;  // [2C][Mp]
+  CUtensorMap wo_h, wo_l;  // [2C][C]
+};
+struct UmmaMaps {
+  CUtensorMap xh, xl;      // [NB][T][C]
+  CUtensorMap zh, zl;      // [NB][T][C]
+  CUtensorMap sh, sl;      // [B][T][Mp]
+};
+struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl
+  int NB, n_cond, T, C, taps, dil, Mp, three;  // three: 1 = bf16x3, 0 = single product
+  const float* bias_cond;  // interleaved [2C]
+  const float* bias_unc;
+  __nv_bfloat16 *zh, *zl;
+};
+struct UmmaOut {   // o = z*Wo^T + bo ; x = (x + o[:C])/sqrt2 ; xin_next = split(x + dnext) ; skip (+)= o[C:]
+  int NB, T, C, three, first, do_res;
+  const float* bias_o;
+  float* x32;
+  float* skip;
+  const float* dnext;  // nullable when !do_res
+  __nv_bfloat16 *xh, *xl;
+};
+int umma_init();  // resolves cuTensorMapEncodeTiled
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0);
+int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g, cudaStream_t s);
+int launch_umma_out(const UmmaMaps& maps, const UmmaLayer& L, const UmmaOut& o, cudaStream_t s);
+
+}  // namespace drb

@@ -1,0 +1,249 @@
+// STFT -> power -> HTK mel -> log -> per-clip min-max -> mask.  Replaces, for one clip batch,
+//   torchaudio MelSpectrogram(...)            model/diffwave.py:635,643   (third-party torchaudio 0.11.0)
+//   torch.log(spec + 1e-6)                    model/diffwave.py:644
+//   Normalization(0,1,'imagewise')            model/diffwave.py:645, model/utils.py:21-32
+//   inpainting masks                          model/diffwave.py:649-654
+// The FFT itself is cuFFT (R2C, batched); framing/windowing is fused into its producer kernel and
+// power/mel/log/min-max into its consumer kernel.  The mel "matmul" uses the band structure of the
+// filterbank (<= ~24 non-zeros per mel bin) instead of a dense [1025 x 229] product.
+#include <cufft.h>
+#include <limits.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace drb {
+
+struct MelPlan {
+  int B, L, n_fft, hop, n_mels, nF, nbins;
+  cufftHandle fft;
+  bool fft_ok;
+  const float* window;  // caller-owned (state_dict buffer)
+  const float* fb;      // caller-owned [nbins][n_mels]
+  float* frames;        // [B*nF][n_fft]
+  float2* spectrum;     // [B*nF][nbins]
+  float* logmel;        // [B][nF][n_mels]
+  int* band_start;      // [n_mels]
+  int* band_len;        // [n_mels]
+  float* wnorm;         // [1] sqrt(sum w^2)
+  int* minmax;          // [B][2] order-preserving int encodings
+  void* fft_work;
+  size_t fft_work_bytes;
+};
+
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+static size_t fft_work_estimate(int n_fft, int batch) {
+  // Deterministic (no CUDA context needed): one spectrum-sized scratch.  mel_create falls back to cuFFT-owned
+  // scratch if the real requirement turns out larger.
+  return align_up((size_t)batch * (n_fft / 2 + 1) * sizeof(float2) + (1 << 20));
+}
+
+size_t mel_workspace_bytes(const drb_config& c) {
+  const int nF = c.wave_len / c.hop_length + 1, nbins = c.n_fft / 2 + 1;
+  const size_t rows = (size_t)c.batch * nF;
+  size_t b = 0;
+  b += align_up(rows * c.n_fft * sizeof(float));
+  b += align_up(rows * nbins * sizeof(float2));
+  b += align_up(rows * c.n_mels * sizeof(float));
+  b += align_up(c.n_mels * sizeof(int)) * 2;
+  b += align_up(sizeof(float));
+  b += align_up((size_t)c.batch * 2 * sizeof(int));
+  b += fft_work_estimate(c.n_fft, (int)rows);
+  return b;
+}
+
+__global__ void band_kernel(const float* __restrict__ fb, int nbins, int n_mels, int* __restrict__ start,
+                            int* __restrict__ len) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_mels) return;
+  int first = -1, last = -1;
+  for (int f = 0; f < nbins; ++f)
+    if (fb[(size_t)f * n_mels + m] != 0.f) { if (first < 0) first = f; last = f; }
+  start[m] = first < 0 ? 0 : first;
+  len[m] = first < 0 ? 0 : last - first + 1;
+}
+
+__global__ void wnorm_kernel(const float* __restrict__ w, int n, float* __restrict__ out) {
+  // window.pow(2.).sum().sqrt()   (torchaudio functional.spectrogram, normalized="window")
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)w[i] * (double)w[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) out[0] = (float)sqrt(red[0]);
+}
+
+__global__ void frame_kernel(const float* __restrict__ wave, const float* __restrict__ window, float* __restrict__ frames,
+                             int L, int n_fft, int hop, int nF) {
+  // center=True, pad_mode='reflect': padded[p] = wave[reflect(p - n_fft/2)]; frame t covers p in [t*hop, t*hop+n_fft)
+  const int t = blockIdx.x, b = blockIdx.y;
+  const float* w = wave + (size_t)b * L;
+  float* out = frames + ((size_t)b * nF + t) * n_fft;
+  const int base = t * hop - n_fft / 2;
+  for (int n = threadIdx.x; n < n_fft; n += blockDim.x) {
+    int i = base + n;
+    if (i < 0) i = -i;
+    if (i >= L) i = 2 * (L - 1) - i;
+    out[n] = window[n] * w[i];
+  }
+}
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void minmax_init_kernel(int* mm, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) { mm[2 * i] = INT_MAX; mm[2 * i + 1] = INT_MIN; }
+}
+
+__global__ void __launch_bounds__(256) power_mel_kernel(const float2* __restrict__ spectrum, const float* __restrict__ fb,
+                                                        const int* __restrict__ band_start, const int* __restrict__ band_len,
+                                                        const float* __restrict__ wnorm, float* __restrict__ logmel,
+                                                        int* __restrict__ minmax, int nbins, int n_mels, int nF) {
+  extern __shared__ float pw[];  // [nbins]
+  __shared__ int smin[8], smax[8];
+  const int t = blockIdx.x, b = blockIdx.y;
+  const float2* sp = spectrum + ((size_t)b * nF + t) * nbins;
+  const float s = wnorm[0];
+  for (int f = threadIdx.x; f < nbins; f += blockDim.x) {
+    float2 v = sp[f];
+    float re = v.x / s, im = v.y / s;  // spec_f /= window.pow(2).sum().sqrt()
+    pw[f] = re * re + im * im;         // .abs().pow(2)
+  }
+  __syncthreads();
+  int lmin = INT_MAX, lmax = INT_MIN;
+  for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
+    const int f0 = band_start[m], n = band_len[m];
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc = fmaf(pw[f0 + i], fb[(size_t)(f0 + i) * n_mels + m], acc);
+    float v = logf(acc + 1e-6f);  // torch.log(spec + 1e-6)
+    logmel[((size_t)b * nF + t) * n_mels + m] = v;
+    if (v == v) { int o = f2ord(v); lmin = min(lmin, o); lmax = max(lmax, o); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lmin; smax[threadIdx.x >> 5] = lmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { lmin = min(lmin, smin[i]); lmax = max(lmax, smax[i]); }
+    atomicMin(&minmax[2 * b], lmin);
+    atomicMax(&minmax[2 * b + 1], lmax);
+  }
+}
+
+__global__ void __launch_bounds__(256) spec_finalize_kernel(const float* __restrict__ logmel, const int* __restrict__ minmax,
+                                                            float* __restrict__ spec_out, float* __restrict__ spec32,
+                                                            __nv_bfloat16* __restrict__ spec_h, __nv_bfloat16* __restrict__ spec_l,
+                                                            int n_mels, int nF, int T, int Mp, int it0, int it1, int if0, int if1) {
+  extern __shared__ float tile[];  // [32][n_mels+1]
+  const int t0 = blockIdx.x * 32, b = blockIdx.y;
+  const float vmin = ord2f(minmax[2 * b]), vmax = ord2f(minmax[2 * b + 1]);
+  const float range = vmax - vmin;
+  const bool has_t = it1 > it0, has_f = if1 > if0;
+  const int ld = n_mels + 1;
+  for (int idx = threadIdx.x; idx < 32 * Mp; idx += blockDim.x) {
+    const int r = idx / Mp, m = idx - r * Mp, t = t0 + r;
+    if (t >= T) continue;
+    float v = 0.f;
+    if (m < n_mels) {
+      v = (logmel[((size_t)b * nF + t) * n_mels + m] - vmin) / range;  // (x - min)/(max - min) * (1-0) + 0
+      if (v != v) v = 0.f;                                             // x_scaled[isnan] = min
+      const bool in_t = t >= it0 && t < it1, in_f = m >= if0 && m < if1;
+      const bool masked = (has_t && has_f) ? (in_t && in_f) : (has_t ? in_t : (has_f ? in_f : false));
+      if (masked) v = -1.f;                                            // model/diffwave.py:649-654
+      tile[r * ld + m] = v;
+    }
+    const size_t o = ((size_t)b * T + t) * Mp + m;
+    if (spec32) spec32[o] = v;
+    if (spec_h) { __nv_bfloat16 h, l; split_bf16(v, h, l); spec_h[o] = h; spec_l[o] = l; }
+  }
+  __syncthreads();
+  if (spec_out) {
+    for (int idx = threadIdx.x; idx < 32 * n_mels; idx += blockDim.x) {
+      const int m = idx >> 5, r = idx & 31, t = t0 + r;
+      if (t < T) spec_out[((size_t)b * n_mels + m) * T + t] = tile[r * ld + m];
+    }
+  }
+}
+
+int mel_create(MelPlan** out, const drb_config& c, const float* window, const float* fb, void* ws, size_t ws_bytes,
+               cudaStream_t s) {
+  MelPlan* p = new MelPlan();
+  p->B = c.batch; p->L = c.wave_len; p->n_fft = c.n_fft; p->hop = c.hop_length; p->n_mels = c.n_mels;
+  p->nF = c.wave_len / c.hop_length + 1; p->nbins = c.n_fft / 2 + 1;
+  p->window = window; p->fb = fb; p->fft_ok = false;
+  const size_t rows = (size_t)p->B * p->nF;
+  char* base = (char*)ws; size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = base + off; off += align_up(bytes); return r; };
+  p->frames = (float*)take(rows * p->n_fft * sizeof(float));
+  p->spectrum = (float2*)take(rows * p->nbins * sizeof(float2));
+  p->logmel = (float*)take(rows * p->n_mels * sizeof(float));
+  p->band_start = (int*)take(p->n_mels * sizeof(int));
+  p->band_len = (int*)take(p->n_mels * sizeof(int));
+  p->wnorm = (float*)take(sizeof(float));
+  p->minmax = (int*)take((size_t)p->B * 2 * sizeof(int));
+  p->fft_work = base + off;
+  p->fft_work_bytes = ws_bytes > off ? ws_bytes - off : 0;
+
+  if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { set_error("cufftCreate failed"); delete p; return DRB_E_CUFFT; }
+  p->fft_ok = true;
+  cufftSetAutoAllocation(p->fft, 0);
+  int n[1] = {p->n_fft};
+  size_t need = 0;
+  cufftResult r = cufftMakePlanMany(p->fft, 1, n, nullptr, 1, p->n_fft, nullptr, 1, p->nbins, CUFFT_R2C, (int)rows, &need);
+  if (r != CUFFT_SUCCESS) { set_error("cufftMakePlanMany failed (%d)", (int)r); mel_destroy(p); return DRB_E_CUFFT; }
+  if (need > p->fft_work_bytes) {
+    // The estimate used to size the workspace was too small for this cuFFT version: let cuFFT own its scratch.
+    cufftDestroy(p->fft);
+    if (cufftCreate(&p->fft) != CUFFT_SUCCESS) { p->fft_ok = false; set_error("cufftCreate failed"); mel_destroy(p); return DRB_E_CUFFT; }
+    r = cufftMakePlanMany(p->fft, 1, n, nullptr, 1, p->n_fft, nullptr, 1, p->nbins, CUFFT_R2C, (int)rows, &need);
+    if (r != CUFFT_SUCCESS) { set_error("cufftMakePlanMany failed (%d)", (int)r); mel_destroy(p); return DRB_E_CUFFT; }
+  } else if (cufftSetWorkArea(p->fft, p->fft_work) != CUFFT_SUCCESS) {
+    set_error("cufftSetWorkArea failed"); mel_destroy(p); return DRB_E_CUFFT;
+  }
+
+  band_kernel<<<(p->n_mels + 127) / 128, 128, 0, s>>>(fb, p->nbins, p->n_mels, p->band_start, p->band_len);
+  DRB_LAUNCH_CHECK();
+  wnorm_kernel<<<1, 256, 0, s>>>(window, p->n_fft, p->wnorm);
+  DRB_LAUNCH_CHECK();
+  *out = p;
+  return 0;
+}
+
+void mel_destroy(MelPlan* p) {
+  if (!p) return;
+  if (p->fft_ok) cufftDestroy(p->fft);
+  delete p;
+}
+
+float* mel_logmel_ptr(MelPlan* p, size_t* bytes) {
+  if (bytes) *bytes = (size_t)p->B * p->nF * p->n_mels * sizeof(float);
+  return p->logmel;
+}
+
+int mel_forward(MelPlan* p, const float* waveform, float* spec_out, float* spec32, __nv_bfloat16* spec_h,
+                __nv_bfloat16* spec_l, int Mp, int T, int it0, int it1, int if0, int if1, cudaStream_t s) {
+  if (T > p->nF) { set_error("mel_forward: T=%d > frames %d", T, p->nF); return DRB_E_INVALID; }
+  dim3 grid(p->nF, p->B);
+  frame_kernel<<<grid, 256, 0, s>>>(waveform, p->window, p->frames, p->L, p->n_fft, p->hop, p->nF);
+  DRB_LAUNCH_CHECK();
+  if (cufftSetStream(p->fft, s) != CUFFT_SUCCESS) { set_error("cufftSetStream failed"); return DRB_E_CUFFT; }
+  cufftResult r = cufftExecR2C(p->fft, p->frames, (cufftComplex*)p->spectrum);
+  if (r != CUFFT_SUCCESS) { set_error("cufftExecR2C failed (%d)", (int)r); return DRB_E_CUFFT; }
+  minmax_init_kernel<<<(p->B + 127) / 128, 128, 0, s>>>(p->minmax, p->B);
+  DRB_LAUNCH_CHECK();
+  power_mel_kernel<<<grid, 256, p->nbins * sizeof(float), s>>>(p->spectrum, p->fb, p->band_start, p->band_len, p->wnorm,
+                                                              p->logmel, p->minmax, p->nbins, p->n_mels, p->nF);
+  DRB_LAUNCH_CHECK();
+  dim3 g2((T + 31) / 32, p->B);
+  size_t sm = (size_t)32 * (p->n_mels + 1) * sizeof(float);
+  spec_finalize_kernel<<<g2, 256, sm, s>>>(p->logmel, p->minmax, spec_out, spec32, spec_h, spec_l, p->n_mels, p->nF, T,
+                                           Mp, it0, it1, if0, if1);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace drb

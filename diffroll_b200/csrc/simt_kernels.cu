@@ -1,0 +1,375 @@
+// fp32 CUDA-core kernels: the generic (dilated-conv-gather) GEMM used by the DRB_PREC_FP32 path and by the
+// small projections of every path, plus the elementwise and weight-repack kernels.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace drb {
+
+// =================================================================================================
+// Generic fp32 GEMM, 128x128x16 tiles, 256 threads, 8x8 outputs per thread (two 4x4 quadrant pairs).
+// =================================================================================================
+constexpr int BM = 128, BN = 128, BK = 16;
+
+struct SimtGemmDev {
+  const float* A; const float* A2; float alpha, beta, a_div; const float* addvec; int lda, T, taps, dil, Ck;
+  const float* W; int ldw; const float* bias; int act, accumulate; float* C; int ldc, M, N, K;
+  int upd_on; drb_update upd; const float* x_t; const float* noise; float* net_out;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v * (1.f / (1.f + expf(-v)));  // x * sigmoid(x)   model/diffwave.py:53-55
+  return v;
+}
+
+__device__ __forceinline__ float posterior_update(const drb_update& u, float net, float x, float n) {
+  // Same operation order as the reference's fp32 tensor expressions (see DRB_UPD_* in diffroll_b200.h).
+  switch (u.mode) {
+    case DRB_UPD_X0: {
+      float r = u.s[0] * net + u.s[1] * (x - u.s[2] * net) / u.s[3];
+      return u.has_noise ? r + u.s[4] * n : r;
+    }
+    case DRB_UPD_X0_FINAL: return net / u.s[0];
+    case DRB_UPD_EPS_DDPM: {
+      float r = u.s[0] * (x - u.s[1] * net / u.s[2]);
+      return u.has_noise ? r + u.s[3] * n : r;
+    }
+    case DRB_UPD_EPS_DDIM: {
+      float r = u.s[0] * ((x - u.s[1] * net) / u.s[2]) + u.s[3] * net;
+      return u.has_noise ? r + u.s[4] * n : r;
+    }
+    case DRB_UPD_EPS_FINAL: return (x - u.s[0] * net) / u.s[1];
+    default: return net;
+  }
+}
+
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmDev g) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // loader mapping: one row, 8 consecutive k per thread
+  const int lrow = tid & 127, lk = (tid >> 7) * 8;
+  const int am = m0 + lrow;
+  const bool a_row_ok = am < g.M;
+  const int seg = a_row_ok ? am / g.T : 0, t = a_row_ok ? am - seg * g.T : 0;
+  const int bn = n0 + lrow;
+  const bool b_row_ok = bn < g.N;
+  const int half = g.taps / 2;
+
+  float4 ra[2], rb[2];
+  auto load_tile = [&](int k0) {
+    // A
+    int tap = k0 / g.Ck, c0 = k0 - tap * g.Ck + lk;
+    int tt = t + (tap - half) * g.dil;
+    bool ok = a_row_ok && tt >= 0 && tt < g.T;
+    const float* ap = g.A + ((size_t)(seg * g.T + tt) * g.lda + c0);
+    const float* ap2 = g.A2 ? g.A2 + ((size_t)(seg * g.T + tt) * g.lda + c0) : nullptr;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && (k0 + lk + q * 4 + 3) < g.K) {
+        v = *reinterpret_cast<const float4*>(ap + q * 4);
+        if (ap2) {
+          float4 w = *reinterpret_cast<const float4*>(ap2 + q * 4);
+          v.x = g.alpha * v.x + g.beta * w.x; v.y = g.alpha * v.y + g.beta * w.y;
+          v.z = g.alpha * v.z + g.beta * w.z; v.w = g.alpha * v.w + g.beta * w.w;
+        }
+        if (g.a_div != 1.f) { v.x /= g.a_div; v.y /= g.a_div; v.z /= g.a_div; v.w /= g.a_div; }
+        if (g.addvec) {
+          float4 d = *reinterpret_cast<const float4*>(g.addvec + c0 + q * 4);
+          v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+        }
+      }
+      ra[q] = v;
+    }
+    // W
+    const float* wp = g.W + ((size_t)bn * g.ldw + k0 + lk);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b_row_ok && (k0 + lk + q * 4 + 3) < g.K) v = *reinterpret_cast<const float4*>(wp + q * 4);
+      rb[q] = v;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      As[buf][lk + q * 4 + 0][lrow] = ra[q].x; As[buf][lk + q * 4 + 1][lrow] = ra[q].y;
+      As[buf][lk + q * 4 + 2][lrow] = ra[q].z; As[buf][lk + q * 4 + 3][lrow] = ra[q].w;
+      Bs[buf][lk + q * 4 + 0][lrow] = rb[q].x; Bs[buf][lk + q * 4 + 1][lrow] = rb[q].y;
+      Bs[buf][lk + q * 4 + 2][lrow] = rb[q].z; Bs[buf][lk + q * 4 + 3][lrow] = rb[q].w;
+    }
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = (g.K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) load_tile((kb + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n];
+      v = act_apply(v, g.act);
+      const size_t idx = (size_t)m * g.ldc + n;
+      if (g.accumulate) v += g.C[idx];
+      if (g.upd_on) {
+        if (g.net_out) g.net_out[idx] = v;
+        float x = (g.upd.mode == DRB_UPD_X0_FINAL || g.upd.mode == DRB_UPD_NONE) ? 0.f : g.x_t[idx];
+        float nz = g.upd.has_noise ? g.noise[idx] : 0.f;
+        v = posterior_update(g.upd, v, x, nz);
+      }
+      g.C[idx] = v;
+    }
+  }
+}
+
+int launch_simt_gemm(const SimtGemm& s, cudaStream_t st) {
+  SimtGemmDev g;
+  g.A = s.A; g.A2 = s.A2; g.alpha = s.alpha; g.beta = s.beta; g.a_div = s.a_div; g.addvec = s.addvec;
+  g.lda = s.lda; g.T = s.T; g.taps = s.taps; g.dil = s.dil; g.Ck = s.Ck; g.W = s.W; g.ldw = s.ldw; g.bias = s.bias;
+  g.act = s.act; g.accumulate = s.accumulate; g.C = s.C; g.ldc = s.ldc; g.M = s.M; g.N = s.N; g.K = s.taps * s.Ck;
+  g.upd_on = s.upd != nullptr; if (s.upd) g.upd = *s.upd; else { g.upd.mode = DRB_UPD_NONE; g.upd.has_noise = 0; }
+  g.x_t = s.x_t; g.noise = s.noise; g.net_out = s.net_out;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || (g.Ck % 4) || (g.lda % 4) || (g.ldw % 4) || (s.taps > 1 && (g.Ck % BK))) {
+    set_error("simt_gemm: unsupported shape M=%d N=%d K=%d Ck=%d lda=%d ldw=%d", g.M, g.N, g.K, g.Ck, g.lda, g.ldw);
+    return DRB_E_INVALID;
+  }
+  dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);
+  simt_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// Elementwise
+// =================================================================================================
+__global__ void gate_kernel(const float* __restrict__ y, float* __restrict__ z, int M, int C) {
+  // z = sigmoid(gate) * tanh(filter)   model/diffwave.py:146-147
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)M * C / 4;
+  if (i >= n) return;
+  size_t m = (i * 4) / C; int c = (int)((i * 4) % C);
+  float4 gt = *reinterpret_cast<const float4*>(y + m * 2 * C + c);
+  float4 ft = *reinterpret_cast<const float4*>(y + m * 2 * C + C + c);
+  float4 o;
+  o.x = (1.f / (1.f + expf(-gt.x))) * tanhf(ft.x);
+  o.y = (1.f / (1.f + expf(-gt.y))) * tanhf(ft.y);
+  o.z = (1.f / (1.f + expf(-gt.z))) * tanhf(ft.z);
+  o.w = (1.f / (1.f + expf(-gt.w))) * tanhf(ft.w);
+  *reinterpret_cast<float4*>(z + m * C + c) = o;
+}
+int launch_gate(const float* y, float* z, int M, int C, cudaStream_t s) {
+  size_t n = (size_t)M * C / 4;
+  gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, z, M, C);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void res_skip_kernel(const float* __restrict__ o, float* __restrict__ x, float* __restrict__ skip, int M,
+                                int C, int first, int do_res) {
+  // x = (x + residual)/sqrt(2) ; skip += skip_l     model/diffwave.py:150-151, 680
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)M * C / 4;
+  if (i >= n) return;
+  size_t m = (i * 4) / C; int c = (int)((i * 4) % C);
+  const float rs2 = 1.41421356237309515f;
+  if (do_res) {
+    float4 r = *reinterpret_cast<const float4*>(o + m * 2 * C + c);
+    float4 xv = *reinterpret_cast<float4*>(x + m * C + c);
+    xv.x = (xv.x + r.x) / rs2; xv.y = (xv.y + r.y) / rs2; xv.z = (xv.z + r.z) / rs2; xv.w = (xv.w + r.w) / rs2;
+    *reinterpret_cast<float4*>(x + m * C + c) = xv;
+  }
+  float4 sk = *reinterpret_cast<const float4*>(o + m * 2 * C + C + c);
+  if (!first) {
+    float4 p = *reinterpret_cast<float4*>(skip + m * C + c);
+    sk.x += p.x; sk.y += p.y; sk.z += p.z; sk.w += p.w;
+  }
+  *reinterpret_cast<float4*>(skip + m * C + c) = sk;
+}
+int launch_res_skip(const float* o, float* x, float* skip, int M, int C, int first, int do_res, cudaStream_t s) {
+  size_t n = (size_t)M * C / 4;
+  res_skip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, x, skip, M, C, first, do_res);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void prep_xin_kernel(float* __restrict__ x32, __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl,
+                                const float* __restrict__ dvec, int Mb, int C, int copies, int write_split) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)Mb * C / 4;
+  if (i >= n) return;
+  size_t e = i * 4; int c = (int)(e % C);
+  float4 v = *reinterpret_cast<const float4*>(x32 + e);
+  uint32_t h0, l0, h1, l1;
+  if (write_split) {
+    float4 d = *reinterpret_cast<const float4*>(dvec + c);
+    split_pack2(v.x + d.x, v.y + d.y, h0, l0);
+    split_pack2(v.z + d.z, v.w + d.w, h1, l1);
+  }
+  for (int r = 0; r < copies; ++r) {
+    size_t off = (size_t)r * Mb * C + e;
+    if (r > 0) *reinterpret_cast<float4*>(x32 + off) = v;
+    if (write_split) {
+      *reinterpret_cast<uint2*>(xh + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(xl + off) = make_uint2(l0, l1);
+    }
+  }
+}
+int launch_prep_xin(float* x32, __nv_bfloat16* xh, __nv_bfloat16* xl, const float* dvec, int Mb, int C, int copies,
+                    int write_split, cudaStream_t s) {
+  if (copies <= 1 && !write_split) return 0;
+  size_t n = (size_t)Mb * C / 4;
+  prep_xin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x32, xh, xl, dvec, Mb, C, copies, write_split);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void split_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ h,
+                                  __nv_bfloat16* __restrict__ l, const float* __restrict__ addvec, int M, int C) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)M * C / 4;
+  if (i >= n) return;
+  size_t e = i * 4; int c = (int)(e % C);
+  float4 v = *reinterpret_cast<const float4*>(src + e);
+  if (addvec) { float4 d = *reinterpret_cast<const float4*>(addvec + c); v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w; }
+  uint32_t h0, l0, h1, l1;
+  split_pack2(v.x, v.y, h0, l0);
+  split_pack2(v.z, v.w, h1, l1);
+  *reinterpret_cast<uint2*>(h + e) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(l + e) = make_uint2(l0, l1);
+}
+int launch_split_rows(const float* src, __nv_bfloat16* h, __nv_bfloat16* l, const float* addvec, int M, int C,
+                      cudaStream_t s) {
+  size_t n = (size_t)M * C / 4;
+  split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, h, l, addvec, M, C);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// Weight repacks (run once per plan)
+// =================================================================================================
+__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ out, int OC, int C, int k) {
+  // [OC][C][k] -> [OC][k][C]   (K index becomes tap-major so one tap is a contiguous channel run)
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)OC * C * k;
+  if (i >= n) return;
+  int c = (int)(i % C); size_t r = i / C; int j = (int)(r % k); int oc = (int)(r / k);
+  out[i] = w[((size_t)oc * C + c) * k + j];
+}
+int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cudaStream_t s) {
+  size_t n = (size_t)OC * C * k;
+  repack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, out, OC, C, k);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void repack_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ h,
+                                    __nv_bfloat16* __restrict__ l, int OC, int Kin, int Kp, int C) {
+  // out row n' <- in row n.  With C>0 rows are permuted so each 256-row block holds 128 gate rows followed by the
+  // matching 128 filter rows: n' = 256*j + i  <- n = 128*j + i (i<128),  n' = 256*j+128+i <- n = C + 128*j + i.
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)OC * Kp;
+  if (idx >= n) return;
+  int kk = (int)(idx % Kp); int np = (int)(idx / Kp);
+  int src = np;
+  if (C > 0) { int j = np >> 8, i = np & 255; src = (i < 128) ? (128 * j + i) : (C + 128 * j + (i - 128)); }
+  float v = (kk < Kin) ? w[(size_t)src * Kin + kk] : 0.f;
+  __nv_bfloat16 hh, ll;
+  split_bf16(v, hh, ll);
+  h[idx] = hh; l[idx] = ll;
+}
+int launch_repack_split(const float* w, __nv_bfloat16* h, __nv_bfloat16* l, int OC, int Kin, int Kp, int interleave_C,
+                        cudaStream_t s) {
+  size_t n = (size_t)OC * Kp;
+  repack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, h, l, OC, Kin, Kp, interleave_C);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int Kin, int Kp) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)rows * Kp;
+  if (idx >= n) return;
+  int kk = (int)(idx % Kp); size_t r = idx / Kp;
+  dst[idx] = (kk < Kin) ? src[r * Kin + kk] : 0.f;
+}
+int launch_pad_rows(const float* src, float* dst, int rows, int Kin, int Kp, cudaStream_t s) {
+  size_t n = (size_t)rows * Kp;
+  pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, rows, Kin, Kp);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void bias1_kernel(const float* __restrict__ bd, const float* __restrict__ bc, const float* __restrict__ wc,
+                             float* __restrict__ out_cond, float* __restrict__ out_unc, float* __restrict__ nat_cond,
+                             float* __restrict__ nat_unc, int C, int n_mels) {
+  // conditional branch:   bias = b_dilated + b_cond
+  // unconditional branch: spec == -1 everywhere, so conditioner_projection(spec) = b_cond - sum_k Wc[n][k]
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= 2 * C) return;
+  double s = 0.0;
+  for (int k = 0; k < n_mels; ++k) s += (double)wc[(size_t)n * n_mels + k];
+  float bcnd = bd[n] + bc[n];
+  float bunc = bd[n] + (float)((double)bc[n] - s);
+  nat_cond[n] = bcnd; nat_unc[n] = bunc;
+  int np;  // interleaved position of natural row n
+  if (n < C) { int j = n >> 7, i = n & 127; np = 256 * j + i; }
+  else { int m = n - C; int j = m >> 7, i = m & 127; np = 256 * j + 128 + i; }
+  out_cond[np] = bcnd; out_unc[np] = bunc;
+}
+int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_cond, float* out_unc, float* nat_cond,
+                 float* nat_unc, int C, int n_mels, cudaStream_t s) {
+  bias1_kernel<<<(2 * C + 127) / 128, 128, 0, s>>>(bd, bc, wc, out_cond, out_unc, nat_cond, nat_unc, C, n_mels);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void fill_kernel(float* p, float v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int launch_fill(float* p, float v, size_t n, cudaStream_t s) {
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, v, n);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace drb

@@ -1,0 +1,183 @@
+"""Thin Python owner of a ``drb_plan``: device workspace, weight pointers, stream plumbing.
+
+PyTorch is used here only for device memory and streams; all arithmetic of the
+sampling path happens inside libdiffroll_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import DrbConfig, DrbUpdate, DrbWeights
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One plan = one (batch, frames, wave_len, precision) configuration on one GPU."""
+
+    def __init__(self, state, hp, batch, frames, wave_len, emb_table, precision="bf16x3",
+                 branches=_lib.BRANCH_COND_UNCOND, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.DrbError("diffroll_b200 needs a CUDA device: there is no CPU path")
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_lib.PRECISIONS)}")
+        sa = hp["spec_args"]
+        L = hp["residual_layers"]
+        cfg = DrbConfig(batch=batch, frames=frames, pitches=88, wave_len=wave_len,
+                        residual_channels=hp["residual_channels"], residual_layers=L,
+                        kernel_size=hp["kernel_size"], dilation_base=hp["dilation_base"],
+                        dilation_bound=hp["dilation_bound"], n_mels=sa["n_mels"], n_fft=sa["n_fft"],
+                        hop_length=sa["hop_length"], timesteps=emb_table.shape[0],
+                        precision=_lib.PRECISIONS[precision], branches=branches, reserved=0)
+        self.cfg = cfg
+        self.precision = precision
+        self.batch, self.frames, self.wave_len = batch, frames, wave_len
+        self.n_mels = sa["n_mels"]
+        need = self.lib.drb_plan_workspace_bytes(C.byref(cfg))
+        if need == 0:
+            raise _lib.DrbError("unsupported configuration: " + self.lib.drb_last_error().decode())
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            base = self.workspace.data_ptr()
+            self._ws_off = (-base) % 256
+            # keep every weight tensor alive and contiguous fp32 on this device
+            self._w = {k: v.detach().to(device=self.device, dtype=torch.float32).contiguous() for k, v in state.items()}
+            w = self._w
+
+            def arr(fmt):
+                a = (C.c_void_p * L)(*[w[fmt.format(i)].data_ptr() for i in range(L)])
+                self._keep.append(a)
+                return C.cast(a, C.POINTER(C.c_void_p))
+
+            self._keep = []
+            ws = DrbWeights(
+                input_projection_w=w["input_projection.weight"].data_ptr(),
+                input_projection_b=w["input_projection.bias"].data_ptr(),
+                emb_projection1_w=w["diffusion_embedding.projection1.weight"].data_ptr(),
+                emb_projection1_b=w["diffusion_embedding.projection1.bias"].data_ptr(),
+                emb_projection2_w=w["diffusion_embedding.projection2.weight"].data_ptr(),
+                emb_projection2_b=w["diffusion_embedding.projection2.bias"].data_ptr(),
+                dilated_conv_w=arr("residual_layers.{}.dilated_conv.weight"),
+                dilated_conv_b=arr("residual_layers.{}.dilated_conv.bias"),
+                diffusion_projection_w=arr("residual_layers.{}.diffusion_projection.weight"),
+                diffusion_projection_b=arr("residual_layers.{}.diffusion_projection.bias"),
+                conditioner_projection_w=arr("residual_layers.{}.conditioner_projection.weight"),
+                conditioner_projection_b=arr("residual_layers.{}.conditioner_projection.bias"),
+                output_projection_w=arr("residual_layers.{}.output_projection.weight"),
+                output_projection_b=arr("residual_layers.{}.output_projection.bias"),
+                skip_projection_w=w["skip_projection.weight"].data_ptr(),
+                skip_projection_b=w["skip_projection.bias"].data_ptr(),
+                head_projection_w=w["output_projection.weight"].data_ptr(),
+                head_projection_b=w["output_projection.bias"].data_ptr(),
+                stft_window=w["mel_layer.spectrogram.window"].data_ptr(),
+                mel_fb=w["mel_layer.mel_scale.fb"].data_ptr(),
+            )
+            plan = C.c_void_p()
+            _lib.check(self.lib.drb_plan_create(C.byref(plan), C.byref(cfg), C.byref(ws),
+                                                C.c_void_p(base + self._ws_off), C.c_size_t(need), _stream()),
+                       "drb_plan_create")
+            self.plan = plan
+            self._emb = emb_table.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            _lib.check(self.lib.drb_time_tables(self.plan, _ptr(self._emb), _stream()), "drb_time_tables")
+        self.branches = branches
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self.lib.drb_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------
+    def set_branches(self, branches):
+        if branches != self.branches:
+            _lib.check(self.lib.drb_plan_set_branches(self.plan, branches), "drb_plan_set_branches")
+            self.branches = branches
+
+    def _check(self, t, shape, name):
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous fp32 tensor on {self.device}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+
+    def mel(self, waveform, inpainting_t=None, inpainting_f=None, want_spec=True):
+        """model/diffwave.py:643-654: returns the normalised, masked spectrogram [B, n_mels, T]."""
+        self._check(waveform, (self.batch, self.wave_len), "waveform")
+        nF = self.wave_len // self.cfg.hop_length + 1
+        it0 = it1 = if0 = if1 = 0
+        if inpainting_t:
+            it0, it1, _ = slice(int(inpainting_t[0]), int(inpainting_t[1])).indices(nF)
+            it1 = max(it1, it0)
+            if it1 == it0:
+                it0 = it1 = 0
+        if inpainting_f:
+            if0, if1, _ = slice(int(inpainting_f[0]), int(inpainting_f[1])).indices(self.n_mels)
+            if1 = max(if1, if0)
+            if if1 == if0:
+                if0 = if1 = 0
+        # a requested-but-empty range masks nothing, exactly like the reference's empty slice assignment
+        spec = torch.empty(self.batch, self.n_mels, self.frames, device=self.device) if want_spec else None
+        _lib.check(self.lib.drb_mel_forward(self.plan, _ptr(waveform), _ptr(spec), it0, it1, if0, if1, _stream()),
+                   "drb_mel_forward")
+        return spec
+
+    def step(self, x_t, noise, t_index, upd: DrbUpdate, out=None, net_out=None):
+        """One reverse-diffusion step: in_proj, residual blocks, head, guidance, posterior update."""
+        shape = (self.batch, 1, self.frames, 88)
+        self._check(x_t, shape, "x_t")
+        if noise is not None:
+            self._check(noise, shape, "noise")
+        if out is None:
+            out = torch.empty_like(x_t)
+        s = _stream()
+        if net_out is None:
+            _lib.check(self.lib.drb_sample_step(self.plan, _ptr(x_t), _ptr(noise), _ptr(out), int(t_index),
+                                                C.byref(upd), s), "drb_sample_step")
+        else:
+            _lib.check(self.lib.drb_in_proj(self.plan, _ptr(x_t), int(t_index), s), "drb_in_proj")
+            for layer in range(self.cfg.residual_layers):
+                _lib.check(self.lib.drb_resblock_forward(self.plan, layer, int(t_index), s), "drb_resblock_forward")
+            _lib.check(self.lib.drb_head_posterior_step(self.plan, _ptr(x_t), _ptr(noise), _ptr(out), _ptr(net_out),
+                                                        C.byref(upd), s), "drb_head_posterior_step")
+        return out
+
+    def loop(self, x, noise, updates, t_start, t_stop=0, trajectory=None):
+        """task/diffusion.py:528-534 for t = t_start-1 .. t_stop, x updated in place."""
+        self._check(x, (self.batch, 1, self.frames, 88), "x")
+        n = t_start - t_stop
+        arr = (DrbUpdate * n)(*updates)
+        n_noise = sum(1 for u in updates if u.has_noise)
+        if n_noise:
+            self._check(noise, (noise.shape[0], self.batch, 1, self.frames, 88), "noise")
+            if noise.shape[0] < n_noise:
+                raise ValueError(f"need {n_noise} noise slices, got {noise.shape[0]}")
+        tp = C.c_void_p(trajectory.data_ptr()) if trajectory is not None else C.c_void_p(0)
+        _lib.check(self.lib.drb_sample_loop(self.plan, _ptr(x), _ptr(noise) if n_noise else C.c_void_p(0), arr,
+                                            int(t_start), int(t_stop), tp, _stream()), "drb_sample_loop")
+        return x
+
+    def buffer(self, name, dtype=torch.float32):
+        """Debug view of a plan-owned device buffer."""
+        p = C.c_void_p()
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.drb_plan_buffer(self.plan, name.encode(), C.byref(p), C.byref(nbytes)), "drb_plan_buffer")
+        off = p.value - self.workspace.data_ptr()
+        return self.workspace[off:off + nbytes.value].view(dtype)
+
+    def launch_count(self, reset=False):
+        return int(self.lib.drb_launch_count(1 if reset else 0))

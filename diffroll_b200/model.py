@@ -1,0 +1,218 @@
+"""``ClassifierFreeDiffRoll`` with the reference's module surface (model/diffwave.py:579-699).
+
+Same constructor keywords, same ``state_dict`` keys and shapes, same
+``forward(x_t, waveform, diffusion_step, sampling=False, inpainting_t=None, inpainting_f=None)
+-> (pred [B,1,T,88], spec [B,n_mels,T])``.  The parameters live in ordinary ``nn.Conv1d`` /
+``nn.Linear`` containers so reference checkpoints load unchanged, but those containers are
+never *called*: every forward goes through the CUDA engine.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from math import sqrt  # noqa: F401  (kept for parity with the reference's namespace)
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .engine import Engine
+from .synthetic import hann_window, melscale_fbanks
+from .task import AttributeDict, SpecRollDiffusion, _upd, to_attr
+
+
+class Normalization:
+    """model/utils.py:2-38 (min-max scaling of label rolls; host-side, not on the hot path)."""
+
+    def __init__(self, min, max, mode='imagewise'):
+        if mode == 'framewise':
+            def normalize(x):
+                x_max = x.max(1, keepdim=True)[0]
+                x_min = x.min(1, keepdim=True)[0]
+                x_std = (x - x_min) / (x_max - x_min)
+                x_std[torch.isnan(x_std)] = 0
+                return x_std * (max - min) + min
+        elif mode == 'imagewise':
+            def normalize(x):
+                x_max = x.flatten(1).max(1, keepdim=True)[0].unsqueeze(1)
+                x_min = x.flatten(1).min(1, keepdim=True)[0].unsqueeze(1)
+                x_std = (x - x_min) / (x_max - x_min)
+                x_scaled = x_std * (max - min) + min
+                x_scaled[torch.isnan(x_scaled)] = min
+                return x_scaled
+        else:
+            print('please choose the correct mode')
+            normalize = None
+        self.normalize = normalize
+
+    def __call__(self, x):
+        return self.normalize(x)
+
+
+def Conv1d(*args, **kwargs):
+    layer = nn.Conv1d(*args, **kwargs)
+    nn.init.kaiming_normal_(layer.weight)  # model/diffwave.py:41-44
+    return layer
+
+
+class DiffusionEmbedding(nn.Module):
+    """Parameter container + the sinusoid table of model/diffwave.py:58-88 (built with the same expression)."""
+
+    def __init__(self, max_steps):
+        super().__init__()
+        self.register_buffer('embedding', self._build_embedding(max_steps), persistent=False)
+        self.projection1 = nn.Linear(128, 512)
+        self.projection2 = nn.Linear(512, 512)
+
+    def _build_embedding(self, max_steps):
+        steps = torch.arange(max_steps).unsqueeze(1)
+        dims = torch.arange(64).unsqueeze(0)
+        table = steps * 10.0 ** (dims * 4.0 / 63.0)
+        return torch.cat([torch.sin(table), torch.cos(table)], dim=1)
+
+
+class ResidualBlock(nn.Module):
+    """Parameter container with the reference's names and shapes (model/diffwave.py:107-132)."""
+
+    def __init__(self, n_mels, residual_channels, dilation, kernel_size=3, uncond=False):
+        super().__init__()
+        self.dilated_conv = Conv1d(residual_channels, 2 * residual_channels, kernel_size,
+                                   padding=((kernel_size - 1) * (dilation - 1) + kernel_size - 1) // 2,
+                                   dilation=dilation)
+        self.diffusion_projection = nn.Linear(512, residual_channels)
+        self.conditioner_projection = None if uncond else Conv1d(n_mels, 2 * residual_channels, 1)
+        self.output_projection = Conv1d(residual_channels, 2 * residual_channels, 1)
+
+
+class _MelBuffers(nn.Module):
+    """Holds ``mel_layer.spectrogram.window`` and ``mel_layer.mel_scale.fb`` under the reference's keys."""
+
+    def __init__(self, sample_rate, n_fft, n_mels, f_min, f_max):
+        super().__init__()
+        self.spectrogram = nn.Module()
+        self.spectrogram.register_buffer("window", hann_window(n_fft))
+        self.mel_scale = nn.Module()
+        self.mel_scale.register_buffer("fb", melscale_fbanks(n_fft // 2 + 1, float(f_min), float(f_max), n_mels, sample_rate))
+
+
+class ClassifierFreeDiffRoll(SpecRollDiffusion):
+    def __init__(self, residual_channels, unconditional, condition, n_mels, norm_args,
+                 residual_layers=30, kernel_size=3, dilation_base=1, dilation_bound=4, spec_args={},
+                 spec_dropout=0.5, inpainting_t=None, inpainting_f=None, precision="bf16x3", **kwargs):
+        spec_args = to_attr(dict(spec_args))
+        self._pending_hparams = AttributeDict(
+            residual_channels=residual_channels, unconditional=unconditional, condition=condition, n_mels=n_mels,
+            norm_args=norm_args, residual_layers=residual_layers, kernel_size=kernel_size,
+            dilation_base=dilation_base, dilation_bound=dilation_bound, spec_args=spec_args,
+            spec_dropout=spec_dropout, inpainting_t=inpainting_t, inpainting_f=inpainting_f)
+        self.spec_dropout = spec_dropout
+        super().__init__(**kwargs)
+        del self._pending_hparams
+        if condition == 'trainable_spec' or condition == 'trainable_z':
+            raise NotImplementedError(f"condition '{condition}' is a training-time variant outside the sampling hot path")
+        elif condition != 'fixed':
+            raise ValueError("unrecognized condition '{condition}'")  # sic: model/diffwave.py:610
+        if unconditional:
+            raise NotImplementedError("unconditional=True (no conditioner_projection) is not built on this path")
+        self.precision = precision
+        self.input_projection = Conv1d(88, residual_channels, 1)
+        self.diffusion_embedding = DiffusionEmbedding(len(self.betas))
+        self.residual_layers = nn.ModuleList([
+            ResidualBlock(n_mels, residual_channels, dilation_base ** (i % dilation_bound), kernel_size, uncond=unconditional)
+            for i in range(residual_layers)])
+        self.skip_projection = Conv1d(residual_channels, residual_channels, 1)
+        self.output_projection = Conv1d(residual_channels, 88, 1)
+        nn.init.zeros_(self.output_projection.weight)
+        self.normalize_spec = Normalization(0, 1, norm_args[2])
+        self.normalize = Normalization(norm_args[0], norm_args[1], norm_args[2])
+        sa = spec_args
+        for key, want in (("center", True), ("normalized", True), ("pad_mode", "reflect")):
+            if sa.get(key, want) != want:
+                raise NotImplementedError(f"mel front-end built for {key}={want!r} (config/spec/mel.yaml)")
+        self.mel_layer = _MelBuffers(sa["sample_rate"], sa["n_fft"], sa["n_mels"], sa.get("f_min", 0), sa.get("f_max", sa["sample_rate"] // 2))
+        self._engines = {}
+        self._mel_key = None
+        self._spec = None
+
+    # ---- engine management ------------------------------------------------------------------------
+    def _weights_version(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def _engine(self, batch, frames, wave_len, device):
+        key = (batch, frames, wave_len, self.precision, str(device))
+        ver = self._weights_version()
+        ent = self._engines.get(key)
+        if ent is not None and ent[1] == ver:
+            return ent[0]
+        if ent is not None:
+            ent[0].close()
+        for k in [k for k, e in self._engines.items() if e[1] != ver]:
+            self._engines.pop(k)[0].close()
+        eng = Engine(self.state_dict(), self.hparams, batch, frames, wave_len, self.diffusion_embedding.embedding,
+                     precision=self.precision, branches=_lib.BRANCH_COND_UNCOND, device=device)
+        self._engines[key] = (eng, ver)
+        self._mel_key = None
+        return eng
+
+    def _prepare(self, x, waveform, branches, inpainting_t=None, inpainting_f=None):
+        """Pick the engine for these shapes, run the (cached) mel front-end, select branches."""
+        if not x.is_cuda:
+            raise _lib.DrbError("ClassifierFreeDiffRoll (diffroll_b200) runs on CUDA tensors only; there is no CPU path")
+        B, _, T, Fp = x.shape
+        if Fp != 88:
+            raise ValueError("piano roll must have 88 pitches")
+        sa = self.hparams.spec_args
+        wave_len = waveform.shape[-1]
+        n_frames = wave_len // sa["hop_length"] + 1
+        T_min = min(T, n_frames)                                  # trim_spec_roll, model/diffwave.py:30-39,662
+        eng = self._engine(B, T_min, wave_len, x.device)
+        xx = x.to(torch.float32)
+        if T_min != T:
+            xx = xx[:, :, :T_min, :]
+        xx = xx.contiguous()
+        if branches == _lib.BRANCH_UNCOND:
+            spec = torch.full((B, sa["n_mels"], T_min), -1.0, device=x.device)   # model/diffwave.py:660
+        else:
+            wav = waveform.to(device=x.device, dtype=torch.float32).contiguous()
+            it = list(inpainting_t) if inpainting_t else None
+            itf = list(inpainting_f) if inpainting_f else None
+            key = (id(eng), wav.data_ptr(), wav._version, tuple(wav.shape), tuple(it or ()), tuple(itf or ()))
+            if key != self._mel_key or self._spec is None:
+                self._spec = eng.mel(wav, it, itf)
+                self._mel_key = key
+            spec = self._spec
+        eng.set_branches(branches)
+        return eng, xx, spec
+
+    def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):
+        eng, xx, spec = self._prepare(x, waveform, branches, inpainting_t, inpainting_f)
+        if upd.has_noise:
+            if noise is None:
+                noise = torch.randn_like(xx)       # task/diffusion.py:1023
+            else:
+                noise = noise.to(device=xx.device, dtype=torch.float32)[:, :, :xx.shape[2], :].contiguous()
+        else:
+            noise = None
+        out = eng.step(xx, noise, t_index, upd)
+        return out, spec
+
+    # ---- reference forward ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x_t, waveform, diffusion_step, sampling=False, inpainting_t=None, inpainting_f=None):
+        """model/diffwave.py:637-686.  ``diffusion_step`` must hold one value for the whole batch
+        (every sampler of the reference passes ``tensor(t).repeat(B)``)."""
+        if self.training:
+            raise NotImplementedError("training-mode forward (spec dropout, autograd) is outside the sampling hot path; call .eval()")
+        if torch.is_tensor(diffusion_step):
+            if diffusion_step.dtype not in (torch.int32, torch.int64):
+                raise NotImplementedError("fractional diffusion steps (_lerp_embedding) are not on the sampling path")
+            t0 = int(diffusion_step.flatten()[0])
+            if not bool((diffusion_step == t0).all()):
+                raise NotImplementedError("per-sample diffusion steps are a training-time feature; the sampling path uses one t per batch")
+        else:
+            t0 = int(diffusion_step)
+        branches = _lib.BRANCH_UNCOND if sampling is True else _lib.BRANCH_COND
+        eng, xx, spec = self._prepare(x_t, waveform, branches, inpainting_t, inpainting_f)
+        pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
+        return pred, spec
+
+    def train(self, mode=True):
+        return super().train(mode)

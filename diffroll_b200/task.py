@@ -1,0 +1,280 @@
+"""Host-side mirror of the reference's task layer for the sampling path.
+
+``SpecRollDiffusion`` keeps the names, argument meaning and error behaviour of
+task/diffusion.py:219-256 (schedule), :513-534 (``predict_step``), :765-790
+(``sampling``) and :804-1055 (the nine ``reverse_diffusion`` samplers).  The
+arithmetic is not here: every sampler reduces to "which branches does the
+network evaluate" plus five fp32 scalars for the fused posterior-update
+epilogue, and hands both to the CUDA engine (diffroll_b200/engine.py).
+
+Lightning is not required: the class is an ``nn.Module`` that offers the bits of
+``LightningModule`` the reference scripts touch (``hparams``,
+``load_from_checkpoint``, ``predict_step``/``test``-style entry points, ``log``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import DrbUpdate
+
+
+class AttributeDict(dict):
+    """Attribute-access dict (stand-in for Lightning's AttributeDict / OmegaConf DictConfig)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def to_attr(obj):
+    if isinstance(obj, AttributeDict):
+        return obj
+    if hasattr(obj, "items") and not isinstance(obj, torch.Tensor):
+        return AttributeDict({k: to_attr(v) for k, v in obj.items()})
+    if isinstance(obj, (list, tuple)) or type(obj).__name__ == "ListConfig":
+        return [to_attr(v) for v in obj]
+    return obj
+
+
+def linear_beta_schedule(beta_start, beta_end, timesteps):
+    return torch.linspace(beta_start, beta_end, timesteps)  # task/diffusion.py:28-29
+
+
+def _upd(mode, s=(), has_noise=False, w=0.0):
+    u = DrbUpdate()
+    u.mode = mode
+    u.has_noise = 1 if has_noise else 0
+    for i, v in enumerate(s):
+        u.s[i] = float(v)
+    u.w = float(w)
+    return u
+
+
+class SpecRollDiffusion(nn.Module):
+    def __init__(self, lr, timesteps, loss_type, loss_keys, beta_start, beta_end, frame_threshold,
+                 training, sampling, debug=False, generation_filter=0.0):
+        super().__init__()
+        hp = getattr(self, "_pending_hparams", AttributeDict())
+        hp.update(dict(lr=lr, timesteps=timesteps, loss_type=loss_type, loss_keys=loss_keys,
+                       beta_start=beta_start, beta_end=beta_end, frame_threshold=frame_threshold,
+                       training=to_attr(training), sampling=to_attr(sampling), debug=debug,
+                       generation_filter=generation_filter))
+        self._hparams = hp
+        # Schedule: the same torch expressions as task/diffusion.py:239-256, plain fp32 CPU tensors.
+        self.betas = linear_beta_schedule(beta_start, beta_end, timesteps=timesteps)
+        alphas = 1. - self.betas
+        alphas_cumprod = torch.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = F.pad(alphas_cumprod[:-1], (1, 0), value=1.0)
+        self.sqrt_recip_alphas = torch.sqrt(1.0 / alphas)
+        self.sqrt_alphas_cumprod = torch.sqrt(alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1. - alphas_cumprod)
+        self.posterior_variance = self.betas * (1. - alphas_cumprod_prev) / (1 - alphas_cumprod)
+        self.alphas = alphas
+        # AttributeError for an unknown sampler name, like the reference's getattr (task/diffusion.py:255)
+        self.reverse_diffusion = getattr(self, self._hparams.sampling.type)
+
+    # ---- Lightning-ish surface ---------------------------------------------------------
+    @property
+    def hparams(self):
+        return self._hparams
+
+    def log(self, *a, **k):
+        pass
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", strict=True, **overrides):
+        """Lightning-format checkpoint: {'state_dict', 'hyper_parameters'}; keyword overrides win
+        (sampling.py:54-65, test.py:30)."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        model = cls(**hp)
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        return model
+
+    # ---- update coefficients: fp32 scalar arithmetic exactly as the reference writes it ----
+    def _x0_update(self, t_index, ddim=False):
+        """task/diffusion.py:1013-1023 (same text at :836-851, :957-967, :985-995; sigma=0 at :860-871, :1043-1053)."""
+        if t_index == 0:
+            return _upd(_lib.UPD_X0_FINAL, [self.sqrt_alphas_cumprod[t_index]])
+        if ddim:
+            sigma = torch.tensor(0.0)
+        else:
+            sigma = (self.sqrt_one_minus_alphas_cumprod[t_index - 1] / self.sqrt_one_minus_alphas_cumprod[t_index]) * (
+                torch.sqrt(1 - self.alphas[t_index]))
+        coef = torch.sqrt(1 - self.sqrt_alphas_cumprod[t_index - 1] ** 2 - sigma ** 2)
+        return _upd(_lib.UPD_X0, [self.sqrt_alphas_cumprod[t_index - 1], coef, self.sqrt_alphas_cumprod[t_index],
+                                  self.sqrt_one_minus_alphas_cumprod[t_index], sigma], has_noise=not ddim)
+
+    def _w(self):
+        return float(self.hparams.sampling.get("w", 0.0) if hasattr(self.hparams.sampling, "get") else self.hparams.sampling.w)
+
+    # ---- samplers: (x, waveform, t_index) -> (x_prev, spec) ----------------------------------
+    def inpainting_ddpm_x0(self, x, waveform, t_index, noise=None):
+        upd = self._x0_update(t_index)
+        upd.w = self._w()
+        return self._step(x, waveform, t_index, upd, _lib.BRANCH_COND_UNCOND, noise,
+                          self.hparams.inpainting_t, self.hparams.inpainting_f)
+
+    def cfdg_ddpm_x0(self, x, waveform, t_index, noise=None):
+        upd = self._x0_update(t_index)
+        upd.w = self._w()
+        return self._step(x, waveform, t_index, upd, _lib.BRANCH_COND_UNCOND, noise)
+
+    def generation_ddpm_x0(self, x, waveform, t_index, noise=None):
+        return self._step(x, waveform, t_index, self._x0_update(t_index), _lib.BRANCH_UNCOND, noise)
+
+    def ddpm_x0(self, x, waveform, t_index, noise=None):
+        return self._step(x, waveform, t_index, self._x0_update(t_index), _lib.BRANCH_COND, noise)
+
+    def ddim_x0(self, x, waveform, t_index, noise=None):
+        return self._step(x, waveform, t_index, self._x0_update(t_index, ddim=True), _lib.BRANCH_COND, noise)
+
+    def cfdg_ddim_x0(self, x, waveform, t_index, noise=None):
+        # task/diffusion.py:1027-1055.  The reference's second forward runs on a zero waveform WITHOUT
+        # sampling=True (:1039), i.e. it is conditioned on an all-zero normalised spectrogram, not on -1.
+        upd = self._x0_update(t_index, ddim=True)
+        upd.w = self._w()
+        return self._step(x, waveform, t_index, upd, _lib.BRANCH_COND_ZEROSPEC, noise)
+
+    def ddpm(self, x, waveform, t_index, noise=None):                       # task/diffusion.py:804-829
+        s = [self.sqrt_recip_alphas[t_index], self.betas[t_index], self.sqrt_one_minus_alphas_cumprod[t_index],
+             torch.sqrt(self.posterior_variance[t_index]) if t_index > 0 else 0.0]
+        return self._step(x, waveform, t_index, _upd(_lib.UPD_EPS_DDPM, s, has_noise=t_index > 0), _lib.BRANCH_COND, noise)
+
+    def ddim(self, x, waveform, t_index, noise=None):                       # task/diffusion.py:877-892
+        if t_index == 0:
+            upd = _upd(_lib.UPD_EPS_FINAL, [self.sqrt_one_minus_alphas_cumprod[0], self.sqrt_alphas_cumprod[0]])
+        else:
+            upd = _upd(_lib.UPD_EPS_DDIM, [self.sqrt_alphas_cumprod[t_index - 1], self.sqrt_one_minus_alphas_cumprod[t_index],
+                                           self.sqrt_alphas_cumprod[t_index], self.sqrt_one_minus_alphas_cumprod[t_index - 1], 0.0])
+        return self._step(x, waveform, t_index, upd, _lib.BRANCH_COND, noise)
+
+    def ddim2ddpm(self, x, waveform, t_index, noise=None):                  # task/diffusion.py:894-911
+        if t_index == 0:
+            upd = _upd(_lib.UPD_EPS_FINAL, [self.sqrt_one_minus_alphas_cumprod[0], self.sqrt_alphas_cumprod[0]])
+        else:
+            sigma = (self.sqrt_one_minus_alphas_cumprod[t_index - 1] / self.sqrt_one_minus_alphas_cumprod[t_index]) * (
+                torch.sqrt(1 - self.alphas[t_index]))
+            upd = _upd(_lib.UPD_EPS_DDIM, [self.sqrt_alphas_cumprod[t_index - 1], self.sqrt_one_minus_alphas_cumprod[t_index],
+                                           self.sqrt_alphas_cumprod[t_index],
+                                           torch.sqrt(1 - self.sqrt_alphas_cumprod[t_index - 1] ** 2 - sigma ** 2), sigma],
+                       has_noise=True)
+        return self._step(x, waveform, t_index, upd, _lib.BRANCH_COND, noise)
+
+    # ---- loops ----------------------------------------------------------------------------------
+    def _all_updates(self):
+        """The drb_update of every step t = T-1 .. 0 for the configured sampler, without running it."""
+        probe = _UpdateProbe(self)
+        ups = []
+        for t_index in reversed(range(self.hparams.timesteps)):
+            ups.append(probe.capture(t_index))
+        return ups, probe.branches, probe.masks
+
+    @torch.no_grad()
+    def sample_loop(self, x_T, waveform, noise=None, keep_trajectory=False):
+        """The loop body of predict_step / sampling (task/diffusion.py:528-534, 779-788) as ONE library call.
+
+        noise: optional pre-drawn [n_noisy_steps, B, 1, T, 88]; by default it is drawn step by step with
+        ``torch.randn_like`` on the roll's device, in the reference's order (descending t, only t with noise).
+        Returns (x_0, spec, trajectory) — trajectory is a pinned host tensor [timesteps, B, 1, T, 88] or None.
+        """
+        ups, branches, masks = self._all_updates()
+        eng, x, spec = self._prepare(x_T, waveform, branches, *masks)
+        x = x.clone()
+        n_noise = sum(1 for u in ups if u.has_noise)
+        if noise is None and n_noise:
+            noise = torch.empty((n_noise,) + tuple(x.shape), device=x.device)
+            for i in range(n_noise):
+                noise[i] = torch.randn_like(x)      # same generator consumption order as task/diffusion.py:1023
+        elif noise is not None:
+            noise = noise.to(device=x.device, dtype=torch.float32)[..., :x.shape[2], :].contiguous()
+        traj = None
+        if keep_trajectory:
+            traj = torch.empty((len(ups),) + tuple(x.shape), dtype=torch.float32, pin_memory=True)
+        eng.loop(x, noise, ups, self.hparams.timesteps, 0, traj)
+        return x, spec, traj
+
+    @torch.no_grad()
+    def predict_step(self, batch, batch_idx=0):
+        """task/diffusion.py:513-534.  batch = (x_T [B,1,T,88], waveform [B,L][, roll_label]).
+
+        The reference copies every intermediate roll to the host (:530) and then writes figures/MIDI
+        (:540-618, out of scope).  Here the per-step copies are asynchronous into pinned memory and the
+        method returns ``(roll_pred, noise_list, spec)`` instead of None; ``noise_list`` has the
+        reference's structure: [(x_T, timesteps), (x_{T-1} as numpy, T-1), ..., (x_0 as numpy, 0)].
+        """
+        noise, waveform = batch[0], batch[1]
+        x0, spec, traj = self.sample_loop(noise, waveform, keep_trajectory=True)
+        torch.cuda.current_stream().synchronize()
+        noise_list = [(noise, self.hparams.timesteps)]
+        tnp = traj.numpy()
+        for i, t_index in enumerate(reversed(range(self.hparams.timesteps))):
+            noise_list.append((tnp[i], t_index))
+        roll_pred = noise_list[-1][0]
+        return roll_pred, noise_list, spec
+
+    @torch.no_grad()
+    def sampling(self, batch, batch_idx=0):
+        """task/diffusion.py:765-790: batch = {'frame': [B,T,88], 'audio': [B,L]} -> (noise_list, spec)."""
+        roll = self.normalize(batch["frame"]).unsqueeze(1)
+        waveform = batch["audio"]
+        noise = torch.randn_like(roll)
+        if self.hparams.debug:
+            raise NotImplementedError("debug=True conditions on the label roll (DiffRollDebug); not on this path")
+        _, noise_list, spec = self.predict_step((noise, waveform), batch_idx)
+        return noise_list, spec
+
+    def p_losses(self, label, prediction, loss_type="l1"):
+        if loss_type == 'l1':
+            return F.l1_loss(label, prediction)
+        elif loss_type == 'l2':
+            return F.mse_loss(label, prediction)
+        elif loss_type == "huber":
+            return F.smooth_l1_loss(label, prediction)
+        raise NotImplementedError()
+
+    # provided by the model subclass
+    def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):
+        raise NotImplementedError
+
+    def _prepare(self, x, waveform, branches, inpainting_t=None, inpainting_f=None):
+        raise NotImplementedError
+
+
+class _UpdateProbe:
+    """Runs a sampler method with ``_step`` intercepted, to read off its update struct, branches and masks."""
+
+    def __init__(self, model):
+        self.model = model
+        self.branches = None
+        self.masks = (None, None)
+
+    def capture(self, t_index):
+        got = {}
+
+        def fake_step(x, waveform, t, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):
+            got["upd"] = upd
+            self.branches = branches
+            self.masks = (inpainting_t, inpainting_f)
+            return None, None
+
+        m = self.model
+        orig = m.__dict__.get("_step")
+        m.__dict__["_step"] = fake_step
+        try:
+            m.reverse_diffusion(None, None, t_index)
+        finally:
+            if orig is None:
+                del m.__dict__["_step"]
+            else:
+                m.__dict__["_step"] = orig
+        return got["upd"]

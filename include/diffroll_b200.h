@@ -1,0 +1,175 @@
+/* diffroll_b200 — C ABI of the B200-native DiffRoll sampling hot path.
+ *
+ * The reference (sony/DiffRoll) is pure Python and has no FFI of its own; the
+ * boundary it exposes for this path is the PyTorch module surface
+ *   ClassifierFreeDiffRoll.forward            model/diffwave.py:637-686
+ *   SpecRollDiffusion.<sampler>(x, wav, t)    task/diffusion.py:804-1055
+ *   SpecRollDiffusion.predict_step / sampling task/diffusion.py:513-534, 765-790
+ * Each entry point below replaces the arithmetic of the cited reference lines.
+ * The Python host side (diffroll_b200/model.py, task.py) keeps the reference's
+ * names and argument meaning and calls these through ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    its name ends in _host;
+ *  - every call is asynchronous on the given stream (a cudaStream_t passed as
+ *    void*), never allocates or frees caller memory, never throws;
+ *  - return value 0 = ok, otherwise a negative DRB_E_* code or a positive
+ *    cudaError_t; drb_last_error() gives the message for the calling thread;
+ *  - a drb_plan owns repacked weights, TMA descriptors and the cuFFT plan; all
+ *    of its device storage lives in the caller-provided workspace.
+ */
+#ifndef DIFFROLL_B200_H
+#define DIFFROLL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRB_VERSION 100
+
+#define DRB_E_INVALID   (-1)  /* bad argument / unsupported shape            */
+#define DRB_E_WORKSPACE (-2)  /* workspace too small or misaligned           */
+#define DRB_E_CUFFT     (-3)
+#define DRB_E_DRIVER    (-4)  /* cuTensorMapEncodeTiled unavailable / failed */
+#define DRB_E_STATE     (-5)  /* call order (e.g. step before time tables)   */
+
+/* arithmetic of the contractions */
+#define DRB_PREC_FP32    0  /* fp32 CUDA-core kernels (validation path)                              */
+#define DRB_PREC_BF16X3  1  /* tcgen05, bf16 hi/lo split, 3 products, fp32 accumulate (parity mode) */
+#define DRB_PREC_BF16    2  /* tcgen05, single bf16 product (fast mode, NOT within 1e-3)            */
+
+/* which network branches one step evaluates */
+#define DRB_BRANCH_COND_UNCOND 0  /* classifier-free pair: (1+w)*cond - w*uncond   task/diffusion.py:1007-1009 */
+#define DRB_BRANCH_COND        1  /* one conditional forward                       task/diffusion.py:839        */
+#define DRB_BRANCH_UNCOND      2  /* spec == -1 (sampling=True)                    task/diffusion.py:979        */
+#define DRB_BRANCH_COND_ZEROSPEC 3 /* pair: cond + cond on a zero waveform (its normalised spectrogram is all 0)
+                                      task/diffusion.py:1038-1040 (cfdg_ddim_x0 omits sampling=True) */
+
+/* posterior-update formulas, evaluated in the reference's operation order with fp32 scalars s[0..4] */
+#define DRB_UPD_X0        0  /* s0*net + s1*(x - s2*net)/s3 + s4*noise      task/diffusion.py:1018-1023 */
+#define DRB_UPD_X0_FINAL  1  /* net / s0                                    task/diffusion.py:1016      */
+#define DRB_UPD_EPS_DDPM  2  /* s0*(x - s1*net/s2) + s3*noise               task/diffusion.py:819-829   */
+#define DRB_UPD_EPS_DDIM  3  /* s0*((x - s1*net)/s2) + s3*net + s4*noise    task/diffusion.py:886-889, 904-909 */
+#define DRB_UPD_EPS_FINAL 4  /* (x - s0*net)/s1                             task/diffusion.py:885, 903  */
+#define DRB_UPD_NONE      5  /* out = net (plain forward)                   model/diffwave.py:686       */
+
+typedef struct drb_config {
+  int32_t batch;             /* B: rolls in this plan                                        */
+  int32_t frames;            /* T: roll frames (640)                                          */
+  int32_t pitches;           /* 88                                                            */
+  int32_t wave_len;          /* L: samples per clip (327680)                                  */
+  int32_t residual_channels; /* C (512)                                                       */
+  int32_t residual_layers;   /* (15)                                                          */
+  int32_t kernel_size;       /* k (9), odd                                                    */
+  int32_t dilation_base;     /* 2                                                             */
+  int32_t dilation_bound;    /* 4 : dilation of layer i = base^(i % bound)  model/diffwave.py:624 */
+  int32_t n_mels;            /* 229                                                           */
+  int32_t n_fft;             /* 2048                                                          */
+  int32_t hop_length;        /* 512                                                           */
+  int32_t timesteps;         /* rows of the diffusion-embedding table                         */
+  int32_t precision;         /* DRB_PREC_*                                                    */
+  int32_t branches;          /* DRB_BRANCH_*                                                  */
+  int32_t reserved;
+} drb_config;
+
+/* fp32 device pointers in the reference's state_dict layout. */
+typedef struct drb_weights {
+  const float* input_projection_w;      /* [C,88,1]   */
+  const float* input_projection_b;      /* [C]        */
+  const float* emb_projection1_w;       /* [512,128]  */
+  const float* emb_projection1_b;       /* [512]      */
+  const float* emb_projection2_w;       /* [512,512]  */
+  const float* emb_projection2_b;       /* [512]      */
+  const float* const* dilated_conv_w;   /* host array of L device ptrs, each [2C,C,k] */
+  const float* const* dilated_conv_b;   /* [2C]       */
+  const float* const* diffusion_projection_w; /* [C,512] */
+  const float* const* diffusion_projection_b; /* [C]     */
+  const float* const* conditioner_projection_w; /* [2C,n_mels,1] */
+  const float* const* conditioner_projection_b; /* [2C]          */
+  const float* const* output_projection_w;      /* [2C,C,1]      */
+  const float* const* output_projection_b;      /* [2C]          */
+  const float* skip_projection_w;       /* [C,C,1]    */
+  const float* skip_projection_b;       /* [C]        */
+  const float* head_projection_w;       /* [88,C,1]  (state_dict key output_projection.weight) */
+  const float* head_projection_b;       /* [88]       */
+  const float* stft_window;             /* [n_fft]            mel_layer.spectrogram.window */
+  const float* mel_fb;                  /* [n_fft/2+1,n_mels] mel_layer.mel_scale.fb       */
+} drb_weights;
+
+typedef struct drb_update {
+  int32_t mode;        /* DRB_UPD_*                           */
+  int32_t has_noise;   /* 0: the noise pointer is not read    */
+  float   s[5];
+  float   w;           /* classifier-free guidance weight     */
+} drb_update;
+
+typedef struct drb_plan drb_plan;
+
+int         drb_version(void);
+const char* drb_last_error(void);
+
+/* Bytes of device workspace a plan for cfg needs (0 on invalid cfg). */
+size_t drb_plan_workspace_bytes(const drb_config* cfg);
+
+/* Repack weights (tap-major, gate/filter interleave, bf16 hi/lo split), build TMA
+ * descriptors and the cuFFT plan.  Replaces module construction + .to(device):
+ * model/diffwave.py:580-635.  Synchronous on `stream` when it returns. */
+int drb_plan_create(drb_plan** plan, const drb_config* cfg, const drb_weights* w,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int drb_plan_destroy(drb_plan* plan);
+
+/* Select which branches the following step calls evaluate (DRB_BRANCH_*).  A plan created with
+ * DRB_BRANCH_COND_UNCOND has room for both and may be switched to either single branch. */
+int drb_plan_set_branches(drb_plan* plan, int32_t branches);
+
+/* DiffusionEmbedding MLP + every layer's diffusion_projection for all timesteps:
+ * model/diffwave.py:65-74,138.  emb_table is the [timesteps,128] sinusoid table
+ * built by the host with the reference's own expression (model/diffwave.py:83-88). */
+int drb_time_tables(drb_plan* plan, const float* emb_table, void* stream);
+
+/* STFT -> power -> HTK mel -> log -> per-clip min-max -> inpainting mask:
+ * model/diffwave.py:643-654 + model/utils.py:21-32 + torchaudio MelSpectrogram.
+ * waveform [B,L]; spec_out [B,n_mels,T] (may be NULL).  it0<it1 / if0<if1 select
+ * the masked frame / mel ranges (set both ends to 0 for "no mask").  Also
+ * precomputes nothing step-dependent; call once per clip. */
+int drb_mel_forward(drb_plan* plan, const float* waveform, float* spec_out,
+                    int32_t it0, int32_t it1, int32_t if0, int32_t if1, void* stream);
+
+/* input_projection + ReLU (model/diffwave.py:640,667-668) for timestep t_index. x_t [B,1,T,88]. */
+int drb_in_proj(drb_plan* plan, const float* x_t, int32_t t_index, void* stream);
+
+/* One ResidualBlock (model/diffwave.py:134-151) on every branch, plus the skip sum (:680). */
+int drb_resblock_forward(drb_plan* plan, int32_t layer, int32_t t_index, void* stream);
+
+/* skip/sqrt(L) -> skip_projection -> ReLU -> output_projection (model/diffwave.py:682-686),
+ * guidance combine and posterior update (task/diffusion.py:1009-1023).
+ * net_out (optional) receives the combined network output [B,1,T,88]. */
+int drb_head_posterior_step(drb_plan* plan, const float* x_t, const float* noise, float* x_prev,
+                            float* net_out, const drb_update* upd, void* stream);
+
+/* drb_in_proj + L x drb_resblock_forward + drb_head_posterior_step. */
+int drb_sample_step(drb_plan* plan, const float* x_t, const float* noise, float* x_prev,
+                    int32_t t_index, const drb_update* upd, void* stream);
+
+/* The loop of predict_step (task/diffusion.py:528-534) for t = t_start-1 .. t_stop:
+ * x [B,1,T,88] is updated in place; noise [n,B,1,T,88] is consumed one slice per step
+ * with has_noise; updates_host is a host array of (t_start-t_stop) drb_update, first
+ * entry = highest t.  trajectory (optional, device or pinned-host-mapped) receives
+ * every step's x, [t_start-t_stop,B,1,T,88]. */
+int drb_sample_loop(drb_plan* plan, float* x, const float* noise, const drb_update* updates_host,
+                    int32_t t_start, int32_t t_stop, float* trajectory, void* stream);
+
+/* Number of kernels launched by this library on the calling thread since the last reset. */
+int64_t drb_launch_count(int32_t reset);
+
+/* Debug / test access to plan-owned device buffers ("x32","skip","xh","xl","zh","zl","spec_h","dtab","logmel"). */
+int drb_plan_buffer(drb_plan* plan, const char* name, void** ptr, size_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFROLL_B200_H */
