@@ -20,6 +20,7 @@ EXPORTS = [
     "drb_version", "drb_last_error", "drb_plan_workspace_bytes", "drb_plan_create", "drb_plan_destroy",
     "drb_plan_set_branches", "drb_time_tables", "drb_mel_forward", "drb_in_proj", "drb_resblock_forward",
     "drb_head_posterior_step", "drb_sample_step", "drb_sample_loop", "drb_launch_count", "drb_plan_buffer",
+    "drb_plan_profile", "drb_plan_profile_read",
 ]
 
 
@@ -91,6 +92,8 @@ def load():
     lib.drb_launch_count.restype = C.c_int64
     lib.drb_launch_count.argtypes = [C.c_int32]
     lib.drb_plan_buffer.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.drb_plan_profile.argtypes = [C.c_void_p, C.c_int32]
+    lib.drb_plan_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("drb_version",):

@@ -96,6 +96,16 @@ struct drb_plan {
   MelPlan* mel;
   UmmaMaps maps;
   std::vector<UmmaLayer> layers;
+  // optional per-kernel timing (drb_plan_profile): events recorded on the launching stream around every kernel class
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_spans[4];  // 0 gate kernel, 1 out kernel, 2 in_proj+prep, 3 head
+  size_t ev_used = 0;
+  int ev_mark(cudaStream_t s) {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return -1; ev_pool.push_back(e); }
+    cudaEventRecord(ev_pool[ev_used], s);
+    return (int)ev_used++;
+  }
   template <class Tp> Tp* at(size_t off) const { return reinterpret_cast<Tp*>(ws + off); }
   float* bias_ptr(int layer, int which) const {  // which: 0 cond-interleaved, 1 unc-interleaved, 2 cond-natural, 3 unc-natural
     return at<float>(lay.bias) + ((size_t)layer * 4 + which) * 2 * cfg.residual_channels;
@@ -206,6 +216,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
 int drb_plan_destroy(drb_plan* p) {
   if (!p) return 0;
   mel_destroy(p->mel);
+  for (auto e : p->ev_pool) cudaEventDestroy(e);
   delete p;
   return 0;
 }
@@ -249,11 +260,14 @@ int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
   SimtGemm g;  // relu(input_projection(x_t))   model/diffwave.py:667-668 ; x_t [B,1,T,88] is already [B*T][88]
   g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = p->in_w; g.ldw = F; g.bias = p->in_b; g.act = 1;
   g.C = p->at<float>(p->lay.x32); g.ldc = C; g.M = B * T; g.N = C;
+  const int e0 = p->prof ? p->ev_mark(s) : -1;
   int r = launch_simt_gemm(g, s); if (r) return r;
   const bool tensor = p->cfg.precision != DRB_PREC_FP32;
-  return launch_prep_xin(p->at<float>(p->lay.x32), tensor ? p->at<__nv_bfloat16>(p->lay.xh) : nullptr,
+  r = launch_prep_xin(p->at<float>(p->lay.x32), tensor ? p->at<__nv_bfloat16>(p->lay.xh) : nullptr,
                          tensor ? p->at<__nv_bfloat16>(p->lay.xl) : nullptr, p->dvec(0, t_index), B * T, C, p->NB / B,
                          tensor ? 1 : 0, s);
+  if (p->prof && r == 0) p->ev_spans[2].push_back({e0, p->ev_mark(s)});
+  return r;
 }
 
 int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stream) {
@@ -298,13 +312,20 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   ug.three = c.precision == DRB_PREC_BF16X3;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
   ug.zh = p->at<__nv_bfloat16>(p->lay.zh); ug.zl = p->at<__nv_bfloat16>(p->lay.zl);
+  const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;
+  const int e1 = p->prof ? p->ev_mark(s) : -1;
   UmmaOut uo;
   uo.NB = NB; uo.T = T; uo.C = C; uo.three = ug.three; uo.first = first; uo.do_res = do_res; uo.bias_o = p->bo[layer];
   uo.x32 = p->at<float>(p->lay.x32); uo.skip = p->at<float>(p->lay.skip);
   uo.dnext = do_res ? p->dvec(layer + 1, t_index) : nullptr;
   uo.xh = p->at<__nv_bfloat16>(p->lay.xh); uo.xl = p->at<__nv_bfloat16>(p->lay.xl);
-  return launch_umma_out(p->maps, p->layers[layer], uo, s);
+  r = launch_umma_out(p->maps, p->layers[layer], uo, s);
+  if (p->prof && r == 0) {
+    const int e2 = p->ev_mark(s);
+    p->ev_spans[0].push_back({e0, e1}); p->ev_spans[1].push_back({e1, e2});
+  }
+  return r;
 }
 
 int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, float* x_prev, float* net_out,
@@ -320,6 +341,7 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
   SimtGemm g;  // relu(skip_projection(skip / sqrt(L)))   model/diffwave.py:682-684
   g.A = p->at<float>(p->lay.skip); g.lda = C; g.T = T; g.Ck = C; g.a_div = sqrtf((float)c.residual_layers);
   g.W = p->skw; g.ldw = C; g.bias = p->skb; g.act = 1; g.C = h; g.ldc = C; g.M = p->NB * T; g.N = C;
+  const int e0 = p->prof ? p->ev_mark(s) : -1;
   int r = launch_simt_gemm(g, s); if (r) return r;
   SimtGemm o;  // output_projection + guidance combine + posterior update
   o.A = h; o.lda = C; o.T = T; o.Ck = C; o.W = p->hdw; o.ldw = C; o.bias = p->hdb;
@@ -327,7 +349,9 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
     o.A2 = h + (size_t)B * T * C; o.alpha = 1.f + upd->w; o.beta = -upd->w;
   }
   o.C = x_prev; o.ldc = F; o.M = B * T; o.N = F; o.upd = upd; o.x_t = x_t; o.noise = noise; o.net_out = net_out;
-  return launch_simt_gemm(o, s);
+  r = launch_simt_gemm(o, s);
+  if (p->prof && r == 0) p->ev_spans[3].push_back({e0, p->ev_mark(s)});
+  return r;
 }
 
 int drb_sample_step(drb_plan* p, const float* x_t, const float* noise, float* x_prev, int32_t t_index,
@@ -351,6 +375,29 @@ int drb_sample_loop(drb_plan* p, float* x, const float* noise, const drb_update*
     if (u->has_noise) { if (!noise) { set_error("sample_loop: noise missing"); return DRB_E_INVALID; } nz = noise + (j++) * n; }
     int r = drb_sample_step(p, x, nz, x, t, u, stream); if (r) return r;
     if (trajectory) DRB_CUDA(cudaMemcpyAsync(trajectory + (size_t)i * n, x, n * sizeof(float), cudaMemcpyDefault, s));
+  }
+  return 0;
+}
+
+int drb_plan_profile(drb_plan* p, int32_t enable) {
+  if (!p) return DRB_E_INVALID;
+  p->prof = enable != 0;
+  p->ev_used = 0;
+  for (auto& v : p->ev_spans) v.clear();
+  return 0;
+}
+
+int drb_plan_profile_read(drb_plan* p, double* ms_total, int64_t* launches) {
+  if (!p || !ms_total || !launches) return DRB_E_INVALID;
+  DRB_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < 4; ++k) {
+    double tot = 0.0;
+    for (auto& sp : p->ev_spans[k]) {
+      float ms = 0.f;
+      DRB_CUDA(cudaEventElapsedTime(&ms, p->ev_pool[sp.first], p->ev_pool[sp.second]));
+      tot += ms;
+    }
+    ms_total[k] = tot; launches[k] = (int64_t)p->ev_spans[k].size();
   }
   return 0;
 }

@@ -179,5 +179,15 @@ class Engine:
         off = p.value - self.workspace.data_ptr()
         return self.workspace[off:off + nbytes.value].view(dtype)
 
+    def profile(self, enable=True):
+        _lib.check(self.lib.drb_plan_profile(self.plan, 1 if enable else 0), "drb_plan_profile")
+
+    def profile_read(self):
+        """{class: (total_ms, spans)} for gate / out / in_proj / head kernels since profile(True)."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        _lib.check(self.lib.drb_plan_profile_read(self.plan, ms, n), "drb_plan_profile_read")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("gate", "out", "in_proj", "head"))}
+
     def launch_count(self, reset=False):
         return int(self.lib.drb_launch_count(1 if reset else 0))

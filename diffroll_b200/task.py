@@ -180,14 +180,21 @@ class SpecRollDiffusion(nn.Module):
         return ups, probe.branches, probe.masks
 
     @torch.no_grad()
-    def sample_loop(self, x_T, waveform, noise=None, keep_trajectory=False):
+    def sample_loop(self, x_T, waveform, noise=None, keep_trajectory=False, n_steps=None):
         """The loop body of predict_step / sampling (task/diffusion.py:528-534, 779-788) as ONE library call.
 
         noise: optional pre-drawn [n_noisy_steps, B, 1, T, 88]; by default it is drawn step by step with
         ``torch.randn_like`` on the roll's device, in the reference's order (descending t, only t with noise).
-        Returns (x_0, spec, trajectory) — trajectory is a pinned host tensor [timesteps, B, 1, T, 88] or None.
+        n_steps: run only the first n_steps of the chain (t = T-1 .. T-n_steps); default the whole chain.
+        Returns (x_0, spec, trajectory) — trajectory is a pinned host tensor [steps, B, 1, T, 88] or None.
         """
         ups, branches, masks = self._all_updates()
+        T_all = self.hparams.timesteps
+        if n_steps is not None:
+            if not 0 < n_steps <= T_all:
+                raise ValueError("n_steps must be in [1, timesteps]")
+            ups = ups[:n_steps]
+        t_stop = T_all - len(ups)
         eng, x, spec = self._prepare(x_T, waveform, branches, *masks)
         x = x.clone()
         n_noise = sum(1 for u in ups if u.has_noise)
@@ -200,7 +207,7 @@ class SpecRollDiffusion(nn.Module):
         traj = None
         if keep_trajectory:
             traj = torch.empty((len(ups),) + tuple(x.shape), dtype=torch.float32, pin_memory=True)
-        eng.loop(x, noise, ups, self.hparams.timesteps, 0, traj)
+        eng.loop(x, noise, ups, T_all, t_stop, traj)
         return x, spec, traj
 
     @torch.no_grad()

@@ -166,6 +166,12 @@ int drb_sample_loop(drb_plan* plan, float* x, const float* noise, const drb_upda
 /* Number of kernels launched by this library on the calling thread since the last reset. */
 int64_t drb_launch_count(int32_t reset);
 
+/* Measurement hooks (bench.py): with profiling enabled every step records CUDA events on the launching stream
+ * around each kernel class; drb_plan_profile_read synchronises and returns, for class k in
+ * {0: gate kernel, 1: out kernel, 2: in_proj, 3: head}, the summed milliseconds and the number of spans. */
+int drb_plan_profile(drb_plan* plan, int32_t enable);
+int drb_plan_profile_read(drb_plan* plan, double* ms_total4, int64_t* launches4);
+
 /* Debug / test access to plan-owned device buffers ("x32","skip","xh","xl","zh","zl","spec_h","dtab","logmel"). */
 int drb_plan_buffer(drb_plan* plan, const char* name, void** ptr, size_t* bytes);
 
