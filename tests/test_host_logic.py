@@ -1,0 +1,217 @@
+"""CPU tests of the host side: module surface, update coefficients, C-ABI exports, sharding (gloo)."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dict, state_dict_shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(**kw):
+    import diffroll_b200 as M
+    hp = default_hparams(**kw)
+    return M.ClassifierFreeDiffRoll(**hp), hp
+
+
+# ---- module surface ------------------------------------------------------------------------------------
+def test_class_lookup_like_sampling_py():
+    import diffroll_b200 as Model
+    assert getattr(Model, "ClassifierFreeDiffRoll").__name__ == "ClassifierFreeDiffRoll"   # sampling.py:54
+
+
+def test_state_dict_keys_and_shapes_match_reference_contract():
+    m, hp = _model()
+    sd = m.state_dict()
+    want = state_dict_shapes(hp)
+    assert len(sd) == 132 and set(sd) == set(want)
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    assert "diffusion_embedding.embedding" not in sd            # persistent=False, model/diffwave.py:61
+    assert float(m.output_projection.weight.abs().max()) == 0.0  # zero-initialised head, model/diffwave.py:630
+    m.load_state_dict(make_state_dict(hp), strict=True)
+
+
+def test_hparams_and_errors():
+    m, hp = _model(inpainting_t=[0, 320])
+    assert m.hparams.timesteps == 200 and m.hparams.sampling.type == "inpainting_ddpm_x0"
+    assert m.hparams.sampling.w == 0.5 and m.hparams.inpainting_t == [0, 320] and m.hparams.condition == "fixed"
+    assert m.hparams.spec_args.n_mels == 229
+    import diffroll_b200 as M
+    bad = default_hparams(); bad["condition"] = "nonsense"
+    with pytest.raises(ValueError):
+        M.ClassifierFreeDiffRoll(**bad)
+    bad = default_hparams(sampling_type="no_such_sampler")
+    with pytest.raises(AttributeError):
+        M.ClassifierFreeDiffRoll(**bad)
+    with pytest.raises(NotImplementedError):
+        m.p_losses(torch.zeros(1), torch.zeros(1), loss_type="nope")
+
+
+def test_load_from_checkpoint_overrides(tmp_path):
+    import diffroll_b200 as M
+    hp = default_hparams(residual_layers=2)
+    sd = make_state_dict(hp)
+    path = tmp_path / "tiny.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": hp}, path)
+    m = M.ClassifierFreeDiffRoll.load_from_checkpoint(str(path), sampling={"type": "generation_ddpm_x0"},
+                                                      inpainting_t=None, generation_filter=0.1)
+    assert m.hparams.sampling.type == "generation_ddpm_x0" and m.hparams.generation_filter == 0.1
+    assert m.reverse_diffusion.__name__ == "generation_ddpm_x0"
+    assert torch.equal(m.state_dict()["skip_projection.weight"], sd["skip_projection.weight"])
+
+
+def test_schedule_and_embedding_tables_equal_oracle():
+    from oracle.diffroll_oracle import Schedule, build_embedding
+    for T in (200, 1000):
+        m, hp = _model(timesteps=T)
+        s = Schedule(hp["beta_start"], hp["beta_end"], T)
+        for name in ("betas", "sqrt_recip_alphas", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                     "posterior_variance", "alphas"):
+            assert torch.equal(getattr(m, name), getattr(s, name)), name
+        assert torch.equal(m.diffusion_embedding.embedding, build_embedding(T))
+
+
+# ---- update coefficients: the fused epilogue formula reproduces the oracle's sampler arithmetic ------------
+def _apply(u, net, x, n):
+    s = [np.float32(v) for v in u.s]
+    net, x, n = net.astype(np.float32), x.astype(np.float32), n.astype(np.float32)
+    if u.mode == 0:
+        r = s[0] * net + s[1] * (x - s[2] * net) / s[3]
+        return r + s[4] * n if u.has_noise else r
+    if u.mode == 1:
+        return net / s[0]
+    if u.mode == 2:
+        r = s[0] * (x - s[1] * net / s[2])
+        return r + s[3] * n if u.has_noise else r
+    if u.mode == 3:
+        r = s[0] * ((x - s[1] * net) / s[2]) + s[3] * net
+        return r + s[4] * n if u.has_noise else r
+    if u.mode == 4:
+        return (x - s[0] * net) / s[1]
+    return net
+
+
+@pytest.mark.parametrize("name", ["inpainting_ddpm_x0", "cfdg_ddpm_x0", "generation_ddpm_x0", "ddpm_x0", "ddim_x0",
+                                  "cfdg_ddim_x0", "ddpm", "ddim", "ddim2ddpm"])
+def test_update_structs_reproduce_oracle_samplers(name):
+    from diffroll_b200 import _lib
+    from oracle.diffroll_oracle import OracleDiffRoll
+    m, hp = _model(sampling_type=name)
+    ups, branches, masks = m._all_updates()
+    assert len(ups) == 200
+    want_branch = {"inpainting_ddpm_x0": _lib.BRANCH_COND_UNCOND, "cfdg_ddpm_x0": _lib.BRANCH_COND_UNCOND,
+                   "generation_ddpm_x0": _lib.BRANCH_UNCOND, "cfdg_ddim_x0": _lib.BRANCH_COND_ZEROSPEC}.get(name, _lib.BRANCH_COND)
+    assert branches == want_branch
+
+    class Fake(OracleDiffRoll):          # network output replaced by a fixed tensor: isolates the posterior arithmetic
+        def forward(self, x_t, waveform, diffusion_step, **kw):
+            return self.net, None
+        __call__ = forward
+
+    o = Fake(hp, {k: v for k, v in make_state_dict(hp).items() if k.startswith("mel")})
+    g = torch.Generator().manual_seed(0)
+    net, x, n = (torch.randn(1, 1, 8, 88, generator=g) for _ in range(3))
+    o.net = net
+    for t_index in (199, 100, 1, 0):
+        u = ups[199 - t_index]
+        ref, _ = o.reverse_diffusion(x, torch.zeros(1, 4), t_index, noise=n)
+        got = _apply(u, net.numpy(), x.numpy(), n.numpy())
+        assert np.abs(got - ref.numpy()).max() < 2e-6 * max(1.0, float(ref.abs().max())), (name, t_index)
+        assert bool(u.has_noise) == (t_index > 0 and name not in ("ddim_x0", "cfdg_ddim_x0", "ddim"))
+
+
+def test_no_cpu_fallback_and_training_mode_guard():
+    from diffroll_b200._lib import DrbError
+    m, hp = _model()
+    x, w = torch.randn(1, 1, 128, 88), torch.randn(1, 65536)
+    with pytest.raises(NotImplementedError):
+        m(x, w, torch.tensor([3]))                 # training mode: spec dropout is not on this path
+    m.eval()
+    with pytest.raises(DrbError):
+        m(x, w, torch.tensor([3]))                 # CPU tensors: no fallback
+    with pytest.raises(DrbError):
+        m.reverse_diffusion(x, w, 5)
+
+
+# ---- C ABI ------------------------------------------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol(lib_built):
+    header = open(os.path.join(ROOT, "include", "diffroll_b200.h")).read()
+    declared = set(re.findall(r"\b(drb_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = C.CDLL(lib_built)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/diffroll_b200.h but not exported"
+    from diffroll_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.load().drb_version() == 100
+
+
+def test_cabi_workspace_query_and_argument_checks(lib_built):
+    from diffroll_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.DrbConfig(batch=32, frames=640, pitches=88, wave_len=327680, residual_channels=512, residual_layers=15,
+                         kernel_size=9, dilation_base=2, dilation_bound=4, n_mels=229, n_fft=2048, hop_length=512,
+                         timesteps=200, precision=_lib.PREC_BF16X3, branches=_lib.BRANCH_COND_UNCOND, reserved=0)
+    need = lib.drb_plan_workspace_bytes(C.byref(cfg))
+    assert 1.0e9 < need < 2.0e9                       # 1.34 GB at the benchmark shape
+    cfg.kernel_size = 8                               # even kernels are not a 'same' convolution
+    assert lib.drb_plan_workspace_bytes(C.byref(cfg)) == 0
+    assert b"invalid" in lib.drb_last_error()
+    cfg.kernel_size = 9; cfg.frames = 700             # more roll frames than spectrogram frames
+    assert lib.drb_plan_workspace_bytes(C.byref(cfg)) == 0
+    assert lib.drb_sample_loop(None, None, None, None, 0, 0, None, None) == -1
+
+
+def test_python_struct_layout_matches_header():
+    from diffroll_b200 import _lib
+    assert C.sizeof(_lib.DrbConfig) == 16 * 4
+    assert C.sizeof(_lib.DrbUpdate) == 4 + 4 + 5 * 4 + 4
+    assert C.sizeof(_lib.DrbWeights) == 20 * C.sizeof(C.c_void_p)
+
+
+# ---- sharding + all-gather, 2 ranks over gloo -------------------------------------------------------------------
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gather_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    from diffroll_b200.dist import all_gather_rolls, shard_bounds
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full = torch.arange(n_total * 6, dtype=torch.float32).reshape(n_total, 1, 2, 3)
+    lo, hi = shard_bounds(n_total, rank, world)
+    out = all_gather_rolls(full[lo:hi].clone(), n_total)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 5])
+def test_all_gather_rolls_gloo_world2(n_total):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_bounds_cover_batch_exactly():
+    from diffroll_b200.dist import shard_bounds
+    for n in (1, 5, 32, 256):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
