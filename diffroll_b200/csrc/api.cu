@@ -26,7 +26,7 @@ static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Layout {  // byte offsets into the workspace
   size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
-  size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol;  // tensor path
+  size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum;  // tensor path
   size_t total;
   int NBcap, Mp, KC;
 };
@@ -68,11 +68,13 @@ static Layout make_layout(const drb_config& c) {
     l.z32 = take(rows * C * 4);
   } else {
     l.xh = take(rows * C * 2); l.xl = take(rows * C * 2);
-    l.zh = take(rows * C * 2); l.zl = take(rows * C * 2);
+    l.zh = take(L * rows * C * 2); l.zl = take(L * rows * C * 2);  // gated activations of every layer (head GEMM)
     l.sh = take(B * T * Mp * 2); l.sl = take(B * T * Mp * 2);
     l.wdh = take(L * 2 * C * k * C * 2); l.wdl = take(L * 2 * C * k * C * 2);
     l.wch = take(L * 2 * C * Mp * 2); l.wcl = take(L * 2 * C * Mp * 2);
     l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
+    l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
+    l.bcomp = take(C * 4); l.bsum = take(C * 4);
   }
   l.total = off;
   return l;
@@ -201,8 +203,18 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
     const uint64_t NBc = lay.NBcap;
     PLAN_TRY(make_tmap_3d(&p->maps.xh, p->ws + lay.xh, NBc, T, C, 128, 64));
     PLAN_TRY(make_tmap_3d(&p->maps.xl, p->ws + lay.xl, NBc, T, C, 128, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, NBc, T, C, 128, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, (uint64_t)L * NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, C, 128, 64));
+    PLAN_TRY(make_tmap_3d_f32(&p->maps.x32, p->ws + lay.x32, NBc, T, C, 128, 32));
+    PLAN_TRY(make_tmap_3d_f32(&p->maps.h32, p->ws + lay.hbuf, NBc, T, C, 128, 32));
+    // skip sum + 1/sqrt(L) + skip_projection composed into one [C][L*C] weight over the stored z of all layers
+    for (int i = 0; i < L; ++i)
+      PLAN_TRY(launch_compose_skip(p->skw, p->wo32[i], p->at<float>(lay.wcomp32), C, L, i, s));
+    PLAN_TRY(launch_compose_bias(p->skw, p->skb, p->bo.data(), C, L, p->at<float>(lay.bsum), p->at<float>(lay.bcomp), s));
+    PLAN_TRY(launch_repack_split(p->at<float>(lay.wcomp32), p->at<__nv_bfloat16>(lay.wcomph), p->at<__nv_bfloat16>(lay.wcompl),
+                                 C, L * C, L * C, 0, s));
+    PLAN_TRY(make_tmap_2d(&p->maps.wcomp_h, p->ws + lay.wcomph, C, (uint64_t)L * C, 256, 64));
+    PLAN_TRY(make_tmap_2d(&p->maps.wcomp_l, p->ws + lay.wcompl, C, (uint64_t)L * C, 256, 64));
     PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, 64));
     PLAN_TRY(make_tmap_3d(&p->maps.sl, p->ws + lay.sl, cfg->batch, T, Mp, 128, 64));
   }
@@ -309,23 +321,23 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   UmmaGate ug;
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
-  ug.three = c.precision == DRB_PREC_BF16X3;
+  ug.three = c.precision == DRB_PREC_BF16X3; ug.z_group0 = layer * p->lay.NBcap;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
-  ug.zh = p->at<__nv_bfloat16>(p->lay.zh); ug.zl = p->at<__nv_bfloat16>(p->lay.zl);
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;
   const int e1 = p->prof ? p->ev_mark(s) : -1;
-  UmmaOut uo;
-  uo.NB = NB; uo.T = T; uo.C = C; uo.three = ug.three; uo.first = first; uo.do_res = do_res; uo.bias_o = p->bo[layer];
-  uo.x32 = p->at<float>(p->lay.x32); uo.skip = p->at<float>(p->lay.skip);
-  uo.dnext = do_res ? p->dvec(layer + 1, t_index) : nullptr;
-  uo.xh = p->at<__nv_bfloat16>(p->lay.xh); uo.xl = p->at<__nv_bfloat16>(p->lay.xl);
-  r = launch_umma_out(p->maps, p->layers[layer], uo, s);
-  if (p->prof && r == 0) {
+  if (do_res) {  // the last layer's residual half is dead; every layer's skip half is deferred to the head GEMM
+    UmmaZGemm uz;
+    uz.NB = NB; uz.T = T; uz.C = C; uz.three = ug.three; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
+    uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
+    uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, t_index);
+    r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
+  }
+  if (p->prof) {
     const int e2 = p->ev_mark(s);
     p->ev_spans[0].push_back({e0, e1}); p->ev_spans[1].push_back({e1, e2});
   }
-  return r;
+  return 0;
 }
 
 int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, float* x_prev, float* net_out,
@@ -342,7 +354,16 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
   g.A = p->at<float>(p->lay.skip); g.lda = C; g.T = T; g.Ck = C; g.a_div = sqrtf((float)c.residual_layers);
   g.W = p->skw; g.ldw = C; g.bias = p->skb; g.act = 1; g.C = h; g.ldc = C; g.M = p->NB * T; g.N = C;
   const int e0 = p->prof ? p->ev_mark(s) : -1;
-  int r = launch_simt_gemm(g, s); if (r) return r;
+  int r;
+  if (c.precision == DRB_PREC_FP32) {
+    r = launch_simt_gemm(g, s); if (r) return r;
+  } else {  // one long-K tensor-core GEMM over the stored z of all layers (skip sum, 1/sqrt(L), skip_projection, ReLU)
+    UmmaZGemm uz;
+    uz.NB = p->NB; uz.T = T; uz.C = C; uz.three = c.precision == DRB_PREC_BF16X3; uz.mode = 1; uz.groups = c.residual_layers;
+    uz.z_group0 = 0; uz.group_stride = p->lay.NBcap; uz.w_h = &p->maps.wcomp_h; uz.w_l = &p->maps.wcomp_l; uz.out32 = &p->maps.h32;
+    uz.bias = p->at<float>(p->lay.bcomp); uz.dnext = nullptr;
+    r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
+  }
   SimtGemm o;  // output_projection + guidance combine + posterior update
   o.A = h; o.lda = C; o.T = T; o.Ck = C; o.W = p->hdw; o.ldw = C; o.bias = p->hdb;
   if (p->NB == 2 * B) {  // (1+w)*x0_c - w*x0_u, applied to the (linear) head's input   task/diffusion.py:1009

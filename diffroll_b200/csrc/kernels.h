@@ -54,6 +54,11 @@ int launch_pad_rows(const float* src, float* dst, int rows, int Kin, int Kp, cud
 int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_cond, float* out_unc,
                  float* out_cond_nat, float* out_unc_nat, int C, int n_mels, cudaStream_t s);
 int launch_fill(float* p, float v, size_t n, cudaStream_t s);
+// Wcomp[n][l*C + k] = sum_j Ws[n][j] * Wo_l[C + j][k] / sqrt(L)   (one layer l per launch)
+int launch_compose_skip(const float* ws, const float* wo, float* wcomp, int C, int L, int layer, cudaStream_t s);
+// bcomp[n] = bs[n] + sum_j Ws[n][j] * bsum[j] / sqrt(L), bsum = sum_l bo_l[C + j]
+int launch_compose_bias(const float* ws, const float* bs, const float* const* bo_dev_ptrs_host, int C, int L, float* bsum_tmp,
+                        float* bcomp, cudaStream_t s);
 
 // ------------------------------- mel front-end (mel.cu) ----------------------------------------
 struct MelPlan;
@@ -75,27 +80,28 @@ struct UmmaLayer {
 };
 struct UmmaMaps {
   CUtensorMap xh, xl;      // [NB][T][C]
-  CUtensorMap zh, zl;      // [NB][T][C]
+  CUtensorMap zh, zl;      // [L*NB][T][C]: gated activations of every layer
+  CUtensorMap x32, h32;    // fp32 [NB][T][C], box 32 channels x 128 frames
+  CUtensorMap wcomp_h, wcomp_l;  // [C][L*C] composed skip/head weights
   CUtensorMap sh, sl;      // [B][T][Mp]
 };
-struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl
-  int NB, n_cond, T, C, taps, dil, Mp, three;  // three: 1 = bf16x3, 0 = single product
+struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl[z_group0 + roll]
+  int NB, n_cond, T, C, taps, dil, Mp, three, z_group0;  // three: 1 = bf16x3, 0 = single product
   const float* bias_cond;  // interleaved [2C]
   const float* bias_unc;
-  __nv_bfloat16 *zh, *zl;
 };
-struct UmmaOut {   // o = z*Wo^T + bo ; x = (x + o[:C])/sqrt2 ; xin_next = split(x + dnext) ; skip (+)= o[C:]
-  int NB, T, C, three, first, do_res;
-  const float* bias_o;
-  float* x32;
-  float* skip;
-  const float* dnext;  // nullable when !do_res
-  __nv_bfloat16 *xh, *xl;
+struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
+  int NB, T, C, three, mode;        // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h
+  int groups, z_group0, group_stride;
+  const CUtensorMap *w_h, *w_l, *out32;
+  const float* bias;
+  const float* dnext;
 };
 int umma_init();  // resolves cuTensorMapEncodeTiled
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0);
 int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g, cudaStream_t s);
-int launch_umma_out(const UmmaMaps& maps, const UmmaLayer& L, const UmmaOut& o, cudaStream_t s);
+int make_tmap_3d_f32(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0);
+int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s);
 
 }  // namespace drb

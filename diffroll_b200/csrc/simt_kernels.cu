@@ -362,6 +362,47 @@ int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_c
   return 0;
 }
 
+// Composed head weights (plan creation only).  skip/sqrt(L) -> skip_projection is linear in every layer's z:
+//   skip_projection(sum_l Wo_l[C:] z_l / sqrt(L)) = sum_l (Ws . Wo_l[C:] / sqrt(L)) z_l  + Ws . (sum_l bo_l[C:]) / sqrt(L) + bs
+__global__ void compose_skip_kernel(const float* __restrict__ ws, const float* __restrict__ wo, float* __restrict__ wcomp,
+                                    int C, int L, int layer) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // input channel of z
+  const int n = blockIdx.y;                             // output channel of skip_projection
+  if (k >= C) return;
+  double acc = 0.0;
+  for (int j = 0; j < C; ++j) acc += (double)ws[(size_t)n * C + j] * (double)wo[(size_t)(C + j) * C + k];
+  wcomp[(size_t)n * L * C + (size_t)layer * C + k] = (float)(acc / sqrt((double)L));
+}
+int launch_compose_skip(const float* ws, const float* wo, float* wcomp, int C, int L, int layer, cudaStream_t s) {
+  dim3 grid((C + 127) / 128, C);
+  compose_skip_kernel<<<grid, 128, 0, s>>>(ws, wo, wcomp, C, L, layer);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void bias_accum_kernel(const float* __restrict__ bo, float* __restrict__ bsum, int C, int first) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < C) bsum[j] = (first ? 0.f : bsum[j]) + bo[C + j];
+}
+__global__ void compose_bias_kernel(const float* __restrict__ ws, const float* __restrict__ bs, const float* __restrict__ bsum,
+                                    float* __restrict__ bcomp, int C, int L) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= C) return;
+  double acc = 0.0;
+  for (int j = 0; j < C; ++j) acc += (double)ws[(size_t)n * C + j] * (double)bsum[j];
+  bcomp[n] = (float)((double)bs[n] + acc / sqrt((double)L));
+}
+int launch_compose_bias(const float* ws, const float* bs, const float* const* bo, int C, int L, float* bsum_tmp, float* bcomp,
+                        cudaStream_t s) {
+  for (int l = 0; l < L; ++l) {
+    bias_accum_kernel<<<(C + 127) / 128, 128, 0, s>>>(bo[l], bsum_tmp, C, l == 0);
+    DRB_LAUNCH_CHECK();
+  }
+  compose_bias_kernel<<<(C + 127) / 128, 128, 0, s>>>(ws, bs, bsum_tmp, bcomp, C, L);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void fill_kernel(float* p, float v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
