@@ -2,6 +2,7 @@
 // per-step entry points.  See include/diffroll_b200.h for the contract and the reference lines replaced.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -26,7 +27,7 @@ static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 struct Layout {  // byte offsets into the workspace
   size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
-  size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum;  // tensor path
+  size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
   size_t total;
   int NBcap, Mp, KC;
 };
@@ -36,7 +37,7 @@ static bool cfg_ok(const drb_config& c) {
   if (c.residual_channels <= 0 || c.residual_channels % 256) return false;
   if (c.residual_layers <= 0 || c.kernel_size <= 0 || !(c.kernel_size & 1)) return false;
   if (c.dilation_base <= 0 || c.dilation_bound <= 0 || c.n_mels <= 0 || c.n_fft <= 0 || c.hop_length <= 0) return false;
-  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 2 || c.branches < 0 || c.branches > 3) return false;
+  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 3 || c.branches < 0 || c.branches > 3) return false;
   if (c.wave_len / c.hop_length + 1 < c.frames) return false;
   if (c.wave_len <= c.n_fft / 2) return false;  // reflect padding needs pad < length
   return true;
@@ -75,6 +76,7 @@ static Layout make_layout(const drb_config& c) {
     l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
     l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
     l.bcomp = take(C * 4); l.bsum = take(C * 4);
+    l.wscale = take((2 * L + 1) * 4 * 4);  // f16f8: {SW, 1/(SA*SW), scratch, -} per gate / out weight set and the head
   }
   l.total = off;
   return l;
@@ -91,6 +93,7 @@ struct drb_plan {
   int NB, n_cond;      // active branches
   bool zero_spec;      // second branch = conditional forward on an all-zero spectrogram (cfdg_ddim_x0)
   bool tables_ready, spec_ready;
+  int multicast = 1;   // 2-CTA clusters sharing weight tiles via TMA multicast (DRB_NO_MULTICAST=1 disables, for A/B runs)
   std::vector<int> dil;
   // weight pointers used in place (caller keeps them alive)
   const float *in_w, *in_b, *e1w, *e1b, *e2w, *e2b, *skw, *skb, *hdw, *hdb;
@@ -112,6 +115,10 @@ struct drb_plan {
   float* bias_ptr(int layer, int which) const {  // which: 0 cond-interleaved, 1 unc-interleaved, 2 cond-natural, 3 unc-natural
     return at<float>(lay.bias) + ((size_t)layer * 4 + which) * 2 * cfg.residual_channels;
   }
+  // tensor-path arithmetic: kernel template mode (0 bf16, 1 bf16x3, 2 f16f8) and operand format (1 bf16 hi/lo, 2 fp16+e4m3)
+  int prec() const { return cfg.precision == DRB_PREC_BF16X3 ? 1 : cfg.precision == DRB_PREC_F16F8 ? 2 : 0; }
+  int fmt() const { return cfg.precision == DRB_PREC_FP32 ? 0 : cfg.precision == DRB_PREC_F16F8 ? 2 : 1; }
+  float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head
   const float* dvec(int layer, int t) const {
     return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
   }
@@ -155,6 +162,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
   drb_plan* p = new drb_plan();
   p->cfg = *cfg; p->lay = lay; p->ws = (char*)workspace; p->mel = nullptr;
   p->tables_ready = false; p->spec_ready = false;
+  { const char* e = getenv("DRB_NO_MULTICAST"); p->multicast = (e && e[0] == '1') ? 0 : 1; }
   const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
   p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
   p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
@@ -180,43 +188,54 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
                                cfg->n_mels, Mp, s));
     } else {
       PLAN_TRY(launch_repack_conv_fp32(w->dilated_conv_w[i], tmp, 2 * C, C, k, s));
-      __nv_bfloat16* wdh = p->at<__nv_bfloat16>(lay.wdh) + (size_t)i * 2 * C * k * C;
-      __nv_bfloat16* wdl = p->at<__nv_bfloat16>(lay.wdl) + (size_t)i * 2 * C * k * C;
-      PLAN_TRY(launch_repack_split(tmp, wdh, wdl, 2 * C, k * C, k * C, C, s));
-      __nv_bfloat16* wch = p->at<__nv_bfloat16>(lay.wch) + (size_t)i * 2 * C * Mp;
-      __nv_bfloat16* wcl = p->at<__nv_bfloat16>(lay.wcl) + (size_t)i * 2 * C * Mp;
-      PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], wch, wcl, 2 * C, cfg->n_mels, Mp, C, s));
-      __nv_bfloat16* woh = p->at<__nv_bfloat16>(lay.woh) + (size_t)i * 2 * C * C;
-      __nv_bfloat16* wol = p->at<__nv_bfloat16>(lay.wol) + (size_t)i * 2 * C * C;
-      PLAN_TRY(launch_repack_split(w->output_projection_w[i], woh, wol, 2 * C, C, C, 0, s));
+      const int fmt = p->fmt();
+      const int dm = fmt == 2 ? 2 : 0, da = fmt == 2 ? 3 : 0, am = fmt == 2 ? 2 : 1;  // tensor-map dtypes, aux width factor
+      if (fmt == 2) {
+        PLAN_TRY(launch_weight_scale(tmp, (size_t)2 * C * k * C, w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels,
+                                     p->wscale(2 * i), s));
+        PLAN_TRY(launch_weight_scale(w->output_projection_w[i], (size_t)2 * C * C, nullptr, 0, p->wscale(2 * i + 1), s));
+      }
+      char* wdh = p->ws + lay.wdh + (size_t)i * 2 * C * k * C * 2;
+      char* wdl = p->ws + lay.wdl + (size_t)i * 2 * C * k * C * 2;
+      PLAN_TRY(launch_repack_split(tmp, wdh, wdl, 2 * C, k * C, k * C, C, fmt, p->wscale(2 * i), s));
+      char* wch = p->ws + lay.wch + (size_t)i * 2 * C * Mp * 2;
+      char* wcl = p->ws + lay.wcl + (size_t)i * 2 * C * Mp * 2;
+      PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], wch, wcl, 2 * C, cfg->n_mels, Mp, C, fmt, p->wscale(2 * i), s));
+      char* woh = p->ws + lay.woh + (size_t)i * 2 * C * C * 2;
+      char* wol = p->ws + lay.wol + (size_t)i * 2 * C * C * 2;
+      PLAN_TRY(launch_repack_split(w->output_projection_w[i], woh, wol, 2 * C, C, C, 0, fmt, p->wscale(2 * i + 1), s));
       UmmaLayer ul;
-      PLAN_TRY(make_tmap_2d(&ul.wd_h, wdh, 2 * C, (uint64_t)k * C, 256, 64));
-      PLAN_TRY(make_tmap_2d(&ul.wd_l, wdl, 2 * C, (uint64_t)k * C, 256, 64));
-      PLAN_TRY(make_tmap_2d(&ul.wc_h, wch, 2 * C, Mp, 256, 64));
-      PLAN_TRY(make_tmap_2d(&ul.wc_l, wcl, 2 * C, Mp, 256, 64));
-      PLAN_TRY(make_tmap_2d(&ul.wo_h, woh, 2 * C, C, 256, 64));
-      PLAN_TRY(make_tmap_2d(&ul.wo_l, wol, 2 * C, C, 256, 64));
+      PLAN_TRY(make_tmap_2d(&ul.wd_h, wdh, 2 * C, (uint64_t)k * C, 128, dm));
+      PLAN_TRY(make_tmap_2d(&ul.wd_l, wdl, 2 * C, (uint64_t)am * k * C, 128, da));
+      PLAN_TRY(make_tmap_2d(&ul.wc_h, wch, 2 * C, Mp, 128, dm));
+      PLAN_TRY(make_tmap_2d(&ul.wc_l, wcl, 2 * C, (uint64_t)am * Mp, 128, da));
+      PLAN_TRY(make_tmap_2d(&ul.wo_h, woh, 2 * C, C, 128, dm));
+      PLAN_TRY(make_tmap_2d(&ul.wo_l, wol, 2 * C, (uint64_t)am * C, 128, da));
       p->layers.push_back(ul);
     }
   }
   if (tensor) {
     const uint64_t NBc = lay.NBcap;
-    PLAN_TRY(make_tmap_3d(&p->maps.xh, p->ws + lay.xh, NBc, T, C, 128, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.xl, p->ws + lay.xl, NBc, T, C, 128, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, (uint64_t)L * NBc, T, C, 128, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, C, 128, 64));
-    PLAN_TRY(make_tmap_3d_f32(&p->maps.x32, p->ws + lay.x32, NBc, T, C, 128, 32));
-    PLAN_TRY(make_tmap_3d_f32(&p->maps.h32, p->ws + lay.hbuf, NBc, T, C, 128, 32));
+    const int fmt = p->fmt();
+    const int dm = fmt == 2 ? 2 : 0, da = fmt == 2 ? 3 : 0;
+    const uint64_t am = fmt == 2 ? 2 : 1;
+    PLAN_TRY(make_tmap_3d(&p->maps.xh, p->ws + lay.xh, NBc, T, C, 128, dm));
+    PLAN_TRY(make_tmap_3d(&p->maps.xl, p->ws + lay.xl, NBc, T, am * C, 128, da));
+    PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, (uint64_t)L * NBc, T, C, 128, dm));
+    PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, am * C, 128, da));
+    PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, dm));
+    PLAN_TRY(make_tmap_3d(&p->maps.sl, p->ws + lay.sl, cfg->batch, T, am * Mp, 128, da));
+    PLAN_TRY(make_tmap_3d(&p->maps.x32, p->ws + lay.x32, NBc, T, C, 128, 1));
+    PLAN_TRY(make_tmap_3d(&p->maps.h32, p->ws + lay.hbuf, NBc, T, C, 128, 1));
     // skip sum + 1/sqrt(L) + skip_projection composed into one [C][L*C] weight over the stored z of all layers
     for (int i = 0; i < L; ++i)
       PLAN_TRY(launch_compose_skip(p->skw, p->wo32[i], p->at<float>(lay.wcomp32), C, L, i, s));
     PLAN_TRY(launch_compose_bias(p->skw, p->skb, p->bo.data(), C, L, p->at<float>(lay.bsum), p->at<float>(lay.bcomp), s));
-    PLAN_TRY(launch_repack_split(p->at<float>(lay.wcomp32), p->at<__nv_bfloat16>(lay.wcomph), p->at<__nv_bfloat16>(lay.wcompl),
-                                 C, L * C, L * C, 0, s));
-    PLAN_TRY(make_tmap_2d(&p->maps.wcomp_h, p->ws + lay.wcomph, C, (uint64_t)L * C, 256, 64));
-    PLAN_TRY(make_tmap_2d(&p->maps.wcomp_l, p->ws + lay.wcompl, C, (uint64_t)L * C, 256, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, 64));
-    PLAN_TRY(make_tmap_3d(&p->maps.sl, p->ws + lay.sl, cfg->batch, T, Mp, 128, 64));
+    if (fmt == 2) PLAN_TRY(launch_weight_scale(p->at<float>(lay.wcomp32), (size_t)C * L * C, nullptr, 0, p->wscale(2 * L), s));
+    PLAN_TRY(launch_repack_split(p->at<float>(lay.wcomp32), p->ws + lay.wcomph, p->ws + lay.wcompl, C, L * C, L * C, 0, fmt,
+                                 p->wscale(2 * L), s));
+    PLAN_TRY(make_tmap_2d(&p->maps.wcomp_h, p->ws + lay.wcomph, C, (uint64_t)L * C, 128, dm));
+    PLAN_TRY(make_tmap_2d(&p->maps.wcomp_l, p->ws + lay.wcompl, C, am * L * C, 128, da));
   }
 #undef PLAN_TRY
   cudaError_t e = cudaStreamSynchronize(s);
@@ -257,9 +276,9 @@ int drb_mel_forward(drb_plan* p, const float* waveform, float* spec_out, int32_t
                     int32_t if1, void* stream) {
   if (!p || !waveform) return DRB_E_INVALID;
   const bool tensor = p->cfg.precision != DRB_PREC_FP32;
-  int r = mel_forward(p->mel, waveform, spec_out, p->at<float>(p->lay.spec32),
-                      tensor ? p->at<__nv_bfloat16>(p->lay.sh) : nullptr, tensor ? p->at<__nv_bfloat16>(p->lay.sl) : nullptr,
-                      p->lay.Mp, p->cfg.frames, it0, it1, if0, if1, (cudaStream_t)stream);
+  int r = mel_forward(p->mel, waveform, spec_out, p->at<float>(p->lay.spec32), tensor ? p->ws + p->lay.sh : nullptr,
+                      tensor ? p->ws + p->lay.sl : nullptr, p->fmt(), p->lay.Mp, p->cfg.frames, it0, it1, if0, if1,
+                      (cudaStream_t)stream);
   if (r == 0) p->spec_ready = true;
   return r;
 }
@@ -275,9 +294,8 @@ int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   int r = launch_simt_gemm(g, s); if (r) return r;
   const bool tensor = p->cfg.precision != DRB_PREC_FP32;
-  r = launch_prep_xin(p->at<float>(p->lay.x32), tensor ? p->at<__nv_bfloat16>(p->lay.xh) : nullptr,
-                         tensor ? p->at<__nv_bfloat16>(p->lay.xl) : nullptr, p->dvec(0, t_index), B * T, C, p->NB / B,
-                         tensor ? 1 : 0, s);
+  r = launch_prep_xin(p->at<float>(p->lay.x32), tensor ? p->ws + p->lay.xh : nullptr, tensor ? p->ws + p->lay.xl : nullptr,
+                      p->dvec(0, t_index), B * T, C, p->NB / B, p->fmt(), s);
   if (p->prof && r == 0) p->ev_spans[2].push_back({e0, p->ev_mark(s)});
   return r;
 }
@@ -321,14 +339,15 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   UmmaGate ug;
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
-  ug.three = c.precision == DRB_PREC_BF16X3; ug.z_group0 = layer * p->lay.NBcap;
+  ug.multicast = p->multicast; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;
   const int e1 = p->prof ? p->ev_mark(s) : -1;
   if (do_res) {  // the last layer's residual half is dead; every layer's skip half is deferred to the head GEMM
     UmmaZGemm uz;
-    uz.NB = NB; uz.T = T; uz.C = C; uz.three = ug.three; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
+    uz.multicast = p->multicast; uz.NB = NB; uz.T = T; uz.C = C; uz.prec = ug.prec; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
+    uz.inv_scale = p->wscale(2 * layer + 1) + 1;
     uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
     uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, t_index);
     r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
@@ -359,7 +378,8 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
     r = launch_simt_gemm(g, s); if (r) return r;
   } else {  // one long-K tensor-core GEMM over the stored z of all layers (skip sum, 1/sqrt(L), skip_projection, ReLU)
     UmmaZGemm uz;
-    uz.NB = p->NB; uz.T = T; uz.C = C; uz.three = c.precision == DRB_PREC_BF16X3; uz.mode = 1; uz.groups = c.residual_layers;
+    uz.multicast = p->multicast; uz.NB = p->NB; uz.T = T; uz.C = C; uz.prec = p->prec(); uz.mode = 1; uz.groups = c.residual_layers;
+    uz.inv_scale = p->wscale(2 * c.residual_layers) + 1;
     uz.z_group0 = 0; uz.group_stride = p->lay.NBcap; uz.w_h = &p->maps.wcomp_h; uz.w_l = &p->maps.wcomp_l; uz.out32 = &p->maps.h32;
     uz.bias = p->at<float>(p->lay.bcomp); uz.dnext = nullptr;
     r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;

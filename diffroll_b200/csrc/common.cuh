@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -52,6 +54,33 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
   split_bf16(b, bh, bl);
   hi = pack_bf16x2(ah, bh);
   lo = pack_bf16x2(al, bl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp16 + fp8 split ("f16f8"):  v ~= h + l,  h = fp16(v),  l = v - h  (|l| <= 2^-12 |v|).
+//   main product   : h_a * h_b                                 (kind::f16, fp16 inputs)
+//   correction     : [l_a*SA | e4m3(h_a)] . [e4m3(h_b*SW) | e4m3(l_b*SA*SW)]   (kind::f8f6f4, K concatenated)
+// Both correction terms carry the common scale SA*SW, so they share one accumulator; the e4m3 rounding (2^-4) of a
+// 2^-12-sized term leaves ~2^-16 relative error, like the bf16 hi/lo 3-product scheme, for 2 MMA-units instead of 3.
+// ---------------------------------------------------------------------------------------------
+constexpr float F8_SA = 4096.f;  // 2^12: scale of the activation residual before e4m3 rounding
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint16_t pack_e4m3x2(float a, float b) {
+  return (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+// 4 consecutive values -> 2 packed fp16 pairs, 4 residual bytes (scaled by F8_SA), 4 e4m3 bytes of the fp16 value
+__device__ __forceinline__ void split_f16f8_x4(const float (&v)[4], uint32_t& h01, uint32_t& h23, uint32_t& lo4, uint32_t& hi4) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  h01 = *reinterpret_cast<const uint32_t*>(&a);
+  h23 = *reinterpret_cast<const uint32_t*>(&b);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  lo4 = (uint32_t)pack_e4m3x2((v[0] - fa.x) * F8_SA, (v[1] - fa.y) * F8_SA) |
+        ((uint32_t)pack_e4m3x2((v[2] - fb.x) * F8_SA, (v[3] - fb.y) * F8_SA) << 16);
+  hi4 = (uint32_t)pack_e4m3x2(fa.x, fa.y) | ((uint32_t)pack_e4m3x2(fb.x, fb.y) << 16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -123,6 +152,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Multicast variant: the box lands at the same smem offset in every CTA of `mask`, and each destination CTA's
+// mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // TMA tile store (shared -> global, bulk async-group completion).  Rows/columns outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -187,9 +232,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 (e4m3 inputs here, fp32 accumulate), K = 32 per instruction.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// Same, arriving on the barrier at this offset in every CTA of `mask` (consumer release for multicast operands).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
 
@@ -226,6 +288,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 // N>>3 [17,23), M>>4 [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp16 inputs (kind::f16, a/b format 0) and e4m3 inputs (kind::f8f6f4, a/b format 0): same bit pattern, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_fmt0(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace drb

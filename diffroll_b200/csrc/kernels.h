@@ -39,16 +39,17 @@ int launch_simt_gemm(const SimtGemm& g, cudaStream_t s);
 // elementwise (simt_kernels.cu)
 int launch_gate(const float* y, float* z, int M, int C, cudaStream_t s);  // z = sigmoid(y[:, :C]) * tanh(y[:, C:])
 int launch_res_skip(const float* o, float* x, float* skip, int M, int C, int first, int do_res, cudaStream_t s);
-// x32 rows [0,Mb) hold relu(in_proj); duplicate them `copies` times (branches) and emit bf16 hi/lo of x + d
-int launch_prep_xin(float* x32, __nv_bfloat16* xh, __nv_bfloat16* xl, const float* dvec, int Mb, int C, int copies,
-                    int write_split, cudaStream_t s);
-int launch_split_rows(const float* src, __nv_bfloat16* h, __nv_bfloat16* l, const float* addvec, int M, int C,
-                      cudaStream_t s);
+// x32 rows [0,Mb) hold relu(in_proj); duplicate them `copies` times (branches) and emit the tensor-path operand of x + d
+// fmt: 0 none, 1 bf16 hi/lo, 2 fp16 + e4m3 correction bytes
+int launch_prep_xin(float* x32, void* xmain, void* xaux, const float* dvec, int Mb, int C, int copies, int fmt, cudaStream_t s);
 // weight repacks
 int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cudaStream_t s);  // [OC][C][k] -> [OC][k][C]
-// [OC=2C][Kin] fp32 (k index already tap-major) -> bf16 hi/lo rows permuted into 256-wide gate/filter blocks, K padded to Kp
-int launch_repack_split(const float* w, __nv_bfloat16* h, __nv_bfloat16* l, int OC, int Kin, int Kp, int interleave_C,
-                        cudaStream_t s);
+// [OC][Kin] fp32 (k index already tap-major) -> operand pair (fmt 1 or 2), rows optionally permuted into 256-wide
+// gate/filter blocks (interleave_C > 0), K padded to Kp; fmt 2 reads SW from scale[0]
+int launch_repack_split(const float* w, void* mainp, void* auxp, int OC, int Kin, int Kp, int interleave_C, int fmt,
+                        const float* scale, cudaStream_t s);
+// scale2[0] = SW, scale2[1] = 1/(SA*SW) from max|w| over one or two tensors (scale2 must have 3 floats of space)
+int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, cudaStream_t s);
 int launch_pad_rows(const float* src, float* dst, int rows, int Kin, int Kp, cudaStream_t s);
 // bias1[n'] (interleaved) = bd[n] + bc[n] (- sum_k Wc[n][k] if uncond)
 int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_cond, float* out_unc,
@@ -67,9 +68,9 @@ int mel_create(MelPlan** mp, const drb_config& c, const float* window, const flo
                cudaStream_t s);
 void mel_destroy(MelPlan* mp);
 // logmel -> normalised -> masked.  spec_out [B][n_mels][T] fp32 (nullable), spec32 [B][T][Mp] fp32 zero-padded,
-// spec_h/spec_l [B][T][Mp] bf16 (nullable)
-int mel_forward(MelPlan* mp, const float* waveform, float* spec_out, float* spec32, __nv_bfloat16* spec_h,
-                __nv_bfloat16* spec_l, int Mp, int T, int it0, int it1, int if0, int if1, cudaStream_t s);
+// spec_main/spec_aux: tensor-path operand pair of the spectrogram (fmt 1: bf16 hi/lo [B][T][Mp]; fmt 2: fp16 + e4m3 bytes)
+int mel_forward(MelPlan* mp, const float* waveform, float* spec_out, float* spec32, void* spec_main, void* spec_aux, int fmt,
+                int Mp, int T, int it0, int it1, int if0, int if1, cudaStream_t s);
 float* mel_logmel_ptr(MelPlan* mp, size_t* bytes);
 
 // ------------------------------- tcgen05 GEMMs (umma_gemm.cu) ----------------------------------
@@ -86,22 +87,26 @@ struct UmmaMaps {
   CUtensorMap sh, sl;      // [B][T][Mp]
 };
 struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl[z_group0 + roll]
-  int NB, n_cond, T, C, taps, dil, Mp, three, z_group0;  // three: 1 = bf16x3, 0 = single product
+  int NB, n_cond, T, C, taps, dil, Mp, prec, z_group0;  // prec: 0 bf16, 1 bf16x3, 2 f16f8
+  int multicast = 1;  // share weight tiles across 2-CTA clusters (TMA multicast) when the M-tile count is even
+  const float* inv_scale;
   const float* bias_cond;  // interleaved [2C]
   const float* bias_unc;
 };
 struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
-  int NB, T, C, three, mode;        // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h
+  int multicast = 1;
+  int NB, T, C, prec, mode;         // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h
+  const float* inv_scale;
   int groups, z_group0, group_stride;
   const CUtensorMap *w_h, *w_l, *out32;
   const float* bias;
   const float* dnext;
 };
 int umma_init();  // resolves cuTensorMapEncodeTiled
-int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
-int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0);
+// dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8; the box always spans 128 bytes of the innermost dimension
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int dtype);
+int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, int dtype);
 int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g, cudaStream_t s);
-int make_tmap_3d_f32(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0);
 int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s);
 
 }  // namespace drb

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) power_mel_kernel(const float2* __restrict
 
 __global__ void __launch_bounds__(256) spec_finalize_kernel(const float* __restrict__ logmel, const int* __restrict__ minmax,
                                                             float* __restrict__ spec_out, float* __restrict__ spec32,
-                                                            __nv_bfloat16* __restrict__ spec_h, __nv_bfloat16* __restrict__ spec_l,
+                                                            void* __restrict__ spec_main, void* __restrict__ spec_aux, int fmt,
                                                             int n_mels, int nF, int T, int Mp, int it0, int it1, int if0, int if1) {
   extern __shared__ float tile[];  // [32][n_mels+1]
   const int t0 = blockIdx.x * 32, b = blockIdx.y;
@@ -158,7 +158,17 @@ __global__ void __launch_bounds__(256) spec_finalize_kernel(const float* __restr
     }
     const size_t o = ((size_t)b * T + t) * Mp + m;
     if (spec32) spec32[o] = v;
-    if (spec_h) { __nv_bfloat16 h, l; split_bf16(v, h, l); spec_h[o] = h; spec_l[o] = l; }
+    if (fmt == 1) {
+      __nv_bfloat16 h, l; split_bf16(v, h, l);
+      reinterpret_cast<__nv_bfloat16*>(spec_main)[o] = h; reinterpret_cast<__nv_bfloat16*>(spec_aux)[o] = l;
+    } else if (fmt == 2) {   // fp16 + e4m3 bytes [lo*SA (64) | hi (64)] per 64-mel chunk
+      const __half h = __float2half_rn(v);
+      const float hf = __half2float(h);
+      reinterpret_cast<__half*>(spec_main)[o] = h;
+      uint8_t* a8 = reinterpret_cast<uint8_t*>(spec_aux) + ((size_t)b * T + t) * 2 * Mp + (size_t)(m >> 6) * 128 + (m & 63);
+      a8[0] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * F8_SA, __NV_SATFINITE, __NV_E4M3);
+      a8[64] = (uint8_t)__nv_cvt_float_to_fp8(hf, __NV_SATFINITE, __NV_E4M3);
+    }
   }
   __syncthreads();
   if (spec_out) {
@@ -224,8 +234,8 @@ float* mel_logmel_ptr(MelPlan* p, size_t* bytes) {
   return p->logmel;
 }
 
-int mel_forward(MelPlan* p, const float* waveform, float* spec_out, float* spec32, __nv_bfloat16* spec_h,
-                __nv_bfloat16* spec_l, int Mp, int T, int it0, int it1, int if0, int if1, cudaStream_t s) {
+int mel_forward(MelPlan* p, const float* waveform, float* spec_out, float* spec32, void* spec_main, void* spec_aux, int fmt,
+                int Mp, int T, int it0, int it1, int if0, int if1, cudaStream_t s) {
   if (T > p->nF) { set_error("mel_forward: T=%d > frames %d", T, p->nF); return DRB_E_INVALID; }
   dim3 grid(p->nF, p->B);
   frame_kernel<<<grid, 256, 0, s>>>(waveform, p->window, p->frames, p->L, p->n_fft, p->hop, p->nF);
@@ -240,8 +250,8 @@ int mel_forward(MelPlan* p, const float* waveform, float* spec_out, float* spec3
   DRB_LAUNCH_CHECK();
   dim3 g2((T + 31) / 32, p->B);
   size_t sm = (size_t)32 * (p->n_mels + 1) * sizeof(float);
-  spec_finalize_kernel<<<g2, 256, sm, s>>>(p->logmel, p->minmax, spec_out, spec32, spec_h, spec_l, p->n_mels, p->nF, T,
-                                           Mp, it0, it1, if0, if1);
+  spec_finalize_kernel<<<g2, 256, sm, s>>>(p->logmel, p->minmax, spec_out, spec32, spec_main, spec_aux, fmt, p->n_mels, p->nF,
+                                           T, Mp, it0, it1, if0, if1);
   DRB_LAUNCH_CHECK();
   return 0;
 }

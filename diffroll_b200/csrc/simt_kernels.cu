@@ -230,55 +230,47 @@ int launch_res_skip(const float* o, float* x, float* skip, int M, int C, int fir
   return 0;
 }
 
-__global__ void prep_xin_kernel(float* __restrict__ x32, __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl,
-                                const float* __restrict__ dvec, int Mb, int C, int copies, int write_split) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t n = (size_t)Mb * C / 4;
-  if (i >= n) return;
-  size_t e = i * 4; int c = (int)(e % C);
-  float4 v = *reinterpret_cast<const float4*>(x32 + e);
-  uint32_t h0, l0, h1, l1;
-  if (write_split) {
-    float4 d = *reinterpret_cast<const float4*>(dvec + c);
-    split_pack2(v.x + d.x, v.y + d.y, h0, l0);
-    split_pack2(v.z + d.z, v.w + d.w, h1, l1);
+// Operand formats of the tensor path: fmt 0 = none, 1 = bf16 hi + bf16 lo, 2 = fp16 + e4m3 bytes [lo*SA (64) | hi (64)] per
+// 64-channel chunk (see common.cuh).  `main` holds 2-byte elements [rows][C]; `aux` bf16 [rows][C] or bytes [rows][2C].
+__device__ __forceinline__ void store_operand4(void* mainp, void* auxp, size_t row, int c, int C, const float (&v)[4], int fmt) {
+  if (fmt == 1) {
+    uint32_t h0, l0, h1, l1;
+    split_pack2(v[0], v[1], h0, l0);
+    split_pack2(v[2], v[3], h1, l1);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(mainp) + row * C + c) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(auxp) + row * C + c) = make_uint2(l0, l1);
+  } else if (fmt == 2) {
+    uint32_t h01, h23, lo4, hi4;
+    split_f16f8_x4(v, h01, h23, lo4, hi4);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(mainp) + row * C + c) = make_uint2(h01, h23);
+    uint8_t* a8 = reinterpret_cast<uint8_t*>(auxp) + row * 2 * C + (size_t)(c >> 6) * 128 + (c & 63);
+    *reinterpret_cast<uint32_t*>(a8) = lo4;
+    *reinterpret_cast<uint32_t*>(a8 + 64) = hi4;
   }
-  for (int r = 0; r < copies; ++r) {
-    size_t off = (size_t)r * Mb * C + e;
-    if (r > 0) *reinterpret_cast<float4*>(x32 + off) = v;
-    if (write_split) {
-      *reinterpret_cast<uint2*>(xh + off) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(xl + off) = make_uint2(l0, l1);
-    }
-  }
-}
-int launch_prep_xin(float* x32, __nv_bfloat16* xh, __nv_bfloat16* xl, const float* dvec, int Mb, int C, int copies,
-                    int write_split, cudaStream_t s) {
-  if (copies <= 1 && !write_split) return 0;
-  size_t n = (size_t)Mb * C / 4;
-  prep_xin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x32, xh, xl, dvec, Mb, C, copies, write_split);
-  DRB_LAUNCH_CHECK();
-  return 0;
 }
 
-__global__ void split_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ h,
-                                  __nv_bfloat16* __restrict__ l, const float* __restrict__ addvec, int M, int C) {
+__global__ void prep_xin_kernel(float* __restrict__ x32, void* __restrict__ xmain, void* __restrict__ xaux,
+                                const float* __restrict__ dvec, int Mb, int C, int copies, int fmt) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t n = (size_t)M * C / 4;
+  size_t n = (size_t)Mb * C / 4;
   if (i >= n) return;
-  size_t e = i * 4; int c = (int)(e % C);
-  float4 v = *reinterpret_cast<const float4*>(src + e);
-  if (addvec) { float4 d = *reinterpret_cast<const float4*>(addvec + c); v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w; }
-  uint32_t h0, l0, h1, l1;
-  split_pack2(v.x, v.y, h0, l0);
-  split_pack2(v.z, v.w, h1, l1);
-  *reinterpret_cast<uint2*>(h + e) = make_uint2(h0, h1);
-  *reinterpret_cast<uint2*>(l + e) = make_uint2(l0, l1);
+  size_t e = i * 4; int c = (int)(e % C); size_t row = e / C;
+  float4 v = *reinterpret_cast<const float4*>(x32 + e);
+  float xin[4] = {v.x, v.y, v.z, v.w};
+  if (fmt) {
+    float4 d = *reinterpret_cast<const float4*>(dvec + c);
+    xin[0] += d.x; xin[1] += d.y; xin[2] += d.z; xin[3] += d.w;
+  }
+  for (int r = 0; r < copies; ++r) {
+    if (r > 0) *reinterpret_cast<float4*>(x32 + (size_t)r * Mb * C + e) = v;
+    if (fmt) store_operand4(xmain, xaux, (size_t)r * Mb + row, c, C, xin, fmt);
+  }
 }
-int launch_split_rows(const float* src, __nv_bfloat16* h, __nv_bfloat16* l, const float* addvec, int M, int C,
-                      cudaStream_t s) {
-  size_t n = (size_t)M * C / 4;
-  split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, h, l, addvec, M, C);
+int launch_prep_xin(float* x32, void* xmain, void* xaux, const float* dvec, int Mb, int C, int copies, int fmt,
+                    cudaStream_t s) {
+  if (copies <= 1 && !fmt) return 0;
+  size_t n = (size_t)Mb * C / 4;
+  prep_xin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x32, xmain, xaux, dvec, Mb, C, copies, fmt);
   DRB_LAUNCH_CHECK();
   return 0;
 }
@@ -301,10 +293,11 @@ int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cu
   return 0;
 }
 
-__global__ void repack_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ h,
-                                    __nv_bfloat16* __restrict__ l, int OC, int Kin, int Kp, int C) {
+__global__ void repack_split_kernel(const float* __restrict__ w, void* __restrict__ mainp, void* __restrict__ auxp, int OC,
+                                    int Kin, int Kp, int C, int fmt, const float* __restrict__ scale) {
   // out row n' <- in row n.  With C>0 rows are permuted so each 256-row block holds 128 gate rows followed by the
   // matching 128 filter rows: n' = 256*j + i  <- n = 128*j + i (i<128),  n' = 256*j+128+i <- n = C + 128*j + i.
+  // fmt 1: bf16 hi / bf16 lo.  fmt 2: fp16 / e4m3 bytes [hi*SW (64) | lo*SA*SW (64)] per 64-wide K chunk, SW = scale[0].
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n = (size_t)OC * Kp;
   if (idx >= n) return;
@@ -312,14 +305,52 @@ __global__ void repack_split_kernel(const float* __restrict__ w, __nv_bfloat16* 
   int src = np;
   if (C > 0) { int j = np >> 8, i = np & 255; src = (i < 128) ? (128 * j + i) : (C + 128 * j + (i - 128)); }
   float v = (kk < Kin) ? w[(size_t)src * Kin + kk] : 0.f;
-  __nv_bfloat16 hh, ll;
-  split_bf16(v, hh, ll);
-  h[idx] = hh; l[idx] = ll;
+  if (fmt == 1) {
+    __nv_bfloat16 hh, ll;
+    split_bf16(v, hh, ll);
+    reinterpret_cast<__nv_bfloat16*>(mainp)[idx] = hh; reinterpret_cast<__nv_bfloat16*>(auxp)[idx] = ll;
+  } else {
+    const float sw = scale[0];
+    const __half hh = __float2half_rn(v);
+    const float hf = __half2float(hh);
+    reinterpret_cast<__half*>(mainp)[idx] = hh;
+    uint8_t* a8 = reinterpret_cast<uint8_t*>(auxp) + (size_t)np * 2 * Kp + (size_t)(kk >> 6) * 128 + (kk & 63);
+    a8[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * sw, __NV_SATFINITE, __NV_E4M3);
+    a8[64] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * (F8_SA * sw), __NV_SATFINITE, __NV_E4M3);
+  }
 }
-int launch_repack_split(const float* w, __nv_bfloat16* h, __nv_bfloat16* l, int OC, int Kin, int Kp, int interleave_C,
-                        cudaStream_t s) {
+int launch_repack_split(const float* w, void* mainp, void* auxp, int OC, int Kin, int Kp, int interleave_C, int fmt,
+                        const float* scale, cudaStream_t s) {
   size_t n = (size_t)OC * Kp;
-  repack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, h, l, OC, Kin, Kp, interleave_C);
+  repack_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, mainp, auxp, OC, Kin, Kp, interleave_C, fmt, scale);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// f16f8 weight scale: SW = 2^floor(log2(224 / max|w|)) over up to two tensors; out[0] = SW, out[1] = 1 / (SA * SW)
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out) {
+  unsigned int m = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(fabsf(w[i])));
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+__global__ void wscale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ out) {
+  float m = __uint_as_float(mx[0]);
+  float sw = 1.f;
+  if (m > 0.f && m < 3.0e38f) sw = exp2f(floorf(log2f(224.f / m)));
+  sw = fminf(fmaxf(sw, 9.5367431640625e-07f), 1048576.f);
+  out[0] = sw;
+  out[1] = 1.f / (F8_SA * sw);
+}
+int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, cudaStream_t s) {
+  unsigned int* tmp = reinterpret_cast<unsigned int*>(scale2 + 2);  // scratch word right behind the two outputs
+  cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(unsigned int), s);
+  if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return (int)e; }
+  absmax_kernel<<<148, 256, 0, s>>>(w0, n0, tmp);
+  DRB_LAUNCH_CHECK();
+  if (w1 && n1) { absmax_kernel<<<148, 256, 0, s>>>(w1, n1, tmp); DRB_LAUNCH_CHECK(); }
+  wscale_kernel<<<1, 1, 0, s>>>(tmp, scale2);
   DRB_LAUNCH_CHECK();
   return 0;
 }

@@ -33,16 +33,23 @@ constexpr int TILE_K = 64;
 constexpr int A_TILE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
 constexpr int B_TILE_BYTES = TILE_N * TILE_K * 2;  // 32 KB
 constexpr int UMMA_K = 16;
-constexpr uint32_t TMEM_COLS = 256;
 constexpr int CHUNK_BYTES = TILE_M * 128;          // one 128-row x 128-byte swizzled staging box (16 KB)
 constexpr int EPI_BAR = 1;                         // named barrier of the 4 epilogue warps
 
-template <bool THREE>
+// Precision modes (template parameter P):
+//   0  bf16     one product                                     main operands only
+//   1  bf16x3   bf16 hi/lo, 3 products into one accumulator      aux = bf16 lo tiles
+//   2  f16f8    fp16 product + e4m3 correction product          aux = e4m3 tiles [lo*SA | hi] / [hi*SW | lo*SA*SW],
+//                                                                second accumulator (TMEM columns 256..511)
+template <int P>
 struct Cfg {
-  static constexpr int kStageBytes = THREE ? 2 * (A_TILE_BYTES + B_TILE_BYTES) : (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int kStages = THREE ? 2 : 4;
+  static constexpr bool kAux = P != 0;
+  static constexpr int kStageBytes = kAux ? 2 * (A_TILE_BYTES + B_TILE_BYTES) : (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int kStages = kAux ? 2 : 4;
   static constexpr int kRingBytes = kStages * kStageBytes;  // 192 KB
   static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kTmemCols = P == 2 ? 512 : 256;
+  static constexpr int kAuxMul = P == 2 ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
 };
 
 struct alignas(64) GateParams {
@@ -50,6 +57,7 @@ struct alignas(64) GateParams {
   int NB, n_cond, T, C, taps, dil, cond_slabs, tiles_t, n_blocks, z_group0;
   const float* bias_cond;
   const float* bias_unc;
+  const float* inv_scale;  // f16f8: 1 / (SA * SW) of this layer's weights (device scalar)
 };
 
 struct alignas(64) ZGemmParams {
@@ -57,6 +65,7 @@ struct alignas(64) ZGemmParams {
   int NB, T, C, tiles_t, n_blocks, nslabs, spg, z_group0, group_stride, mode;  // mode 0 = RES, 1 = HEAD
   const float* bias;
   const float* dnext;
+  const float* inv_scale;
 };
 
 struct SmemView {
@@ -68,64 +77,82 @@ struct SmemView {
   uint32_t* tmem_ptr;
 };
 
-template <bool THREE>
+template <int P>
 __device__ __forceinline__ SmemView carve(uint8_t* raw) {
   uint32_t a = smem_u32(raw);
   uint32_t pad = ((a + 1023u) & ~1023u) - a;
   SmemView v;
   v.stage0 = raw + pad;
-  uint8_t* bars = v.stage0 + Cfg<THREE>::kRingBytes;
+  uint8_t* bars = v.stage0 + Cfg<P>::kRingBytes;
   v.full = reinterpret_cast<uint64_t*>(bars);
-  v.empty = v.full + Cfg<THREE>::kStages;
-  v.tmem_full = v.empty + Cfg<THREE>::kStages;
+  v.empty = v.full + Cfg<P>::kStages;
+  v.tmem_full = v.empty + Cfg<P>::kStages;
   v.xin_full = v.tmem_full + 1;
   v.tmem_ptr = reinterpret_cast<uint32_t*>(v.xin_full + 1);
   return v;
 }
 
-template <bool THREE>
+// MC = true: the kernel runs as 2-CTA clusters that share the weight (B) tile: each CTA fetches half of it and TMA
+// multicasts that half into both CTAs' smem, halving the L2 traffic of the B operand.  A slot is reused only after
+// BOTH CTAs' MMAs have consumed it (empty barriers count 2, released by multicast tcgen05.commit).
+template <int P, bool MC>
 __device__ __forceinline__ void prologue(const SmemView& sv, int warp) {
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < Cfg<THREE>::kStages; ++i) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], 1); }
+    for (int i = 0; i < Cfg<P>::kStages; ++i) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], MC ? 2 : 1); }
     mbar_init(sv.tmem_full, 1);
     mbar_init(sv.xin_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(sv.tmem_ptr, TMEM_COLS); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(sv.tmem_ptr, Cfg<P>::kTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // peer barriers are initialised before any multicast load / remote arrive targets them
   tc_fence_after();
 }
 
-// MMA issue for one K-slab (64 channels = 4 UMMA K-steps) resident in stage memory.
-template <bool THREE>
-__device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool first_slab) {
-  const uint32_t a_hi = smem_u32(st);
-  const uint32_t a_lo = a_hi + A_TILE_BYTES;
-  const uint32_t b_hi = a_hi + (THREE ? 2 * A_TILE_BYTES : A_TILE_BYTES);
-  const uint32_t b_lo = b_hi + B_TILE_BYTES;
-  constexpr uint32_t idesc = make_idesc_bf16(TILE_M, TILE_N);
-#pragma unroll
-  for (int k = 0; k < TILE_K / UMMA_K; ++k) {
-    const uint32_t ko = k * UMMA_K * 2;  // byte advance inside the 128-byte swizzled row
-    const uint64_t da_hi = make_sw128_desc(a_hi + ko), db_hi = make_sw128_desc(b_hi + ko);
-    umma_bf16(tmem_d, da_hi, db_hi, idesc, (first_slab && k == 0) ? 0u : 1u);
-    if (THREE) {
-      umma_bf16(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
-      umma_bf16(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
-    }
+// One weight tile = two 128-row boxes.  MC: this CTA loads box `rank` and multicasts it to both CTAs.
+template <bool MC>
+__device__ __forceinline__ void load_b_tile(uint8_t* b_tile, const void* tmap, uint64_t* bar, int col, int row0, uint32_t rank) {
+  if (MC) {
+    tma_load_2d_mc(b_tile + rank * (B_TILE_BYTES / 2), tmap, bar, col, row0 + (int)rank * (TILE_N / 2), (uint16_t)0x3);
+  } else {
+    tma_load_2d(b_tile, tmap, bar, col, row0);
+    tma_load_2d(b_tile + B_TILE_BYTES / 2, tmap, bar, col, row0 + TILE_N / 2);
   }
 }
 
-template <bool THREE>
+// MMA issue for one K-slab (64 channels = 4 UMMA K-steps) resident in stage memory.
+template <int P>
+__device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool first_slab) {
+  const uint32_t a_hi = smem_u32(st);
+  const uint32_t a_lo = a_hi + A_TILE_BYTES;
+  const uint32_t b_hi = a_hi + (Cfg<P>::kAux ? 2 * A_TILE_BYTES : A_TILE_BYTES);
+  const uint32_t b_lo = b_hi + B_TILE_BYTES;
+  constexpr uint32_t idesc = P == 2 ? make_idesc_fmt0(TILE_M, TILE_N) : make_idesc_bf16(TILE_M, TILE_N);
+  const uint32_t acc0 = first_slab ? 0u : 1u;
+#pragma unroll
+  for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+    const uint32_t ko = k * UMMA_K * 2;  // byte advance inside the 128-byte swizzled row (16 x 2 B, or 32 x 1 B for e4m3)
+    const uint64_t da_hi = make_sw128_desc(a_hi + ko), db_hi = make_sw128_desc(b_hi + ko);
+    umma_bf16(tmem_d, da_hi, db_hi, idesc, k == 0 ? acc0 : 1u);   // kind::f16: bf16 or fp16 per idesc
+    if (P == 1) {
+      umma_bf16(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
+      umma_bf16(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
+    }
+    if (P == 2) umma_f8(tmem_d + 256, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc, k == 0 ? acc0 : 1u);
+  }
+}
+
+template <int P, bool MC>
 __device__ __forceinline__ void mma_loop(const SmemView& sv, uint32_t tmem_base, int nslabs) {
   int stage = 0; uint32_t phase = 0;
   for (int s = 0; s < nslabs; ++s) {
     mbar_wait(&sv.full[stage], phase);
     tc_fence_after();
-    issue_slab<THREE>(sv.stage0 + stage * Cfg<THREE>::kStageBytes, tmem_base, s == 0);
-    umma_commit(&sv.empty[stage]);  // frees the smem slot when these MMAs retire
-    if (++stage == Cfg<THREE>::kStages) { stage = 0; phase ^= 1; }
+    issue_slab<P>(sv.stage0 + stage * Cfg<P>::kStageBytes, tmem_base, s == 0);
+    if (MC) umma_commit_mc(&sv.empty[stage], (uint16_t)0x3);  // frees the slot in both CTAs when these MMAs retire
+    else umma_commit(&sv.empty[stage]);
+    if (++stage == Cfg<P>::kStages) { stage = 0; phase ^= 1; }
   }
   umma_commit(sv.tmem_full);
 }
@@ -137,30 +164,85 @@ __device__ __forceinline__ float gate_act(float g, float f) {
   return sg * th;
 }
 
+// 32 consecutive accumulator columns of this thread's row; f16f8 adds the scaled correction accumulator.
+// The whole warp must be converged at the call (tcgen05.ld is .sync.aligned).
+template <int P>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float inv_scale, float (&v)[32]) {
+  uint32_t r[32];
+  __syncwarp();
+  tmem_ld32(taddr, r);
+  if (P == 2) {
+    uint32_t c[32];
+    tmem_ld32(taddr + 256, c);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(c[i]), inv_scale, __uint_as_float(r[i]));
+  } else {
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  }
+}
+
+// Stage 16 consecutive channel values (channel offset ch inside a 64-channel box, multiple of 16) of one row into the
+// swizzled operand boxes of the next GEMM.  main box: [128 rows][64 channels] of 2-byte elements; aux box: bf16 lo
+// parts (same shape) or e4m3 bytes [lo*SA (64) | hi (64)] per row.
+template <int P>
+__device__ __forceinline__ void stage16(uint32_t main_box, uint32_t aux_box, int row, int ch, const float (&v)[16]) {
+  if (P == 2) {
+    uint32_t h[8], lo[4], hi[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float t[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
+      split_f16f8_x4(t, h[2 * q], h[2 * q + 1], lo[q], hi[q]);
+    }
+    sts128u(main_box + sw128_off(row, ch / 8), h[0], h[1], h[2], h[3]);
+    sts128u(main_box + sw128_off(row, ch / 8 + 1), h[4], h[5], h[6], h[7]);
+    sts128u(aux_box + sw128_off(row, ch / 16), lo[0], lo[1], lo[2], lo[3]);
+    sts128u(aux_box + sw128_off(row, 4 + ch / 16), hi[0], hi[1], hi[2], hi[3]);
+  } else {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_pack2(v[8 * hf + 2 * e], v[8 * hf + 2 * e + 1], hi[e], lo[e]);
+      sts128u(main_box + sw128_off(row, ch / 8 + hf), hi[0], hi[1], hi[2], hi[3]);
+      if (P == 1) sts128u(aux_box + sw128_off(row, ch / 8 + hf), lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // gate kernel
 // ---------------------------------------------------------------------------------------------
-template <bool THREE>
+template <int P, bool MC>
 __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant__ GateParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemView sv = carve<THREE>(smem_raw);
+  const SmemView sv = carve<P>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  int bid = blockIdx.x;
-  const int nblk = bid % p.n_blocks; bid /= p.n_blocks;
-  const int tt = bid % p.tiles_t;
-  const int nb = bid / p.tiles_t;
+  // tile mapping: a cluster (MC) = two consecutive M tiles (frames x roll) of the same N block
+  const uint32_t rank = MC ? cluster_ctarank() : 0u;
+  int cid = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nblk = cid % p.n_blocks; cid /= p.n_blocks;
+  const int mt = MC ? cid * 2 + (int)rank : cid;
+  const int tt = mt % p.tiles_t;
+  const int nb = mt / p.tiles_t;
   const int t0 = tt * TILE_M;
   const int cpt = p.C / TILE_K;  // K-slabs per tap
   const int conv_slabs = p.taps * cpt;
-  const int nslabs = conv_slabs + (nb < p.n_cond ? p.cond_slabs : 0);
+  // Both CTAs of a cluster run the same slab list.  If only the first tile of the pair is conditional, the second
+  // one runs the conditioner slabs too: its spectrogram coordinate (roll >= n_cond) is out of bounds, so TMA feeds zeros.
+  const int nb_first = MC ? (cid * 2) / p.tiles_t : nb;
+  const int nslabs = conv_slabs + (nb_first < p.n_cond ? p.cond_slabs : 0);
   const int half = p.taps / 2;
+  constexpr int AM = Cfg<P>::kAuxMul;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.zh);
-    if (THREE) { tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l); tma_prefetch_desc(&p.zl); }
+    if (Cfg<P>::kAux) { tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l); tma_prefetch_desc(&p.zl); }
   }
-  prologue<THREE>(sv, warp);
+  prologue<P, MC>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
 
   if (warp == 0) {
@@ -168,33 +250,33 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int s = 0; s < nslabs; ++s) {
         mbar_wait(&sv.empty[stage], phase ^ 1);
-        uint8_t* st = sv.stage0 + stage * Cfg<THREE>::kStageBytes;
+        uint8_t* st = sv.stage0 + stage * Cfg<P>::kStageBytes;
         uint8_t* a_hi = st; uint8_t* a_lo = st + A_TILE_BYTES;
-        uint8_t* b_hi = st + (THREE ? 2 * A_TILE_BYTES : A_TILE_BYTES); uint8_t* b_lo = b_hi + B_TILE_BYTES;
-        mbar_expect_tx(&sv.full[stage], Cfg<THREE>::kStageBytes);
+        uint8_t* b_hi = st + (Cfg<P>::kAux ? 2 * A_TILE_BYTES : A_TILE_BYTES); uint8_t* b_lo = b_hi + B_TILE_BYTES;
+        mbar_expect_tx(&sv.full[stage], Cfg<P>::kStageBytes);
         if (s < conv_slabs) {
           const int tap = s / cpt, cc = s - tap * cpt;
           const int trow = t0 + (tap - half) * p.dil;
           tma_load_3d(a_hi, &p.xh, &sv.full[stage], cc * TILE_K, trow, nb);
-          tma_load_2d(b_hi, &p.wd_h, &sv.full[stage], tap * p.C + cc * TILE_K, nblk * TILE_N);
-          if (THREE) {
-            tma_load_3d(a_lo, &p.xl, &sv.full[stage], cc * TILE_K, trow, nb);
-            tma_load_2d(b_lo, &p.wd_l, &sv.full[stage], tap * p.C + cc * TILE_K, nblk * TILE_N);
+          load_b_tile<MC>(b_hi, &p.wd_h, &sv.full[stage], tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
+          if (Cfg<P>::kAux) {
+            tma_load_3d(a_lo, &p.xl, &sv.full[stage], AM * cc * TILE_K, trow, nb);
+            load_b_tile<MC>(b_lo, &p.wd_l, &sv.full[stage], AM * (tap * p.C + cc * TILE_K), nblk * TILE_N, rank);
           }
         } else {
           const int cc = s - conv_slabs;
           tma_load_3d(a_hi, &p.sh, &sv.full[stage], cc * TILE_K, t0, nb);
-          tma_load_2d(b_hi, &p.wc_h, &sv.full[stage], cc * TILE_K, nblk * TILE_N);
-          if (THREE) {
-            tma_load_3d(a_lo, &p.sl, &sv.full[stage], cc * TILE_K, t0, nb);
-            tma_load_2d(b_lo, &p.wc_l, &sv.full[stage], cc * TILE_K, nblk * TILE_N);
+          load_b_tile<MC>(b_hi, &p.wc_h, &sv.full[stage], cc * TILE_K, nblk * TILE_N, rank);
+          if (Cfg<P>::kAux) {
+            tma_load_3d(a_lo, &p.sl, &sv.full[stage], AM * cc * TILE_K, t0, nb);
+            load_b_tile<MC>(b_lo, &p.wc_l, &sv.full[stage], AM * cc * TILE_K, nblk * TILE_N, rank);
           }
         }
-        if (++stage == Cfg<THREE>::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == Cfg<P>::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) mma_loop<THREE>(sv, tmem_base, nslabs);
+    if (elect_one()) mma_loop<P, MC>(sv, tmem_base, nslabs);
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -202,31 +284,24 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
     mbar_wait(sv.tmem_full, 0);  // every MMA has retired: accumulator complete, ring memory free
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    // staging: z hi boxes 0,1 then z lo boxes 0,1; each [128 frames][64 channels] bf16, 128-byte swizzled
+    // staging: z main boxes 0,1 then z aux boxes 0,1; each [128 frames][128 bytes], 128-byte swizzled
     const uint32_t stg = smem_u32(sv.stage0);
+    const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
-      uint32_t g[32], f[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: the whole warp must arrive together
-      tmem_ld32(taddr + ch * 32, g);
-      tmem_ld32(taddr + 128 + ch * 32, f);
-      tmem_ld_wait();
-      const uint32_t box_h = stg + (ch >> 1) * CHUNK_BYTES, box_l = box_h + 2 * CHUNK_BYTES;
+      float g[32], f[32];
+      load_acc32<P>(taddr + ch * 32, inv, g);
+      load_acc32<P>(taddr + 128 + ch * 32, inv, f);
+      const uint32_t box_m = stg + (ch >> 1) * CHUNK_BYTES, box_a = box_m + 2 * CHUNK_BYTES;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        uint32_t hi[4], lo[4];
+      for (int hf = 0; hf < 2; ++hf) {
+        float z[16];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = v * 8 + e * 2;
-          const float z0 = gate_act(__uint_as_float(g[i]) + __ldg(bias + ch * 32 + i),
-                                    __uint_as_float(f[i]) + __ldg(bias + 128 + ch * 32 + i));
-          const float z1 = gate_act(__uint_as_float(g[i + 1]) + __ldg(bias + ch * 32 + i + 1),
-                                    __uint_as_float(f[i + 1]) + __ldg(bias + 128 + ch * 32 + i + 1));
-          split_pack2(z0, z1, hi[e], lo[e]);
+        for (int i = 0; i < 16; ++i) {
+          const int j = hf * 16 + i;
+          z[i] = gate_act(g[j] + __ldg(bias + ch * 32 + j), f[j] + __ldg(bias + 128 + ch * 32 + j));
         }
-        const uint32_t off = sw128_off(row, (ch & 1) * 4 + v);
-        sts128u(box_h + off, hi[0], hi[1], hi[2], hi[3]);
-        sts128u(box_l + off, lo[0], lo[1], lo[2], lo[3]);
+        stage16<P>(box_m, box_a, row, (ch & 1) * 32 + hf * 16, z);
       }
     }
     tc_fence_before();
@@ -236,40 +311,44 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
       const int c0 = nblk * (TILE_N / 2);
       tma_store_3d(&p.zh, sv.stage0, c0, t0, p.z_group0 + nb);
       tma_store_3d(&p.zh, sv.stage0 + CHUNK_BYTES, c0 + 64, t0, p.z_group0 + nb);
-      if (THREE) {
-        tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, c0, t0, p.z_group0 + nb);
-        tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, c0 + 64, t0, p.z_group0 + nb);
+      if (Cfg<P>::kAux) {
+        tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, AM * c0, t0, p.z_group0 + nb);
+        tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, AM * (c0 + 64), t0, p.z_group0 + nb);
       }
       tma_store_commit();
       tma_store_wait_read<0>();  // smem must stay valid until the bulk stores have read it
     }
   }
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (MC) cluster_sync_all();  // the peer may still signal this CTA's barriers until its own MMAs have retired
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg<P>::kTmemCols); }
 }
 
 // ---------------------------------------------------------------------------------------------
 // zgemm kernel: A = stored z of one layer (RES) or of all layers (HEAD)
 // ---------------------------------------------------------------------------------------------
-template <bool THREE>
+template <int P, bool MC>
 __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constant__ ZGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemView sv = carve<THREE>(smem_raw);
+  const SmemView sv = carve<P>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  int bid = blockIdx.x;
-  const int nblk = bid % p.n_blocks; bid /= p.n_blocks;
-  const int tt = bid % p.tiles_t;
-  const int nb = bid / p.tiles_t;
+  const uint32_t rank = MC ? cluster_ctarank() : 0u;
+  int cid = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nblk = cid % p.n_blocks; cid /= p.n_blocks;
+  const int mt = MC ? cid * 2 + (int)rank : cid;
+  const int tt = mt % p.tiles_t;
+  const int nb = mt / p.tiles_t;
   const int t0 = tt * TILE_M;
   const int n_base = nblk * TILE_N;
   const bool res = p.mode == 0;
+  constexpr int AM = Cfg<P>::kAuxMul;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.w_h); tma_prefetch_desc(&p.out32);
-    if (THREE) { tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_l); }
+    if (Cfg<P>::kAux) { tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_l); }
   }
-  prologue<THREE>(sv, warp);
+  prologue<P, MC>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
 
   if (warp == 0) {
@@ -277,19 +356,19 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
       int stage = 0; uint32_t phase = 0;
       for (int s = 0; s < p.nslabs; ++s) {
         mbar_wait(&sv.empty[stage], phase ^ 1);
-        uint8_t* st = sv.stage0 + stage * Cfg<THREE>::kStageBytes;
+        uint8_t* st = sv.stage0 + stage * Cfg<P>::kStageBytes;
         uint8_t* a_hi = st; uint8_t* a_lo = st + A_TILE_BYTES;
-        uint8_t* b_hi = st + (THREE ? 2 * A_TILE_BYTES : A_TILE_BYTES); uint8_t* b_lo = b_hi + B_TILE_BYTES;
+        uint8_t* b_hi = st + (Cfg<P>::kAux ? 2 * A_TILE_BYTES : A_TILE_BYTES); uint8_t* b_lo = b_hi + B_TILE_BYTES;
         const int grp = s / p.spg, cc = s - grp * p.spg;
         const int zrow = p.z_group0 + grp * p.group_stride + nb;
-        mbar_expect_tx(&sv.full[stage], Cfg<THREE>::kStageBytes);
+        mbar_expect_tx(&sv.full[stage], Cfg<P>::kStageBytes);
         tma_load_3d(a_hi, &p.zh, &sv.full[stage], cc * TILE_K, t0, zrow);
-        tma_load_2d(b_hi, &p.w_h, &sv.full[stage], s * TILE_K, n_base);
-        if (THREE) {
-          tma_load_3d(a_lo, &p.zl, &sv.full[stage], cc * TILE_K, t0, zrow);
-          tma_load_2d(b_lo, &p.w_l, &sv.full[stage], s * TILE_K, n_base);
+        load_b_tile<MC>(b_hi, &p.w_h, &sv.full[stage], s * TILE_K, n_base, rank);
+        if (Cfg<P>::kAux) {
+          tma_load_3d(a_lo, &p.zl, &sv.full[stage], AM * cc * TILE_K, t0, zrow);
+          load_b_tile<MC>(b_lo, &p.w_l, &sv.full[stage], AM * s * TILE_K, n_base, rank);
         }
-        if (++stage == Cfg<THREE>::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == Cfg<P>::kStages) { stage = 0; phase ^= 1; }
       }
       if (res) {
         // Residual update needs the fp32 x tile: fetch it into the (now free) ring as 8 swizzled [128][32] fp32 boxes.
@@ -299,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) mma_loop<THREE>(sv, tmem_base, p.nslabs);
+    if (elect_one()) mma_loop<P, MC>(sv, tmem_base, p.nslabs);
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -310,87 +389,75 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = smem_u32(sv.stage0);
     const float rs2 = 1.41421356237309515f;
+    const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
     if (res) mbar_wait(sv.xin_full, 0);
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {       // 64 output channels per iteration
-      uint32_t o[64];
-      __syncwarp();
-      tmem_ld32(taddr + it * 64, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-      tmem_ld32(taddr + it * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-      tmem_ld_wait();
-      if (res) {
-        // bf16 staging (x + d_next split): two alternating sets of {hi box, lo box} behind the 8 fp32 boxes
-        const uint32_t set = stg + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES;
-        if (it >= 2) {                     // the TMA stores of iteration it-2 must have finished reading this set
-          if (issuer) tma_store_wait_read<1>();
-          named_bar_sync(EPI_BAR, 128);
-        }
-#pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {   // fp32 box (32 channels) inside this iteration
-          const uint32_t xbox = stg + (it * 2 + hc) * CHUNK_BYTES;
+      // operand staging of the next layer (x + d_next split): two alternating sets of {main box, aux box}
+      const uint32_t set = stg + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES;
+      if (res && it >= 2) {                // the TMA stores of iteration it-2 must have finished reading this set
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(EPI_BAR, 128);
+      }
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {     // one fp32 box (32 channels) at a time
+        float o[32];
+        load_acc32<P>(taddr + it * 64 + hc * 32, inv, o);
+        const uint32_t box = stg + (it * 2 + hc) * CHUNK_BYTES;
+        const float* bs = bias + it * 64 + hc * 32;
+        if (res) {
           const float* dn = p.dnext + n_base + it * 64 + hc * 32;
 #pragma unroll
-          for (int v = 0; v < 8; v += 2) {
-            uint32_t hi[4], lo[4];
+          for (int g16 = 0; g16 < 2; ++g16) {
+            float xin[16];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int i = hc * 32 + (v + u) * 4;
-              const uint32_t xa = xbox + sw128_off(row, v + u);
+            for (int u = 0; u < 4; ++u) {
+              const int v = g16 * 4 + u, i = v * 4;
+              const uint32_t xa = box + sw128_off(row, v);
               float4 x = lds128(xa);
-              const float4 d = __ldg(reinterpret_cast<const float4*>(dn + (v + u) * 4));
-              x.x = (x.x + (__uint_as_float(o[i + 0]) + __ldg(bias + it * 64 + i + 0))) / rs2;
-              x.y = (x.y + (__uint_as_float(o[i + 1]) + __ldg(bias + it * 64 + i + 1))) / rs2;
-              x.z = (x.z + (__uint_as_float(o[i + 2]) + __ldg(bias + it * 64 + i + 2))) / rs2;
-              x.w = (x.w + (__uint_as_float(o[i + 3]) + __ldg(bias + it * 64 + i + 3))) / rs2;
+              const float4 d = __ldg(reinterpret_cast<const float4*>(dn + i));
+              x.x = (x.x + (o[i + 0] + __ldg(bs + i + 0))) / rs2;   // (x + residual) / sqrt(2.0)   diffwave.py:151
+              x.y = (x.y + (o[i + 1] + __ldg(bs + i + 1))) / rs2;
+              x.z = (x.z + (o[i + 2] + __ldg(bs + i + 2))) / rs2;
+              x.w = (x.w + (o[i + 3] + __ldg(bs + i + 3))) / rs2;
               sts128(xa, x);  // in place: same thread, same address
-              split_pack2(x.x + d.x, x.y + d.y, hi[u * 2 + 0], lo[u * 2 + 0]);
-              split_pack2(x.z + d.z, x.w + d.w, hi[u * 2 + 1], lo[u * 2 + 1]);
+              xin[u * 4 + 0] = x.x + d.x; xin[u * 4 + 1] = x.y + d.y; xin[u * 4 + 2] = x.z + d.z; xin[u * 4 + 3] = x.w + d.w;
             }
-            const uint32_t off = sw128_off(row, hc * 4 + (v >> 1));
-            sts128u(set + off, hi[0], hi[1], hi[2], hi[3]);
-            sts128u(set + CHUNK_BYTES + off, lo[0], lo[1], lo[2], lo[3]);
+            stage16<P>(set, set + CHUNK_BYTES, row, hc * 32 + g16 * 16, xin);
           }
-        }
-        fence_proxy_async();
-        named_bar_sync(EPI_BAR, 128);
-        if (issuer) {
-          const int c0 = n_base + it * 64;
-          tma_store_3d(&p.out32, sv.stage0 + (it * 2) * CHUNK_BYTES, c0, t0, nb);
-          tma_store_3d(&p.out32, sv.stage0 + (it * 2 + 1) * CHUNK_BYTES, c0 + 32, t0, nb);
-          tma_store_3d(&p.xh, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
-          if (THREE) tma_store_3d(&p.xl, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, c0, t0, nb);
-          tma_store_commit();
-        }
-      } else {
-#pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
-          const uint32_t hbox = stg + (it * 2 + hc) * CHUNK_BYTES;
+        } else {
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
-            const int i = hc * 32 + v * 4;
+            const int i = v * 4;
             float4 h;
-            h.x = fmaxf(__uint_as_float(o[i + 0]) + __ldg(bias + it * 64 + i + 0), 0.f);
-            h.y = fmaxf(__uint_as_float(o[i + 1]) + __ldg(bias + it * 64 + i + 1), 0.f);
-            h.z = fmaxf(__uint_as_float(o[i + 2]) + __ldg(bias + it * 64 + i + 2), 0.f);
-            h.w = fmaxf(__uint_as_float(o[i + 3]) + __ldg(bias + it * 64 + i + 3), 0.f);
-            sts128(hbox + sw128_off(row, v), h);
+            h.x = fmaxf(o[i + 0] + __ldg(bs + i + 0), 0.f);
+            h.y = fmaxf(o[i + 1] + __ldg(bs + i + 1), 0.f);
+            h.z = fmaxf(o[i + 2] + __ldg(bs + i + 2), 0.f);
+            h.w = fmaxf(o[i + 3] + __ldg(bs + i + 3), 0.f);
+            sts128(box + sw128_off(row, v), h);
           }
         }
-        fence_proxy_async();
-        named_bar_sync(EPI_BAR, 128);
-        if (issuer) {
-          const int c0 = n_base + it * 64;
-          tma_store_3d(&p.out32, sv.stage0 + (it * 2) * CHUNK_BYTES, c0, t0, nb);
-          tma_store_3d(&p.out32, sv.stage0 + (it * 2 + 1) * CHUNK_BYTES, c0 + 32, t0, nb);
-          tma_store_commit();
+      }
+      fence_proxy_async();
+      named_bar_sync(EPI_BAR, 128);
+      if (issuer) {
+        const int c0 = n_base + it * 64;
+        tma_store_3d(&p.out32, sv.stage0 + (it * 2) * CHUNK_BYTES, c0, t0, nb);
+        tma_store_3d(&p.out32, sv.stage0 + (it * 2 + 1) * CHUNK_BYTES, c0 + 32, t0, nb);
+        if (res) {
+          tma_store_3d(&p.xh, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
+          if (Cfg<P>::kAux)
+            tma_store_3d(&p.xl, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, AM * c0, t0, nb);
         }
+        tma_store_commit();
       }
     }
     tc_fence_before();
     if (issuer) tma_store_wait_read<0>();
   }
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (MC) cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg<P>::kTmemCols); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -411,49 +478,71 @@ int umma_init() {
     return DRB_E_DRIVER;
   }
   g_encode = (EncodeTiledFn)fn;
-  cudaError_t e1, e2, e3, e4;
-  e1 = cudaFuncSetAttribute(umma_gate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::kSmemBytes);
-  e2 = cudaFuncSetAttribute(umma_gate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::kSmemBytes);
-  e3 = cudaFuncSetAttribute(umma_zgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::kSmemBytes);
-  e4 = cudaFuncSetAttribute(umma_zgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::kSmemBytes);
-  if (e1 || e2 || e3 || e4) {
-    set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e1 ? e1 : e2 ? e2 : e3 ? e3 : e4));
+  cudaError_t ee = cudaSuccess;
+  auto set = [&](const void* fn, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess && ee == cudaSuccess) ee = e;
+  };
+  set((const void*)umma_gate_kernel<0, false>, Cfg<0>::kSmemBytes); set((const void*)umma_gate_kernel<0, true>, Cfg<0>::kSmemBytes);
+  set((const void*)umma_gate_kernel<1, false>, Cfg<1>::kSmemBytes); set((const void*)umma_gate_kernel<1, true>, Cfg<1>::kSmemBytes);
+  set((const void*)umma_gate_kernel<2, false>, Cfg<2>::kSmemBytes); set((const void*)umma_gate_kernel<2, true>, Cfg<2>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<0, false>, Cfg<0>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<1, false>, Cfg<1>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<2, false>, Cfg<2>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2>::kSmemBytes);
+  if (ee) {
+    set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ee));
     g_encode = nullptr;
-    return (int)(e1 ? e1 : e2 ? e2 : e3 ? e3 : e4);
+    return (int)ee;
   }
   return 0;
 }
 
 static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, bool f32) {
+                  const cuuint32_t* box, int dtype) {  // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8
   if (!g_encode) { int r = umma_init(); if (r) return r; }
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                 : dtype == 3 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = g_encode(m, dt, (cuuint32_t)rank,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DRB_E_DRIVER; }
   return 0;
 }
 
-int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+static int esize(int dtype) { return dtype == 1 ? 4 : dtype == 3 ? 1 : 2; }
+
+// [rows][cols] row-major, box = box_rows x (128 bytes of columns)
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int dtype) {
+  const int es = esize(dtype);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  return encode(m, base, 2, dims, strides, box, false);
+  cuuint64_t strides[1] = {cols * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), box_rows};
+  return encode(m, base, 2, dims, strides, box, dtype);
 }
 
-int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0) {
+// [d2][d1][d0], box = 1 x box1 x (128 bytes of d0)
+int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, int dtype) {
+  const int es = esize(dtype);
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d1 * d0 * 2};
-  cuuint32_t box[3] = {box0, box1, 1};
-  return encode(m, base, 3, dims, strides, box, false);
+  cuuint64_t strides[2] = {d0 * es, d1 * d0 * es};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / es), box1, 1};
+  return encode(m, base, 3, dims, strides, box, dtype);
 }
 
-int make_tmap_3d_f32(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0) {
-  cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 4, d1 * d0 * 4};
-  cuuint32_t box[3] = {box0, box1, 1};
-  return encode(m, base, 3, dims, strides, box, true);
+// Launch `kernel` on `grid` CTAs of 256 threads; cluster = 2 consecutive CTAs when mc.
+template <class Params>
+static int launch_k(void (*kernel)(Params), const Params& p, int grid, int smem, bool mc, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = mc ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+  count_launch();
+  if (e != cudaSuccess) { set_error("cudaLaunchKernelEx: %s", cudaGetErrorString(e)); return (int)e; }
+  return 0;
 }
 
 int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g, cudaStream_t s) {
@@ -469,10 +558,14 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   p.z_group0 = g.z_group0;
   p.bias_cond = g.bias_cond; p.bias_unc = g.bias_unc;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
-  if (g.three) umma_gate_kernel<true><<<grid, 256, Cfg<true>::kSmemBytes, s>>>(p);
-  else umma_gate_kernel<false><<<grid, 256, Cfg<false>::kSmemBytes, s>>>(p);
-  DRB_LAUNCH_CHECK();
-  return 0;
+  p.inv_scale = g.inv_scale;
+  const bool mc = g.multicast && ((p.NB * p.tiles_t) % 2 == 0);
+  if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1>::kSmemBytes, true, s)
+                             : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1>::kSmemBytes, false, s);
+  if (g.prec == 2) return mc ? launch_k(umma_gate_kernel<2, true>, p, grid, Cfg<2>::kSmemBytes, true, s)
+                             : launch_k(umma_gate_kernel<2, false>, p, grid, Cfg<2>::kSmemBytes, false, s);
+  return mc ? launch_k(umma_gate_kernel<0, true>, p, grid, Cfg<0>::kSmemBytes, true, s)
+            : launch_k(umma_gate_kernel<0, false>, p, grid, Cfg<0>::kSmemBytes, false, s);
 }
 
 int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) {
@@ -483,10 +576,14 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg; p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
-  if (z.three) umma_zgemm_kernel<true><<<grid, 256, Cfg<true>::kSmemBytes, s>>>(p);
-  else umma_zgemm_kernel<false><<<grid, 256, Cfg<false>::kSmemBytes, s>>>(p);
-  DRB_LAUNCH_CHECK();
-  return 0;
+  p.inv_scale = z.inv_scale;
+  const bool mc = z.multicast && ((p.NB * p.tiles_t) % 2 == 0);
+  if (z.prec == 1) return mc ? launch_k(umma_zgemm_kernel<1, true>, p, grid, Cfg<1>::kSmemBytes, true, s)
+                             : launch_k(umma_zgemm_kernel<1, false>, p, grid, Cfg<1>::kSmemBytes, false, s);
+  if (z.prec == 2) return mc ? launch_k(umma_zgemm_kernel<2, true>, p, grid, Cfg<2>::kSmemBytes, true, s)
+                             : launch_k(umma_zgemm_kernel<2, false>, p, grid, Cfg<2>::kSmemBytes, false, s);
+  return mc ? launch_k(umma_zgemm_kernel<0, true>, p, grid, Cfg<0>::kSmemBytes, true, s)
+            : launch_k(umma_zgemm_kernel<0, false>, p, grid, Cfg<0>::kSmemBytes, false, s);
 }
 
 }  // namespace drb

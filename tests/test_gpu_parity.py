@@ -16,9 +16,9 @@ from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dic
 pytestmark = pytest.mark.gpu
 
 TOL_FINAL = 1e-3
-TOL_STEP = {"fp32": 2e-4, "bf16x3": 5e-4}
+TOL_STEP = {"fp32": 2e-4, "bf16x3": 5e-4, "f16f8": 5e-4}
 TOL_SPEC = 2e-4
-PRECS = ["fp32", "bf16x3"]
+PRECS = ["fp32", "bf16x3", "f16f8"]
 _models = {}
 
 
@@ -120,7 +120,7 @@ def test_sampler_single_steps_vs_golden(name, precision):
         assert maxabs(x_prev, ref) < TOL_STEP[precision] * scale, (name, t_index)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3"])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
 def test_chain_transcription_200_vs_golden(precision):
     """configs[0]/[1]: 200-step inpainting_ddpm_x0 (w=0.5, no masks) on a full 640-frame clip, B=1."""
     g = golden("chain_transcription_b1_200.npz")
@@ -147,34 +147,37 @@ def test_chain_fp32_path_first_50_steps():
     assert maxabs(x, g["t150"]) < TOL_FINAL
 
 
-def test_chain_inpainting_T128_vs_golden():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_chain_inpainting_T128_vs_golden(precision):
     """configs[3] shape: 50 % of the frames masked to -1 (model/diffwave.py:649-650)."""
     g = golden("chain_inpaint_b2_200_T128.npz")
-    m = model_for("bf16x3", inpainting_t=[0, 64])
+    m = model_for(precision, inpainting_t=[0, 64])
     x_T, wav, noise = make_inputs(2, 200, seed=11, T=128, wav_len=65536)
     x0, spec, _ = m.sample_loop(x_T.cuda(), wav.cuda(), noise=noise.cuda())
-    record(f"chain_inpaint_T128[bf16x3] final max|delta| = {maxabs(x0, g['final']):.3e}")
+    record(f"chain_inpaint_T128[{precision}] final max|delta| = {maxabs(x0, g['final']):.3e}")
     assert maxabs(x0, g["final"]) < TOL_FINAL
     assert float(spec[:, :, :64].max()) == -1.0
 
 
-def test_chain_generation_1000_T128_vs_golden():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_chain_generation_1000_T128_vs_golden(precision):
     """configs[2] shape: unconditional generation, 1000 steps (timesteps=1000 table and schedule)."""
     g = golden("chain_generation_b1_1000_T128.npz")
-    m = model_for("bf16x3", timesteps=1000, sampling_type="generation_ddpm_x0")
+    m = model_for(precision, timesteps=1000, sampling_type="generation_ddpm_x0")
     x_T, wav, noise = make_inputs(1, 1000, seed=5, T=128, wav_len=65536)
     x0, spec, _ = m.sample_loop(x_T.cuda(), wav.cuda(), noise=noise.cuda())
-    record(f"chain_generation_1000_T128[bf16x3] final max|delta| = {maxabs(x0, g['final']):.3e}")
+    record(f"chain_generation_1000_T128[{precision}] final max|delta| = {maxabs(x0, g['final']):.3e}")
     assert maxabs(x0, g["final"]) < TOL_FINAL
     assert float(spec.max()) == -1.0
 
 
-def test_tensor_path_matches_fp32_path_per_layer():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_tensor_path_matches_fp32_path_per_layer(precision):
     """tcgen05 kernels against the fp32 CUDA-core kernels, layer by layer, through the C ABI entry points."""
     import ctypes as C
     from diffroll_b200 import _lib
     from diffroll_b200.task import _upd
-    mf, mt = model_for("fp32"), model_for("bf16x3")
+    mf, mt = model_for("fp32"), model_for(precision)
     x_T, wav, _ = make_inputs(2, 200, seed=3, n_noise=0)
     x, w = x_T.cuda(), wav.cuda()
     engs = []
@@ -208,7 +211,7 @@ def test_tensor_path_matches_fp32_path_per_layer():
     err = float((a - b).abs().max()); ref = float(a.abs().max())
     assert err < 2e-4 * max(ref, 1.0), ("h", err, ref)
     assert float((outs[0] - outs[1]).abs().max()) < 2e-4 * max(1.0, float(outs[0].abs().max()))
-    record(f"tensor-vs-fp32 per layer worst rel err = {worst:.3e}, head rel err = {err / max(ref, 1.0):.3e}")
+    record(f"[{precision}] tensor-vs-fp32 per layer worst rel err = {worst:.3e}, head rel err = {err / max(ref, 1.0):.3e}")
 
 
 def test_loop_equals_repeated_steps_bitwise():
