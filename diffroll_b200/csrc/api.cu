@@ -93,7 +93,7 @@ struct drb_plan {
   int NB, n_cond;      // active branches
   bool zero_spec;      // second branch = conditional forward on an all-zero spectrogram (cfdg_ddim_x0)
   bool tables_ready, spec_ready;
-  int multicast = 1;   // 2-CTA clusters sharing weight tiles via TMA multicast (DRB_NO_MULTICAST=1 disables, for A/B runs)
+  int pair = 1;        // CTA pairs (cta_group::2); DRB_NO_PAIR=1 selects the single-CTA kernels, for A/B runs
   std::vector<int> dil;
   // weight pointers used in place (caller keeps them alive)
   const float *in_w, *in_b, *e1w, *e1b, *e2w, *e2b, *skw, *skb, *hdw, *hdb;
@@ -162,7 +162,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
   drb_plan* p = new drb_plan();
   p->cfg = *cfg; p->lay = lay; p->ws = (char*)workspace; p->mel = nullptr;
   p->tables_ready = false; p->spec_ready = false;
-  { const char* e = getenv("DRB_NO_MULTICAST"); p->multicast = (e && e[0] == '1') ? 0 : 1; }
+  { const char* e = getenv("DRB_NO_PAIR"); p->pair = (e && e[0] == '1') ? 0 : 1; }
   const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
   p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
   p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
@@ -339,14 +339,14 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   UmmaGate ug;
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
-  ug.multicast = p->multicast; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
+  ug.pair = p->pair; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;
   const int e1 = p->prof ? p->ev_mark(s) : -1;
   if (do_res) {  // the last layer's residual half is dead; every layer's skip half is deferred to the head GEMM
     UmmaZGemm uz;
-    uz.multicast = p->multicast; uz.NB = NB; uz.T = T; uz.C = C; uz.prec = ug.prec; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
+    uz.pair = p->pair; uz.NB = NB; uz.T = T; uz.C = C; uz.prec = ug.prec; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
     uz.inv_scale = p->wscale(2 * layer + 1) + 1;
     uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
     uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, t_index);
@@ -378,7 +378,7 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
     r = launch_simt_gemm(g, s); if (r) return r;
   } else {  // one long-K tensor-core GEMM over the stored z of all layers (skip sum, 1/sqrt(L), skip_projection, ReLU)
     UmmaZGemm uz;
-    uz.multicast = p->multicast; uz.NB = p->NB; uz.T = T; uz.C = C; uz.prec = p->prec(); uz.mode = 1; uz.groups = c.residual_layers;
+    uz.pair = p->pair; uz.NB = p->NB; uz.T = T; uz.C = C; uz.prec = p->prec(); uz.mode = 1; uz.groups = c.residual_layers;
     uz.inv_scale = p->wscale(2 * c.residual_layers) + 1;
     uz.z_group0 = 0; uz.group_stride = p->lay.NBcap; uz.w_h = &p->maps.wcomp_h; uz.w_l = &p->maps.wcomp_l; uz.out32 = &p->maps.h32;
     uz.bias = p->at<float>(p->lay.bcomp); uz.dnext = nullptr;

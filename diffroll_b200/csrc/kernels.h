@@ -88,13 +88,13 @@ struct UmmaMaps {
 };
 struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl[z_group0 + roll]
   int NB, n_cond, T, C, taps, dil, Mp, prec, z_group0;  // prec: 0 bf16, 1 bf16x3, 2 f16f8
-  int multicast = 1;  // share weight tiles across 2-CTA clusters (TMA multicast) when the M-tile count is even
+  int pair = 1;  // CTA pairs (cta_group::2, M = 256) when the M-tile count is even
   const float* inv_scale;
   const float* bias_cond;  // interleaved [2C]
   const float* bias_unc;
 };
 struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
-  int multicast = 1;
+  int pair = 1;
   int NB, T, C, prec, mode;         // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h
   const float* inv_scale;
   int groups, z_group0, group_stride;

@@ -19,6 +19,11 @@
 // activations and weights are kept as bf16 hi + lo pairs and every K-step issues three MMAs into the same TMEM
 // accumulator: hi*hi + lo*hi + hi*lo.
 //
+// CTA pairs (PAIR = true, the default when the number of M tiles is even): two CTAs of a cluster issue ONE
+// tcgen05.mma.cta_group::2 with M = 256.  Each CTA stages its own 128 activation rows and only HALF of the weight
+// tile (128 of the 256 output rows), so the shared-memory traffic per MMA (operand reads + TMA fills), which bounds
+// the single-CTA kernel, drops by a third and the ring holds 3 stages instead of 2.
+//
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
 // (TMEM -> registers -> swizzled smem staging -> TMA store).  smem ring: full/empty mbarriers per stage; after the last
 // MMA retires the ring memory is reused as epilogue staging.
@@ -41,15 +46,19 @@ constexpr int EPI_BAR = 1;                         // named barrier of the 4 epi
 //   1  bf16x3   bf16 hi/lo, 3 products into one accumulator      aux = bf16 lo tiles
 //   2  f16f8    fp16 product + e4m3 correction product          aux = e4m3 tiles [lo*SA | hi] / [hi*SW | lo*SA*SW],
 //                                                                second accumulator (TMEM columns 256..511)
-template <int P>
+template <int P, bool PAIR>
 struct Cfg {
   static constexpr bool kAux = P != 0;
-  static constexpr int kStageBytes = kAux ? 2 * (A_TILE_BYTES + B_TILE_BYTES) : (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int kStages = kAux ? 2 : 4;
-  static constexpr int kRingBytes = kStages * kStageBytes;  // 192 KB
+  static constexpr int kBBytes = PAIR ? B_TILE_BYTES / 2 : B_TILE_BYTES;  // weight rows staged by this CTA: 128 or 256
+  static constexpr int kStageBytes = (kAux ? 2 : 1) * (A_TILE_BYTES + kBBytes);
+  static constexpr int kRingBytes = 196608;                                // 192 KB: also the epilogue staging area
+  static constexpr int kStages = kRingBytes / kStageBytes;                 // 2 (single) / 3 (pair) with aux operands
   static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr uint32_t kTmemCols = P == 2 ? 512 : 256;
   static constexpr int kAuxMul = P == 2 ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
+  static constexpr int kAOff = 0, kAAuxOff = A_TILE_BYTES;
+  static constexpr int kBOff = (kAux ? 2 : 1) * A_TILE_BYTES, kBAuxOff = kBOff + kBBytes;
+  static constexpr int kMaxStages = 6;
 };
 
 struct alignas(64) GateParams {
@@ -77,84 +86,117 @@ struct SmemView {
   uint32_t* tmem_ptr;
 };
 
-template <int P>
+template <int P, bool PAIR>
 __device__ __forceinline__ SmemView carve(uint8_t* raw) {
   uint32_t a = smem_u32(raw);
   uint32_t pad = ((a + 1023u) & ~1023u) - a;
   SmemView v;
   v.stage0 = raw + pad;
-  uint8_t* bars = v.stage0 + Cfg<P>::kRingBytes;
+  uint8_t* bars = v.stage0 + Cfg<P, PAIR>::kRingBytes;
   v.full = reinterpret_cast<uint64_t*>(bars);
-  v.empty = v.full + Cfg<P>::kStages;
-  v.tmem_full = v.empty + Cfg<P>::kStages;
+  v.empty = v.full + Cfg<P, PAIR>::kMaxStages;
+  v.tmem_full = v.empty + Cfg<P, PAIR>::kMaxStages;
   v.xin_full = v.tmem_full + 1;
   v.tmem_ptr = reinterpret_cast<uint32_t*>(v.xin_full + 1);
   return v;
 }
 
-// MC = true: the kernel runs as 2-CTA clusters that share the weight (B) tile: each CTA fetches half of it and TMA
-// multicasts that half into both CTAs' smem, halving the L2 traffic of the B operand.  A slot is reused only after
-// BOTH CTAs' MMAs have consumed it (empty barriers count 2, released by multicast tcgen05.commit).
-template <int P, bool MC>
+template <int P, bool PAIR>
 __device__ __forceinline__ void prologue(const SmemView& sv, int warp) {
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < Cfg<P>::kStages; ++i) { mbar_init(&sv.full[i], 1); mbar_init(&sv.empty[i], MC ? 2 : 1); }
+    // pair: the leader's full barrier collects one arrive.expect_tx from each CTA's producer
+    for (int i = 0; i < Cfg<P, PAIR>::kStages; ++i) { mbar_init(&sv.full[i], PAIR ? 2 : 1); mbar_init(&sv.empty[i], 1); }
     mbar_init(sv.tmem_full, 1);
     mbar_init(sv.xin_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(sv.tmem_ptr, Cfg<P>::kTmemCols); tmem_relinquish(); }
+  if (warp == 2) {
+    if (PAIR) { tmem_alloc_pair(sv.tmem_ptr, Cfg<P, PAIR>::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(sv.tmem_ptr, Cfg<P, PAIR>::kTmemCols); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // peer barriers are initialised before any multicast load / remote arrive targets them
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers and TMEM exist before any remote arrive / paired MMA
   tc_fence_after();
 }
 
-// One weight tile = two 128-row boxes.  MC: this CTA loads box `rank` and multicasts it to both CTAs.
-template <bool MC>
-__device__ __forceinline__ void load_b_tile(uint8_t* b_tile, const void* tmap, uint64_t* bar, int col, int row0, uint32_t rank) {
-  if (MC) {
-    tma_load_2d_mc(b_tile + rank * (B_TILE_BYTES / 2), tmap, bar, col, row0 + (int)rank * (TILE_N / 2), (uint16_t)0x3);
+template <int P, bool PAIR>
+__device__ __forceinline__ void teardown(uint32_t tmem_base, int warp) {
+  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still touch this CTA's barriers / TMEM until its work has retired
+  if (warp == 2) {
+    tc_fence_after();
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg<P, PAIR>::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg<P, PAIR>::kTmemCols);
+  }
+}
+
+// Producer-side helpers.  `fb` is the address the TMA completion goes to: this CTA's full barrier, or (pair) the
+// leader CTA's full barrier as a shared::cluster address.
+template <bool PAIR>
+__device__ __forceinline__ void prod_expect(uint64_t* full_local, uint32_t fb, uint32_t bytes) {
+  if (PAIR) mbar_expect_tx_cluster(fb, bytes); else mbar_expect_tx(full_local, bytes);
+}
+template <bool PAIR>
+__device__ __forceinline__ void load_a(uint8_t* dst, const void* tmap, uint64_t* full_local, uint32_t fb, int c0, int c1, int c2) {
+  if (PAIR) tma_load_3d_pair(dst, tmap, fb, c0, c1, c2); else tma_load_3d(dst, tmap, full_local, c0, c1, c2);
+}
+// weight tile: 256 rows = two 128-row boxes (single CTA), or this CTA's 128-row half (pair)
+template <bool PAIR>
+__device__ __forceinline__ void load_b(uint8_t* dst, const void* tmap, uint64_t* full_local, uint32_t fb, int col, int row0, uint32_t rank) {
+  if (PAIR) {
+    tma_load_2d_pair(dst, tmap, fb, col, row0 + (int)rank * (TILE_N / 2));
   } else {
-    tma_load_2d(b_tile, tmap, bar, col, row0);
-    tma_load_2d(b_tile + B_TILE_BYTES / 2, tmap, bar, col, row0 + TILE_N / 2);
+    tma_load_2d(dst, tmap, full_local, col, row0);
+    tma_load_2d(dst + B_TILE_BYTES / 2, tmap, full_local, col, row0 + TILE_N / 2);
   }
 }
 
 // MMA issue for one K-slab (64 channels = 4 UMMA K-steps) resident in stage memory.
-template <int P>
+template <int P, bool PAIR>
 __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool first_slab) {
-  const uint32_t a_hi = smem_u32(st);
-  const uint32_t a_lo = a_hi + A_TILE_BYTES;
-  const uint32_t b_hi = a_hi + (Cfg<P>::kAux ? 2 * A_TILE_BYTES : A_TILE_BYTES);
-  const uint32_t b_lo = b_hi + B_TILE_BYTES;
-  constexpr uint32_t idesc = P == 2 ? make_idesc_fmt0(TILE_M, TILE_N) : make_idesc_bf16(TILE_M, TILE_N);
+  using C = Cfg<P, PAIR>;
+  const uint32_t a_hi = smem_u32(st) + C::kAOff, a_lo = smem_u32(st) + C::kAAuxOff;
+  const uint32_t b_hi = smem_u32(st) + C::kBOff, b_lo = smem_u32(st) + C::kBAuxOff;
+  constexpr int M = PAIR ? 2 * TILE_M : TILE_M;
+  constexpr uint32_t idesc = P == 2 ? make_idesc_fmt0(M, TILE_N) : make_idesc_bf16(M, TILE_N);
   const uint32_t acc0 = first_slab ? 0u : 1u;
 #pragma unroll
   for (int k = 0; k < TILE_K / UMMA_K; ++k) {
     const uint32_t ko = k * UMMA_K * 2;  // byte advance inside the 128-byte swizzled row (16 x 2 B, or 32 x 1 B for e4m3)
     const uint64_t da_hi = make_sw128_desc(a_hi + ko), db_hi = make_sw128_desc(b_hi + ko);
-    umma_bf16(tmem_d, da_hi, db_hi, idesc, k == 0 ? acc0 : 1u);   // kind::f16: bf16 or fp16 per idesc
-    if (P == 1) {
-      umma_bf16(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
-      umma_bf16(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
+    const uint32_t acc = k == 0 ? acc0 : 1u;
+    if (PAIR) {
+      umma_bf16_pair(tmem_d, da_hi, db_hi, idesc, acc);   // kind::f16: bf16 or fp16 per idesc
+      if (P == 1) {
+        umma_bf16_pair(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
+        umma_bf16_pair(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
+      }
+      if (P == 2) umma_f8_pair(tmem_d + 256, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc, acc);
+    } else {
+      umma_bf16(tmem_d, da_hi, db_hi, idesc, acc);
+      if (P == 1) {
+        umma_bf16(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
+        umma_bf16(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
+      }
+      if (P == 2) umma_f8(tmem_d + 256, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc, acc);
     }
-    if (P == 2) umma_f8(tmem_d + 256, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc, k == 0 ? acc0 : 1u);
   }
 }
 
-template <int P, bool MC>
+// Consumer loop, one elected thread (pair: of the leader CTA only).
+template <int P, bool PAIR>
 __device__ __forceinline__ void mma_loop(const SmemView& sv, uint32_t tmem_base, int nslabs) {
   int stage = 0; uint32_t phase = 0;
   for (int s = 0; s < nslabs; ++s) {
     mbar_wait(&sv.full[stage], phase);
     tc_fence_after();
-    issue_slab<P>(sv.stage0 + stage * Cfg<P>::kStageBytes, tmem_base, s == 0);
-    if (MC) umma_commit_mc(&sv.empty[stage], (uint16_t)0x3);  // frees the slot in both CTAs when these MMAs retire
+    issue_slab<P, PAIR>(sv.stage0 + stage * Cfg<P, PAIR>::kStageBytes, tmem_base, s == 0);
+    if (PAIR) umma_commit_pair(&sv.empty[stage]);  // frees the slot in both CTAs when these MMAs retire
     else umma_commit(&sv.empty[stage]);
-    if (++stage == Cfg<P>::kStages) { stage = 0; phase ^= 1; }
+    if (++stage == Cfg<P, PAIR>::kStages) { stage = 0; phase ^= 1; }
   }
-  umma_commit(sv.tmem_full);
+  if (PAIR) umma_commit_pair(sv.tmem_full); else umma_commit(sv.tmem_full);
 }
 
 // sigmoid(g) * tanh(f) with the SFU exp2/rcp approximations (abs error ~2e-7, far below the bf16 hi/lo split error)
@@ -215,17 +257,18 @@ __device__ __forceinline__ void stage16(uint32_t main_box, uint32_t aux_box, int
 // ---------------------------------------------------------------------------------------------
 // gate kernel
 // ---------------------------------------------------------------------------------------------
-template <int P, bool MC>
+template <int P, bool PAIR>
 __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant__ GateParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemView sv = carve<P>(smem_raw);
+  const SmemView sv = carve<P, PAIR>(smem_raw);
+  using CF = Cfg<P, PAIR>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // tile mapping: a cluster (MC) = two consecutive M tiles (frames x roll) of the same N block
-  const uint32_t rank = MC ? cluster_ctarank() : 0u;
-  int cid = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  // tile mapping: a CTA pair = two consecutive M tiles (frames x roll) of the same N block
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nblk = cid % p.n_blocks; cid /= p.n_blocks;
-  const int mt = MC ? cid * 2 + (int)rank : cid;
+  const int mt = PAIR ? cid * 2 + (int)rank : cid;
   const int tt = mt % p.tiles_t;
   const int nb = mt / p.tiles_t;
   const int t0 = tt * TILE_M;
@@ -233,16 +276,16 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
   const int conv_slabs = p.taps * cpt;
   // Both CTAs of a cluster run the same slab list.  If only the first tile of the pair is conditional, the second
   // one runs the conditioner slabs too: its spectrogram coordinate (roll >= n_cond) is out of bounds, so TMA feeds zeros.
-  const int nb_first = MC ? (cid * 2) / p.tiles_t : nb;
+  const int nb_first = PAIR ? (cid * 2) / p.tiles_t : nb;
   const int nslabs = conv_slabs + (nb_first < p.n_cond ? p.cond_slabs : 0);
   const int half = p.taps / 2;
-  constexpr int AM = Cfg<P>::kAuxMul;
+  constexpr int AM = CF::kAuxMul;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.zh);
-    if (Cfg<P>::kAux) { tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l); tma_prefetch_desc(&p.zl); }
+    if (CF::kAux) { tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l); tma_prefetch_desc(&p.zl); }
   }
-  prologue<P, MC>(sv, warp);
+  prologue<P, PAIR>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
 
   if (warp == 0) {
@@ -250,33 +293,33 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int s = 0; s < nslabs; ++s) {
         mbar_wait(&sv.empty[stage], phase ^ 1);
-        uint8_t* st = sv.stage0 + stage * Cfg<P>::kStageBytes;
-        uint8_t* a_hi = st; uint8_t* a_lo = st + A_TILE_BYTES;
-        uint8_t* b_hi = st + (Cfg<P>::kAux ? 2 * A_TILE_BYTES : A_TILE_BYTES); uint8_t* b_lo = b_hi + B_TILE_BYTES;
-        mbar_expect_tx(&sv.full[stage], Cfg<P>::kStageBytes);
+        uint8_t* st = sv.stage0 + stage * CF::kStageBytes;
+        uint64_t* fl = &sv.full[stage];
+        const uint32_t fb = PAIR ? mapa_cluster(smem_u32(fl), 0) : 0u;
+        prod_expect<PAIR>(fl, fb, CF::kStageBytes);
         if (s < conv_slabs) {
           const int tap = s / cpt, cc = s - tap * cpt;
           const int trow = t0 + (tap - half) * p.dil;
-          tma_load_3d(a_hi, &p.xh, &sv.full[stage], cc * TILE_K, trow, nb);
-          load_b_tile<MC>(b_hi, &p.wd_h, &sv.full[stage], tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
-          if (Cfg<P>::kAux) {
-            tma_load_3d(a_lo, &p.xl, &sv.full[stage], AM * cc * TILE_K, trow, nb);
-            load_b_tile<MC>(b_lo, &p.wd_l, &sv.full[stage], AM * (tap * p.C + cc * TILE_K), nblk * TILE_N, rank);
+          load_a<PAIR>(st + CF::kAOff, &p.xh, fl, fb, cc * TILE_K, trow, nb);
+          load_b<PAIR>(st + CF::kBOff, &p.wd_h, fl, fb, tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
+          if (CF::kAux) {
+            load_a<PAIR>(st + CF::kAAuxOff, &p.xl, fl, fb, AM * cc * TILE_K, trow, nb);
+            load_b<PAIR>(st + CF::kBAuxOff, &p.wd_l, fl, fb, AM * (tap * p.C + cc * TILE_K), nblk * TILE_N, rank);
           }
         } else {
           const int cc = s - conv_slabs;
-          tma_load_3d(a_hi, &p.sh, &sv.full[stage], cc * TILE_K, t0, nb);
-          load_b_tile<MC>(b_hi, &p.wc_h, &sv.full[stage], cc * TILE_K, nblk * TILE_N, rank);
-          if (Cfg<P>::kAux) {
-            tma_load_3d(a_lo, &p.sl, &sv.full[stage], AM * cc * TILE_K, t0, nb);
-            load_b_tile<MC>(b_lo, &p.wc_l, &sv.full[stage], AM * cc * TILE_K, nblk * TILE_N, rank);
+          load_a<PAIR>(st + CF::kAOff, &p.sh, fl, fb, cc * TILE_K, t0, nb);
+          load_b<PAIR>(st + CF::kBOff, &p.wc_h, fl, fb, cc * TILE_K, nblk * TILE_N, rank);
+          if (CF::kAux) {
+            load_a<PAIR>(st + CF::kAAuxOff, &p.sl, fl, fb, AM * cc * TILE_K, t0, nb);
+            load_b<PAIR>(st + CF::kBAuxOff, &p.wc_l, fl, fb, AM * cc * TILE_K, nblk * TILE_N, rank);
           }
         }
-        if (++stage == Cfg<P>::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) mma_loop<P, MC>(sv, tmem_base, nslabs);
+    if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, nslabs);
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -311,7 +354,7 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
       const int c0 = nblk * (TILE_N / 2);
       tma_store_3d(&p.zh, sv.stage0, c0, t0, p.z_group0 + nb);
       tma_store_3d(&p.zh, sv.stage0 + CHUNK_BYTES, c0 + 64, t0, p.z_group0 + nb);
-      if (Cfg<P>::kAux) {
+      if (CF::kAux) {
         tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, AM * c0, t0, p.z_group0 + nb);
         tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, AM * (c0 + 64), t0, p.z_group0 + nb);
       }
@@ -319,36 +362,35 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
       tma_store_wait_read<0>();  // smem must stay valid until the bulk stores have read it
     }
   }
-  __syncthreads();
-  if (MC) cluster_sync_all();  // the peer may still signal this CTA's barriers until its own MMAs have retired
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg<P>::kTmemCols); }
+  teardown<P, PAIR>(tmem_base, warp);
 }
 
 // ---------------------------------------------------------------------------------------------
 // zgemm kernel: A = stored z of one layer (RES) or of all layers (HEAD)
 // ---------------------------------------------------------------------------------------------
-template <int P, bool MC>
+template <int P, bool PAIR>
 __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constant__ ZGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const SmemView sv = carve<P>(smem_raw);
+  const SmemView sv = carve<P, PAIR>(smem_raw);
+  using CF = Cfg<P, PAIR>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t rank = MC ? cluster_ctarank() : 0u;
-  int cid = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nblk = cid % p.n_blocks; cid /= p.n_blocks;
-  const int mt = MC ? cid * 2 + (int)rank : cid;
+  const int mt = PAIR ? cid * 2 + (int)rank : cid;
   const int tt = mt % p.tiles_t;
   const int nb = mt / p.tiles_t;
   const int t0 = tt * TILE_M;
   const int n_base = nblk * TILE_N;
   const bool res = p.mode == 0;
-  constexpr int AM = Cfg<P>::kAuxMul;
+  constexpr int AM = CF::kAuxMul;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.w_h); tma_prefetch_desc(&p.out32);
-    if (Cfg<P>::kAux) { tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_l); }
+    if (CF::kAux) { tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_l); }
   }
-  prologue<P, MC>(sv, warp);
+  prologue<P, PAIR>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
 
   if (warp == 0) {
@@ -356,19 +398,19 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
       int stage = 0; uint32_t phase = 0;
       for (int s = 0; s < p.nslabs; ++s) {
         mbar_wait(&sv.empty[stage], phase ^ 1);
-        uint8_t* st = sv.stage0 + stage * Cfg<P>::kStageBytes;
-        uint8_t* a_hi = st; uint8_t* a_lo = st + A_TILE_BYTES;
-        uint8_t* b_hi = st + (Cfg<P>::kAux ? 2 * A_TILE_BYTES : A_TILE_BYTES); uint8_t* b_lo = b_hi + B_TILE_BYTES;
+        uint8_t* st = sv.stage0 + stage * CF::kStageBytes;
+        uint64_t* fl = &sv.full[stage];
+        const uint32_t fb = PAIR ? mapa_cluster(smem_u32(fl), 0) : 0u;
         const int grp = s / p.spg, cc = s - grp * p.spg;
         const int zrow = p.z_group0 + grp * p.group_stride + nb;
-        mbar_expect_tx(&sv.full[stage], Cfg<P>::kStageBytes);
-        tma_load_3d(a_hi, &p.zh, &sv.full[stage], cc * TILE_K, t0, zrow);
-        load_b_tile<MC>(b_hi, &p.w_h, &sv.full[stage], s * TILE_K, n_base, rank);
-        if (Cfg<P>::kAux) {
-          tma_load_3d(a_lo, &p.zl, &sv.full[stage], AM * cc * TILE_K, t0, zrow);
-          load_b_tile<MC>(b_lo, &p.w_l, &sv.full[stage], AM * s * TILE_K, n_base, rank);
+        prod_expect<PAIR>(fl, fb, CF::kStageBytes);
+        load_a<PAIR>(st + CF::kAOff, &p.zh, fl, fb, cc * TILE_K, t0, zrow);
+        load_b<PAIR>(st + CF::kBOff, &p.w_h, fl, fb, s * TILE_K, n_base, rank);
+        if (CF::kAux) {
+          load_a<PAIR>(st + CF::kAAuxOff, &p.zl, fl, fb, AM * cc * TILE_K, t0, zrow);
+          load_b<PAIR>(st + CF::kBAuxOff, &p.w_l, fl, fb, AM * s * TILE_K, n_base, rank);
         }
-        if (++stage == Cfg<P>::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
       }
       if (res) {
         // Residual update needs the fp32 x tile: fetch it into the (now free) ring as 8 swizzled [128][32] fp32 boxes.
@@ -378,7 +420,7 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) mma_loop<P, MC>(sv, tmem_base, p.nslabs);
+    if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, p.nslabs);
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -446,7 +488,7 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
         tma_store_3d(&p.out32, sv.stage0 + (it * 2 + 1) * CHUNK_BYTES, c0 + 32, t0, nb);
         if (res) {
           tma_store_3d(&p.xh, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
-          if (Cfg<P>::kAux)
+          if (CF::kAux)
             tma_store_3d(&p.xl, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, AM * c0, t0, nb);
         }
         tma_store_commit();
@@ -455,9 +497,7 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
     tc_fence_before();
     if (issuer) tma_store_wait_read<0>();
   }
-  __syncthreads();
-  if (MC) cluster_sync_all();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg<P>::kTmemCols); }
+  teardown<P, PAIR>(tmem_base, warp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -483,12 +523,12 @@ int umma_init() {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess && ee == cudaSuccess) ee = e;
   };
-  set((const void*)umma_gate_kernel<0, false>, Cfg<0>::kSmemBytes); set((const void*)umma_gate_kernel<0, true>, Cfg<0>::kSmemBytes);
-  set((const void*)umma_gate_kernel<1, false>, Cfg<1>::kSmemBytes); set((const void*)umma_gate_kernel<1, true>, Cfg<1>::kSmemBytes);
-  set((const void*)umma_gate_kernel<2, false>, Cfg<2>::kSmemBytes); set((const void*)umma_gate_kernel<2, true>, Cfg<2>::kSmemBytes);
-  set((const void*)umma_zgemm_kernel<0, false>, Cfg<0>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0>::kSmemBytes);
-  set((const void*)umma_zgemm_kernel<1, false>, Cfg<1>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1>::kSmemBytes);
-  set((const void*)umma_zgemm_kernel<2, false>, Cfg<2>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2>::kSmemBytes);
+  set((const void*)umma_gate_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_gate_kernel<0, true>, Cfg<0, false>::kSmemBytes);
+  set((const void*)umma_gate_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_gate_kernel<1, true>, Cfg<1, false>::kSmemBytes);
+  set((const void*)umma_gate_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_gate_kernel<2, true>, Cfg<2, false>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2, false>::kSmemBytes);
   if (ee) {
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ee));
     g_encode = nullptr;
@@ -530,7 +570,7 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uin
   return encode(m, base, 3, dims, strides, box, dtype);
 }
 
-// Launch `kernel` on `grid` CTAs of 256 threads; cluster = 2 consecutive CTAs when mc.
+// Launch `kernel` on `grid` CTAs of 256 threads; cluster = 2 consecutive CTAs (a CTA pair) when mc.
 template <class Params>
 static int launch_k(void (*kernel)(Params), const Params& p, int grid, int smem, bool mc, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
@@ -559,13 +599,13 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   p.bias_cond = g.bias_cond; p.bias_unc = g.bias_unc;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = g.inv_scale;
-  const bool mc = g.multicast && ((p.NB * p.tiles_t) % 2 == 0);
-  if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1>::kSmemBytes, true, s)
-                             : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1>::kSmemBytes, false, s);
-  if (g.prec == 2) return mc ? launch_k(umma_gate_kernel<2, true>, p, grid, Cfg<2>::kSmemBytes, true, s)
-                             : launch_k(umma_gate_kernel<2, false>, p, grid, Cfg<2>::kSmemBytes, false, s);
-  return mc ? launch_k(umma_gate_kernel<0, true>, p, grid, Cfg<0>::kSmemBytes, true, s)
-            : launch_k(umma_gate_kernel<0, false>, p, grid, Cfg<0>::kSmemBytes, false, s);
+  const bool mc = g.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
+                             : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
+  if (g.prec == 2) return mc ? launch_k(umma_gate_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)
+                             : launch_k(umma_gate_kernel<2, false>, p, grid, Cfg<2, false>::kSmemBytes, false, s);
+  return mc ? launch_k(umma_gate_kernel<0, true>, p, grid, Cfg<0, false>::kSmemBytes, true, s)
+            : launch_k(umma_gate_kernel<0, false>, p, grid, Cfg<0, false>::kSmemBytes, false, s);
 }
 
 int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) {
@@ -577,13 +617,13 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = z.inv_scale;
-  const bool mc = z.multicast && ((p.NB * p.tiles_t) % 2 == 0);
-  if (z.prec == 1) return mc ? launch_k(umma_zgemm_kernel<1, true>, p, grid, Cfg<1>::kSmemBytes, true, s)
-                             : launch_k(umma_zgemm_kernel<1, false>, p, grid, Cfg<1>::kSmemBytes, false, s);
-  if (z.prec == 2) return mc ? launch_k(umma_zgemm_kernel<2, true>, p, grid, Cfg<2>::kSmemBytes, true, s)
-                             : launch_k(umma_zgemm_kernel<2, false>, p, grid, Cfg<2>::kSmemBytes, false, s);
-  return mc ? launch_k(umma_zgemm_kernel<0, true>, p, grid, Cfg<0>::kSmemBytes, true, s)
-            : launch_k(umma_zgemm_kernel<0, false>, p, grid, Cfg<0>::kSmemBytes, false, s);
+  const bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  if (z.prec == 1) return mc ? launch_k(umma_zgemm_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
+                             : launch_k(umma_zgemm_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
+  if (z.prec == 2) return mc ? launch_k(umma_zgemm_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)
+                             : launch_k(umma_zgemm_kernel<2, false>, p, grid, Cfg<2, false>::kSmemBytes, false, s);
+  return mc ? launch_k(umma_zgemm_kernel<0, true>, p, grid, Cfg<0, false>::kSmemBytes, true, s)
+            : launch_k(umma_zgemm_kernel<0, false>, p, grid, Cfg<0, false>::kSmemBytes, false, s);
 }
 
 }  // namespace drb
