@@ -25,7 +25,7 @@ void count_launch(int n) { g_launches += n; }
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 struct Layout {  // byte offsets into the workspace
-  size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel;
+  size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel, xpp;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
   size_t total;
@@ -62,6 +62,7 @@ static Layout make_layout(const drb_config& c) {
   l.bias = take(L * 4 * 2 * C * 4);
   l.wtmp = take(2 * C * k * C * 4);
   l.mel = take(mel_workspace_bytes(c));
+  l.xpp = take(B * T * c.pitches * 4);
   if (c.precision == DRB_PREC_FP32) {
     l.wd32 = take(L * 2 * C * k * C * 4);
     l.wc32 = take(L * 2 * C * Mp * 4);
@@ -102,6 +103,8 @@ struct drb_plan {
   UmmaMaps maps;
   std::vector<UmmaLayer> layers;
   // optional per-kernel timing (drb_plan_profile): events recorded on the launching stream around every kernel class
+  cudaStream_t copy_stream = nullptr;  // trajectory copies (drb_sample_loop)
+  cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
   bool prof = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_spans[4];  // 0 gate kernel, 1 out kernel, 2 in_proj+prep, 3 head
@@ -248,6 +251,11 @@ int drb_plan_destroy(drb_plan* p) {
   if (!p) return 0;
   mel_destroy(p->mel);
   for (auto e : p->ev_pool) cudaEventDestroy(e);
+  if (p->copy_stream) {
+    cudaStreamSynchronize(p->copy_stream);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(p->ev_step[k]); cudaEventDestroy(p->ev_copy[k]); }
+    cudaStreamDestroy(p->copy_stream);
+  }
   delete p;
   return 0;
 }
@@ -410,13 +418,42 @@ int drb_sample_loop(drb_plan* p, float* x, const float* noise, const drb_update*
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)p->cfg.batch * p->cfg.frames * p->cfg.pitches;
   size_t j = 0;
-  for (int t = t_start - 1, i = 0; t >= t_stop; --t, ++i) {
+  if (!trajectory) {
+    for (int t = t_start - 1, i = 0; t >= t_stop; --t, ++i) {
+      const drb_update* u = &updates_host[i];
+      const float* nz = nullptr;
+      if (u->has_noise) { if (!noise) { set_error("sample_loop: noise missing"); return DRB_E_INVALID; } nz = noise + (j++) * n; }
+      int r = drb_sample_step(p, x, nz, x, t, u, stream); if (r) return r;
+    }
+    return 0;
+  }
+  // With a trajectory (the reference's per-step host copy, task/diffusion.py:530) the roll ping-pongs between the
+  // caller's buffer and a plan-owned one, so the copy of step i (on a side stream) overlaps the compute of step i+1.
+  if (!p->copy_stream) {
+    DRB_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      DRB_CUDA(cudaEventCreateWithFlags(&p->ev_step[k], cudaEventDisableTiming));
+      DRB_CUDA(cudaEventCreateWithFlags(&p->ev_copy[k], cudaEventDisableTiming));
+    }
+  }
+  float* buf[2] = {x, p->at<float>(p->lay.xpp)};
+  int i = 0;
+  for (int t = t_start - 1; t >= t_stop; --t, ++i) {
     const drb_update* u = &updates_host[i];
     const float* nz = nullptr;
     if (u->has_noise) { if (!noise) { set_error("sample_loop: noise missing"); return DRB_E_INVALID; } nz = noise + (j++) * n; }
-    int r = drb_sample_step(p, x, nz, x, t, u, stream); if (r) return r;
-    if (trajectory) DRB_CUDA(cudaMemcpyAsync(trajectory + (size_t)i * n, x, n * sizeof(float), cudaMemcpyDefault, s));
+    float* src = buf[i & 1];
+    float* dst = buf[(i + 1) & 1];
+    if (i >= 2) DRB_CUDA(cudaStreamWaitEvent(s, p->ev_copy[i & 1], 0));  // dst was the source of the copy of step i-2
+    int r = drb_sample_step(p, src, nz, dst, t, u, stream); if (r) return r;
+    DRB_CUDA(cudaEventRecord(p->ev_step[i & 1], s));
+    DRB_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_step[i & 1], 0));
+    DRB_CUDA(cudaMemcpyAsync(trajectory + (size_t)i * n, dst, n * sizeof(float), cudaMemcpyDefault, p->copy_stream));
+    DRB_CUDA(cudaEventRecord(p->ev_copy[i & 1], p->copy_stream));
   }
+  if (i & 1) DRB_CUDA(cudaMemcpyAsync(x, buf[1], n * sizeof(float), cudaMemcpyDeviceToDevice, s));  // result back in place
+  DRB_CUDA(cudaStreamWaitEvent(s, p->ev_copy[0], 0));   // the caller's stream now also covers the trajectory copies
+  if (i >= 2) DRB_CUDA(cudaStreamWaitEvent(s, p->ev_copy[1], 0));
   return 0;
 }
 

@@ -186,7 +186,8 @@ class SpecRollDiffusion(nn.Module):
         noise: optional pre-drawn [n_noisy_steps, B, 1, T, 88]; by default it is drawn step by step with
         ``torch.randn_like`` on the roll's device, in the reference's order (descending t, only t with noise).
         n_steps: run only the first n_steps of the chain (t = T-1 .. T-n_steps); default the whole chain.
-        Returns (x_0, spec, trajectory) — trajectory is a pinned host tensor [steps, B, 1, T, 88] or None.
+        Returns (x_0, spec, trajectory) — trajectory is a pinned host tensor [steps, B, 1, T, 88] or None; it is
+        reused by the next call with the same shape (copy it if you need to keep it).
         """
         ups, branches, masks = self._all_updates()
         T_all = self.hparams.timesteps
@@ -206,7 +207,12 @@ class SpecRollDiffusion(nn.Module):
             noise = noise.to(device=x.device, dtype=torch.float32)[..., :x.shape[2], :].contiguous()
         traj = None
         if keep_trajectory:
-            traj = torch.empty((len(ups),) + tuple(x.shape), dtype=torch.float32, pin_memory=True)
+            # pinned host memory is expensive to allocate (~0.5 s per GB): keep one buffer per shape
+            shape = (len(ups),) + tuple(x.shape)
+            traj = self.__dict__.get("_traj_buf")
+            if traj is None or tuple(traj.shape) != shape:
+                traj = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+                self.__dict__["_traj_buf"] = traj
         eng.loop(x, noise, ups, T_all, t_stop, traj)
         return x, spec, traj
 
@@ -217,7 +223,8 @@ class SpecRollDiffusion(nn.Module):
         The reference copies every intermediate roll to the host (:530) and then writes figures/MIDI
         (:540-618, out of scope).  Here the per-step copies are asynchronous into pinned memory and the
         method returns ``(roll_pred, noise_list, spec)`` instead of None; ``noise_list`` has the
-        reference's structure: [(x_T, timesteps), (x_{T-1} as numpy, T-1), ..., (x_0 as numpy, 0)].
+        reference's structure: [(x_T, timesteps), (x_{T-1} as numpy, T-1), ..., (x_0 as numpy, 0)].  The numpy entries
+        are views of one pinned host buffer that the next call with the same shape overwrites; ``roll_pred`` is a copy.
         """
         noise, waveform = batch[0], batch[1]
         x0, spec, traj = self.sample_loop(noise, waveform, keep_trajectory=True)
@@ -226,7 +233,7 @@ class SpecRollDiffusion(nn.Module):
         tnp = traj.numpy()
         for i, t_index in enumerate(reversed(range(self.hparams.timesteps))):
             noise_list.append((tnp[i], t_index))
-        roll_pred = noise_list[-1][0]
+        roll_pred = noise_list[-1][0].copy()   # independent of the reused pinned trajectory buffer
         return roll_pred, noise_list, spec
 
     @torch.no_grad()
