@@ -39,7 +39,9 @@ constexpr int A_TILE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
 constexpr int B_TILE_BYTES = TILE_N * TILE_K * 2;  // 32 KB
 constexpr int UMMA_K = 16;
 constexpr int CHUNK_BYTES = TILE_M * 128;          // one 128-row x 128-byte swizzled staging box (16 KB)
-constexpr int EPI_BAR = 1;                         // named barrier of the 4 epilogue warps
+constexpr int EPI_BAR = 1;                         // named barrier of the epilogue warps
+constexpr int NUM_THREADS = 384;                   // warps 0-3: producer / MMA / TMEM / bias staging; warps 4-11: epilogue
+constexpr int EPI_THREADS = 256;
 
 // Precision modes (template parameter P):
 //   0  bf16     one product                                     main operands only
@@ -53,7 +55,7 @@ struct Cfg {
   static constexpr int kStageBytes = (kAux ? 2 : 1) * (A_TILE_BYTES + kBBytes);
   static constexpr int kRingBytes = 196608;                                // 192 KB: also the epilogue staging area
   static constexpr int kStages = kRingBytes / kStageBytes;                 // 2 (single) / 3 (pair) with aux operands
-  static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, d_next*/;
   static constexpr uint32_t kTmemCols = P == 2 ? 512 : 256;
   static constexpr int kAuxMul = P == 2 ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
   static constexpr int kAOff = 0, kAAuxOff = A_TILE_BYTES;
@@ -82,8 +84,10 @@ struct SmemView {
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tmem_full;
-  uint64_t* xin_full;
+  uint64_t* xin_full;   // [2]: early / late x-tile boxes (zgemm RES)
   uint32_t* tmem_ptr;
+  float* sbias;         // [256] bias of this tile's columns
+  float* sdn;           // [256] d_next of this tile's channels (zgemm RES)
 };
 
 template <int P, bool PAIR>
@@ -97,7 +101,9 @@ __device__ __forceinline__ SmemView carve(uint8_t* raw) {
   v.empty = v.full + Cfg<P, PAIR>::kMaxStages;
   v.tmem_full = v.empty + Cfg<P, PAIR>::kMaxStages;
   v.xin_full = v.tmem_full + 1;
-  v.tmem_ptr = reinterpret_cast<uint32_t*>(v.xin_full + 1);
+  v.tmem_ptr = reinterpret_cast<uint32_t*>(v.xin_full + 2);
+  v.sbias = reinterpret_cast<float*>(bars + 256);
+  v.sdn = v.sbias + 256;
   return v;
 }
 
@@ -107,7 +113,7 @@ __device__ __forceinline__ void prologue(const SmemView& sv, int warp) {
     // pair: the leader's full barrier collects one arrive.expect_tx from each CTA's producer
     for (int i = 0; i < Cfg<P, PAIR>::kStages; ++i) { mbar_init(&sv.full[i], PAIR ? 2 : 1); mbar_init(&sv.empty[i], 1); }
     mbar_init(sv.tmem_full, 1);
-    mbar_init(sv.xin_full, 1);
+    mbar_init(&sv.xin_full[0], 1); mbar_init(&sv.xin_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -186,7 +192,7 @@ __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool fi
 
 // Consumer loop, one elected thread (pair: of the leader CTA only).
 template <int P, bool PAIR>
-__device__ __forceinline__ void mma_loop(const SmemView& sv, uint32_t tmem_base, int nslabs) {
+__device__ __forceinline__ void mma_loop(const SmemView& sv, uint32_t tmem_base, int nslabs, int nst) {
   int stage = 0; uint32_t phase = 0;
   for (int s = 0; s < nslabs; ++s) {
     mbar_wait(&sv.full[stage], phase);
@@ -194,7 +200,7 @@ __device__ __forceinline__ void mma_loop(const SmemView& sv, uint32_t tmem_base,
     issue_slab<P, PAIR>(sv.stage0 + stage * Cfg<P, PAIR>::kStageBytes, tmem_base, s == 0);
     if (PAIR) umma_commit_pair(&sv.empty[stage]);  // frees the slot in both CTAs when these MMAs retire
     else umma_commit(&sv.empty[stage]);
-    if (++stage == Cfg<P, PAIR>::kStages) { stage = 0; phase ^= 1; }
+    if (++stage == nst) { stage = 0; phase ^= 1; }
   }
   if (PAIR) umma_commit_pair(sv.tmem_full); else umma_commit(sv.tmem_full);
 }
@@ -258,7 +264,7 @@ __device__ __forceinline__ void stage16(uint32_t main_box, uint32_t aux_box, int
 // gate kernel
 // ---------------------------------------------------------------------------------------------
 template <int P, bool PAIR>
-__global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant__ GateParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_kernel(const __grid_constant__ GateParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemView sv = carve<P, PAIR>(smem_raw);
   using CF = Cfg<P, PAIR>;
@@ -284,6 +290,10 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.zh);
     if (CF::kAux) { tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l); tma_prefetch_desc(&p.zl); }
+  }
+  if (warp == 3) {  // this tile's 256 bias values -> smem (the epilogue reads them as warp-wide broadcasts)
+    const float* bsrc = (nb < p.n_cond ? p.bias_cond : p.bias_unc) + nblk * TILE_N;
+    for (int i = lane; i < TILE_N; i += 32) sv.sbias[i] = __ldg(bsrc + i);
   }
   prologue<P, PAIR>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
@@ -319,11 +329,12 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, nslabs);
+    if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, nslabs, CF::kStages);
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;       // two groups of 4 warps split the tile's channels
     const int row = q * 32 + lane;
-    const float* bias = (nb < p.n_cond ? p.bias_cond : p.bias_unc) + nblk * TILE_N;
+    const float* bias = sv.sbias;
     mbar_wait(sv.tmem_full, 0);  // every MMA has retired: accumulator complete, ring memory free
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -331,7 +342,8 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
     const uint32_t stg = smem_u32(sv.stage0);
     const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int ch = grp * 2 + c2;         // 32 gate + 32 filter columns; group g fills box g
       float g[32], f[32];
       load_acc32<P>(taddr + ch * 32, inv, g);
       load_acc32<P>(taddr + 128 + ch * 32, inv, f);
@@ -342,14 +354,14 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int j = hf * 16 + i;
-          z[i] = gate_act(g[j] + __ldg(bias + ch * 32 + j), f[j] + __ldg(bias + 128 + ch * 32 + j));
+          z[i] = gate_act(g[j] + bias[ch * 32 + j], f[j] + bias[128 + ch * 32 + j]);
         }
         stage16<P>(box_m, box_a, row, (ch & 1) * 32 + hf * 16, z);
       }
     }
     tc_fence_before();
     fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA (async proxy)
-    named_bar_sync(EPI_BAR, 128);
+    named_bar_sync(EPI_BAR, EPI_THREADS);
     if (warp == 4 && elect_one()) {
       const int c0 = nblk * (TILE_N / 2);
       tma_store_3d(&p.zh, sv.stage0, c0, t0, p.z_group0 + nb);
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(256, 1) umma_gate_kernel(const __grid_constant
 // zgemm kernel: A = stored z of one layer (RES) or of all layers (HEAD)
 // ---------------------------------------------------------------------------------------------
 template <int P, bool PAIR>
-__global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constant__ ZGemmParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid_constant__ ZGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const SmemView sv = carve<P, PAIR>(smem_raw);
   using CF = Cfg<P, PAIR>;
@@ -390,11 +402,29 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
     tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.w_h); tma_prefetch_desc(&p.out32);
     if (CF::kAux) { tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_l); }
   }
+  if (warp == 3) {
+    for (int i = lane; i < TILE_N; i += 32) {
+      sv.sbias[i] = __ldg(p.bias + n_base + i);
+      if (res) sv.sdn[i] = __ldg(p.dnext + n_base + i);
+    }
+  }
+  // RES on CTA pairs: the K loop is only C/64 slabs, so it runs on a 2-stage ring and the third stage's 64 KB hold the
+  // first four fp32 x boxes, prefetched while the MMAs run; the other four follow once the ring is free.
+  const bool early = res && PAIR && CF::kAux;
+  const int nst = early ? 2 : CF::kStages;
+  auto xbox_off = [&](int c) -> uint32_t {
+    return early ? (c < 4 ? 2u * CF::kStageBytes + (uint32_t)c * CHUNK_BYTES : (uint32_t)(c - 4) * CHUNK_BYTES) : (uint32_t)c * CHUNK_BYTES;
+  };
+  const uint32_t set_off = early ? 4u * CHUNK_BYTES : 8u * CHUNK_BYTES;
   prologue<P, PAIR>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
 
   if (warp == 0) {
     if (elect_one()) {
+      if (early) {
+        mbar_expect_tx(&sv.xin_full[0], 4 * CHUNK_BYTES);
+        for (int c = 0; c < 4; ++c) tma_load_3d(sv.stage0 + xbox_off(c), &p.out32, &sv.xin_full[0], n_base + c * 32, t0, nb);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int s = 0; s < p.nslabs; ++s) {
         mbar_wait(&sv.empty[stage], phase ^ 1);
@@ -410,86 +440,84 @@ __global__ void __launch_bounds__(256, 1) umma_zgemm_kernel(const __grid_constan
           load_a<PAIR>(st + CF::kAAuxOff, &p.zl, fl, fb, AM * cc * TILE_K, t0, zrow);
           load_b<PAIR>(st + CF::kBAuxOff, &p.w_l, fl, fb, AM * s * TILE_K, n_base, rank);
         }
-        if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
       }
       if (res) {
-        // Residual update needs the fp32 x tile: fetch it into the (now free) ring as 8 swizzled [128][32] fp32 boxes.
+        // Residual update needs the fp32 x tile: fetch the remaining boxes into the (now free) ring.
         mbar_wait(sv.tmem_full, 0);
-        mbar_expect_tx(sv.xin_full, 8 * CHUNK_BYTES);
-        for (int c = 0; c < 8; ++c) tma_load_3d(sv.stage0 + c * CHUNK_BYTES, &p.out32, sv.xin_full, n_base + c * 32, t0, nb);
+        const int c_lo = early ? 4 : 0;
+        mbar_expect_tx(&sv.xin_full[1], (8 - c_lo) * CHUNK_BYTES);
+        for (int c = c_lo; c < 8; ++c) tma_load_3d(sv.stage0 + xbox_off(c), &p.out32, &sv.xin_full[1], n_base + c * 32, t0, nb);
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, p.nslabs);
+    if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, p.nslabs, nst);
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int hc = (warp - 4) >> 2;        // two groups of 4 warps: each takes one 32-channel fp32 box per iteration
     const int row = q * 32 + lane;
-    const float* bias = p.bias + n_base;
     const bool issuer = (warp == 4) && (lane == 0);
     mbar_wait(sv.tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = smem_u32(sv.stage0);
-    const float rs2 = 1.41421356237309515f;
+    const float rsqrt2 = 0.70710678118654752f;
     const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
-    if (res) mbar_wait(sv.xin_full, 0);
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {       // 64 output channels per iteration
       // operand staging of the next layer (x + d_next split): two alternating sets of {main box, aux box}
-      const uint32_t set = stg + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES;
+      const uint32_t set = stg + set_off + (it & 1) * 2 * CHUNK_BYTES;
       if (res && it >= 2) {                // the TMA stores of iteration it-2 must have finished reading this set
         if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(EPI_BAR, 128);
+        named_bar_sync(EPI_BAR, EPI_THREADS);
       }
-#pragma unroll 1
-      for (int hc = 0; hc < 2; ++hc) {     // one fp32 box (32 channels) at a time
-        float o[32];
-        load_acc32<P>(taddr + it * 64 + hc * 32, inv, o);
-        const uint32_t box = stg + (it * 2 + hc) * CHUNK_BYTES;
-        const float* bs = bias + it * 64 + hc * 32;
-        if (res) {
-          const float* dn = p.dnext + n_base + it * 64 + hc * 32;
+      const int cbox = it * 2 + hc;
+      float o[32];
+      load_acc32<P>(taddr + cbox * 32, inv, o);
+      const uint32_t box = stg + xbox_off(cbox);
+      const float* bs = sv.sbias + cbox * 32;
+      if (res) {
+        if (it == 0 || (early && it == 2) ) mbar_wait(&sv.xin_full[(early && it == 0) ? 0 : 1], 0);
+        const float* dn = sv.sdn + cbox * 32;
 #pragma unroll
-          for (int g16 = 0; g16 < 2; ++g16) {
-            float xin[16];
+        for (int g16 = 0; g16 < 2; ++g16) {
+          float xin[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int v = g16 * 4 + u, i = v * 4;
-              const uint32_t xa = box + sw128_off(row, v);
-              float4 x = lds128(xa);
-              const float4 d = __ldg(reinterpret_cast<const float4*>(dn + i));
-              x.x = (x.x + (o[i + 0] + __ldg(bs + i + 0))) / rs2;   // (x + residual) / sqrt(2.0)   diffwave.py:151
-              x.y = (x.y + (o[i + 1] + __ldg(bs + i + 1))) / rs2;
-              x.z = (x.z + (o[i + 2] + __ldg(bs + i + 2))) / rs2;
-              x.w = (x.w + (o[i + 3] + __ldg(bs + i + 3))) / rs2;
-              sts128(xa, x);  // in place: same thread, same address
-              xin[u * 4 + 0] = x.x + d.x; xin[u * 4 + 1] = x.y + d.y; xin[u * 4 + 2] = x.z + d.z; xin[u * 4 + 3] = x.w + d.w;
-            }
-            stage16<P>(set, set + CHUNK_BYTES, row, hc * 32 + g16 * 16, xin);
+          for (int u = 0; u < 4; ++u) {
+            const int v = g16 * 4 + u, i = v * 4;
+            const uint32_t xa = box + sw128_off(row, v);
+            float4 x = lds128(xa);
+            x.x = (x.x + (o[i + 0] + bs[i + 0])) * rsqrt2;   // (x + residual) / sqrt(2.0)   diffwave.py:151
+            x.y = (x.y + (o[i + 1] + bs[i + 1])) * rsqrt2;
+            x.z = (x.z + (o[i + 2] + bs[i + 2])) * rsqrt2;
+            x.w = (x.w + (o[i + 3] + bs[i + 3])) * rsqrt2;
+            sts128(xa, x);  // in place: same thread, same address
+            xin[u * 4 + 0] = x.x + dn[i + 0]; xin[u * 4 + 1] = x.y + dn[i + 1];
+            xin[u * 4 + 2] = x.z + dn[i + 2]; xin[u * 4 + 3] = x.w + dn[i + 3];
           }
-        } else {
+          stage16<P>(set, set + CHUNK_BYTES, row, hc * 32 + g16 * 16, xin);
+        }
+      } else {
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const int i = v * 4;
-            float4 h;
-            h.x = fmaxf(o[i + 0] + __ldg(bs + i + 0), 0.f);
-            h.y = fmaxf(o[i + 1] + __ldg(bs + i + 1), 0.f);
-            h.z = fmaxf(o[i + 2] + __ldg(bs + i + 2), 0.f);
-            h.w = fmaxf(o[i + 3] + __ldg(bs + i + 3), 0.f);
-            sts128(box + sw128_off(row, v), h);
-          }
+        for (int v = 0; v < 8; ++v) {
+          const int i = v * 4;
+          float4 h;
+          h.x = fmaxf(o[i + 0] + bs[i + 0], 0.f);
+          h.y = fmaxf(o[i + 1] + bs[i + 1], 0.f);
+          h.z = fmaxf(o[i + 2] + bs[i + 2], 0.f);
+          h.w = fmaxf(o[i + 3] + bs[i + 3], 0.f);
+          sts128(box + sw128_off(row, v), h);
         }
       }
       fence_proxy_async();
-      named_bar_sync(EPI_BAR, 128);
+      named_bar_sync(EPI_BAR, EPI_THREADS);
       if (issuer) {
         const int c0 = n_base + it * 64;
-        tma_store_3d(&p.out32, sv.stage0 + (it * 2) * CHUNK_BYTES, c0, t0, nb);
-        tma_store_3d(&p.out32, sv.stage0 + (it * 2 + 1) * CHUNK_BYTES, c0 + 32, t0, nb);
+        tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2), c0, t0, nb);
+        tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2 + 1), c0 + 32, t0, nb);
         if (res) {
-          tma_store_3d(&p.xh, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
-          if (CF::kAux)
-            tma_store_3d(&p.xl, sv.stage0 + 8 * CHUNK_BYTES + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, AM * c0, t0, nb);
+          tma_store_3d(&p.xh, sv.stage0 + set_off + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
+          if (CF::kAux) tma_store_3d(&p.xl, sv.stage0 + set_off + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, AM * c0, t0, nb);
         }
         tma_store_commit();
       }
@@ -574,7 +602,7 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uin
 template <class Params>
 static int launch_k(void (*kernel)(Params), const Params& p, int grid, int smem, bool mc, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = mc ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
