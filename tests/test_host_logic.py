@@ -160,7 +160,7 @@ def test_cabi_workspace_query_and_argument_checks(lib_built):
                          kernel_size=9, dilation_base=2, dilation_bound=4, n_mels=229, n_fft=2048, hop_length=512,
                          timesteps=200, precision=_lib.PREC_BF16X3, branches=_lib.BRANCH_COND_UNCOND, reserved=0)
     need = lib.drb_plan_workspace_bytes(C.byref(cfg))
-    assert 1.0e9 < need < 2.0e9                       # 1.34 GB at the benchmark shape
+    assert 1.0e9 < need < 4.0e9                       # 2.6 GB at the benchmark shape (z of all 15 layers is kept)
     cfg.kernel_size = 8                               # even kernels are not a 'same' convolution
     assert lib.drb_plan_workspace_bytes(C.byref(cfg)) == 0
     assert b"invalid" in lib.drb_last_error()
