@@ -252,6 +252,10 @@ def run_b200(args, rank, world, local):
     xd = x_host.to(dev, non_blocking=True)
     wd = w_host.to(dev, non_blocking=True)
     x0, _, traj = model.sample_loop(xd, wd, keep_trajectory=True, n_steps=Ke)
+    if world > 1:   # the path's only collective: one all-gather of the finished rolls over NCCL / NVLink
+        from diffroll_b200.dist import all_gather_rolls
+        rolls = all_gather_rolls(x0, world * args.batch)
+        assert rolls.shape[0] == world * args.batch
     e1.record()
     torch.cuda.synchronize(); barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -304,7 +308,8 @@ def run_b200(args, rank, world, local):
         "config": {"workload": f"configs[1]: batch={args.batch} per GPU, synthetic 640x88 rolls + 229-bin mel, "
                                "inpainting_ddpm_x0 w=0.5 (2 network forwards/step), timesteps=200, ClassifierFreeDiffRoll k=9, random weights",
                    "l2": "per-step working set (weights 0.6 GB + activations 0.6 GB) exceeds the 126 MB L2; no flush needed",
-                   "parallelism": f"dp{world} (independent batch shards, no data-path collective)"},
+                   "parallelism": f"dp{world} (independent batch shards, no data-path collective; one all-gather of the "
+                                  "finished rolls inside the e2e region when N>1)"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "ms_per_step": ms_e2e / Ke},
@@ -330,6 +335,8 @@ def main():
         run_reference(args, rank)
         return
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
