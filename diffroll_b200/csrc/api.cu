@@ -102,6 +102,8 @@ struct drb_plan {
   MelPlan* mel;
   UmmaMaps maps;
   std::vector<UmmaLayer> layers;
+  std::vector<CUtensorMap> win_h, win_l;  // per layer: x operand maps whose box covers the layer's whole tap window
+  int window = 1;
   // optional per-kernel timing (drb_plan_profile): events recorded on the launching stream around every kernel class
   cudaStream_t copy_stream = nullptr;  // trajectory copies (drb_sample_loop)
   cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -166,6 +168,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
   p->cfg = *cfg; p->lay = lay; p->ws = (char*)workspace; p->mel = nullptr;
   p->tables_ready = false; p->spec_ready = false;
   { const char* e = getenv("DRB_NO_PAIR"); p->pair = (e && e[0] == '1') ? 0 : 1; }
+  { const char* e = getenv("DRB_NO_WINDOW"); p->window = (e && e[0] == '1') ? 0 : 1; }
   const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
   p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
   p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
@@ -224,6 +227,15 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
     const uint64_t am = fmt == 2 ? 2 : 1;
     PLAN_TRY(make_tmap_3d(&p->maps.xh, p->ws + lay.xh, NBc, T, C, 128, dm));
     PLAN_TRY(make_tmap_3d(&p->maps.xl, p->ws + lay.xl, NBc, T, am * C, 128, da));
+    for (int i = 0; i < L; ++i) {
+      const int rows = 128 + (k - 1) * p->dil[i];
+      CUtensorMap mh, ml;
+      if (rows <= 192) {
+        PLAN_TRY(make_tmap_3d(&mh, p->ws + lay.xh, NBc, T, C, rows, dm));
+        PLAN_TRY(make_tmap_3d(&ml, p->ws + lay.xl, NBc, T, am * C, rows, da));
+      } else { mh = p->maps.xh; ml = p->maps.xl; }
+      p->win_h.push_back(mh); p->win_l.push_back(ml);
+    }
     PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, (uint64_t)L * NBc, T, C, 128, dm));
     PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, am * C, 128, da));
     PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, dm));
@@ -347,7 +359,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   UmmaGate ug;
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
-  ug.pair = p->pair; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
+  ug.pair = p->pair; ug.window = p->window; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;

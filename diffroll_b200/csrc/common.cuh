@@ -316,14 +316,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row
 // groups 1024 B apart).  Fields: start>>4 [0,14), LBO>>4 [16,30) (ignored for swizzled K-major),
-// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout SWIZZLE_128B=2 [61,64).
+// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52) = 0, layout SWIZZLE_128B=2 [61,64).
+// The start may be ANY 16-byte-aligned address inside a swizzled tile (e.g. a view shifted by r rows = r*128 B into a
+// TMA-written window): measured on B200, the swizzle XOR is taken from the absolute shared-memory address bits, so a
+// row-shifted view needs base_offset = 0; setting base_offset = (addr >> 7) & 7 produces garbage.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)((saddr >> 7) & 0x7) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }

@@ -27,6 +27,7 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
 // (TMEM -> registers -> swizzled smem staging -> TMA store).  smem ring: full/empty mbarriers per stage; after the last
 // MMA retires the ring memory is reused as epilogue staging.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -65,6 +66,8 @@ struct Cfg {
 
 struct alignas(64) GateParams {
   CUtensorMap xh, xl, sh, sl, wd_h, wd_l, wc_h, wc_l, zh, zl;
+  CUtensorMap xwh, xwl;  // activation maps whose box spans the whole tap window: 128 + (taps-1)*dil frames
+  int win_rows;
   int NB, n_cond, T, C, taps, dil, cond_slabs, tiles_t, n_blocks, z_group0;
   const float* bias_cond;
   const float* bias_unc;
@@ -85,6 +88,8 @@ struct SmemView {
   uint64_t* empty;
   uint64_t* tmem_full;
   uint64_t* xin_full;   // [2]: early / late x-tile boxes (zgemm RES)
+  uint64_t* afull;      // [2] activation-window buffers (gate window kernel)
+  uint64_t* aempty;     // [2]
   uint32_t* tmem_ptr;
   float* sbias;         // [256] bias of this tile's columns
   float* sdn;           // [256] d_next of this tile's channels (zgemm RES)
@@ -101,7 +106,9 @@ __device__ __forceinline__ SmemView carve(uint8_t* raw) {
   v.empty = v.full + Cfg<P, PAIR>::kMaxStages;
   v.tmem_full = v.empty + Cfg<P, PAIR>::kMaxStages;
   v.xin_full = v.tmem_full + 1;
-  v.tmem_ptr = reinterpret_cast<uint32_t*>(v.xin_full + 2);
+  v.afull = v.xin_full + 2;
+  v.aempty = v.afull + 2;
+  v.tmem_ptr = reinterpret_cast<uint32_t*>(v.aempty + 2);
   v.sbias = reinterpret_cast<float*>(bars + 256);
   v.sdn = v.sbias + 256;
   return v;
@@ -114,6 +121,7 @@ __device__ __forceinline__ void prologue(const SmemView& sv, int warp) {
     for (int i = 0; i < Cfg<P, PAIR>::kStages; ++i) { mbar_init(&sv.full[i], PAIR ? 2 : 1); mbar_init(&sv.empty[i], 1); }
     mbar_init(sv.tmem_full, 1);
     mbar_init(&sv.xin_full[0], 1); mbar_init(&sv.xin_full[1], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sv.afull[i], PAIR ? 2 : 1); mbar_init(&sv.aempty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -260,6 +268,54 @@ __device__ __forceinline__ void stage16(uint32_t main_box, uint32_t aux_box, int
   }
 }
 
+// Gate epilogue (8 warps): accumulator -> bias -> sigmoid*tanh -> operand split -> swizzled staging -> TMA store of z.
+template <int P>
+__device__ __forceinline__ void gate_epilogue(const SmemView& sv, const GateParams& p, uint32_t tmem_base, int warp, int lane,
+                                              int nb, int nblk, int t0) {
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;       // two groups of 4 warps split the tile's channels
+    const int row = q * 32 + lane;
+    const float* bias = sv.sbias;
+    mbar_wait(sv.tmem_full, 0);  // every MMA has retired: accumulator complete, ring memory free
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    // staging: z main boxes 0,1 then z aux boxes 0,1; each [128 frames][128 bytes], 128-byte swizzled
+    const uint32_t stg = smem_u32(sv.stage0);
+    const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int ch = grp * 2 + c2;         // 32 gate + 32 filter columns; group g fills box g
+      float g[32], f[32];
+      load_acc32<P>(taddr + ch * 32, inv, g);
+      load_acc32<P>(taddr + 128 + ch * 32, inv, f);
+      const uint32_t box_m = stg + (ch >> 1) * CHUNK_BYTES, box_a = box_m + 2 * CHUNK_BYTES;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = hf * 16 + i;
+          z[i] = gate_act(g[j] + bias[ch * 32 + j], f[j] + bias[128 + ch * 32 + j]);
+        }
+        stage16<P>(box_m, box_a, row, (ch & 1) * 32 + hf * 16, z);
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA (async proxy)
+    named_bar_sync(EPI_BAR, EPI_THREADS);
+    if (warp == 4 && elect_one()) {
+      const int c0 = nblk * (TILE_N / 2);
+      tma_store_3d(&p.zh, sv.stage0, c0, t0, p.z_group0 + nb);
+      tma_store_3d(&p.zh, sv.stage0 + CHUNK_BYTES, c0 + 64, t0, p.z_group0 + nb);
+      if ((P != 0)) {
+        tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, (P == 2 ? 2 : 1) * c0, t0, p.z_group0 + nb);
+        tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, (P == 2 ? 2 : 1) * (c0 + 64), t0, p.z_group0 + nb);
+      }
+      tma_store_commit();
+      tma_store_wait_read<0>();  // smem must stay valid until the bulk stores have read it
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // gate kernel
 // ---------------------------------------------------------------------------------------------
@@ -331,48 +387,139 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_kernel(const __grid_
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, nslabs, CF::kStages);
   } else if (warp >= 4) {
-    const int q = warp & 3;                // TMEM lane quarter this warp may access
-    const int grp = (warp - 4) >> 2;       // two groups of 4 warps split the tile's channels
-    const int row = q * 32 + lane;
-    const float* bias = sv.sbias;
-    mbar_wait(sv.tmem_full, 0);  // every MMA has retired: accumulator complete, ring memory free
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    // staging: z main boxes 0,1 then z aux boxes 0,1; each [128 frames][128 bytes], 128-byte swizzled
-    const uint32_t stg = smem_u32(sv.stage0);
-    const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
-#pragma unroll 1
-    for (int c2 = 0; c2 < 2; ++c2) {
-      const int ch = grp * 2 + c2;         // 32 gate + 32 filter columns; group g fills box g
-      float g[32], f[32];
-      load_acc32<P>(taddr + ch * 32, inv, g);
-      load_acc32<P>(taddr + 128 + ch * 32, inv, f);
-      const uint32_t box_m = stg + (ch >> 1) * CHUNK_BYTES, box_a = box_m + 2 * CHUNK_BYTES;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float z[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = hf * 16 + i;
-          z[i] = gate_act(g[j] + bias[ch * 32 + j], f[j] + bias[128 + ch * 32 + j]);
+    gate_epilogue<P>(sv, p, tmem_base, warp, lane, nb, nblk, t0);
+  }
+  teardown<P, PAIR>(tmem_base, warp);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// gate kernel, window variant (CTA pairs, aux operands).  The 9 dilated taps of one 64-channel chunk read the SAME
+// activation rows shifted by tap*dil frames, so the window [t0 - 4*dil, t0 + 128 + 4*dil) is fetched ONCE per chunk and
+// every tap's A descriptor just starts tap*dil rows (x 128 B) further into it.  Shared-memory fill traffic per K-slab
+// drops from 64 KB to ~37 KB (the weight half-tile dominates), which matters because MMA operand reads + TMA fills
+// run right at the 128 B/clk shared-memory limit otherwise.
+//   ring: 2 window buffers x (24 KB main + 24 KB aux)  |  3 weight stages x (16 KB main + 16 KB aux)
+// ---------------------------------------------------------------------------------------------
+constexpr int WIN_BUF_BYTES = 49152;   // 192 rows x 128 B, main + aux
+constexpr int WIN_HALF = 24576;
+constexpr int WIN_BSTAGE = 32768;
+constexpr int WIN_BSTAGES = 3;
+
+template <int P>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_win_kernel(const __grid_constant__ GateParams p) {
+  static_assert(P != 0, "window kernel needs aux operands");
+  constexpr bool PAIR = true;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemView sv = carve<P, PAIR>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  int cid = (int)(blockIdx.x >> 1);
+  const int nblk = cid % p.n_blocks; cid /= p.n_blocks;
+  const int mt = cid * 2 + (int)rank;
+  const int tt = mt % p.tiles_t;
+  const int nb = mt / p.tiles_t;
+  const int t0 = tt * TILE_M;
+  const int cpt = p.C / TILE_K;                       // conv chunks (64 channels each)
+  const int nb_first = (cid * 2) / p.tiles_t;
+  const int nchunks = cpt + (nb_first < p.n_cond ? p.cond_slabs : 0);   // conditioner chunks have a single slab
+  const int half = p.taps / 2;
+  constexpr int AM = P == 2 ? 2 : 1;
+  uint8_t* const wbuf = sv.stage0;                                   // 2 window buffers
+  uint8_t* const bring = sv.stage0 + 2 * WIN_BUF_BYTES;              // 3 weight stages
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.xwh); tma_prefetch_desc(&p.xwl); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.wd_l);
+    tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.zl);
+  }
+  if (warp == 3) {
+    const float* bsrc = (nb < p.n_cond ? p.bias_cond : p.bias_unc) + nblk * TILE_N;
+    for (int i = lane; i < TILE_N; i += 32) sv.sbias[i] = __ldg(bsrc + i);
+  }
+  prologue<P, PAIR>(sv, warp);
+  const uint32_t tmem_base = *sv.tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int a_fill = 0;                 // chunks whose window load has been issued
+      auto issue_window = [&](int c) {
+        const int ai = c & 1;
+        mbar_wait(&sv.aempty[ai], ((c >> 1) & 1) ^ 1);
+        const uint32_t fb = mapa_cluster(smem_u32(&sv.afull[ai]), 0);
+        uint8_t* dst = wbuf + ai * WIN_BUF_BYTES;
+        if (c < cpt) {
+          mbar_expect_tx_cluster(fb, 2u * (uint32_t)p.win_rows * 128u);
+          tma_load_3d_pair(dst, &p.xwh, fb, c * TILE_K, t0 - half * p.dil, nb);
+          tma_load_3d_pair(dst + WIN_HALF, &p.xwl, fb, AM * c * TILE_K, t0 - half * p.dil, nb);
+        } else {
+          mbar_expect_tx_cluster(fb, 2u * A_TILE_BYTES);
+          tma_load_3d_pair(dst, &p.sh, fb, (c - cpt) * TILE_K, t0, nb);
+          tma_load_3d_pair(dst + WIN_HALF, &p.sl, fb, AM * (c - cpt) * TILE_K, t0, nb);
         }
-        stage16<P>(box_m, box_a, row, (ch & 1) * 32 + hf * 16, z);
+        a_fill = c + 1;
+      };
+      issue_window(0);
+      int bs = 0; uint32_t bphase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int nsl = c < cpt ? p.taps : 1;
+        for (int j = 0; j < nsl; ++j) {
+          // prefetch the next chunk's window once the MMAs are safely past the previous user of that buffer
+          if (a_fill == c + 1 && c + 1 < nchunks && j >= (nsl > 4 ? 4 : nsl - 1)) issue_window(c + 1);
+          mbar_wait(&sv.empty[bs], bphase ^ 1);
+          const uint32_t fb = mapa_cluster(smem_u32(&sv.full[bs]), 0);
+          uint8_t* dst = bring + bs * WIN_BSTAGE;
+          mbar_expect_tx_cluster(fb, WIN_BSTAGE);
+          const int row0 = nblk * TILE_N + (int)rank * (TILE_N / 2);
+          if (c < cpt) {
+            const int col = j * p.C + c * TILE_K;
+            tma_load_2d_pair(dst, &p.wd_h, fb, col, row0);
+            tma_load_2d_pair(dst + WIN_BSTAGE / 2, &p.wd_l, fb, AM * col, row0);
+          } else {
+            const int col = (c - cpt) * TILE_K;
+            tma_load_2d_pair(dst, &p.wc_h, fb, col, row0);
+            tma_load_2d_pair(dst + WIN_BSTAGE / 2, &p.wc_l, fb, AM * col, row0);
+          }
+          if (++bs == WIN_BSTAGES) { bs = 0; bphase ^= 1; }
+        }
       }
     }
-    tc_fence_before();
-    fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA (async proxy)
-    named_bar_sync(EPI_BAR, EPI_THREADS);
-    if (warp == 4 && elect_one()) {
-      const int c0 = nblk * (TILE_N / 2);
-      tma_store_3d(&p.zh, sv.stage0, c0, t0, p.z_group0 + nb);
-      tma_store_3d(&p.zh, sv.stage0 + CHUNK_BYTES, c0 + 64, t0, p.z_group0 + nb);
-      if (CF::kAux) {
-        tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, AM * c0, t0, p.z_group0 + nb);
-        tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, AM * (c0 + 64), t0, p.z_group0 + nb);
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = P == 2 ? make_idesc_fmt0(2 * TILE_M, TILE_N) : make_idesc_bf16(2 * TILE_M, TILE_N);
+      int bs = 0; uint32_t bphase = 0;
+      bool first = true;
+      for (int c = 0; c < nchunks; ++c) {
+        const int ai = c & 1;
+        mbar_wait(&sv.afull[ai], (c >> 1) & 1);
+        const int nsl = c < cpt ? p.taps : 1;
+        const uint32_t a_main = smem_u32(wbuf + ai * WIN_BUF_BYTES), a_aux = a_main + WIN_HALF;
+        for (int j = 0; j < nsl; ++j) {
+          mbar_wait(&sv.full[bs], bphase);
+          tc_fence_after();
+          const uint32_t shift = c < cpt ? (uint32_t)(j * p.dil) * 128u : 0u;   // tap j starts j*dil frames into the window
+          const uint32_t b_main = smem_u32(bring + bs * WIN_BSTAGE), b_aux = b_main + WIN_BSTAGE / 2;
+#pragma unroll
+          for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+            const uint32_t ko = k * UMMA_K * 2;
+            const uint64_t da = make_sw128_desc(a_main + shift + ko), db = make_sw128_desc(b_main + ko);
+            const uint32_t acc = (first && k == 0) ? 0u : 1u;
+            umma_bf16_pair(tmem_base, da, db, idesc, acc);
+            if (P == 1) {
+              umma_bf16_pair(tmem_base, make_sw128_desc(a_aux + shift + ko), db, idesc, 1u);
+              umma_bf16_pair(tmem_base, da, make_sw128_desc(b_aux + ko), idesc, 1u);
+            }
+            if (P == 2) umma_f8_pair(tmem_base + 256, make_sw128_desc(a_aux + shift + ko), make_sw128_desc(b_aux + ko), idesc, acc);
+          }
+          first = false;
+          umma_commit_pair(&sv.empty[bs]);
+          if (++bs == WIN_BSTAGES) { bs = 0; bphase ^= 1; }
+        }
+        umma_commit_pair(&sv.aempty[ai]);   // window buffer free (in both CTAs) once this chunk's MMAs retire
       }
-      tma_store_commit();
-      tma_store_wait_read<0>();  // smem must stay valid until the bulk stores have read it
+      umma_commit_pair(sv.tmem_full);
     }
+  } else if (warp >= 4) {
+    gate_epilogue<P>(sv, p, tmem_base, warp, lane, nb, nblk, t0);
   }
   teardown<P, PAIR>(tmem_base, warp);
 }
@@ -554,6 +701,7 @@ int umma_init() {
   set((const void*)umma_gate_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_gate_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_gate_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_gate_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_gate_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_gate_kernel<2, true>, Cfg<2, false>::kSmemBytes);
+  set((const void*)umma_gate_win_kernel<1>, Cfg<1, true>::kSmemBytes); set((const void*)umma_gate_win_kernel<2>, Cfg<2, true>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2, false>::kSmemBytes);
@@ -628,6 +776,14 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = g.inv_scale;
   const bool mc = g.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  // window variant: the tap window 128 + (taps-1)*dil frames must fit the 192-row buffers
+  const int win_rows = TILE_M + (g.taps - 1) * g.dil;
+  if (mc && g.window && g.prec != 0 && win_rows <= 192 && g.xwh && g.xwl) {
+    p.xwh = *g.xwh; p.xwl = *g.xwl; p.win_rows = win_rows;
+    return g.prec == 1 ? launch_k(umma_gate_win_kernel<1>, p, grid, Cfg<1, true>::kSmemBytes, true, s)
+                       : launch_k(umma_gate_win_kernel<2>, p, grid, Cfg<2, true>::kSmemBytes, true, s);
+  }
+  p.xwh = maps.xh; p.xwl = maps.xl; p.win_rows = TILE_M;
   if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
                              : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
   if (g.prec == 2) return mc ? launch_k(umma_gate_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)

@@ -6,6 +6,8 @@ Tolerances (written here, as BASELINE.json's north_star asks):
   * one network forward / one sampler step: 2e-4 for the fp32 CUDA-core path, 5e-4 for bf16x3
   * normalised log-mel spectrogram (values in [0,1]): 2e-4
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -197,7 +199,10 @@ def test_tensor_path_matches_fp32_path_per_layer(precision):
         a, b = engs[0].buffer("x32"), engs[1].buffer("x32")
         err = float((a - b).abs().max()); ref = float(a.abs().max())
         worst = max(worst, err / max(ref, 1.0))
-        assert err < 2e-4 * max(ref, 1.0), (layer, "x32", err, ref)
+        if os.environ.get("DRB_TRACE_LAYERS"):
+            record(f"  layer {layer} (dil {2 ** (layer % 4)}): x32 err {err:.3e} ref {ref:.3e}")
+        else:
+            assert err < 2e-4 * max(ref, 1.0), (layer, "x32", err, ref)
     # head: the fp32 path sums a skip buffer and applies skip_projection; the tensor path runs one long-K GEMM over
     # the stored z of all layers with composed weights.  Both leave relu(skip_projection(...)) in "h".
     outs = []
