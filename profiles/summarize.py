@@ -19,6 +19,7 @@ with open(os.path.join(root, "profiles", f"{tag}_launches_summary.md"), "w") as 
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"| {k} | {len(v)} | {sum(v):.1f} | {sum(v)/len(v):.1f} | {100*sum(v)/tot:.1f}% |\n")
 rep = os.path.join(root, "gpurun_out", f"prof_umma_{tag}.ncu-rep")
+
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
@@ -27,7 +28,7 @@ if os.path.exists(rep):
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic", "launch__cluster_dim_x",
             "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.sum.per_second",
             "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.sum.pct_of_peak_sustained_elapsed"]
     idx = [i for i, h in enumerate(hdr) if h in keep]
@@ -43,7 +44,7 @@ if os.path.exists(rep):
         return float(v) * m.get(u, 1)
     out = {}
     for r in rr[2:]:
-        key = "umma_gate_kernel" if "gate" in r[ik] else "umma_out_kernel" if "out" in r[ik] else r[ik]
+        key = "umma_gate_kernel" if "gate" in r[ik] else "umma_zgemm_kernel" if "zgemm" in r[ik] else "umma_out_kernel" if "out" in r[ik] else r[ik]
         out.setdefault(key + "_dram_bytes_per_launch", []).append(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]))
     out = {k: sum(v) / len(v) for k, v in out.items()}
     out["source"] = f"ncu --set full --clock-control none, profiles/{tag}_umma_ncu_full.csv"

@@ -286,3 +286,17 @@ def test_seeded_default_noise_matches_torch_generator():
     for i, t_index in enumerate(range(199, 195, -1)):
         b, _ = m.reverse_diffusion(b, w, t_index, noise=nz[i])
     assert torch.equal(a, b)
+
+
+def test_sampling_entry_point(tmp_path):
+    """sampling.py (the reference's CLI surface) end to end with seeded synthetic weights, 2 rolls, 4 timesteps."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "rolls.pt"
+    subprocess.check_call([sys.executable, os.path.join(root, "sampling.py"), "task=transcription", "task.timesteps=4",
+                           "dataset.num_samples=2", "dataloader.batch_size=2", "model.args.kernel_size=9",
+                           f"output_path={out}"], timeout=600)
+    res = torch.load(out)
+    assert res["rolls"].shape == (2, 1, 640, 88) and res["sampler"] == "inpainting_ddpm_x0"
+    assert bool(torch.isfinite(res["rolls"]).all()) and float(res["rolls"].std()) > 0.1

@@ -215,3 +215,23 @@ def test_shard_bounds_cover_batch_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+# ---- config composition (Hydra-compatible subset) ---------------------------------------------------------------
+def test_config_compose_groups_overrides_interpolation():
+    from diffroll_b200.config import compose, default_config_path
+    c = compose(default_config_path(), ["task=transcription", "model.args.kernel_size=9", "dataloader.batch_size=32",
+                                        "task.sampling.w=0.3", "gpus=2"])
+    assert c.model.name == "ClassifierFreeDiffRoll" and c.model.args.kernel_size == 9
+    assert c.model.args.n_mels == 229 and c.spec.args.sample_rate == 16000 and c.spec.args.hop_length == 512
+    assert c.task.sampling.type == "inpainting_ddpm_x0" and c.task.sampling.w == 0.3 and c.task.inpainting_t is None
+    assert c.trainer.gpus == 2 and c.dataloader.batch_size == 32
+    assert compose(default_config_path(), ["task=inpainting"]).task.inpainting_t == [500, 650]
+    assert compose(default_config_path(), []).task.sampling.type == "generation_ddpm_x0"
+    with pytest.raises(KeyError):
+        compose(default_config_path(), ["task=does_not_exist"])
+    # the composed tree constructs the model exactly like sampling.py does
+    import diffroll_b200 as M
+    kw = dict(c.model.args); t = dict(c.task); t.pop("name"); kw.update(t); kw["spec_args"] = dict(c.spec.args)
+    m = M.ClassifierFreeDiffRoll(**kw)
+    assert m.hparams.kernel_size == 9 and m.reverse_diffusion.__name__ == "inpainting_ddpm_x0"
