@@ -285,7 +285,7 @@ def run_b200(args, rank, world, local):
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": traffic,
         "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step); burst {peaks['bf16']}",
-        "mma_multiplicity": {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1),
+        "mma_multiplicity": {"bf16x3": 3, "f16f8": 2, "f16e5": 2}.get(args.precision, 1),
         "algorithmic_flops_per_launch": gate_flops,
         "avg_launch_ms": gate_avg_s * 1e3, "launches_timed": gate_n,
         "share_of_step": (gate_ms / n_prof) / step_ms_prof if step_ms_prof else None,
@@ -303,7 +303,8 @@ def run_b200(args, rank, world, local):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16x3": "bf16x3 (bf16 hi/lo split, 3 tcgen05 products, fp32 accumulate)",
-                  "f16f8": "f16f8 (fp16 tcgen05 product + e4m3 correction product, fp32 accumulate)"}.get(args.precision, args.precision),
+                  "f16f8": "f16f8 (fp16 tcgen05 product + e4m3 correction product, fp32 accumulate)",
+                  "f16e5": "f16e5 (fp16 tcgen05 product + e5m2 correction product, one fp32 accumulator)"}.get(args.precision, args.precision),
         "data": "synthetic",
         "config": {"workload": f"configs[1]: batch={args.batch} per GPU, synthetic 640x88 rolls + 229-bin mel, "
                                "inpainting_ddpm_x0 w=0.5 (2 network forwards/step), timesteps=200, ClassifierFreeDiffRoll k=9, random weights",
@@ -325,7 +326,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="f16f8", choices=["f16f8", "bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="f16f8", choices=["f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -37,7 +37,7 @@ static bool cfg_ok(const drb_config& c) {
   if (c.residual_channels <= 0 || c.residual_channels % 256) return false;
   if (c.residual_layers <= 0 || c.kernel_size <= 0 || !(c.kernel_size & 1)) return false;
   if (c.dilation_base <= 0 || c.dilation_bound <= 0 || c.n_mels <= 0 || c.n_fft <= 0 || c.hop_length <= 0) return false;
-  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 3 || c.branches < 0 || c.branches > 3) return false;
+  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 4 || c.branches < 0 || c.branches > 3) return false;
   if (c.wave_len / c.hop_length + 1 < c.frames) return false;
   if (c.wave_len <= c.n_fft / 2) return false;  // reflect padding needs pad < length
   return true;
@@ -103,7 +103,7 @@ struct drb_plan {
   UmmaMaps maps;
   std::vector<UmmaLayer> layers;
   std::vector<CUtensorMap> win_h, win_l;  // per layer: x operand maps whose box covers the layer's whole tap window
-  int window = 1;
+  int window = 1, persistent = 1;
   // optional per-kernel timing (drb_plan_profile): events recorded on the launching stream around every kernel class
   cudaStream_t copy_stream = nullptr;  // trajectory copies (drb_sample_loop)
   cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -121,8 +121,8 @@ struct drb_plan {
     return at<float>(lay.bias) + ((size_t)layer * 4 + which) * 2 * cfg.residual_channels;
   }
   // tensor-path arithmetic: kernel template mode (0 bf16, 1 bf16x3, 2 f16f8) and operand format (1 bf16 hi/lo, 2 fp16+e4m3)
-  int prec() const { return cfg.precision == DRB_PREC_BF16X3 ? 1 : cfg.precision == DRB_PREC_F16F8 ? 2 : 0; }
-  int fmt() const { return cfg.precision == DRB_PREC_FP32 ? 0 : cfg.precision == DRB_PREC_F16F8 ? 2 : 1; }
+  int prec() const { return cfg.precision == DRB_PREC_BF16X3 ? 1 : cfg.precision == DRB_PREC_F16F8 ? 2 : cfg.precision == DRB_PREC_F16E5 ? 3 : 0; }
+  int fmt() const { return cfg.precision == DRB_PREC_FP32 ? 0 : cfg.precision == DRB_PREC_F16F8 ? 2 : cfg.precision == DRB_PREC_F16E5 ? 3 : 1; }
   float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head
   const float* dvec(int layer, int t) const {
     return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
@@ -169,6 +169,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
   p->tables_ready = false; p->spec_ready = false;
   { const char* e = getenv("DRB_NO_PAIR"); p->pair = (e && e[0] == '1') ? 0 : 1; }
   { const char* e = getenv("DRB_NO_WINDOW"); p->window = (e && e[0] == '1') ? 0 : 1; }
+  { const char* e = getenv("DRB_NO_PERSIST"); p->persistent = (e && e[0] == '1') ? 0 : 1; }
   const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
   p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
   p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
@@ -195,7 +196,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
     } else {
       PLAN_TRY(launch_repack_conv_fp32(w->dilated_conv_w[i], tmp, 2 * C, C, k, s));
       const int fmt = p->fmt();
-      const int dm = fmt == 2 ? 2 : 0, da = fmt == 2 ? 3 : 0, am = fmt == 2 ? 2 : 1;  // tensor-map dtypes, aux width factor
+      const int dm = fmt >= 2 ? 2 : 0, da = fmt >= 2 ? 3 : 0, am = fmt >= 2 ? 2 : 1;  // tensor-map dtypes, aux width factor
       if (fmt == 2) {
         PLAN_TRY(launch_weight_scale(tmp, (size_t)2 * C * k * C, w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels,
                                      p->wscale(2 * i), s));
@@ -223,8 +224,8 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
   if (tensor) {
     const uint64_t NBc = lay.NBcap;
     const int fmt = p->fmt();
-    const int dm = fmt == 2 ? 2 : 0, da = fmt == 2 ? 3 : 0;
-    const uint64_t am = fmt == 2 ? 2 : 1;
+    const int dm = fmt >= 2 ? 2 : 0, da = fmt >= 2 ? 3 : 0;
+    const uint64_t am = fmt >= 2 ? 2 : 1;
     PLAN_TRY(make_tmap_3d(&p->maps.xh, p->ws + lay.xh, NBc, T, C, 128, dm));
     PLAN_TRY(make_tmap_3d(&p->maps.xl, p->ws + lay.xl, NBc, T, am * C, 128, da));
     for (int i = 0; i < L; ++i) {
@@ -359,7 +360,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   UmmaGate ug;
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
-  ug.pair = p->pair; ug.window = p->window; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
+  ug.pair = p->pair; ug.window = p->window; ug.persistent = p->persistent; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;

@@ -83,6 +83,24 @@ __device__ __forceinline__ void split_f16f8_x4(const float (&v)[4], uint32_t& h0
   hi4 = (uint32_t)pack_e4m3x2(fa.x, fa.y) | ((uint32_t)pack_e4m3x2(fb.x, fb.y) << 16);
 }
 
+// "f16e5": same idea with e5m2 corrections whose scales multiply to ONE, so the correction MMA accumulates straight into the
+// main accumulator (no second accumulator -> TMEM has room for two accumulator stages):
+//   [l_a*2^4 | e5m2(h_a*2^-8)] . [e5m2(h_b*2^-4) | e5m2(l_b*2^8)]     (e5m2's 5 exponent bits give the range, its 2 mantissa
+//   bits leave ~2^-15 relative error: 200-step chain error ~2e-4 instead of ~1e-4, still 5x inside the 1e-3 bar)
+__device__ __forceinline__ uint16_t pack_e5m2x2(float a, float b) {
+  return (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+}
+__device__ __forceinline__ void split_f16e5_x4(const float (&v)[4], uint32_t& h01, uint32_t& h23, uint32_t& lo4, uint32_t& hi4) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  h01 = *reinterpret_cast<const uint32_t*>(&a);
+  h23 = *reinterpret_cast<const uint32_t*>(&b);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  lo4 = (uint32_t)pack_e5m2x2((v[0] - fa.x) * 16.f, (v[1] - fa.y) * 16.f) |
+        ((uint32_t)pack_e5m2x2((v[2] - fb.x) * 16.f, (v[3] - fb.y) * 16.f) << 16);
+  hi4 = (uint32_t)pack_e5m2x2(fa.x * 0.00390625f, fa.y * 0.00390625f) |
+        ((uint32_t)pack_e5m2x2(fb.x * 0.00390625f, fb.y * 0.00390625f) << 16);
+}
+
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------
@@ -162,6 +180,10 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) 
 // arrive + expect_tx on a (possibly remote) barrier given by its shared::cluster address
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+// plain arrive on a (possibly remote) barrier given by its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair: data lands in the issuing CTA's smem, completion bytes go to the barrier
 // at `bar_cluster_addr` (the leader CTA's full barrier).

@@ -89,6 +89,7 @@ struct UmmaMaps {
 struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl[z_group0 + roll]
   int NB, n_cond, T, C, taps, dil, Mp, prec, z_group0;  // prec: 0 bf16, 1 bf16x3, 2 f16f8
   int pair = 1;  // CTA pairs (cta_group::2, M = 256) when the M-tile count is even
+  int persistent = 1;  // persistent CTA pairs with two TMEM accumulator stages (bf16x3 / f16e5 only)
   int window = 1;  // fetch the tap window once per channel chunk (needs pair, aux operands and the window maps)
   const CUtensorMap *xwh = nullptr, *xwl = nullptr;  // activation maps with box rows = 128 + (taps-1)*dil
   const float* inv_scale;

@@ -161,13 +161,18 @@ __global__ void __launch_bounds__(256) spec_finalize_kernel(const float* __restr
     if (fmt == 1) {
       __nv_bfloat16 h, l; split_bf16(v, h, l);
       reinterpret_cast<__nv_bfloat16*>(spec_main)[o] = h; reinterpret_cast<__nv_bfloat16*>(spec_aux)[o] = l;
-    } else if (fmt == 2) {   // fp16 + e4m3 bytes [lo*SA (64) | hi (64)] per 64-mel chunk
+    } else if (fmt >= 2) {   // fp16 + fp8 bytes [lo (64) | hi (64)] per 64-mel chunk (scales: see common.cuh)
       const __half h = __float2half_rn(v);
       const float hf = __half2float(h);
       reinterpret_cast<__half*>(spec_main)[o] = h;
       uint8_t* a8 = reinterpret_cast<uint8_t*>(spec_aux) + ((size_t)b * T + t) * 2 * Mp + (size_t)(m >> 6) * 128 + (m & 63);
-      a8[0] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * F8_SA, __NV_SATFINITE, __NV_E4M3);
-      a8[64] = (uint8_t)__nv_cvt_float_to_fp8(hf, __NV_SATFINITE, __NV_E4M3);
+      if (fmt == 2) {
+        a8[0] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * F8_SA, __NV_SATFINITE, __NV_E4M3);
+        a8[64] = (uint8_t)__nv_cvt_float_to_fp8(hf, __NV_SATFINITE, __NV_E4M3);
+      } else {
+        a8[0] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * 16.f, __NV_SATFINITE, __NV_E5M2);
+        a8[64] = (uint8_t)__nv_cvt_float_to_fp8(hf * 0.00390625f, __NV_SATFINITE, __NV_E5M2);
+      }
     }
   }
   __syncthreads();

@@ -239,9 +239,9 @@ __device__ __forceinline__ void store_operand4(void* mainp, void* auxp, size_t r
     split_pack2(v[2], v[3], h1, l1);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(mainp) + row * C + c) = make_uint2(h0, h1);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(auxp) + row * C + c) = make_uint2(l0, l1);
-  } else if (fmt == 2) {
+  } else if (fmt >= 2) {
     uint32_t h01, h23, lo4, hi4;
-    split_f16f8_x4(v, h01, h23, lo4, hi4);
+    if (fmt == 2) split_f16f8_x4(v, h01, h23, lo4, hi4); else split_f16e5_x4(v, h01, h23, lo4, hi4);
     *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(mainp) + row * C + c) = make_uint2(h01, h23);
     uint8_t* a8 = reinterpret_cast<uint8_t*>(auxp) + row * 2 * C + (size_t)(c >> 6) * 128 + (c & 63);
     *reinterpret_cast<uint32_t*>(a8) = lo4;
@@ -310,13 +310,18 @@ __global__ void repack_split_kernel(const float* __restrict__ w, void* __restric
     split_bf16(v, hh, ll);
     reinterpret_cast<__nv_bfloat16*>(mainp)[idx] = hh; reinterpret_cast<__nv_bfloat16*>(auxp)[idx] = ll;
   } else {
-    const float sw = scale[0];
     const __half hh = __float2half_rn(v);
     const float hf = __half2float(hh);
     reinterpret_cast<__half*>(mainp)[idx] = hh;
     uint8_t* a8 = reinterpret_cast<uint8_t*>(auxp) + (size_t)np * 2 * Kp + (size_t)(kk >> 6) * 128 + (kk & 63);
-    a8[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * sw, __NV_SATFINITE, __NV_E4M3);
-    a8[64] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * (F8_SA * sw), __NV_SATFINITE, __NV_E4M3);
+    if (fmt == 2) {
+      const float sw = scale[0];
+      a8[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * sw, __NV_SATFINITE, __NV_E4M3);
+      a8[64] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * (F8_SA * sw), __NV_SATFINITE, __NV_E4M3);
+    } else {  // f16e5: [hi * 2^-4 | lo * 2^8], pairs with activations [lo * 2^4 | hi * 2^-8]
+      a8[0] = (uint8_t)__nv_cvt_float_to_fp8(hf * 0.0625f, __NV_SATFINITE, __NV_E5M2);
+      a8[64] = (uint8_t)__nv_cvt_float_to_fp8((v - hf) * 256.f, __NV_SATFINITE, __NV_E5M2);
+    }
   }
 }
 int launch_repack_split(const float* w, void* mainp, void* auxp, int OC, int Kin, int Kp, int interleave_C, int fmt,

@@ -49,6 +49,7 @@ constexpr int EPI_THREADS = 256;
 //   1  bf16x3   bf16 hi/lo, 3 products into one accumulator      aux = bf16 lo tiles
 //   2  f16f8    fp16 product + e4m3 correction product          aux = e4m3 tiles [lo*SA | hi] / [hi*SW | lo*SA*SW],
 //                                                                second accumulator (TMEM columns 256..511)
+//   3  f16e5    fp16 product + e5m2 correction product          aux = e5m2 tiles, unit total scale: same accumulator
 template <int P, bool PAIR>
 struct Cfg {
   static constexpr bool kAux = P != 0;
@@ -58,7 +59,7 @@ struct Cfg {
   static constexpr int kStages = kRingBytes / kStageBytes;                 // 2 (single) / 3 (pair) with aux operands
   static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, d_next*/;
   static constexpr uint32_t kTmemCols = P == 2 ? 512 : 256;
-  static constexpr int kAuxMul = P == 2 ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
+  static constexpr int kAuxMul = P >= 2 ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
   static constexpr int kAOff = 0, kAAuxOff = A_TILE_BYTES;
   static constexpr int kBOff = (kAux ? 2 : 1) * A_TILE_BYTES, kBAuxOff = kBOff + kBBytes;
   static constexpr int kMaxStages = 6;
@@ -67,7 +68,7 @@ struct Cfg {
 struct alignas(64) GateParams {
   CUtensorMap xh, xl, sh, sl, wd_h, wd_l, wc_h, wc_l, zh, zl;
   CUtensorMap xwh, xwl;  // activation maps whose box spans the whole tap window: 128 + (taps-1)*dil frames
-  int win_rows;
+  int win_rows, n_items;
   int NB, n_cond, T, C, taps, dil, cond_slabs, tiles_t, n_blocks, z_group0;
   const float* bias_cond;
   const float* bias_unc;
@@ -173,7 +174,8 @@ __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool fi
   const uint32_t a_hi = smem_u32(st) + C::kAOff, a_lo = smem_u32(st) + C::kAAuxOff;
   const uint32_t b_hi = smem_u32(st) + C::kBOff, b_lo = smem_u32(st) + C::kBAuxOff;
   constexpr int M = PAIR ? 2 * TILE_M : TILE_M;
-  constexpr uint32_t idesc = P == 2 ? make_idesc_fmt0(M, TILE_N) : make_idesc_bf16(M, TILE_N);
+  constexpr uint32_t idesc = P >= 2 ? make_idesc_fmt0(M, TILE_N) : make_idesc_bf16(M, TILE_N);
+  constexpr uint32_t idesc_e5 = make_idesc_bf16(M, TILE_N);   // kind::f8f6f4 format code 1 = e5m2 (same bits as bf16 for kind::f16)
   const uint32_t acc0 = first_slab ? 0u : 1u;
 #pragma unroll
   for (int k = 0; k < TILE_K / UMMA_K; ++k) {
@@ -187,6 +189,7 @@ __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool fi
         umma_bf16_pair(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
       }
       if (P == 2) umma_f8_pair(tmem_d + 256, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc, acc);
+      if (P == 3) umma_f8_pair(tmem_d, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc_e5, 1u);
     } else {
       umma_bf16(tmem_d, da_hi, db_hi, idesc, acc);
       if (P == 1) {
@@ -194,6 +197,7 @@ __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool fi
         umma_bf16(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
       }
       if (P == 2) umma_f8(tmem_d + 256, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc, acc);
+      if (P == 3) umma_f8(tmem_d, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc_e5, 1u);
     }
   }
 }
@@ -245,12 +249,13 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float inv_scale, floa
 // parts (same shape) or e4m3 bytes [lo*SA (64) | hi (64)] per row.
 template <int P>
 __device__ __forceinline__ void stage16(uint32_t main_box, uint32_t aux_box, int row, int ch, const float (&v)[16]) {
-  if (P == 2) {
+  if (P >= 2) {
     uint32_t h[8], lo[4], hi[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float t[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
-      split_f16f8_x4(t, h[2 * q], h[2 * q + 1], lo[q], hi[q]);
+      if (P == 2) split_f16f8_x4(t, h[2 * q], h[2 * q + 1], lo[q], hi[q]);
+      else split_f16e5_x4(t, h[2 * q], h[2 * q + 1], lo[q], hi[q]);
     }
     sts128u(main_box + sw128_off(row, ch / 8), h[0], h[1], h[2], h[3]);
     sts128u(main_box + sw128_off(row, ch / 8 + 1), h[4], h[5], h[6], h[7]);
@@ -308,8 +313,8 @@ __device__ __forceinline__ void gate_epilogue(const SmemView& sv, const GatePara
       tma_store_3d(&p.zh, sv.stage0, c0, t0, p.z_group0 + nb);
       tma_store_3d(&p.zh, sv.stage0 + CHUNK_BYTES, c0 + 64, t0, p.z_group0 + nb);
       if ((P != 0)) {
-        tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, (P == 2 ? 2 : 1) * c0, t0, p.z_group0 + nb);
-        tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, (P == 2 ? 2 : 1) * (c0 + 64), t0, p.z_group0 + nb);
+        tma_store_3d(&p.zl, sv.stage0 + 2 * CHUNK_BYTES, (P >= 2 ? 2 : 1) * c0, t0, p.z_group0 + nb);
+        tma_store_3d(&p.zl, sv.stage0 + 3 * CHUNK_BYTES, (P >= 2 ? 2 : 1) * (c0 + 64), t0, p.z_group0 + nb);
       }
       tma_store_commit();
       tma_store_wait_read<0>();  // smem must stay valid until the bulk stores have read it
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_win_kernel(const __g
   const int nb_first = (cid * 2) / p.tiles_t;
   const int nchunks = cpt + (nb_first < p.n_cond ? p.cond_slabs : 0);   // conditioner chunks have a single slab
   const int half = p.taps / 2;
-  constexpr int AM = P == 2 ? 2 : 1;
+  constexpr int AM = P >= 2 ? 2 : 1;
   uint8_t* const wbuf = sv.stage0;                                   // 2 window buffers
   uint8_t* const bring = sv.stage0 + 2 * WIN_BUF_BYTES;              // 3 weight stages
 
@@ -485,7 +490,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_win_kernel(const __g
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = P == 2 ? make_idesc_fmt0(2 * TILE_M, TILE_N) : make_idesc_bf16(2 * TILE_M, TILE_N);
+      constexpr uint32_t idesc = P >= 2 ? make_idesc_fmt0(2 * TILE_M, TILE_N) : make_idesc_bf16(2 * TILE_M, TILE_N);
+      constexpr uint32_t idesc_e5 = make_idesc_bf16(2 * TILE_M, TILE_N);
       int bs = 0; uint32_t bphase = 0;
       bool first = true;
       for (int c = 0; c < nchunks; ++c) {
@@ -509,6 +515,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_win_kernel(const __g
               umma_bf16_pair(tmem_base, da, make_sw128_desc(b_aux + ko), idesc, 1u);
             }
             if (P == 2) umma_f8_pair(tmem_base + 256, make_sw128_desc(a_aux + shift + ko), make_sw128_desc(b_aux + ko), idesc, acc);
+            if (P == 3) umma_f8_pair(tmem_base, make_sw128_desc(a_aux + shift + ko), make_sw128_desc(b_aux + ko), idesc_e5, 1u);
           }
           first = false;
           umma_commit_pair(&sv.empty[bs]);
@@ -522,6 +529,277 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_win_kernel(const __g
     gate_epilogue<P>(sv, p, tmem_base, warp, lane, nb, nblk, t0);
   }
   teardown<P, PAIR>(tmem_base, warp);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// gate kernel, persistent window variant (CTA pairs; precisions with ONE 256-column accumulator: bf16x3, f16e5).
+// One CTA pair per SM pair loops over its tiles; TMEM holds two accumulator stages, so the epilogue of tile i (TMEM
+// reads, gate math, operand split, TMA store) overlaps the MMAs of tile i+1, and barrier setup / TMEM allocation / the
+// first TMA round trip are paid once per launch instead of once per tile.
+//   smem: 2 window buffers (96 KB) | 3 weight stages (96 KB) | 32 KB epilogue staging (main boxes, then aux boxes)
+// ---------------------------------------------------------------------------------------------
+constexpr int PW_RING = 2 * WIN_BUF_BYTES + WIN_BSTAGES * WIN_BSTAGE;   // 192 KB
+constexpr int PW_STAGING = 2 * CHUNK_BYTES;                             // 32 KB
+constexpr int PW_SMEM = PW_RING + PW_STAGING + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
+
+template <int P>
+__device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&m)[8], uint32_t (&a)[8]) {
+  if (P >= 2) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float t[4] = {v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]};
+      if (P == 2) split_f16f8_x4(t, m[2 * q], m[2 * q + 1], a[q], a[4 + q]);
+      else split_f16e5_x4(t, m[2 * q], m[2 * q + 1], a[q], a[4 + q]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_pack2(v[2 * e], v[2 * e + 1], m[e], a[e]);
+  }
+}
+
+struct GateTile { int nblk, nb, t0, nchunks; };
+
+template <int P>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __grid_constant__ GateParams p) {
+  static_assert(P == 1 || P == 3, "needs a single 256-column accumulator");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  constexpr int AM = P >= 2 ? 2 : 1;
+
+  uint8_t* ring;
+  { uint32_t a = smem_u32(smem_raw); ring = smem_raw + (((a + 1023u) & ~1023u) - a); }
+  uint8_t* const wbuf = ring;
+  uint8_t* const bring = ring + 2 * WIN_BUF_BYTES;
+  uint8_t* const staging = ring + PW_RING;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + PW_RING + PW_STAGING);
+  uint64_t* const bfull = bars;            // [3]
+  uint64_t* const bempty = bars + 3;       // [3]
+  uint64_t* const afull = bars + 6;        // [2]
+  uint64_t* const aempty = bars + 8;       // [2]
+  uint64_t* const tfull = bars + 10;       // [2]
+  uint64_t* const tempty = bars + 12;      // [2]
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  float* const sbias = reinterpret_cast<float*>(ring + PW_RING + PW_STAGING + 256);
+
+  const int cpt = p.C / TILE_K;
+  const int half = p.taps / 2;
+  auto tile_of = [&](int item) -> GateTile {
+    GateTile t;
+    t.nblk = item % p.n_blocks;
+    const int pm = item / p.n_blocks;
+    const int mt = pm * 2 + (int)rank;
+    t.nb = mt / p.tiles_t;
+    t.t0 = (mt % p.tiles_t) * TILE_M;
+    const int nb_first = (pm * 2) / p.tiles_t;
+    t.nchunks = cpt + (nb_first < p.n_cond ? p.cond_slabs : 0);
+    return t;
+  };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.xwh); tma_prefetch_desc(&p.xwl); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.wd_l);
+    tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.zl);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&bfull[i], 2); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&afull[i], 2); mbar_init(&aempty[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16);   // 8 epilogue warps x 2 CTAs drain an accumulator stage
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- producer: windows and weight stages for every tile of this pair, in order ----------------
+      int a_issued = 0;            // windows issued so far (global over tiles)
+      int w_item = pair_id, w_c = 0;                // next window to issue
+      GateTile wt = tile_of(w_item < p.n_items ? w_item : 0);
+      auto issue_window = [&]() {
+        const int ai = a_issued & 1;
+        mbar_wait(&aempty[ai], ((a_issued >> 1) & 1) ^ 1);
+        const uint32_t fb = mapa_cluster(smem_u32(&afull[ai]), 0);
+        uint8_t* dst = wbuf + ai * WIN_BUF_BYTES;
+        if (w_c < cpt) {
+          mbar_expect_tx_cluster(fb, 2u * (uint32_t)p.win_rows * 128u);
+          tma_load_3d_pair(dst, &p.xwh, fb, w_c * TILE_K, wt.t0 - half * p.dil, wt.nb);
+          tma_load_3d_pair(dst + WIN_HALF, &p.xwl, fb, AM * w_c * TILE_K, wt.t0 - half * p.dil, wt.nb);
+        } else {
+          mbar_expect_tx_cluster(fb, 2u * A_TILE_BYTES);
+          tma_load_3d_pair(dst, &p.sh, fb, (w_c - cpt) * TILE_K, wt.t0, wt.nb);
+          tma_load_3d_pair(dst + WIN_HALF, &p.sl, fb, AM * (w_c - cpt) * TILE_K, wt.t0, wt.nb);
+        }
+        ++a_issued;
+        if (++w_c == wt.nchunks) { w_c = 0; w_item += n_pairs; if (w_item < p.n_items) wt = tile_of(w_item); }
+      };
+      int gidx = 0;                // global index of the chunk whose weight slabs are being issued
+      int bcnt = 0;
+      if (w_item < p.n_items) issue_window();
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const GateTile ti = tile_of(item);
+        const int row0 = ti.nblk * TILE_N + (int)rank * (TILE_N / 2);
+        for (int c = 0; c < ti.nchunks; ++c, ++gidx) {
+          const int nsl = c < cpt ? p.taps : 1;
+          for (int j = 0; j < nsl; ++j) {
+            if (a_issued == gidx + 1 && w_item < p.n_items && j >= (nsl > 4 ? 4 : nsl - 1)) issue_window();
+            const int bs = bcnt % WIN_BSTAGES;
+            mbar_wait(&bempty[bs], ((bcnt / WIN_BSTAGES) & 1) ^ 1);
+            const uint32_t fb = mapa_cluster(smem_u32(&bfull[bs]), 0);
+            uint8_t* dst = bring + bs * WIN_BSTAGE;
+            mbar_expect_tx_cluster(fb, WIN_BSTAGE);
+            if (c < cpt) {
+              const int col = j * p.C + c * TILE_K;
+              tma_load_2d_pair(dst, &p.wd_h, fb, col, row0);
+              tma_load_2d_pair(dst + WIN_BSTAGE / 2, &p.wd_l, fb, AM * col, row0);
+            } else {
+              const int col = (c - cpt) * TILE_K;
+              tma_load_2d_pair(dst, &p.wc_h, fb, col, row0);
+              tma_load_2d_pair(dst + WIN_BSTAGE / 2, &p.wc_l, fb, AM * col, row0);
+            }
+            ++bcnt;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ---------------- MMA issuer (leader CTA) ----------------
+      constexpr uint32_t idesc = P >= 2 ? make_idesc_fmt0(2 * TILE_M, TILE_N) : make_idesc_bf16(2 * TILE_M, TILE_N);
+      constexpr uint32_t idesc_e5 = make_idesc_bf16(2 * TILE_M, TILE_N);
+      int gidx = 0, bcnt = 0, tcnt = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs, ++tcnt) {
+        const GateTile ti = tile_of(item);
+        const int as = tcnt & 1;
+        mbar_wait(&tempty[as], ((tcnt >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * 256u;
+        bool first = true;
+        for (int c = 0; c < ti.nchunks; ++c, ++gidx) {
+          const int ai = gidx & 1;
+          mbar_wait(&afull[ai], (gidx >> 1) & 1);
+          const int nsl = c < cpt ? p.taps : 1;
+          const uint32_t a_main = smem_u32(wbuf + ai * WIN_BUF_BYTES), a_aux = a_main + WIN_HALF;
+          for (int j = 0; j < nsl; ++j, ++bcnt) {
+            const int bs = bcnt % WIN_BSTAGES;
+            mbar_wait(&bfull[bs], (bcnt / WIN_BSTAGES) & 1);
+            tc_fence_after();
+            const uint32_t shift = c < cpt ? (uint32_t)(j * p.dil) * 128u : 0u;
+            const uint32_t b_main = smem_u32(bring + bs * WIN_BSTAGE), b_aux = b_main + WIN_BSTAGE / 2;
+#pragma unroll
+            for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+              const uint32_t ko = k * UMMA_K * 2;
+              const uint64_t da = make_sw128_desc(a_main + shift + ko), db = make_sw128_desc(b_main + ko);
+              umma_bf16_pair(tmem_d, da, db, idesc, (first && k == 0) ? 0u : 1u);
+              if (P == 1) {
+                umma_bf16_pair(tmem_d, make_sw128_desc(a_aux + shift + ko), db, idesc, 1u);
+                umma_bf16_pair(tmem_d, da, make_sw128_desc(b_aux + ko), idesc, 1u);
+              }
+              if (P == 3) umma_f8_pair(tmem_d, make_sw128_desc(a_aux + shift + ko), make_sw128_desc(b_aux + ko), idesc_e5, 1u);
+            }
+            first = false;
+            umma_commit_pair(&bempty[bs]);
+          }
+          umma_commit_pair(&aempty[ai]);
+        }
+        umma_commit_pair(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (8 warps), overlapped with the next tile's MMAs ----------------
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = (int)threadIdx.x - 128;
+    const bool issuer = (warp == 4) && (lane == 0);
+    const uint32_t stg = smem_u32(staging);
+    int tcnt = 0;
+    for (int item = pair_id; item < p.n_items; item += n_pairs, ++tcnt) {
+      const GateTile ti = tile_of(item);
+      const int as = tcnt & 1;
+      // previous tile: every thread is done with sbias, and the aux stores have finished reading the staging area
+      if (issuer) tma_store_wait_read<0>();
+      named_bar_sync(EPI_BAR, EPI_THREADS);
+      sbias[etid] = __ldg((ti.nb < p.n_cond ? p.bias_cond : p.bias_unc) + ti.nblk * TILE_N + etid);
+      named_bar_sync(EPI_BAR, EPI_THREADS);
+      mbar_wait(&tfull[as], (tcnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+      uint32_t zm[2][2][8], za[2][2][8];   // [c2][hf]: packed main / aux words of 16 channels
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int ch = grp * 2 + c2;
+        float g[32], f[32];
+        load_acc32<P>(taddr + ch * 32, 0.f, g);
+        load_acc32<P>(taddr + 128 + ch * 32, 0.f, f);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float z[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int j = hf * 16 + i;
+            z[i] = gate_act(g[j] + sbias[ch * 32 + j], f[j] + sbias[128 + ch * 32 + j]);
+          }
+          pack16<P>(z, zm[c2][hf], za[c2][hf]);
+        }
+      }
+      // this warp's TMEM reads are complete: hand the accumulator stage back to the MMA issuer (leader CTA)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
+      // pass A: main boxes (group g owns box g)
+      const uint32_t box = stg + grp * CHUNK_BYTES;
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int chn = c2 * 32 + hf * 16;
+          sts128u(box + sw128_off(row, chn / 8), zm[c2][hf][0], zm[c2][hf][1], zm[c2][hf][2], zm[c2][hf][3]);
+          sts128u(box + sw128_off(row, chn / 8 + 1), zm[c2][hf][4], zm[c2][hf][5], zm[c2][hf][6], zm[c2][hf][7]);
+        }
+      fence_proxy_async();
+      named_bar_sync(EPI_BAR, EPI_THREADS);
+      const int c0 = ti.nblk * (TILE_N / 2);
+      if (issuer) {
+        tma_store_3d(&p.zh, staging, c0, ti.t0, p.z_group0 + ti.nb);
+        tma_store_3d(&p.zh, staging + CHUNK_BYTES, c0 + 64, ti.t0, p.z_group0 + ti.nb);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+      }
+      named_bar_sync(EPI_BAR, EPI_THREADS);
+      // pass B: aux boxes
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int chn = c2 * 32 + hf * 16;
+          if (P >= 2) {
+            sts128u(box + sw128_off(row, chn / 16), za[c2][hf][0], za[c2][hf][1], za[c2][hf][2], za[c2][hf][3]);
+            sts128u(box + sw128_off(row, 4 + chn / 16), za[c2][hf][4], za[c2][hf][5], za[c2][hf][6], za[c2][hf][7]);
+          } else {
+            sts128u(box + sw128_off(row, chn / 8), za[c2][hf][0], za[c2][hf][1], za[c2][hf][2], za[c2][hf][3]);
+            sts128u(box + sw128_off(row, chn / 8 + 1), za[c2][hf][4], za[c2][hf][5], za[c2][hf][6], za[c2][hf][7]);
+          }
+        }
+      fence_proxy_async();
+      named_bar_sync(EPI_BAR, EPI_THREADS);
+      if (issuer) {
+        tma_store_3d(&p.zl, staging, AM * c0, ti.t0, p.z_group0 + ti.nb);
+        tma_store_3d(&p.zl, staging + CHUNK_BYTES, AM * (c0 + 64), ti.t0, p.z_group0 + ti.nb);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_read<0>();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -701,10 +979,14 @@ int umma_init() {
   set((const void*)umma_gate_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_gate_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_gate_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_gate_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_gate_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_gate_kernel<2, true>, Cfg<2, false>::kSmemBytes);
+  set((const void*)umma_gate_kernel<3, false>, Cfg<3, false>::kSmemBytes); set((const void*)umma_gate_kernel<3, true>, Cfg<3, false>::kSmemBytes);
   set((const void*)umma_gate_win_kernel<1>, Cfg<1, true>::kSmemBytes); set((const void*)umma_gate_win_kernel<2>, Cfg<2, true>::kSmemBytes);
+  set((const void*)umma_gate_win_kernel<3>, Cfg<3, true>::kSmemBytes);
+  set((const void*)umma_gate_pers_kernel<1>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3>, PW_SMEM);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2, false>::kSmemBytes);
+  set((const void*)umma_zgemm_kernel<3, false>, Cfg<3, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<3, true>, Cfg<3, false>::kSmemBytes);
   if (ee) {
     set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(ee));
     g_encode = nullptr;
@@ -780,14 +1062,25 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   const int win_rows = TILE_M + (g.taps - 1) * g.dil;
   if (mc && g.window && g.prec != 0 && win_rows <= 192 && g.xwh && g.xwl) {
     p.xwh = *g.xwh; p.xwl = *g.xwl; p.win_rows = win_rows;
+    p.n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+    if (g.persistent && (g.prec == 1 || g.prec == 3)) {   // one CTA pair per SM pair, looping over its tiles
+      int n_sm = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+      const int pairs = p.n_items < n_sm / 2 ? p.n_items : n_sm / 2;
+      return g.prec == 1 ? launch_k(umma_gate_pers_kernel<1>, p, 2 * pairs, PW_SMEM, true, s)
+                         : launch_k(umma_gate_pers_kernel<3>, p, 2 * pairs, PW_SMEM, true, s);
+    }
     return g.prec == 1 ? launch_k(umma_gate_win_kernel<1>, p, grid, Cfg<1, true>::kSmemBytes, true, s)
-                       : launch_k(umma_gate_win_kernel<2>, p, grid, Cfg<2, true>::kSmemBytes, true, s);
+         : g.prec == 2 ? launch_k(umma_gate_win_kernel<2>, p, grid, Cfg<2, true>::kSmemBytes, true, s)
+                       : launch_k(umma_gate_win_kernel<3>, p, grid, Cfg<3, true>::kSmemBytes, true, s);
   }
-  p.xwh = maps.xh; p.xwl = maps.xl; p.win_rows = TILE_M;
+  p.xwh = maps.xh; p.xwl = maps.xl; p.win_rows = TILE_M; p.n_items = 0;
   if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
                              : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
   if (g.prec == 2) return mc ? launch_k(umma_gate_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)
                              : launch_k(umma_gate_kernel<2, false>, p, grid, Cfg<2, false>::kSmemBytes, false, s);
+  if (g.prec == 3) return mc ? launch_k(umma_gate_kernel<3, true>, p, grid, Cfg<3, false>::kSmemBytes, true, s)
+                             : launch_k(umma_gate_kernel<3, false>, p, grid, Cfg<3, false>::kSmemBytes, false, s);
   return mc ? launch_k(umma_gate_kernel<0, true>, p, grid, Cfg<0, false>::kSmemBytes, true, s)
             : launch_k(umma_gate_kernel<0, false>, p, grid, Cfg<0, false>::kSmemBytes, false, s);
 }
@@ -806,6 +1099,8 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
                              : launch_k(umma_zgemm_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
   if (z.prec == 2) return mc ? launch_k(umma_zgemm_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)
                              : launch_k(umma_zgemm_kernel<2, false>, p, grid, Cfg<2, false>::kSmemBytes, false, s);
+  if (z.prec == 3) return mc ? launch_k(umma_zgemm_kernel<3, true>, p, grid, Cfg<3, false>::kSmemBytes, true, s)
+                             : launch_k(umma_zgemm_kernel<3, false>, p, grid, Cfg<3, false>::kSmemBytes, false, s);
   return mc ? launch_k(umma_zgemm_kernel<0, true>, p, grid, Cfg<0, false>::kSmemBytes, true, s)
             : launch_k(umma_zgemm_kernel<0, false>, p, grid, Cfg<0, false>::kSmemBytes, false, s);
 }

@@ -42,6 +42,7 @@ extern "C" {
 #define DRB_PREC_BF16X3  1  /* tcgen05, bf16 hi/lo split, 3 products, fp32 accumulate (parity mode) */
 #define DRB_PREC_BF16    2  /* tcgen05, single bf16 product (fast mode, NOT within 1e-3)            */
 #define DRB_PREC_F16F8   3  /* tcgen05, fp16 product + e4m3 correction product (2 MMA units, parity-grade) */
+#define DRB_PREC_F16E5   4  /* tcgen05, fp16 product + e5m2 correction product into the same accumulator   */
 
 /* which network branches one step evaluates */
 #define DRB_BRANCH_COND_UNCOND 0  /* classifier-free pair: (1+w)*cond - w*uncond   task/diffusion.py:1007-1009 */
