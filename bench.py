@@ -326,7 +326,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="f16f8", choices=["f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="f16e5", choices=["f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
