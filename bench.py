@@ -281,7 +281,9 @@ def run_b200(args, rank, world, local):
             traffic = None
     step_ms_prof = sum(v[0] for v in prof.values()) / n_prof
     roofline = {
-        "kernel": f"umma_gate_kernel<{args.precision}>",
+        "kernel": {"f16e5": "umma_gate_pers_kernel<3> (f16e5, persistent CTA pairs, tap window)",
+                   "f16f8": "umma_gate_win_kernel<2> (f16f8, CTA pairs, tap window)",
+                   "bf16x3": "umma_gate_pers_kernel<1> (bf16x3, persistent CTA pairs, tap window)"}.get(args.precision, f"umma_gate_kernel<{args.precision}>"),
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": traffic,
         "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step); burst {peaks['bf16']}",
