@@ -367,7 +367,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   const int e1 = p->prof ? p->ev_mark(s) : -1;
   if (do_res) {  // the last layer's residual half is dead; every layer's skip half is deferred to the head GEMM
     UmmaZGemm uz;
-    uz.pair = p->pair; uz.NB = NB; uz.T = T; uz.C = C; uz.prec = ug.prec; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
+    uz.pair = p->pair; uz.persistent = p->persistent; uz.NB = NB; uz.T = T; uz.C = C; uz.prec = ug.prec; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
     uz.inv_scale = p->wscale(2 * layer + 1) + 1;
     uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
     uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, t_index);

@@ -97,7 +97,7 @@ struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filt
   const float* bias_unc;
 };
 struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
-  int pair = 1;
+  int pair = 1, persistent = 1;
   int NB, T, C, prec, mode;         // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h
   const float* inv_scale;
   int groups, z_group0, group_stride;

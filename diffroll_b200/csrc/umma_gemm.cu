@@ -953,6 +953,216 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
   teardown<P, PAIR>(tmem_base, warp);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// zgemm RES, persistent variant (CTA pairs; bf16x3 / f16e5).  The K loop of the residual GEMM is only C/64 slabs, so the
+// one-tile-per-CTA kernel is dominated by its epilogue and per-CTA setup.  Here one CTA pair per SM pair loops over its
+// tiles with two TMEM accumulator stages; the fp32 x tile streams through a 4-box ring filled by a second producer
+// thread, is updated in place, and leaves (with the next layer's operand pair) through TMA stores, all overlapped with
+// the MMAs of the following tile.
+//   smem: 2 operand stages (128 KB) | x ring 4 x 16 KB | operand staging 32 KB
+// ---------------------------------------------------------------------------------------------
+constexpr int RP_STAGE = 65536;
+constexpr int RP_STAGES = 2;
+constexpr int RP_XBOXES = 4;
+constexpr int RP_RING = RP_STAGES * RP_STAGE + RP_XBOXES * CHUNK_BYTES;   // 192 KB
+constexpr int RP_SMEM = RP_RING + 2 * CHUNK_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;   // 231,680 <= 227 KB
+
+template <int P>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __grid_constant__ ZGemmParams p) {
+  static_assert(P == 1 || P == 3, "needs a single 256-column accumulator");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  constexpr int AM = P >= 2 ? 2 : 1;
+
+  uint8_t* ring;
+  { uint32_t a = smem_u32(smem_raw); ring = smem_raw + (((a + 1023u) & ~1023u) - a); }
+  uint8_t* const xring = ring + RP_STAGES * RP_STAGE;
+  uint8_t* const staging = ring + RP_RING;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + RP_RING + 2 * CHUNK_BYTES);
+  uint64_t* const full = bars;             // [2] operand stages (leader's is used)
+  uint64_t* const empty = bars + 2;        // [2]
+  uint64_t* const tfull = bars + 4;        // [2]
+  uint64_t* const tempty = bars + 6;       // [2]
+  uint64_t* const xfull = bars + 8;        // [4] x boxes (per CTA)
+  uint64_t* const xempty = bars + 12;      // [4]
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  float* const sbias = reinterpret_cast<float*>(ring + RP_RING + 2 * CHUNK_BYTES + 256);
+
+  struct Tile { int n_base, nb, t0; };
+  auto tile_of = [&](int item) -> Tile {
+    Tile t;
+    t.n_base = (item % p.n_blocks) * TILE_N;
+    const int mt = (item / p.n_blocks) * 2 + (int)rank;
+    t.nb = mt / p.tiles_t;
+    t.t0 = (mt % p.tiles_t) * TILE_M;
+    return t;
+  };
+  const int n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_h); tma_prefetch_desc(&p.w_l);
+    tma_prefetch_desc(&p.out32); tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.xl);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 2); mbar_init(&empty[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16);
+    }
+    for (int i = 0; i < RP_XBOXES; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {          // operand producer
+      int cnt = 0;
+      for (int item = pair_id; item < n_items; item += n_pairs) {
+        const Tile ti = tile_of(item);
+        for (int s = 0; s < p.nslabs; ++s, ++cnt) {
+          const int st_i = cnt % RP_STAGES;
+          mbar_wait(&empty[st_i], ((cnt / RP_STAGES) & 1) ^ 1);
+          uint8_t* st = ring + st_i * RP_STAGE;
+          const uint32_t fb = mapa_cluster(smem_u32(&full[st_i]), 0);
+          mbar_expect_tx_cluster(fb, RP_STAGE);
+          const int zrow = p.z_group0 + ti.nb;
+          const int row0 = ti.n_base + (int)rank * (TILE_N / 2);
+          tma_load_3d_pair(st, &p.zh, fb, s * TILE_K, ti.t0, zrow);
+          tma_load_3d_pair(st + A_TILE_BYTES, &p.zl, fb, AM * s * TILE_K, ti.t0, zrow);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES, &p.w_h, fb, s * TILE_K, row0);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES + B_TILE_BYTES / 2, &p.w_l, fb, AM * s * TILE_K, row0);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (elect_one()) {          // x-box producer (this CTA's fp32 residual tiles)
+      int gb = 0;
+      for (int item = pair_id; item < n_items; item += n_pairs) {
+        const Tile ti = tile_of(item);
+        for (int c = 0; c < 8; ++c, ++gb) {
+          const int sl = gb % RP_XBOXES;
+          mbar_wait(&xempty[sl], ((gb / RP_XBOXES) & 1) ^ 1);
+          mbar_expect_tx(&xfull[sl], CHUNK_BYTES);
+          tma_load_3d(xring + sl * CHUNK_BYTES, &p.out32, &xfull[sl], ti.n_base + c * 32, ti.t0, ti.nb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {   // MMA issuer
+      constexpr uint32_t idesc = P >= 2 ? make_idesc_fmt0(2 * TILE_M, TILE_N) : make_idesc_bf16(2 * TILE_M, TILE_N);
+      constexpr uint32_t idesc_e5 = make_idesc_bf16(2 * TILE_M, TILE_N);
+      int cnt = 0, tcnt = 0;
+      for (int item = pair_id; item < n_items; item += n_pairs, ++tcnt) {
+        const int as = tcnt & 1;
+        mbar_wait(&tempty[as], ((tcnt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * 256u;
+        for (int s = 0; s < p.nslabs; ++s, ++cnt) {
+          const int st_i = cnt % RP_STAGES;
+          mbar_wait(&full[st_i], (cnt / RP_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_main = smem_u32(ring + st_i * RP_STAGE), a_aux = a_main + A_TILE_BYTES;
+          const uint32_t b_main = a_main + 2 * A_TILE_BYTES, b_aux = b_main + B_TILE_BYTES / 2;
+#pragma unroll
+          for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+            const uint32_t ko = k * UMMA_K * 2;
+            const uint64_t da = make_sw128_desc(a_main + ko), db = make_sw128_desc(b_main + ko);
+            umma_bf16_pair(tmem_d, da, db, idesc, (s == 0 && k == 0) ? 0u : 1u);
+            if (P == 1) {
+              umma_bf16_pair(tmem_d, make_sw128_desc(a_aux + ko), db, idesc, 1u);
+              umma_bf16_pair(tmem_d, da, make_sw128_desc(b_aux + ko), idesc, 1u);
+            }
+            if (P == 3) umma_f8_pair(tmem_d, make_sw128_desc(a_aux + ko), make_sw128_desc(b_aux + ko), idesc_e5, 1u);
+          }
+          umma_commit_pair(&empty[st_i]);
+        }
+        umma_commit_pair(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, hc = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = (int)threadIdx.x - 128;
+    const bool issuer = (warp == 4) && (lane == 0);
+    const uint32_t stg = smem_u32(staging);
+    const float rsqrt2 = 0.70710678118654752f;
+    int tcnt = 0, git = 0;
+    for (int item = pair_id; item < n_items; item += n_pairs, ++tcnt) {
+      const Tile ti = tile_of(item);
+      const int as = tcnt & 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it, ++git) {
+        if (issuer) {
+          tma_store_wait_read<0>();                 // the previous iteration's stores no longer read smem
+          if (git > 0) { mbar_arrive(&xempty[(2 * (git - 1)) % RP_XBOXES]); mbar_arrive(&xempty[(2 * (git - 1) + 1) % RP_XBOXES]); }
+        }
+        named_bar_sync(EPI_BAR, EPI_THREADS);       // staging (and, at it == 0, sbias/sdn) may be overwritten
+        if (it == 0) {
+          sbias[etid] = __ldg(p.bias + ti.n_base + etid);
+          named_bar_sync(EPI_BAR, EPI_THREADS);
+          mbar_wait(&tfull[as], (tcnt >> 1) & 1);
+          tc_fence_after();
+        }
+        const int gb = 2 * git + hc;
+        const int sl = gb % RP_XBOXES;
+        mbar_wait(&xfull[sl], (gb / RP_XBOXES) & 1);
+        const int cbox = it * 2 + hc;
+        float o[32];
+        load_acc32<P>(taddr + cbox * 32, 0.f, o);
+        if (it == 3) {                              // last TMEM read of this tile: hand the accumulator stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
+        }
+        const uint32_t box = smem_u32(xring + sl * CHUNK_BYTES);
+        const float* bs = sbias + cbox * 32;
+        const float* dn = p.dnext + ti.n_base + cbox * 32;   // warp-uniform addresses: L1 broadcast, off the critical path
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          float xin[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int v = g16 * 4 + u, i = v * 4;
+            const uint32_t xa = box + sw128_off(row, v);
+            float4 x = lds128(xa);
+            x.x = (x.x + (o[i + 0] + bs[i + 0])) * rsqrt2;
+            x.y = (x.y + (o[i + 1] + bs[i + 1])) * rsqrt2;
+            x.z = (x.z + (o[i + 2] + bs[i + 2])) * rsqrt2;
+            x.w = (x.w + (o[i + 3] + bs[i + 3])) * rsqrt2;
+            sts128(xa, x);
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(dn + i));
+            xin[u * 4 + 0] = x.x + d4.x; xin[u * 4 + 1] = x.y + d4.y;
+            xin[u * 4 + 2] = x.z + d4.z; xin[u * 4 + 3] = x.w + d4.w;
+          }
+          stage16<P>(stg, stg + CHUNK_BYTES, row, hc * 32 + g16 * 16, xin);
+        }
+        fence_proxy_async();
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+        if (issuer) {
+          const int c0 = ti.n_base + it * 64;
+          tma_store_3d(&p.out32, xring + ((2 * git) % RP_XBOXES) * CHUNK_BYTES, c0, ti.t0, ti.nb);
+          tma_store_3d(&p.out32, xring + ((2 * git + 1) % RP_XBOXES) * CHUNK_BYTES, c0 + 32, ti.t0, ti.nb);
+          tma_store_3d(&p.xh, staging, c0, ti.t0, ti.nb);
+          tma_store_3d(&p.xl, staging + CHUNK_BYTES, AM * c0, ti.t0, ti.nb);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read<0>();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -983,6 +1193,7 @@ int umma_init() {
   set((const void*)umma_gate_win_kernel<1>, Cfg<1, true>::kSmemBytes); set((const void*)umma_gate_win_kernel<2>, Cfg<2, true>::kSmemBytes);
   set((const void*)umma_gate_win_kernel<3>, Cfg<3, true>::kSmemBytes);
   set((const void*)umma_gate_pers_kernel<1>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3>, PW_SMEM);
+  set((const void*)umma_res_pers_kernel<1>, RP_SMEM); set((const void*)umma_res_pers_kernel<3>, RP_SMEM);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2, false>::kSmemBytes);
@@ -1095,6 +1306,14 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = z.inv_scale;
   const bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  if (mc && z.persistent && z.mode == 0 && (z.prec == 1 || z.prec == 3)) {
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+    const int pairs = n_items < n_sm / 2 ? n_items : n_sm / 2;
+    return z.prec == 1 ? launch_k(umma_res_pers_kernel<1>, p, 2 * pairs, RP_SMEM, true, s)
+                       : launch_k(umma_res_pers_kernel<3>, p, 2 * pairs, RP_SMEM, true, s);
+  }
   if (z.prec == 1) return mc ? launch_k(umma_zgemm_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
                              : launch_k(umma_zgemm_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
   if (z.prec == 2) return mc ? launch_k(umma_zgemm_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)
