@@ -247,6 +247,16 @@ class SpecRollDiffusion(nn.Module):
         _, noise_list, spec = self.predict_step((noise, waveform), batch_idx)
         return noise_list, spec
 
+    @torch.no_grad()
+    def notes_from_rolls(self, rolls):
+        """The first half of predict_step's MIDI tail (task/diffusion.py:599-602) on the GPU: for every finished roll
+        ``extract_notes_wo_velocity(np_frame, np_frame)`` with the default 0.5 thresholds.  rolls: CUDA tensor
+        [B,1,T,88] -> list of (pitches, intervals) numpy arrays in the reference's order.  Scaling to seconds / Hz
+        and writing .mid files stay on the host (I/O, out of scope)."""
+        from .notes import extract_notes_batch
+        r = rolls[:, 0] if rolls.ndim == 4 else rolls
+        return extract_notes_batch(r, r)
+
     def p_losses(self, label, prediction, loss_type="l1"):
         if loss_type == 'l1':
             return F.l1_loss(label, prediction)
