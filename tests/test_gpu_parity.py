@@ -307,8 +307,8 @@ def test_sampling_entry_point(tmp_path):
 def test_full_size_batch_independence_and_determinism():
     """BASELINE configs[1] size (B=32, 640 frames): size-independent properties instead of an oracle run.
     Every roll's chain is independent, so roll i of a 32-batch must equal the same roll sampled in a batch of 2
-    (bit for bit: same tiles, same K order), a second run must reproduce the first, and the masked spectrogram
-    columns must be exactly -1."""
+    (to rounding: cuFFT may pick a different plan for a different batch count, everything else is tile-identical),
+    a second run must reproduce the first bit for bit, and the masked spectrogram columns must be exactly -1."""
     m = model_for("f16e5", inpainting_t=[0, 320])
     x_T, wav, noise = make_inputs(32, 200, seed=2024, n_noise=3)
     x, w, nz = x_T.cuda(), wav.cuda(), noise.cuda()
@@ -321,4 +321,4 @@ def test_full_size_batch_independence_and_determinism():
         j = (i + 5) % 32
         idx = [i, j]
         sub, _, _ = m.sample_loop(x[idx].contiguous(), w[idx].contiguous(), noise=nz[:, idx].contiguous(), n_steps=3)
-        assert torch.equal(sub[0], a[i]) and torch.equal(sub[1], a[j])
+        assert float((sub[0] - a[i]).abs().max()) < 2e-5 and float((sub[1] - a[j]).abs().max()) < 2e-5
