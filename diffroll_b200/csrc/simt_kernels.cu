@@ -14,6 +14,7 @@ struct SimtGemmDev {
   const float* A; const float* A2; float alpha, beta, a_div; const float* addvec; int lda, T, taps, dil, Ck;
   const float* W; int ldw; const float* bias; int act, accumulate; float* C; int ldc, M, N, K;
   int upd_on; drb_update upd; const float* x_t; const float* noise; float* net_out;
+  int vec;  // 16-byte epilogue accesses are legal (row stride and every pointer 16-byte aligned)
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -43,32 +44,36 @@ __device__ __forceinline__ float posterior_update(const drb_update& u, float net
   }
 }
 
-__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmDev g) {
-  __shared__ __align__(16) float As[2][BK][BM + 4];
+// TBM = rows per block: 128 (8x8 outputs per thread) or 64 (4x8; used when N is small so that the grid still fills the SMs)
+template <int TBM>
+__global__ void __launch_bounds__(256, 2) simt_gemm_kernel(const SimtGemmDev g) {
+  constexpr int RI = TBM / 16;           // rows per thread: 8 or 4
+  constexpr int AK = 16 * TBM / 256;     // A floats per thread per K-block: 8 or 4
+  __shared__ __align__(16) float As[2][BK][TBM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  // loader mapping: one row, 8 consecutive k per thread
-  const int lrow = tid & 127, lk = (tid >> 7) * 8;
-  const int am = m0 + lrow;
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
+  // loader mapping: one row, AK (A) / 8 (W) consecutive k per thread
+  const int larow = tid % TBM, lak = (tid / TBM) * AK;
+  const int lbrow = tid & 127, lbk = (tid >> 7) * 8;
+  const int am = m0 + larow;
   const bool a_row_ok = am < g.M;
   const int seg = a_row_ok ? am / g.T : 0, t = a_row_ok ? am - seg * g.T : 0;
-  const int bn = n0 + lrow;
+  const int bn = n0 + lbrow;
   const bool b_row_ok = bn < g.N;
   const int half = g.taps / 2;
 
-  float4 ra[2], rb[2];
+  float4 ra[AK / 4], rb[2];
   auto load_tile = [&](int k0) {
-    // A
-    int tap = k0 / g.Ck, c0 = k0 - tap * g.Ck + lk;
+    int tap = k0 / g.Ck, c0 = k0 - tap * g.Ck + lak;
     int tt = t + (tap - half) * g.dil;
     bool ok = a_row_ok && tt >= 0 && tt < g.T;
     const float* ap = g.A + ((size_t)(seg * g.T + tt) * g.lda + c0);
     const float* ap2 = g.A2 ? g.A2 + ((size_t)(seg * g.T + tt) * g.lda + c0) : nullptr;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < AK / 4; ++q) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok && (k0 + lk + q * 4 + 3) < g.K) {
+      if (ok && (k0 + lak + q * 4 + 3) < g.K) {
         v = *reinterpret_cast<const float4*>(ap + q * 4);
         if (ap2) {
           float4 w = *reinterpret_cast<const float4*>(ap2 + q * 4);
@@ -83,29 +88,31 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmDev g) {
       }
       ra[q] = v;
     }
-    // W
-    const float* wp = g.W + ((size_t)bn * g.ldw + k0 + lk);
+    const float* wp = g.W + ((size_t)bn * g.ldw + k0 + lbk);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b_row_ok && (k0 + lk + q * 4 + 3) < g.K) v = *reinterpret_cast<const float4*>(wp + q * 4);
+      if (b_row_ok && (k0 + lbk + q * 4 + 3) < g.K) v = *reinterpret_cast<const float4*>(wp + q * 4);
       rb[q] = v;
     }
   };
   auto store_tile = [&](int buf) {
 #pragma unroll
+    for (int q = 0; q < AK / 4; ++q) {
+      As[buf][lak + q * 4 + 0][larow] = ra[q].x; As[buf][lak + q * 4 + 1][larow] = ra[q].y;
+      As[buf][lak + q * 4 + 2][larow] = ra[q].z; As[buf][lak + q * 4 + 3][larow] = ra[q].w;
+    }
+#pragma unroll
     for (int q = 0; q < 2; ++q) {
-      As[buf][lk + q * 4 + 0][lrow] = ra[q].x; As[buf][lk + q * 4 + 1][lrow] = ra[q].y;
-      As[buf][lk + q * 4 + 2][lrow] = ra[q].z; As[buf][lk + q * 4 + 3][lrow] = ra[q].w;
-      Bs[buf][lk + q * 4 + 0][lrow] = rb[q].x; Bs[buf][lk + q * 4 + 1][lrow] = rb[q].y;
-      Bs[buf][lk + q * 4 + 2][lrow] = rb[q].z; Bs[buf][lk + q * 4 + 3][lrow] = rb[q].w;
+      Bs[buf][lbk + q * 4 + 0][lbrow] = rb[q].x; Bs[buf][lbk + q * 4 + 1][lbrow] = rb[q].y;
+      Bs[buf][lbk + q * 4 + 2][lbrow] = rb[q].z; Bs[buf][lbk + q * 4 + 3][lbrow] = rb[q].w;
     }
   };
 
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[RI][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
@@ -118,14 +125,18 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmDev g) {
     if (kb + 1 < nk) load_tile((kb + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float av[RI];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+      if (RI == 8) {
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][(TBM / 2) + ty * 4]);
+        av[RI - 4] = a1.x; av[RI - 3] = a1.y; av[RI - 2] = a1.z; av[RI - 1] = a1.w;
+      }
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -135,27 +146,51 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmDev g) {
     }
   }
 
-  // epilogue
+  // epilogue: two groups of 4 consecutive columns per row, 16-byte accesses when the group is inside N
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < RI; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : (TBM / 2) + ty * 4 + (i - 4));
     if (m >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    for (int jg = 0; jg < 2; ++jg) {
+      const int n = n0 + jg * 64 + tx * 4;
       if (n >= g.N) continue;
-      float v = acc[i][j];
-      if (g.bias) v += g.bias[n];
-      v = act_apply(v, g.act);
       const size_t idx = (size_t)m * g.ldc + n;
-      if (g.accumulate) v += g.C[idx];
-      if (g.upd_on) {
-        if (g.net_out) g.net_out[idx] = v;
-        float x = (g.upd.mode == DRB_UPD_X0_FINAL || g.upd.mode == DRB_UPD_NONE) ? 0.f : g.x_t[idx];
-        float nz = g.upd.has_noise ? g.noise[idx] : 0.f;
-        v = posterior_update(g.upd, v, x, nz);
+      float v[4] = {acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]};
+      const bool full = g.vec && (n + 3 < g.N);
+      const int cnt = full ? 4 : min(4, g.N - n);
+      if (g.bias) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (e < cnt) v[e] += g.bias[n + e];
       }
-      g.C[idx] = v;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.act);
+      if (full) {
+        if (g.accumulate) { const float4 c = *reinterpret_cast<const float4*>(g.C + idx); v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w; }
+        if (g.upd_on) {
+          if (g.net_out) *reinterpret_cast<float4*>(g.net_out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f), nz = x;
+          if (!(g.upd.mode == DRB_UPD_X0_FINAL || g.upd.mode == DRB_UPD_NONE)) x = *reinterpret_cast<const float4*>(g.x_t + idx);
+          if (g.upd.has_noise) nz = *reinterpret_cast<const float4*>(g.noise + idx);
+          v[0] = posterior_update(g.upd, v[0], x.x, nz.x); v[1] = posterior_update(g.upd, v[1], x.y, nz.y);
+          v[2] = posterior_update(g.upd, v[2], x.z, nz.z); v[3] = posterior_update(g.upd, v[3], x.w, nz.w);
+        }
+        *reinterpret_cast<float4*>(g.C + idx) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (e >= cnt) continue;
+          float o = v[e];
+          if (g.accumulate) o += g.C[idx + e];
+          if (g.upd_on) {
+            if (g.net_out) g.net_out[idx + e] = o;
+            const float x = (g.upd.mode == DRB_UPD_X0_FINAL || g.upd.mode == DRB_UPD_NONE) ? 0.f : g.x_t[idx + e];
+            const float nz = g.upd.has_noise ? g.noise[idx + e] : 0.f;
+            o = posterior_update(g.upd, o, x, nz);
+          }
+          g.C[idx + e] = o;
+        }
+      }
     }
   }
 }
@@ -171,8 +206,16 @@ int launch_simt_gemm(const SimtGemm& s, cudaStream_t st) {
     set_error("simt_gemm: unsupported shape M=%d N=%d K=%d Ck=%d lda=%d ldw=%d", g.M, g.N, g.K, g.Ck, g.lda, g.ldw);
     return DRB_E_INVALID;
   }
-  dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN);
-  simt_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  g.vec = ((g.ldc & 3) == 0) && al16(g.C) && al16(g.x_t) && al16(g.noise) && al16(g.net_out);
+  const int ncol = (g.N + BN - 1) / BN;
+  if (ncol * ((g.M + BM - 1) / BM) < 2 * 148) {      // few tiles (small N): 64-row tiles keep every SM busy
+    dim3 grid((g.M + 63) / 64, ncol);
+    simt_gemm_kernel<64><<<grid, 256, 0, st>>>(g);
+  } else {
+    dim3 grid((g.M + BM - 1) / BM, ncol);
+    simt_gemm_kernel<128><<<grid, 256, 0, st>>>(g);
+  }
   DRB_LAUNCH_CHECK();
   return 0;
 }
