@@ -199,6 +199,10 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* tma
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Programmatic dependent launch: `pdl_trigger` lets the next kernel of the stream start its prologue while this grid is
+// still running; `pdl_wait` blocks until the previous grid has completed and its memory is visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

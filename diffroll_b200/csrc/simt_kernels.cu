@@ -195,7 +195,23 @@ __global__ void __launch_bounds__(256, 2) simt_gemm_kernel(const SimtGemmDev g) 
   }
 }
 
+__global__ void prep_xin_kernel(float* __restrict__ x32, void* __restrict__ xmain, void* __restrict__ xaux,
+                                const float* __restrict__ dvec, int Mb, int C, int copies, int fmt);
+
+// The tensor-core kernels around these launches run with the SM's largest shared-memory carve-out; asking for the same
+// carve-out here avoids an L1/shared reconfiguration (which drains the SM) at every kernel-type boundary of a step.
+static void prefer_max_smem_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncSetAttribute((const void*)simt_gemm_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void*)simt_gemm_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void*)prep_xin_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+}
+
 int launch_simt_gemm(const SimtGemm& s, cudaStream_t st) {
+  prefer_max_smem_once();
   SimtGemmDev g;
   g.A = s.A; g.A2 = s.A2; g.alpha = s.alpha; g.beta = s.beta; g.a_div = s.a_div; g.addvec = s.addvec;
   g.lda = s.lda; g.T = s.T; g.taps = s.taps; g.dil = s.dil; g.Ck = s.Ck; g.W = s.W; g.ldw = s.ldw; g.bias = s.bias;

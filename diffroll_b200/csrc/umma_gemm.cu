@@ -129,10 +129,12 @@ __device__ __forceinline__ void prologue(const SmemView& sv, int warp) {
     if (PAIR) { tmem_alloc_pair(sv.tmem_ptr, Cfg<P, PAIR>::kTmemCols); tmem_relinquish_pair(); }
     else { tmem_alloc(sv.tmem_ptr, Cfg<P, PAIR>::kTmemCols); tmem_relinquish(); }
   }
+  pdl_trigger();                 // the next kernel may start its own prologue on SMs this grid has left
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();  // both CTAs' barriers and TMEM exist before any remote arrive / paired MMA
   tc_fence_after();
+  pdl_wait();                    // everything above touched only constants; from here on we read the previous kernel's output
 }
 
 template <int P, bool PAIR>
@@ -611,10 +613,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -1015,10 +1019,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -1239,15 +1245,20 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uin
   return encode(m, base, 3, dims, strides, box, dtype);
 }
 
+static int g_pdl = -1;
+
 // Launch `kernel` on `grid` CTAs of 256 threads; cluster = 2 consecutive CTAs (a CTA pair) when mc.
 template <class Params>
 static int launch_k(void (*kernel)(Params), const Params& p, int grid, int smem, bool mc, cudaStream_t s) {
+  if (g_pdl < 0) { const char* e = getenv("DRB_NO_PDL"); g_pdl = (e && e[0] == '1') ? 0 : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = mc ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this kernel's prologue with its predecessor
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
   count_launch();
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx: %s", cudaGetErrorString(e)); return (int)e; }
