@@ -118,6 +118,13 @@ def cpu_steps_per_s(n_steps, warmup, budget_s, fixed_batch=None):
     import torch
     from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dict
     from oracle.diffroll_oracle import OracleDiffRoll
+    # torchrun exports OMP_NUM_THREADS=1 to every worker; the CPU arm must still use all the host cores it can
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail:
+        torch.set_num_threads(avail)
     threads = torch.get_num_threads()
     hp = default_hparams()
     orc = OracleDiffRoll(hp, make_state_dict(hp))
@@ -338,8 +345,9 @@ def main():
         run_reference(args, rank)
         return
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+        # NCCL prints its version banner on stdout at the VERSION/WARN/INFO levels: send its log to stderr instead so
+        # that stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
