@@ -28,6 +28,7 @@ struct Layout {  // byte offsets into the workspace
   size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel, xpp;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
+  size_t wcpad, cond;                                   // fp32 Wc of every layer padded to Mp; conditioner projections of the spectrogram [L][B][T][2C]
   size_t total;
   int NBcap, Mp, KC;
 };
@@ -78,6 +79,9 @@ static Layout make_layout(const drb_config& c) {
     l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
     l.bcomp = take(C * 4); l.bsum = take(C * 4);
     l.wscale = take((2 * L + 1) * 4 * 4);  // f16f8: {SW, 1/(SA*SW), scratch, -} per gate / out weight set and the head
+    if (c.branches != DRB_BRANCH_UNCOND && c.precision != DRB_PREC_F16F8 && c.precision != DRB_PREC_BF16) {
+      l.wcpad = take(L * 2 * C * Mp * 4); l.cond = take(L * B * T * 2 * C * 4);
+    }
   }
   l.total = off;
   return l;
@@ -104,6 +108,8 @@ struct drb_plan {
   std::vector<UmmaLayer> layers;
   std::vector<CUtensorMap> win_h, win_l;  // per layer: x operand maps whose box covers the layer's whole tap window
   int window = 1, persistent = 1;
+  int condpre = 1;     // conditioner projections precomputed per clip, added in the gate epilogue (DRB_NO_CONDPRE=1: off)
+  int share0 = 1;      // layer-0 branch sharing (DRB_NO_SHARE0=1 turns it off, for A/B runs); needs condpre
   // optional per-kernel timing (drb_plan_profile): events recorded on the launching stream around every kernel class
   cudaStream_t copy_stream = nullptr;  // trajectory copies (drb_sample_loop)
   cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
@@ -170,6 +176,10 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
   { const char* e = getenv("DRB_NO_PAIR"); p->pair = (e && e[0] == '1') ? 0 : 1; }
   { const char* e = getenv("DRB_NO_WINDOW"); p->window = (e && e[0] == '1') ? 0 : 1; }
   { const char* e = getenv("DRB_NO_PERSIST"); p->persistent = (e && e[0] == '1') ? 0 : 1; }
+  { const char* e = getenv("DRB_NO_SHARE0"); p->share0 = (e && e[0] == '1') ? 0 : 1; }
+  { const char* e = getenv("DRB_NO_CONDPRE"); p->condpre = (e && e[0] == '1') ? 0 : 1; }
+  if (lay.cond == 0 || !p->persistent) p->condpre = 0;   // only the persistent gate kernel (bf16x3 / f16e5) implements it
+  if (!p->condpre || lay.NBcap != 2 * cfg->batch) p->share0 = 0;
   const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
   p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
   p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
@@ -221,6 +231,10 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
       p->layers.push_back(ul);
     }
   }
+  if (p->condpre)   // fp32 conditioner weights, K padded to Mp (the spectrogram rows are zero-padded alike)
+    for (int i = 0; i < L; ++i)
+      PLAN_TRY(launch_pad_rows(w->conditioner_projection_w[i], p->at<float>(lay.wcpad) + (size_t)i * 2 * C * Mp, 2 * C,
+                               cfg->n_mels, Mp, s));
   if (tensor) {
     const uint64_t NBc = lay.NBcap;
     const int fmt = p->fmt();
@@ -300,6 +314,19 @@ int drb_mel_forward(drb_plan* p, const float* waveform, float* spec_out, int32_t
   int r = mel_forward(p->mel, waveform, spec_out, p->at<float>(p->lay.spec32), tensor ? p->ws + p->lay.sh : nullptr,
                       tensor ? p->ws + p->lay.sl : nullptr, p->fmt(), p->lay.Mp, p->cfg.frames, it0, it1, if0, if1,
                       (cudaStream_t)stream);
+  if (r == 0 && p->condpre) {
+    // conditioner_projection_l(spec) (model/diffwave.py:143) does not depend on the timestep: computed here once per
+    // clip, in fp32, for every layer; the gate kernel adds it in its epilogue
+    const drb_config& c = p->cfg;
+    const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)c.batch * c.frames * C2;
+    for (int l = 0; l < c.residual_layers && r == 0; ++l) {
+      SimtGemm g;
+      g.A = p->at<float>(p->lay.spec32); g.lda = p->lay.Mp; g.T = c.frames; g.Ck = p->lay.Mp;
+      g.W = p->at<float>(p->lay.wcpad) + (size_t)l * C2 * p->lay.Mp; g.ldw = p->lay.Mp;
+      g.C = p->at<float>(p->lay.cond) + (size_t)l * per; g.ldc = (int)C2; g.M = c.batch * c.frames; g.N = (int)C2;
+      r = launch_simt_gemm(g, (cudaStream_t)stream);
+    }
+  }
   if (r == 0) p->spec_ready = true;
   return r;
 }
@@ -362,6 +389,10 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
   ug.pair = p->pair; ug.window = p->window; ug.persistent = p->persistent; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
+  if (p->condpre && nc > 0) {
+    ug.cond = p->at<float>(p->lay.cond) + (size_t)layer * B * T * 2 * C;
+    if (first && p->share0 && NB == 2 * B && nc == B) ug.dual_B = B;
+  }
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   r = launch_umma_gate(p->maps, p->layers[layer], ug, s); if (r) return r;
   const int e1 = p->prof ? p->ev_mark(s) : -1;

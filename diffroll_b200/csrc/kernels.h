@@ -95,6 +95,11 @@ struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filt
   const float* inv_scale;
   const float* bias_cond;  // interleaved [2C]
   const float* bias_unc;
+  // Persistent kernel only.  cond: this layer's conditioner projection of the spectrogram, fp32 [n_cond][T][2C], computed
+  // once per clip and added in the epilogue of conditional rolls (nullptr = contract it as K-slabs every step).
+  // dual_B > 0 (layer 0, both branches read the same x): conv once over dual_B rolls, two gated outputs per tile.
+  const float* cond = nullptr;
+  int dual_B = 0;
 };
 struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
   int pair = 1, persistent = 1;

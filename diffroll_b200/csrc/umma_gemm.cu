@@ -73,6 +73,15 @@ struct alignas(64) GateParams {
   const float* bias_cond;
   const float* bias_unc;
   const float* inv_scale;  // f16f8: 1 / (SA * SW) of this layer's weights (device scalar)
+  // Persistent kernel only.  The conditioner projection is step-invariant, so it is computed once per clip in fp32
+  // (cond[roll][t][2C], natural channel order: gate 0..C-1, filter C..2C-1) and ADDED IN THE EPILOGUE of conditional
+  // rolls (nb < n_cond) instead of being re-contracted every step as extra K-slabs (those run for nb < n_cond_mma).
+  // Layer-0 branch sharing (DUAL): both guidance branches read the SAME x at layer 0, so the dilated conv is computed
+  // once per roll and the epilogue emits two gated outputs: the unconditional one (bias_unc) into roll nb + dual_off and
+  // the conditional one (bias_cond + cond) into roll nb.
+  const float* cond;
+  int n_cond_mma;
+  int dual_off;
 };
 
 struct alignas(64) ZGemmParams {
@@ -562,7 +571,7 @@ __device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&m)[8], u
 
 struct GateTile { int nblk, nb, t0, nchunks; };
 
-template <int P>
+template <int P, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __grid_constant__ GateParams p) {
   static_assert(P == 1 || P == 3, "needs a single 256-column accumulator");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -596,7 +605,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
     t.nb = mt / p.tiles_t;
     t.t0 = (mt % p.tiles_t) * TILE_M;
     const int nb_first = (pm * 2) / p.tiles_t;
-    t.nchunks = cpt + (nb_first < p.n_cond ? p.cond_slabs : 0);
+    t.nchunks = cpt + (nb_first < p.n_cond_mma ? p.cond_slabs : 0);
     return t;
   };
 
@@ -727,12 +736,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
     for (int item = pair_id; item < p.n_items; item += n_pairs, ++tcnt) {
       const GateTile ti = tile_of(item);
       const int as = tcnt & 1;
+#pragma unroll 1
+      for (int pass = 0; pass < (DUAL ? 2 : 1); ++pass) {
+      // DUAL: pass 0 = unconditional output (roll nb + dual_off), pass 1 = conditional output (roll nb)
+      const bool is_cond = DUAL ? (pass == 1) : (ti.nb < p.n_cond);
+      const int zroll = p.z_group0 + ti.nb + ((DUAL && pass == 0) ? p.dual_off : 0);
       // previous tile: every thread is done with sbias, and the aux stores have finished reading the staging area
       if (issuer) tma_store_wait_read<0>();
       named_bar_sync(EPI_BAR, EPI_THREADS);
-      sbias[etid] = __ldg((ti.nb < p.n_cond ? p.bias_cond : p.bias_unc) + ti.nblk * TILE_N + etid);
+      sbias[etid] = __ldg((is_cond ? p.bias_cond : p.bias_unc) + ti.nblk * TILE_N + etid);
       named_bar_sync(EPI_BAR, EPI_THREADS);
-      mbar_wait(&tfull[as], (tcnt >> 1) & 1);
+      if (pass == 0) mbar_wait(&tfull[as], (tcnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
       uint32_t zm[2][2][8], za[2][2][8];   // [c2][hf]: packed main / aux words of 16 channels
@@ -742,6 +756,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
         float g[32], f[32];
         load_acc32<P>(taddr + ch * 32, 0.f, g);
         load_acc32<P>(taddr + 128 + ch * 32, 0.f, f);
+        if (is_cond && p.cond != nullptr) {   // + conditioner_projection(spec) of this frame, fp32, computed once per clip
+          const int tf = ti.t0 + row;
+          if (tf < p.T) {
+            const float* cg = p.cond + ((size_t)ti.nb * p.T + tf) * (size_t)(2 * p.C) + ti.nblk * (TILE_N / 2) + ch * 32;
+            const float* cf = cg + p.C;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(cg) + v);
+              const float4 b = __ldg(reinterpret_cast<const float4*>(cf) + v);
+              g[4 * v] += a.x; g[4 * v + 1] += a.y; g[4 * v + 2] += a.z; g[4 * v + 3] += a.w;
+              f[4 * v] += b.x; f[4 * v + 1] += b.y; f[4 * v + 2] += b.z; f[4 * v + 3] += b.w;
+            }
+          }
+        }
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           float z[16];
@@ -756,7 +784,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
       // this warp's TMEM reads are complete: hand the accumulator stage back to the MMA issuer (leader CTA)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
+      if ((!DUAL || pass == 1) && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
       // pass A: main boxes (group g owns box g)
       const uint32_t box = stg + grp * CHUNK_BYTES;
 #pragma unroll
@@ -771,8 +799,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
       named_bar_sync(EPI_BAR, EPI_THREADS);
       const int c0 = ti.nblk * (TILE_N / 2);
       if (issuer) {
-        tma_store_3d(&p.zh, staging, c0, ti.t0, p.z_group0 + ti.nb);
-        tma_store_3d(&p.zh, staging + CHUNK_BYTES, c0 + 64, ti.t0, p.z_group0 + ti.nb);
+        tma_store_3d(&p.zh, staging, c0, ti.t0, zroll);
+        tma_store_3d(&p.zh, staging + CHUNK_BYTES, c0 + 64, ti.t0, zroll);
         tma_store_commit();
         tma_store_wait_read<0>();
       }
@@ -794,10 +822,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
       fence_proxy_async();
       named_bar_sync(EPI_BAR, EPI_THREADS);
       if (issuer) {
-        tma_store_3d(&p.zl, staging, AM * c0, ti.t0, p.z_group0 + ti.nb);
-        tma_store_3d(&p.zl, staging + CHUNK_BYTES, AM * (c0 + 64), ti.t0, p.z_group0 + ti.nb);
+        tma_store_3d(&p.zl, staging, AM * c0, ti.t0, zroll);
+        tma_store_3d(&p.zl, staging + CHUNK_BYTES, AM * (c0 + 64), ti.t0, zroll);
         tma_store_commit();
       }
+      }   // pass
     }
     if (issuer) tma_store_wait_read<0>();
   }
@@ -1198,7 +1227,8 @@ int umma_init() {
   set((const void*)umma_gate_kernel<3, false>, Cfg<3, false>::kSmemBytes); set((const void*)umma_gate_kernel<3, true>, Cfg<3, false>::kSmemBytes);
   set((const void*)umma_gate_win_kernel<1>, Cfg<1, true>::kSmemBytes); set((const void*)umma_gate_win_kernel<2>, Cfg<2, true>::kSmemBytes);
   set((const void*)umma_gate_win_kernel<3>, Cfg<3, true>::kSmemBytes);
-  set((const void*)umma_gate_pers_kernel<1>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3>, PW_SMEM);
+  set((const void*)umma_gate_pers_kernel<1, false>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3, false>, PW_SMEM);
+  set((const void*)umma_gate_pers_kernel<1, true>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3, true>, PW_SMEM);
   set((const void*)umma_res_pers_kernel<1>, RP_SMEM); set((const void*)umma_res_pers_kernel<3>, RP_SMEM);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
@@ -1277,6 +1307,7 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   p.cond_slabs = g.Mp / TILE_K; p.tiles_t = (g.T + TILE_M - 1) / TILE_M; p.n_blocks = 2 * g.C / TILE_N;
   p.z_group0 = g.z_group0;
   p.bias_cond = g.bias_cond; p.bias_unc = g.bias_unc;
+  p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = g.inv_scale;
   const bool mc = g.pair && ((p.NB * p.tiles_t) % 2 == 0);
@@ -1288,9 +1319,18 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
     if (g.persistent && (g.prec == 1 || g.prec == 3)) {   // one CTA pair per SM pair, looping over its tiles
       int n_sm = 148;
       { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+      if (g.cond) { p.cond = g.cond; p.n_cond_mma = 0; }   // conditioner term added in the epilogue, no cond K-slabs
+      // layer-0 branch sharing: conv tiles over the conditional rolls only, two gated outputs per tile
+      const bool dual = g.dual_B > 0 && g.cond && g.NB == 2 * g.dual_B && ((g.dual_B * p.tiles_t) % 2 == 0);
+      if (dual) {
+        p.NB = g.dual_B; p.dual_off = g.dual_B;
+        p.n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+      }
       const int pairs = p.n_items < n_sm / 2 ? p.n_items : n_sm / 2;
-      return g.prec == 1 ? launch_k(umma_gate_pers_kernel<1>, p, 2 * pairs, PW_SMEM, true, s)
-                         : launch_k(umma_gate_pers_kernel<3>, p, 2 * pairs, PW_SMEM, true, s);
+      if (dual) return g.prec == 1 ? launch_k(umma_gate_pers_kernel<1, true>, p, 2 * pairs, PW_SMEM, true, s)
+                                   : launch_k(umma_gate_pers_kernel<3, true>, p, 2 * pairs, PW_SMEM, true, s);
+      return g.prec == 1 ? launch_k(umma_gate_pers_kernel<1, false>, p, 2 * pairs, PW_SMEM, true, s)
+                         : launch_k(umma_gate_pers_kernel<3, false>, p, 2 * pairs, PW_SMEM, true, s);
     }
     return g.prec == 1 ? launch_k(umma_gate_win_kernel<1>, p, grid, Cfg<1, true>::kSmemBytes, true, s)
          : g.prec == 2 ? launch_k(umma_gate_win_kernel<2>, p, grid, Cfg<2, true>::kSmemBytes, true, s)

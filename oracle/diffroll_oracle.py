@@ -87,12 +87,14 @@ def normalize_imagewise(x, lo=0.0, hi=1.0):
 class OracleDiffRoll:
     """Functional restatement of ClassifierFreeDiffRoll + SpecRollDiffusion (eval mode, condition='fixed')."""
 
-    def __init__(self, hp, state_dict, dtype=torch.float32):
+    def __init__(self, hp, state_dict, dtype=torch.float32, device=None):
+        # device: None/CPU for the checker and the CPU baseline; "cuda" runs the same torch ops eagerly on the GPU
+        # (cuDNN/cuBLAS), which is what the reference itself does on a GPU box (tests/test_gpu_eager_baseline.py)
         self.hp = hp
         self.dtype = dtype
-        self.sd = {k: v.to(dtype) for k, v in state_dict.items()}
+        self.sd = {k: v.to(device=device, dtype=dtype) for k, v in state_dict.items()}
         self.sched = Schedule(hp["beta_start"], hp["beta_end"], hp["timesteps"])
-        self.embedding = build_embedding(hp["timesteps"]).to(dtype)
+        self.embedding = build_embedding(hp["timesteps"]).to(device=device, dtype=dtype)
         self.L = hp["residual_layers"]
         self.k = hp["kernel_size"]
         self.dilations = [hp["dilation_base"] ** (i % hp["dilation_bound"]) for i in range(self.L)]

@@ -322,3 +322,38 @@ def test_full_size_batch_independence_and_determinism():
         idx = [i, j]
         sub, _, _ = m.sample_loop(x[idx].contiguous(), w[idx].contiguous(), noise=nz[:, idx].contiguous(), n_steps=3)
         assert float((sub[0] - a[i]).abs().max()) < 2e-5 and float((sub[1] - a[j]).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("switch", ["DRB_NO_SHARE0", "DRB_NO_CONDPRE"])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16e5"])
+def test_hoisted_conditioner_and_layer0_sharing_match_plain_kernels(precision, switch, monkeypatch):
+    """Two hoists of the persistent gate kernel, each A/B-tested against the plain kernels (switches read at plan
+    creation) and against the CPU oracle, on a shape where both are active (B * tiles even):
+      DRB_NO_CONDPRE  the conditioner projection (step-invariant) is computed once per clip in fp32 and added in the
+                      epilogue instead of being contracted as extra K-slabs every step;
+      DRB_NO_SHARE0   layer 0 of both guidance branches reads the same x, so its dilated conv is computed once and the
+                      epilogue emits two gated outputs."""
+    import diffroll_b200 as M
+    from oracle.diffroll_oracle import OracleDiffRoll
+    hp = default_hparams(inpainting_t=[100, 420])
+    sd = make_state_dict(hp)
+    x_T, wav, noise = make_inputs(2, 200, seed=77, n_noise=2)
+    outs = []
+    for off in ("1", "0"):
+        monkeypatch.setenv(switch, off)
+        m = M.ClassifierFreeDiffRoll(**hp, precision=precision)
+        m.load_state_dict(sd)
+        m = m.cuda().eval()
+        x0, _, _ = m.sample_loop(x_T.cuda(), wav.cuda(), noise=noise.cuda(), n_steps=2)
+        outs.append(x0.cpu())
+        for e, _ in m._engines.values():
+            e.close()
+    d = float((outs[0] - outs[1]).abs().max())
+    record(f"{switch}[{precision}] hoisted-vs-plain after 2 steps max|delta| = {d:.3e}")
+    assert 0.0 < d < 2e-4          # different arithmetic for the conditioner term (fp32 vs operand pair), same result
+    orc = OracleDiffRoll(hp, sd)
+    x = x_T
+    with torch.no_grad():
+        for i, t_index in enumerate((199, 198)):
+            x, _ = orc.reverse_diffusion(x, wav, t_index, noise=noise[i])
+    assert maxabs(outs[1], x.numpy()) < TOL_STEP[precision]
