@@ -108,6 +108,7 @@ struct drb_plan {
   std::vector<UmmaLayer> layers;
   std::vector<CUtensorMap> win_h, win_l;  // per layer: x operand maps whose box covers the layer's whole tap window
   int window = 1, persistent = 1;
+  const int32_t* steps = nullptr;   // per-sample diffusion steps (device, [batch]); nullptr = the t_index arguments
   int condpre = 1;     // conditioner projections precomputed per clip, added in the gate epilogue (DRB_NO_CONDPRE=1: off)
   int share0 = 1;      // layer-0 branch sharing (DRB_NO_SHARE0=1 turns it off, for A/B runs); needs condpre
   // optional per-kernel timing (drb_plan_profile): events recorded on the launching stream around every kernel class
@@ -157,6 +158,12 @@ int drb_plan_set_branches(drb_plan* p, int32_t branches) {
   else { set_error("bad branches %d", branches); return DRB_E_INVALID; }
   if (NB > p->lay.NBcap) { set_error("plan was created for a single branch"); return DRB_E_INVALID; }
   p->NB = NB; p->n_cond = nc; p->zero_spec = branches == DRB_BRANCH_COND_ZEROSPEC;
+  return 0;
+}
+
+int drb_plan_set_steps(drb_plan* p, const int32_t* steps_dev) {
+  if (!p) return DRB_E_INVALID;
+  p->steps = steps_dev;
   return 0;
 }
 
@@ -336,14 +343,19 @@ int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
   if (!p->tables_ready) { set_error("drb_time_tables has not been called"); return DRB_E_STATE; }
   cudaStream_t s = (cudaStream_t)stream;
   const int B = p->cfg.batch, T = p->cfg.frames, C = p->cfg.residual_channels, F = p->cfg.pitches;
-  SimtGemm g;  // relu(input_projection(x_t))   model/diffwave.py:667-668 ; x_t [B,1,T,88] is already [B*T][88]
-  g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = p->in_w; g.ldw = F; g.bias = p->in_b; g.act = 1;
-  g.C = p->at<float>(p->lay.x32); g.ldc = C; g.M = B * T; g.N = C;
-  const int e0 = p->prof ? p->ev_mark(s) : -1;
-  int r = launch_simt_gemm(g, s); if (r) return r;
   const bool tensor = p->cfg.precision != DRB_PREC_FP32;
-  r = launch_prep_xin(p->at<float>(p->lay.x32), tensor ? p->ws + p->lay.xh : nullptr, tensor ? p->ws + p->lay.xl : nullptr,
-                      p->dvec(0, t_index), B * T, C, p->NB / B, p->fmt(), s);
+  const int e0 = p->prof ? p->ev_mark(s) : -1;
+  int r;
+  if (tensor) {  // relu(input_projection(x_t)) for every branch copy + operand pair of x + d_0(t), one kernel
+    r = launch_in_proj_fused(x_t, p->in_w, p->in_b, p->dvec(0, 0), p->steps, t_index, B * T, T, F, C, p->NB / B, p->fmt(),
+                             p->at<float>(p->lay.x32), p->ws + p->lay.xh, p->ws + p->lay.xl, s);
+  } else {
+    SimtGemm g;  // relu(input_projection(x_t))   model/diffwave.py:667-668 ; x_t [B,1,T,88] is already [B*T][88]
+    g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = p->in_w; g.ldw = F; g.bias = p->in_b; g.act = 1;
+    g.C = p->at<float>(p->lay.x32); g.ldc = C; g.M = B * T; g.N = C;
+    r = launch_simt_gemm(g, s); if (r) return r;
+    r = launch_prep_xin(p->at<float>(p->lay.x32), nullptr, nullptr, nullptr, B * T, C, p->NB / B, 0, s);
+  }
   if (p->prof && r == 0) p->ev_spans[2].push_back({e0, p->ev_mark(s)});
   return r;
 }
@@ -363,7 +375,8 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   if (c.precision == DRB_PREC_FP32) {
     float* x32 = p->at<float>(p->lay.x32); float* y = p->at<float>(p->lay.ybuf); float* z = p->at<float>(p->lay.z32);
     SimtGemm g;  // dilated_conv(x + d)   model/diffwave.py:138-139
-    g.lda = C; g.T = T; g.taps = k; g.dil = p->dil[layer]; g.Ck = C; g.addvec = p->dvec(layer, t_index);
+    g.lda = C; g.T = T; g.taps = k; g.dil = p->dil[layer]; g.Ck = C; g.addvec = p->dvec(layer, p->steps ? 0 : t_index);
+    g.addvec_steps = p->steps; g.addvec_mod = B; g.addvec_stride = C;
     g.W = p->at<float>(p->lay.wd32) + (size_t)layer * 2 * C * k * C; g.ldw = k * C; g.ldc = 2 * C; g.N = 2 * C;
     if (nc > 0) {
       g.A = x32; g.C = y; g.M = nc * T; g.bias = p->bias_ptr(layer, 2);
@@ -401,7 +414,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
     uz.pair = p->pair; uz.persistent = p->persistent; uz.NB = NB; uz.T = T; uz.C = C; uz.prec = ug.prec; uz.mode = 0; uz.groups = 1; uz.z_group0 = ug.z_group0;
     uz.inv_scale = p->wscale(2 * layer + 1) + 1;
     uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
-    uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, t_index);
+    uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, 0); uz.t_uniform = t_index; uz.steps = p->steps; uz.bsamp = B;
     r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
   }
   if (p->prof) {

@@ -17,6 +17,9 @@ struct SimtGemm {
   const float* A2 = nullptr;  // optional second source (guidance combine), same indexing
   float alpha = 1.f, beta = 0.f, a_div = 1.f;  // Aeff = (alpha*A + beta*A2) / a_div + addvec
   const float* addvec = nullptr;  // [Ck], optional
+  // per-segment addvec row (per-sample diffusion steps): row = addvec + addvec_steps[seg % addvec_mod] * addvec_stride
+  const int* addvec_steps = nullptr;
+  int addvec_mod = 1, addvec_stride = 0;
   int lda = 0;
   int T = 1;  // rows per segment (conv boundary)
   int taps = 1, dil = 1, Ck = 0;
@@ -42,6 +45,10 @@ int launch_res_skip(const float* o, float* x, float* skip, int M, int C, int fir
 // x32 rows [0,Mb) hold relu(in_proj); duplicate them `copies` times (branches) and emit the tensor-path operand of x + d
 // fmt: 0 none, 1 bf16 hi/lo, 2 fp16 + e4m3 correction bytes
 int launch_prep_xin(float* x32, void* xmain, void* xaux, const float* dvec, int Mb, int C, int copies, int fmt, cudaStream_t s);
+// tensor path: relu(input_projection(x_t)) -> fp32 x32 for every branch copy + operand pair of x + dtab0[t] in ONE kernel;
+// t = steps[row / T] when steps != nullptr (per-sample diffusion steps), else the uniform t
+int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, const float* dtab0, const int* steps, int t,
+                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux, cudaStream_t s);
 // weight repacks
 int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cudaStream_t s);  // [OC][C][k] -> [OC][k][C]
 // [OC][Kin] fp32 (k index already tap-major) -> operand pair (fmt 1 or 2), rows optionally permuted into 256-wide
@@ -108,7 +115,10 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
   int groups, z_group0, group_stride;
   const CUtensorMap *w_h, *w_l, *out32;
   const float* bias;
-  const float* dnext;
+  const float* dnext;               // RES: diffusion_projection table of the NEXT layer, [timesteps][C]
+  int t_uniform = 0;                // row of dnext when steps == nullptr
+  const int* steps = nullptr;       // per-sample diffusion steps [bsamp] (device); roll nb uses steps[nb % bsamp]
+  int bsamp = 1;
 };
 int umma_init();  // resolves cuTensorMapEncodeTiled
 // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8; the box always spans 128 bytes of the innermost dimension

@@ -15,6 +15,7 @@ struct SimtGemmDev {
   const float* W; int ldw; const float* bias; int act, accumulate; float* C; int ldc, M, N, K;
   int upd_on; drb_update upd; const float* x_t; const float* noise; float* net_out;
   int vec;  // 16-byte epilogue accesses are legal (row stride and every pointer 16-byte aligned)
+  const int* av_steps; int av_mod, av_stride;  // addvec row of segment seg: addvec + av_steps[seg % av_mod] * av_stride
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(256, 2) simt_gemm_kernel(const SimtGemmDev g) 
         }
         if (g.a_div != 1.f) { v.x /= g.a_div; v.y /= g.a_div; v.z /= g.a_div; v.w /= g.a_div; }
         if (g.addvec) {
-          float4 d = *reinterpret_cast<const float4*>(g.addvec + c0 + q * 4);
+          const float* av = g.av_steps ? g.addvec + (size_t)__ldg(g.av_steps + seg % g.av_mod) * g.av_stride : g.addvec;
+          float4 d = *reinterpret_cast<const float4*>(av + c0 + q * 4);
           v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
         }
       }
@@ -218,6 +220,7 @@ int launch_simt_gemm(const SimtGemm& s, cudaStream_t st) {
   g.act = s.act; g.accumulate = s.accumulate; g.C = s.C; g.ldc = s.ldc; g.M = s.M; g.N = s.N; g.K = s.taps * s.Ck;
   g.upd_on = s.upd != nullptr; if (s.upd) g.upd = *s.upd; else { g.upd.mode = DRB_UPD_NONE; g.upd.has_noise = 0; }
   g.x_t = s.x_t; g.noise = s.noise; g.net_out = s.net_out;
+  g.av_steps = s.addvec_steps; g.av_mod = s.addvec_mod > 0 ? s.addvec_mod : 1; g.av_stride = s.addvec_stride;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || (g.Ck % 4) || (g.lda % 4) || (g.ldw % 4) || (s.taps > 1 && (g.Ck % BK))) {
     set_error("simt_gemm: unsupported shape M=%d N=%d K=%d Ck=%d lda=%d ldw=%d", g.M, g.N, g.K, g.Ck, g.lda, g.ldw);
     return DRB_E_INVALID;
@@ -330,6 +333,98 @@ int launch_prep_xin(float* x32, void* xmain, void* xaux, const float* dvec, int 
   if (copies <= 1 && !fmt) return 0;
   size_t n = (size_t)Mb * C / 4;
   prep_xin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x32, xmain, xaux, dvec, Mb, C, copies, fmt);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// Fused input projection of the tensor path: relu(input_projection(x_t)) (model/diffwave.py:667-668) written once per
+// guidance branch as the fp32 residual stream, plus the operand pair of x + diffusion_projection_0(t) (:138) that the
+// first gate kernel reads.  K = 88 pitches fits shared memory whole: one load phase, one sync, 8x4 outputs per thread.
+// =================================================================================================
+constexpr int IP_BM = 128, IP_BN = 64;
+struct InProjDev {
+  const float* x; const float* W; const float* bias; const float* dtab; const int* steps;
+  int t, M, T, F, C, copies, fmt;
+  float* x32; void* xmain; void* xaux;
+};
+__global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
+  extern __shared__ __align__(16) float ip_smem[];
+  float* As = ip_smem;                             // [F][IP_BM + 4]
+  float* Bs = ip_smem + g.F * (IP_BM + 4);         // [F][IP_BN + 4]
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * IP_BM, n0 = blockIdx.y * IP_BN;
+  const int f4 = g.F / 4;
+  // lanes walk ROWS (consecutive smem words per transposed store: conflict-free); the 16-byte pieces of a 352-byte
+  // input row are picked up by successive iterations out of L1
+  for (int idx = tid; idx < IP_BM * f4; idx += 256) {
+    const int row = idx % IP_BM, q = idx / IP_BM;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + row < g.M) v = __ldg(reinterpret_cast<const float4*>(g.x + (size_t)(m0 + row) * g.F) + q);
+    As[(4 * q + 0) * (IP_BM + 4) + row] = v.x; As[(4 * q + 1) * (IP_BM + 4) + row] = v.y;
+    As[(4 * q + 2) * (IP_BM + 4) + row] = v.z; As[(4 * q + 3) * (IP_BM + 4) + row] = v.w;
+  }
+  for (int idx = tid; idx < IP_BN * f4; idx += 256) {
+    const int row = idx % IP_BN, q = idx / IP_BN;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g.W + (size_t)(n0 + row) * g.F) + q);
+    Bs[(4 * q + 0) * (IP_BN + 4) + row] = v.x; Bs[(4 * q + 1) * (IP_BN + 4) + row] = v.y;
+    Bs[(4 * q + 2) * (IP_BN + 4) + row] = v.z; Bs[(4 * q + 3) * (IP_BN + 4) + row] = v.w;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < g.F; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(As + k * (IP_BM + 4) + ty * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(As + k * (IP_BM + 4) + ty * 8 + 4);
+    const float4 b = *reinterpret_cast<const float4*>(Bs + k * (IP_BN + 4) + tx * 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+  const int n = n0 + tx * 4;
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= g.M) continue;
+    float4 v;
+    v.x = fmaxf(acc[i][0] + bias.x, 0.f); v.y = fmaxf(acc[i][1] + bias.y, 0.f);
+    v.z = fmaxf(acc[i][2] + bias.z, 0.f); v.w = fmaxf(acc[i][3] + bias.w, 0.f);
+    const int tsel = g.steps ? __ldg(g.steps + m / g.T) : g.t;
+    const float4 d = __ldg(reinterpret_cast<const float4*>(g.dtab + (size_t)tsel * g.C + n));
+    const float xin[4] = {v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w};
+    for (int r = 0; r < g.copies; ++r) {
+      const size_t row = (size_t)r * g.M + m;
+      *reinterpret_cast<float4*>(g.x32 + row * g.C + n) = v;
+      store_operand4(g.xmain, g.xaux, row, n, g.C, xin, g.fmt);
+    }
+  }
+}
+int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, const float* dtab0, const int* steps, int t,
+                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux, cudaStream_t s) {
+  if ((F % 4) || (C % IP_BN) || fmt <= 0) { set_error("in_proj_fused: unsupported F=%d C=%d fmt=%d", F, C, fmt); return DRB_E_INVALID; }
+  const int smem = F * (IP_BM + 4 + IP_BN + 4) * (int)sizeof(float);
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)in_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("in_proj_fused: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    cudaFuncSetAttribute((const void*)in_proj_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+    smem_set = smem;
+  }
+  InProjDev g;
+  g.x = x_t; g.W = W; g.bias = bias; g.dtab = dtab0; g.steps = steps; g.t = t; g.M = M; g.T = T; g.F = F; g.C = C;
+  g.copies = copies; g.fmt = fmt; g.x32 = x32; g.xmain = xmain; g.xaux = xaux;
+  dim3 grid((M + IP_BM - 1) / IP_BM, C / IP_BN);
+  in_proj_kernel<<<grid, 256, smem, s>>>(g);
   DRB_LAUNCH_CHECK();
   return 0;
 }

@@ -88,8 +88,10 @@ struct alignas(64) ZGemmParams {
   CUtensorMap zh, zl, w_h, w_l, out32, xh, xl;
   int NB, T, C, tiles_t, n_blocks, nslabs, spg, z_group0, group_stride, mode;  // mode 0 = RES, 1 = HEAD
   const float* bias;
-  const float* dnext;
+  const float* dnext;      // RES: next layer's diffusion_projection table [timesteps][C]
   const float* inv_scale;
+  const int* steps;        // per-sample diffusion steps (device, [bsamp]) or nullptr: every roll uses row t_uniform
+  int t_uniform, bsamp;
 };
 
 struct SmemView {
@@ -863,7 +865,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
   if (warp == 3) {
     for (int i = lane; i < TILE_N; i += 32) {
       sv.sbias[i] = __ldg(p.bias + n_base + i);
-      if (res) sv.sdn[i] = __ldg(p.dnext + n_base + i);
+      if (res) sv.sdn[i] = __ldg(p.dnext + (size_t)(p.steps ? __ldg(p.steps + nb % p.bsamp) : p.t_uniform) * p.C + n_base + i);
     }
   }
   // RES on CTA pairs: the K loop is only C/64 slabs, so it runs on a 2-stage ring and the third stage's 64 KB hold the
@@ -1159,7 +1161,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
         }
         const uint32_t box = smem_u32(xring + sl * CHUNK_BYTES);
         const float* bs = sbias + cbox * 32;
-        const float* dn = p.dnext + ti.n_base + cbox * 32;   // warp-uniform addresses: L1 broadcast, off the critical path
+        // warp-uniform addresses: L1 broadcast, off the critical path
+        const float* dn = p.dnext + (size_t)(p.steps ? __ldg(p.steps + ti.nb % p.bsamp) : p.t_uniform) * p.C + ti.n_base + cbox * 32;
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
           float xin[16];
@@ -1353,7 +1356,7 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   p.zh = maps.zh; p.zl = maps.zl; p.w_h = *z.w_h; p.w_l = *z.w_l; p.out32 = *z.out32; p.xh = maps.xh; p.xl = maps.xl;
   p.NB = z.NB; p.T = z.T; p.C = z.C; p.tiles_t = (z.T + TILE_M - 1) / TILE_M; p.n_blocks = z.C / TILE_N;
   p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg; p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
-  p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext;
+  p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = z.inv_scale;
   const bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);

@@ -109,6 +109,19 @@ class Engine:
             _lib.check(self.lib.drb_plan_set_branches(self.plan, branches), "drb_plan_set_branches")
             self.branches = branches
 
+    def set_steps(self, steps):
+        """Per-sample diffusion steps for the following step()/forward calls (model/diffwave.py:637,670: ``diffusion_step``
+        is int64[B]); ``None`` returns to the uniform ``t_index`` argument.  The int32 device copy is kept alive here."""
+        if steps is None:
+            self._steps = None
+            _lib.check(self.lib.drb_plan_set_steps(self.plan, C.c_void_p(0)), "drb_plan_set_steps")
+            return
+        st = steps.to(device=self.device, dtype=torch.int32).contiguous()
+        if tuple(st.shape) != (self.batch,):
+            raise ValueError(f"diffusion_step: expected shape ({self.batch},), got {tuple(st.shape)}")
+        self._steps = st
+        _lib.check(self.lib.drb_plan_set_steps(self.plan, _ptr(st)), "drb_plan_set_steps")
+
     def _check(self, t, shape, name):
         if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError(f"{name}: expected a contiguous fp32 tensor on {self.device}")

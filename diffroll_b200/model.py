@@ -34,6 +34,9 @@ class Normalization:
                 return x_std * (max - min) + min
         elif mode == 'imagewise':
             def normalize(x):
+                if x.is_cuda:   # label rolls already on the GPU (the validation step): one kernel, model/utils.py:25-32
+                    from .diffusion_ops import normalize_imagewise
+                    return normalize_imagewise(x, min, max)
                 x_max = x.flatten(1).max(1, keepdim=True)[0].unsqueeze(1)
                 x_min = x.flatten(1).min(1, keepdim=True)[0].unsqueeze(1)
                 x_std = (x - x_min) / (x_max - x_min)
@@ -204,21 +207,31 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
     # ---- reference forward ---------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x_t, waveform, diffusion_step, sampling=False, inpainting_t=None, inpainting_f=None):
-        """model/diffwave.py:637-686.  ``diffusion_step`` must hold one value for the whole batch
-        (every sampler of the reference passes ``tensor(t).repeat(B)``)."""
+        """model/diffwave.py:637-686.  ``diffusion_step``: int64[B]; the samplers pass one value repeated
+        (``tensor(t).repeat(B)``), the training / validation step a different one per roll (task/diffusion.py:667)."""
         if self.training:
             raise NotImplementedError("training-mode forward (spec dropout, autograd) is outside the sampling hot path; call .eval()")
         if torch.is_tensor(diffusion_step):
             if diffusion_step.dtype not in (torch.int32, torch.int64):
                 raise NotImplementedError("fractional diffusion steps (_lerp_embedding) are not on the sampling path")
-            t0 = int(diffusion_step.flatten()[0])
-            if not bool((diffusion_step == t0).all()):
-                raise NotImplementedError("per-sample diffusion steps are a training-time feature; the sampling path uses one t per batch")
+            steps = diffusion_step.flatten()
+            if steps.numel() != x_t.shape[0]:
+                raise ValueError("diffusion_step must hold one step per roll")
+            lo, hi = int(steps.min()), int(steps.max())
+            if lo < 0 or hi >= len(self.betas):
+                raise IndexError(f"diffusion_step out of range [0, {len(self.betas)})")   # the embedding lookup of :670 would raise
+            t0, per_roll = lo, lo != hi
         else:
-            t0 = int(diffusion_step)
+            t0, per_roll = int(diffusion_step), False
         branches = _lib.BRANCH_UNCOND if sampling is True else _lib.BRANCH_COND
         eng, xx, spec = self._prepare(x_t, waveform, branches, inpainting_t, inpainting_f)
-        pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
+        if not per_roll:
+            return eng.step(xx, None, t0, _upd(_lib.UPD_NONE)), spec
+        eng.set_steps(steps)
+        try:
+            pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
+        finally:
+            eng.set_steps(None)
         return pred, spec
 
     def train(self, mode=True):

@@ -122,3 +122,16 @@ def make_inputs(batch, timesteps, seed=123, n_noise=None, T=640, wav_len=327680)
     n = timesteps - 1 if n_noise is None else n_noise
     noise = torch.randn(n, batch, 1, T, 88, generator=g) if n > 0 else torch.empty(0, batch, 1, T, 88)
     return x_T, waveform, noise
+
+
+def make_labelled_batch(B=4, T=128, wav_len=65536, seed=77):
+    """Synthetic labelled batch of the (validation) step, task/diffusion.py:651-670: a binary piano roll [B,T,88] (the
+    last roll empty: the Normalization NaN -> min case of model/utils.py:31), a waveform, one diffusion step per roll
+    and the label noise [B,1,T,88].  Returns (frame, audio, t, noise)."""
+    g = torch.Generator().manual_seed(seed)
+    frame = (torch.rand(B, T, 88, generator=g) < 0.06).float()
+    frame[B - 1] = 0.0
+    audio = torch.randn(B, wav_len, generator=g)
+    t = torch.tensor([3, 150, 0, 199, 77, 12, 181, 64][:B])
+    noise = torch.randn(B, 1, T, 88, generator=g)
+    return frame, audio, t, noise

@@ -258,13 +258,68 @@ class SpecRollDiffusion(nn.Module):
         return extract_notes_batch(r, r)
 
     def p_losses(self, label, prediction, loss_type="l1"):
-        if loss_type == 'l1':
-            return F.l1_loss(label, prediction)
-        elif loss_type == 'l2':
-            return F.mse_loss(label, prediction)
-        elif loss_type == "huber":
-            return F.smooth_l1_loss(label, prediction)
-        raise NotImplementedError()
+        """task/diffusion.py:792-802 (mean l1 / l2 / smooth-l1) as one reduction kernel; 0-dim CUDA tensor."""
+        from .diffusion_ops import p_losses
+        return p_losses(label, prediction, loss_type)
+
+    @torch.no_grad()
+    def step(self, batch, t=None, noise=None):
+        """task/diffusion.py:651-763, forward only (what ``validation_step`` :271-276 runs): draw a diffusion step per
+        roll, ``q_sample`` the normalised label roll, one network forward at per-roll steps, and the diffusion loss.
+
+        batch: {'frame': [B,T,88], 'audio': [B,L]} on the GPU, or a list of two such dicts (the second one is run
+        unconditionally, :707-719).  ``t`` / ``noise`` default to the reference's draws (``torch.randint`` :667,
+        ``torch.randn_like`` :670, in that order on the roll's device) and can be injected for parity tests.
+        Returns (losses, tensors) with the reference's keys.  Gradients are not built: the backward pass is SURVEY.md
+        row f3, not part of this path."""
+        from .diffusion_ops import extract_x0, q_sample
+        two = isinstance(batch, list)
+        first = batch[0] if two else batch
+        roll = self.normalize(first["frame"]).unsqueeze(1)
+        waveform = first["audio"]
+        batch_size = roll.shape[0]
+        device = roll.device
+        if t is None:
+            t = torch.randint(0, self.hparams.timesteps, (batch_size,), device=device).long()
+        if noise is None:
+            noise = torch.randn_like(roll)
+        sa, s1 = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
+        x_t = q_sample(roll, t, sa, s1, noise)
+        mode = self.hparams.training.mode
+        if self.hparams.debug:
+            raise NotImplementedError("debug=True conditions on the label roll (DiffRollDebug); not on this path")
+        losses, tensors = {}, {}
+        if mode == 'epsilon':
+            epsilon_pred, spec = self(x_t, waveform, t)
+            losses["diffusion_loss"] = self.p_losses(noise, epsilon_pred, loss_type=self.hparams.loss_type)
+            pred_roll = extract_x0(x_t, epsilon_pred, t, sa, s1)
+        elif mode == 'x_0':
+            pred_roll, spec = self(x_t, waveform, t)
+            losses["diffusion_loss"] = self.p_losses(roll, pred_roll, loss_type=self.hparams.loss_type)
+            if two:
+                roll2 = self.normalize(batch[1]["frame"]).unsqueeze(1)
+                x_t2 = q_sample(roll2, t, sa, s1, noise)
+                pred_roll2, spec2 = self(x_t2, batch[1]["audio"], t, sampling=True)
+                losses["unconditional_diffusion_loss"] = self.p_losses(roll2, pred_roll2, loss_type=self.hparams.loss_type)
+                tensors.update(spec2=spec2, label_roll2=roll2, pred_roll2=pred_roll2)
+        elif mode == 'ex_0':
+            epsilon_pred, spec = self(x_t, waveform, t)
+            pred_roll = extract_x0(x_t, epsilon_pred, t, sa, s1)
+            losses["diffusion_loss"] = self.p_losses(roll, pred_roll, loss_type=self.hparams.loss_type)
+        else:
+            raise ValueError(f"training mode {mode} is not supported. Please either use 'x_0' or 'epsilon'.")
+        tensors.update(pred_roll=pred_roll, label_roll=roll, spec=spec)
+        return losses, tensors
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx=0):
+        """task/diffusion.py:271-276 without the figure logging: returns the summed loss over ``hparams.loss_keys``."""
+        losses, _ = self.step(batch)
+        total_loss = 0
+        for k in self.hparams.loss_keys:
+            total_loss = total_loss + losses[k]
+            self.log(f"Val/{k}", losses[k])
+        return total_loss
 
     # provided by the model subclass
     def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):

@@ -128,6 +128,13 @@ int drb_plan_destroy(drb_plan* plan);
  * DRB_BRANCH_COND_UNCOND has room for both and may be switched to either single branch. */
 int drb_plan_set_branches(drb_plan* plan, int32_t branches);
 
+/* Per-sample diffusion steps (ClassifierFreeDiffRoll.forward takes diffusion_step int64[B], model/diffwave.py:637,670;
+ * the samplers pass one value repeated, the training / validation step a different one per roll,
+ * task/diffusion.py:667).  steps_dev: device array of `batch` int32 values in [0, timesteps), read by the following
+ * drb_in_proj / drb_resblock_forward / drb_sample_step calls INSTEAD of their t_index argument (it must stay valid
+ * until they have run); NULL returns to the uniform t_index. */
+int drb_plan_set_steps(drb_plan* plan, const int32_t* steps_dev);
+
 /* DiffusionEmbedding MLP + every layer's diffusion_projection for all timesteps:
  * model/diffwave.py:65-74,138.  emb_table is the [timesteps,128] sinusoid table
  * built by the host with the reference's own expression (model/diffwave.py:83-88). */
@@ -177,6 +184,23 @@ size_t drb_extract_notes_scratch_bytes(int32_t B, int32_t T, int32_t P);
 int drb_extract_notes(const float* onsets, const float* frames, int32_t B, int32_t T, int32_t P, float onset_threshold,
                       float frame_threshold, void* scratch, int32_t* pitches, int32_t* intervals, int32_t* counts,
                       int32_t max_notes, void* stream);
+
+/* Forward-only part of the reference's (validation) step around the network forward, SURVEY section 8 row f3
+ * (task/diffusion.py:651-763).  steps: device int32[B], one diffusion step per roll; the two tables are the
+ * [timesteps] fp32 schedule tensors of task/diffusion.py:250-251 on the device; n_per = elements per roll, % 4 == 0.
+ *   drb_q_sample    x_t = sqrt_alphas_cumprod[t]*x_start + sqrt_one_minus_alphas_cumprod[t]*noise   task/diffusion.py:31-46
+ *   drb_extract_x0  x0  = (x_t - sqrt_one_minus_alphas_cumprod[t]*epsilon)/sqrt_alphas_cumprod[t]   task/diffusion.py:49-65
+ *   drb_p_losses    loss_type 0: mean|a-b| (F.l1_loss), 1: mean (a-b)^2, 2: smooth-l1 (beta 1)       task/diffusion.py:792-802
+ *                   -> loss_out[0] (device); scratch: drb_p_losses_scratch_bytes() bytes
+ *   drb_normalize_imagewise  per-roll min-max to [lo,hi], NaN (constant roll) -> lo                  model/utils.py:21-32 */
+int drb_q_sample(const float* x_start, const float* noise, const int32_t* steps, const float* sqrt_alphas_cumprod,
+                 const float* sqrt_one_minus_alphas_cumprod, float* x_t, int32_t B, int64_t n_per, void* stream);
+int drb_extract_x0(const float* x_t, const float* epsilon, const int32_t* steps, const float* sqrt_alphas_cumprod,
+                   const float* sqrt_one_minus_alphas_cumprod, float* x0, int32_t B, int64_t n_per, void* stream);
+size_t drb_p_losses_scratch_bytes(void);
+int drb_p_losses(const float* label, const float* prediction, int64_t n, int32_t loss_type, void* scratch,
+                 float* loss_out, void* stream);
+int drb_normalize_imagewise(const float* x, float* out, int32_t B, int64_t n_per, float lo, float hi, void* stream);
 
 /* Measurement hooks (bench.py): with profiling enabled every step records CUDA events on the launching stream
  * around each kernel class; drb_plan_profile_read synchronises and returns, for class k in

@@ -240,6 +240,55 @@ class OracleDiffRoll:
         return (s.sqrt_alphas_cumprod[t_index - 1] * x0
                 + torch.sqrt(1 - s.sqrt_alphas_cumprod[t_index - 1] ** 2 - sigma ** 2) * eps + sigma * noise), spec
 
+    # ---- forward-only (validation) step: task/diffusion.py:651-763 as run by validation_step :271-276 -------------
+    @torch.no_grad()
+    def step(self, batch, t, noise):
+        """t [B] and noise [B,1,T,88] are injected instead of torch.randint (:667) / torch.randn_like (:670)."""
+        hp, s = self.hp, self.sched
+        two = isinstance(batch, list)
+        first = batch[0] if two else batch
+        lo, hi = hp["norm_args"][0], hp["norm_args"][1]
+        roll = normalize_imagewise(first["frame"].to(self.dtype), lo, hi).unsqueeze(1)
+        waveform = first["audio"]
+
+        def q_sample(x_start):                                        # task/diffusion.py:31-46
+            a = s.sqrt_alphas_cumprod[t][:, None, None, None].to(x_start.device)
+            b = s.sqrt_one_minus_alphas_cumprod[t][:, None, None, None].to(x_start.device)
+            return a * x_start + b * noise
+
+        def extract_x0(x_t, eps):                                     # task/diffusion.py:49-65
+            a = s.sqrt_alphas_cumprod[t][:, None, None, None].to(x_t.device)
+            b = s.sqrt_one_minus_alphas_cumprod[t][:, None, None, None].to(x_t.device)
+            return (x_t - b * eps) / a
+
+        def p_losses(label, prediction):                              # task/diffusion.py:792-802
+            fn = {"l1": F.l1_loss, "l2": F.mse_loss, "huber": F.smooth_l1_loss}[hp["loss_type"]]
+            return fn(label, prediction)
+
+        x_t = q_sample(roll)
+        mode = hp["training"]["mode"]
+        losses, tensors = {}, {}
+        if mode == "epsilon":
+            eps, spec = self(x_t, waveform, t)
+            losses["diffusion_loss"] = p_losses(noise, eps)
+            pred_roll = extract_x0(x_t, eps)
+        elif mode == "x_0":
+            pred_roll, spec = self(x_t, waveform, t)
+            losses["diffusion_loss"] = p_losses(roll, pred_roll)
+            if two:
+                roll2 = normalize_imagewise(batch[1]["frame"].to(self.dtype), lo, hi).unsqueeze(1)
+                pred_roll2, spec2 = self(q_sample(roll2), batch[1]["audio"], t, sampling=True)
+                losses["unconditional_diffusion_loss"] = p_losses(roll2, pred_roll2)
+                tensors.update(spec2=spec2, label_roll2=roll2, pred_roll2=pred_roll2)
+        elif mode == "ex_0":
+            eps, spec = self(x_t, waveform, t)
+            pred_roll = extract_x0(x_t, eps)
+            losses["diffusion_loss"] = p_losses(roll, pred_roll)
+        else:
+            raise ValueError(mode)
+        tensors.update(pred_roll=pred_roll, label_roll=roll, spec=spec)
+        return losses, tensors
+
     # ---- the loop (task/diffusion.py:513-534), noise[i] used at the i-th step with t>0 -------
     @torch.no_grad()
     def sample_loop(self, x_T, waveform, noise, t_start=None, t_stop=0, keep_numpy=True):

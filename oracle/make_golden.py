@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (container only).
 
-    python oracle/make_golden.py [--only forward,steps,chain,chain_inpaint,chain_gen]
+    python oracle/make_golden.py [--only forward,steps,chain,chain_inpaint,chain_gen,valstep]
 
 The reference is imported from /root/reference through oracle/ref_shim.py, loaded
 with the seeded weights of diffroll_b200/synthetic.py (strict=True, so the
@@ -23,7 +23,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dict  # noqa: E402
+from diffroll_b200.synthetic import default_hparams, make_inputs, make_labelled_batch, make_state_dict  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -116,9 +116,50 @@ def gen_chain(tag, hp, B, seed, T=640, wav_len=327680, keep=(), fp64=False):
     print(tag, "done in", dt, "s", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+def gen_valstep():
+    """SpecRollDiffusion.step (task/diffusion.py:651-763) in eval mode, i.e. what validation_step (:271-276) runs:
+    normalise, q_sample at per-roll steps, forward, loss -- for the three training modes and the three loss types,
+    plus the two-dataset variant (:707-719).  torch.randint / randn_like are pinned to the injected t / noise."""
+    frame, audio, t, noise = make_labelled_batch()
+    frame2, audio2, _, _ = make_labelled_batch(seed=78)
+    out = {}
+    orig_randint = torch.randint
+    for mode, loss_type in (("x_0", "l2"), ("x_0", "l1"), ("epsilon", "huber"), ("ex_0", "l2")):
+        hp = default_hparams()
+        hp["training"] = dict(mode=mode)
+        hp["loss_type"] = loss_type
+        m = ref_model(hp)
+        torch.randint = lambda *a, **k: t.clone()
+        try:
+            with NoiseQueue() as nq, torch.no_grad():
+                nq.q = [noise.clone()]
+                losses, tensors = m.step({"frame": frame.clone(), "audio": audio.clone()})
+        finally:
+            torch.randint = orig_randint
+        tag = f"{mode}_{loss_type}"
+        out[f"{tag}_loss"] = np.float64(losses["diffusion_loss"].item())
+        out[f"{tag}_pred_roll"] = tensors["pred_roll"].numpy()
+        out["label_roll"] = tensors["label_roll"].numpy()      # the same normalised label for every mode
+    hp = default_hparams()
+    m = ref_model(hp)
+    torch.randint = lambda *a, **k: t.clone()
+    try:
+        with NoiseQueue() as nq, torch.no_grad():
+            nq.q = [noise.clone()]
+            losses, tensors = m.step([{"frame": frame.clone(), "audio": audio.clone()},
+                                      {"frame": frame2.clone(), "audio": audio2.clone()}])
+    finally:
+        torch.randint = orig_randint
+    out["two_loss"] = np.float64(losses["diffusion_loss"].item())
+    out["two_uncond_loss"] = np.float64(losses["unconditional_diffusion_loss"].item())
+    out["two_pred_roll2"] = tensors["pred_roll2"].numpy()
+    np.savez_compressed(os.path.join(GOLD, "valstep_b4_T128.npz"), **out)
+    print({k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="forward,steps,chain,chain_inpaint,chain_gen")
+    ap.add_argument("--only", default="forward,steps,chain,chain_inpaint,chain_gen,valstep")
     a = ap.parse_args()
     only = set(a.only.split(","))
     os.makedirs(GOLD, exist_ok=True)
@@ -127,6 +168,8 @@ def main():
         gen_forward(); print("forward done")
     if "steps" in only:
         gen_steps(); print("steps done")
+    if "valstep" in only:
+        gen_valstep(); print("valstep done")
     if "chain" in only:       # configs[0]/[1] shape: transcription, 200 steps, full 640-frame clip
         gen_chain("transcription_b1_200", default_hparams(), 1, seed=123, keep=(150, 100, 50), fp64=True)
     if "chain_inpaint" in only:  # configs[3] shape: 50 % frame mask

@@ -106,3 +106,38 @@ def test_mel_restatement_matches_torchaudio():
     assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
     fb = layer.mel_scale.fb
     assert int((fb != 0).sum()) == 2034 and int((fb != 0).sum(0).max()) <= 24
+
+
+VALSTEP_CASES = [("x_0", "l2"), ("x_0", "l1"), ("epsilon", "huber"), ("ex_0", "l2")]
+
+
+@pytest.mark.parametrize("mode,loss_type", VALSTEP_CASES)
+def test_validation_step_vs_reference(mode, loss_type):
+    """SpecRollDiffusion.step in eval mode (task/diffusion.py:651-763): per-roll diffusion steps, q_sample, forward, loss."""
+    from diffroll_b200.synthetic import make_labelled_batch
+    g = golden("valstep_b4_T128.npz")
+    hp = default_hparams()
+    hp["training"] = dict(mode=mode)
+    hp["loss_type"] = loss_type
+    o = OracleDiffRoll(hp, make_state_dict(hp))
+    frame, audio, t, noise = make_labelled_batch()
+    losses, tensors = o.step({"frame": frame, "audio": audio}, t, noise)
+    tag = f"{mode}_{loss_type}"
+    ref = g[f"{tag}_pred_roll"]
+    assert _err(tensors["pred_roll"], ref) < TOL * max(1.0, float(np.abs(ref).max()))
+    assert _err(tensors["label_roll"], g["label_roll"]) == 0.0
+    assert float(tensors["label_roll"][-1].abs().max()) == 0.0          # empty roll: NaN -> min (model/utils.py:31)
+    assert abs(float(losses["diffusion_loss"]) - float(g[f"{tag}_loss"])) < 1e-5 * max(1.0, float(g[f"{tag}_loss"]))
+
+
+def test_validation_step_two_datasets_vs_reference():
+    from diffroll_b200.synthetic import make_labelled_batch
+    g = golden("valstep_b4_T128.npz")
+    hp = default_hparams()
+    o = OracleDiffRoll(hp, make_state_dict(hp))
+    frame, audio, t, noise = make_labelled_batch()
+    frame2, audio2, _, _ = make_labelled_batch(seed=78)
+    losses, tensors = o.step([{"frame": frame, "audio": audio}, {"frame": frame2, "audio": audio2}], t, noise)
+    assert abs(float(losses["diffusion_loss"]) - float(g["two_loss"])) < 1e-5 * max(1.0, float(g["two_loss"]))
+    assert abs(float(losses["unconditional_diffusion_loss"]) - float(g["two_uncond_loss"])) < 1e-5 * max(1.0, float(g["two_uncond_loss"]))
+    assert _err(tensors["pred_roll2"], g["two_pred_roll2"]) < TOL * max(1.0, float(np.abs(g["two_pred_roll2"]).max()))
