@@ -62,9 +62,41 @@ __global__ void __launch_bounds__(128) notes_compact_kernel(const int16_t* __res
   if (threadIdx.x == 0) counts[b] = base;
 }
 
+// Frame-level confusion counts of test_step's precision_recall_fscore_support(label.flatten(), pred.flatten() > thr,
+// average='binary') (task/diffusion.py:378-380): TP, FP, FN over all elements.  One coalesced pass, integer counts.
+__global__ void __launch_bounds__(256) frame_counts_kernel(const float* __restrict__ pred, const float* __restrict__ label, size_t n,
+                                                           float thr, unsigned long long* __restrict__ counts) {
+  unsigned tp = 0, fp = 0, fn = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const bool p = pred[i] > thr, l = label[i] == 1.0f;      // pos_label = 1
+    tp += p && l; fp += p && !l; fn += !p && l;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tp += __shfl_down_sync(0xffffffffu, tp, o); fp += __shfl_down_sync(0xffffffffu, fp, o); fn += __shfl_down_sync(0xffffffffu, fn, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (tp) atomicAdd(counts + 0, (unsigned long long)tp);
+    if (fp) atomicAdd(counts + 1, (unsigned long long)fp);
+    if (fn) atomicAdd(counts + 2, (unsigned long long)fn);
+  }
+}
+
 }  // namespace drb
 
 using namespace drb;
+
+extern "C" int drb_frame_counts(const float* pred, const float* label, int64_t n, float threshold, uint64_t* counts3, void* stream) {
+  if (!pred || !label || !counts3 || n <= 0) { set_error("frame_counts: bad argument"); return DRB_E_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  DRB_CUDA(cudaMemsetAsync(counts3, 0, 3 * sizeof(uint64_t), s));
+  size_t blocks = ((size_t)n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  frame_counts_kernel<<<(unsigned)blocks, 256, 0, s>>>(pred, label, (size_t)n, threshold, reinterpret_cast<unsigned long long*>(counts3));
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" size_t drb_extract_notes_scratch_bytes(int32_t B, int32_t T, int32_t P) {
   if (B <= 0 || T <= 0 || P <= 0) return 0;

@@ -348,25 +348,31 @@ struct InProjDev {
   int t, M, T, F, C, copies, fmt;
   float* x32; void* xmain; void* xaux;
 };
+// FC: compile-time pitch count (88: every load loop fully unrolled, so all of a thread's global loads are in flight at
+// once instead of one L2 round trip per iteration) or 0 for the generic run-time F.
+template <int FC>
 __global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
   extern __shared__ __align__(16) float ip_smem[];
+  const int F = FC > 0 ? FC : g.F;
   float* As = ip_smem;                             // [F][IP_BM + 4]
-  float* Bs = ip_smem + g.F * (IP_BM + 4);         // [F][IP_BN + 4]
+  float* Bs = ip_smem + F * (IP_BM + 4);           // [F][IP_BN + 4]
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * IP_BM, n0 = blockIdx.y * IP_BN;
-  const int f4 = g.F / 4;
+  const int f4 = F / 4;
   // lanes walk ROWS (consecutive smem words per transposed store: conflict-free); the 16-byte pieces of a 352-byte
   // input row are picked up by successive iterations out of L1
+#pragma unroll
   for (int idx = tid; idx < IP_BM * f4; idx += 256) {
     const int row = idx % IP_BM, q = idx / IP_BM;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m0 + row < g.M) v = __ldg(reinterpret_cast<const float4*>(g.x + (size_t)(m0 + row) * g.F) + q);
+    if (m0 + row < g.M) v = __ldg(reinterpret_cast<const float4*>(g.x + (size_t)(m0 + row) * F) + q);
     As[(4 * q + 0) * (IP_BM + 4) + row] = v.x; As[(4 * q + 1) * (IP_BM + 4) + row] = v.y;
     As[(4 * q + 2) * (IP_BM + 4) + row] = v.z; As[(4 * q + 3) * (IP_BM + 4) + row] = v.w;
   }
+#pragma unroll
   for (int idx = tid; idx < IP_BN * f4; idx += 256) {
     const int row = idx % IP_BN, q = idx / IP_BN;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(g.W + (size_t)(n0 + row) * g.F) + q);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g.W + (size_t)(n0 + row) * F) + q);
     Bs[(4 * q + 0) * (IP_BN + 4) + row] = v.x; Bs[(4 * q + 1) * (IP_BN + 4) + row] = v.y;
     Bs[(4 * q + 2) * (IP_BN + 4) + row] = v.z; Bs[(4 * q + 3) * (IP_BN + 4) + row] = v.w;
   }
@@ -377,8 +383,8 @@ __global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < g.F; ++k) {
+#pragma unroll 8
+  for (int k = 0; k < F; ++k) {
     const float4 a0 = *reinterpret_cast<const float4*>(As + k * (IP_BM + 4) + ty * 8);
     const float4 a1 = *reinterpret_cast<const float4*>(As + k * (IP_BM + 4) + ty * 8 + 4);
     const float4 b = *reinterpret_cast<const float4*>(Bs + k * (IP_BN + 4) + tx * 4);
@@ -414,9 +420,11 @@ int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, co
   const int smem = F * (IP_BM + 4 + IP_BN + 4) * (int)sizeof(float);
   static int smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)in_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("in_proj_fused: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    cudaFuncSetAttribute((const void*)in_proj_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    for (const void* fn : {(const void*)in_proj_kernel<88>, (const void*)in_proj_kernel<0>}) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) { set_error("in_proj_fused: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+      cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     cudaGetLastError();
     smem_set = smem;
   }
@@ -424,7 +432,8 @@ int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, co
   g.x = x_t; g.W = W; g.bias = bias; g.dtab = dtab0; g.steps = steps; g.t = t; g.M = M; g.T = T; g.F = F; g.C = C;
   g.copies = copies; g.fmt = fmt; g.x32 = x32; g.xmain = xmain; g.xaux = xaux;
   dim3 grid((M + IP_BM - 1) / IP_BM, C / IP_BN);
-  in_proj_kernel<<<grid, 256, smem, s>>>(g);
+  if (F == 88) in_proj_kernel<88><<<grid, 256, smem, s>>>(g);
+  else in_proj_kernel<0><<<grid, 256, smem, s>>>(g);
   DRB_LAUNCH_CHECK();
   return 0;
 }

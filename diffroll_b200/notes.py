@@ -57,3 +57,26 @@ def extract_notes_wo_velocity(onsets, frames, onset_threshold=0.5, frame_thresho
     same = frames is onsets
     on = onsets.unsqueeze(0)
     return extract_notes_batch(on, on if same else frames.unsqueeze(0), onset_threshold, frame_threshold, rule)[0]
+
+
+def frame_precision_recall_f1(label, pred, threshold=0.5):
+    """precision_recall_fscore_support(label.flatten(), pred.flatten() > threshold, average='binary')[:3] of
+    task/diffusion.py:378-380 from one counting kernel (positive class = 1).  Returns (precision, recall, f1, (tp, fp, fn));
+    an empty denominator gives 0.0 like sklearn's zero_division default (without its warning)."""
+    if not (torch.is_tensor(label) and label.is_cuda and torch.is_tensor(pred) and pred.is_cuda):
+        raise _lib.DrbError("frame_precision_recall_f1: CUDA tensors required (no CPU path)")
+    if label.numel() != pred.numel():
+        raise ValueError("label and prediction must have the same number of elements")
+    lib = _lib.load()
+    la = label.to(torch.float32).contiguous()
+    pr = pred.to(torch.float32).contiguous()
+    counts = torch.empty(3, dtype=torch.int64, device=pr.device)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    with torch.cuda.device(pr.device):
+        _lib.check(lib.drb_frame_counts(C.c_void_p(pr.data_ptr()), C.c_void_p(la.data_ptr()), C.c_int64(pr.numel()),
+                                        C.c_float(threshold), C.c_void_p(counts.data_ptr()), stream), "drb_frame_counts")
+    tp, fp, fn = (int(v) for v in counts.cpu())
+    precision = tp / (tp + fp) if tp + fp else 0.0
+    recall = tp / (tp + fn) if tp + fn else 0.0
+    f1 = 2 * precision * recall / (precision + recall) if precision + recall else 0.0
+    return precision, recall, f1, (tp, fp, fn)

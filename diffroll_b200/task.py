@@ -257,6 +257,29 @@ class SpecRollDiffusion(nn.Module):
         r = rolls[:, 0] if rolls.ndim == 4 else rolls
         return extract_notes_batch(r, r)
 
+    @torch.no_grad()
+    def test_step(self, batch, batch_idx=0):
+        """task/diffusion.py:312-418 up to the host-library boundary: ``sampling`` (the whole reverse chain from fresh
+        noise), the frame-level precision / recall / F1 of :378-380 and the note lists of :382-396 for the estimate
+        and the label, all on the GPU.  The mir_eval note metrics, figures, GIF, audio and MIDI files of the reference
+        are host I/O and not built.  batch = {'frame': [B,T,88], 'audio': [B,L]} on the GPU.
+        Returns a dict: frame_p, frame_r, frame_f1, counts (tp, fp, fn), notes_est / notes_ref (lists of
+        (pitches, intervals) in frames, the reference's order), roll_pred (numpy [B,1,T,88]), spec."""
+        from .notes import extract_notes_batch, frame_precision_recall_f1
+        noise_list, spec = self.sampling(batch, batch_idx)
+        roll_pred = noise_list[-1][0]
+        thr = self.hparams.frame_threshold
+        label = batch["frame"]
+        pred_dev = torch.from_numpy(roll_pred).to(label.device)
+        T = pred_dev.shape[2]
+        lab = label[:, :T, :].to(torch.float32).contiguous()          # trim_spec_roll may have shortened the roll
+        p, r, f1, counts = frame_precision_recall_f1(lab, pred_dev[:, 0], thr)
+        self.log("Test/Frame_F1", f1)
+        est = extract_notes_batch(pred_dev[:, 0], pred_dev[:, 0], thr, thr)
+        ref = extract_notes_batch(lab, lab, thr, thr)
+        return dict(frame_p=p, frame_r=r, frame_f1=f1, counts=counts, notes_est=est, notes_ref=ref,
+                    roll_pred=roll_pred, spec=spec)
+
     def p_losses(self, label, prediction, loss_type="l1"):
         """task/diffusion.py:792-802 (mean l1 / l2 / smooth-l1) as one reduction kernel; 0-dim CUDA tensor."""
         from .diffusion_ops import p_losses

@@ -185,6 +185,11 @@ int drb_extract_notes(const float* onsets, const float* frames, int32_t B, int32
                       float frame_threshold, void* scratch, int32_t* pitches, int32_t* intervals, int32_t* counts,
                       int32_t max_notes, void* stream);
 
+/* Frame-level confusion counts behind test_step's precision_recall_fscore_support(label.flatten(),
+ * pred.flatten() > threshold, average='binary'), task/diffusion.py:378-380: counts3 (device) = {TP, FP, FN} with
+ * positive label == 1.0f.  precision = TP/(TP+FP), recall = TP/(TP+FN), f1 = 2PR/(P+R) are left to the host. */
+int drb_frame_counts(const float* pred, const float* label, int64_t n, float threshold, uint64_t* counts3, void* stream);
+
 /* Forward-only part of the reference's (validation) step around the network forward, SURVEY section 8 row f3
  * (task/diffusion.py:651-763).  steps: device int32[B], one diffusion step per roll; the two tables are the
  * [timesteps] fp32 schedule tensors of task/diffusion.py:250-251 on the device; n_per = elements per roll, % 4 == 0.

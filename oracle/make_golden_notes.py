@@ -42,7 +42,22 @@ def main():
     p, i = ref_fn(on, fr, onset_threshold=0.7, frame_threshold=0.4)
     res["two_on"], res["two_fr"] = on, fr
     res["two_p"], res["two_i"] = np.asarray(p, dtype=np.int64), np.asarray(i, dtype=np.int64).reshape(-1, 2)
+    # frame-level precision / recall / F1 as test_step computes them (task/diffusion.py:378-380), sklearn's own outputs
+    import warnings
+    from sklearn.metrics import precision_recall_fscore_support
+    rng = np.random.default_rng(13)
+    label = (rng.random((4, 1, 640, 88)) < 0.05).astype(np.float32)
+    pred = np.clip(label * 0.8 + rng.normal(0, 0.35, label.shape), -1, 2).astype(np.float32)
+    prf = {}
+    for name, (la, pr) in {"mixed": (label, pred), "nopos": (np.zeros_like(label), pred), "nopred": (label, np.zeros_like(pred))}.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            p, r, f, _ = precision_recall_fscore_support(la.flatten(), pr.flatten() > 0.5, average="binary")
+        prf[name] = (p, r, f)
+        res[f"prf_{name}"] = np.array([p, r, f], dtype=np.float64)
+    res["prf_label"], res["prf_pred"] = label, pred
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "notes.npz"), **res)
+    print(prf)
     print({k: v.shape for k, v in res.items() if k.endswith("_p")})
 
 

@@ -35,3 +35,17 @@ def extract_notes_wo_velocity(onsets, frames, onset_threshold=0.5, frame_thresho
             pitches.append(pitch)
             intervals.append([frame, offset])
     return np.array(pitches), np.array(intervals)
+
+
+def frame_precision_recall_f1(label, pred, threshold=0.5):
+    """precision_recall_fscore_support(label.flatten(), pred.flatten() > threshold, average='binary') of
+    task/diffusion.py:378-380 (third-party: scikit-learn, requirements.txt) restated from its published definition for
+    the binary average with pos_label = 1: P = TP/(TP+FP), R = TP/(TP+FN), F1 = 2PR/(P+R), 0 on an empty denominator.
+    Pinned by tests/golden/notes.npz (sklearn's own outputs, oracle/make_golden_notes.py)."""
+    y = np.asarray(label).reshape(-1) == 1
+    p = np.asarray(pred).reshape(-1) > threshold
+    tp, fp, fn = int((p & y).sum()), int((p & ~y).sum()), int((~p & y).sum())
+    prec = tp / (tp + fp) if tp + fp else 0.0
+    rec = tp / (tp + fn) if tp + fn else 0.0
+    f1 = 2 * prec * rec / (prec + rec) if prec + rec else 0.0
+    return prec, rec, f1, (tp, fp, fn)

@@ -19,18 +19,19 @@ with open(os.path.join(root, "profiles", f"{tag}_launches_summary.md"), "w") as 
     for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"| {k} | {len(v)} | {sum(v):.1f} | {sum(v)/len(v):.1f} | {100*sum(v)/tot:.1f}% |\n")
 rep = os.path.join(root, "gpurun_out", f"prof_umma_{tag}.ncu-rep")
-
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
+rawcsv = os.path.join(root, "gpurun_out", f"prof_umma_{tag}_raw.csv")   # `ncu -i ... --page raw --csv` run on the GPU box
+                                                                         # (a --set full report of a whole step exceeds gpurun's 64 MiB)
+if os.path.exists(rep) or os.path.exists(rawcsv):
+    raw = (subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+           if os.path.exists(rep) else open(rawcsv).read())
+    rr = [r for r in csv.reader(raw.splitlines()) if len(r) > 10]
     hdr, units = rr[0], rr[1]
     keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic", "launch__cluster_dim_x",
-            "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.sum.per_second",
-            "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.sum.pct_of_peak_sustained_elapsed"]
+            "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second"]
     idx = [i for i, h in enumerate(hdr) if h in keep]
     with open(os.path.join(root, "profiles", f"{tag}_umma_ncu_full.csv"), "w") as f:
         w = csv.writer(f)
@@ -44,7 +45,9 @@ if os.path.exists(rep):
         return float(v) * m.get(u, 1)
     out = {}
     for r in rr[2:]:
-        key = "umma_gate_kernel" if "gate" in r[ik] else "umma_zgemm_kernel" if "zgemm" in r[ik] else "umma_out_kernel" if "out" in r[ik] else r[ik]
+        nm = r[ik].split("(")[0].replace("void ", "").replace("drb::", "")
+        key = ("umma_gate_dual_kernel" if "gate_pers_kernel<3, 1>" in nm or "gate_pers_kernel<1, 1>" in nm else "umma_gate_kernel" if "gate" in nm
+               else "umma_res_kernel" if "res_pers" in nm else "umma_zgemm_kernel" if "zgemm" in nm else nm)
         out.setdefault(key + "_dram_bytes_per_launch", []).append(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]))
     out = {k: sum(v) / len(v) for k, v in out.items()}
     out["source"] = f"ncu --set full --clock-control none, profiles/{tag}_umma_ncu_full.csv"

@@ -62,3 +62,63 @@ def test_cuda_notes_two_inputs_batch_and_full_size():
         assert np.all(np.diff(key) > 0) and np.all(i[:, 1] > i[:, 0]) and i[:, 1].max() <= 640
         on = rolls[b] > 0.6
         assert np.all(on[i[:, 0], p]) and np.all((i[:, 0] == 0) | ~on[np.maximum(i[:, 0] - 1, 0), p])
+
+
+PRF_CASES = ["mixed", "nopos", "nopred"]
+
+
+def _prf_inputs(g, name):
+    label, pred = g["prf_label"], g["prf_pred"]
+    if name == "nopos":
+        label = np.zeros_like(label)
+    if name == "nopred":
+        pred = np.zeros_like(pred)
+    return label, pred
+
+
+@pytest.mark.parametrize("name", PRF_CASES)
+def test_oracle_frame_prf_matches_sklearn_golden(name):
+    """test_step's frame metrics (task/diffusion.py:378-380): the restated definition against sklearn's own outputs."""
+    from oracle.notes_oracle import frame_precision_recall_f1
+    g = golden("notes.npz")
+    label, pred = _prf_inputs(g, name)
+    p, r, f, _ = frame_precision_recall_f1(label, pred, 0.5)
+    assert np.allclose([p, r, f], g[f"prf_{name}"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PRF_CASES)
+def test_cuda_frame_prf_vs_golden_and_oracle(name):
+    from diffroll_b200.notes import frame_precision_recall_f1 as cuda_prf
+    from oracle.notes_oracle import frame_precision_recall_f1 as oracle_prf
+    g = golden("notes.npz")
+    label, pred = _prf_inputs(g, name)
+    p, r, f, counts = cuda_prf(torch.from_numpy(label).cuda(), torch.from_numpy(pred).cuda(), 0.5)
+    assert counts == oracle_prf(label, pred, 0.5)[3]                       # integer counts: bit-exact
+    assert np.allclose([p, r, f], g[f"prf_{name}"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.gpu
+def test_test_step_end_to_end_short_chain():
+    """test_step (task/diffusion.py:312-418 up to the mir_eval boundary): sampling from fresh noise, frame metrics and
+    note lists; the metrics must equal the oracle's on the returned roll, the label notes the oracle's on the label."""
+    import diffroll_b200 as M
+    from diffroll_b200.synthetic import default_hparams, make_labelled_batch, make_state_dict
+    from oracle.notes_oracle import frame_precision_recall_f1 as oracle_prf
+    hp = default_hparams(timesteps=6)
+    m = M.ClassifierFreeDiffRoll(**hp)
+    m.load_state_dict(make_state_dict(hp))
+    m = m.cuda().eval()
+    frame, audio, _, _ = make_labelled_batch(B=2)
+    torch.manual_seed(3)
+    out = m.test_step({"frame": frame.cuda(), "audio": audio.cuda()}, 0)
+    assert out["roll_pred"].shape == (2, 1, 128, 88)
+    p, r, f, counts = oracle_prf(frame.numpy(), out["roll_pred"][:, 0], 0.5)
+    assert counts == out["counts"] and (p, r, f) == (out["frame_p"], out["frame_r"], out["frame_f1"])
+    for b in range(2):
+        pr, ir = oracle_notes(frame[b].numpy(), frame[b].numpy())
+        assert _same(out["notes_ref"][b][0], pr) and _same(out["notes_ref"][b][1], ir)
+        pe, ie = oracle_notes(out["roll_pred"][b, 0], out["roll_pred"][b, 0])
+        assert _same(out["notes_est"][b][0], pe) and _same(out["notes_est"][b][1], ie)
+    for e, _ in m._engines.values():
+        e.close()
