@@ -81,3 +81,55 @@ def test_full_size_step_vs_gpu_eager_oracle_and_eager_timing():
     with open(os.path.join(ROOT, "gpurun_out", "eager_baseline.json"), "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res))
+
+
+@pytest.mark.parametrize("case", ["configs2_generation_b64_1000", "configs3_inpaint_shard_b8", "configs4_shard_b32_cfdg"])
+def test_full_size_other_configs_vs_gpu_eager_oracle(case):
+    """The other BASELINE.json configurations at their full per-GPU sizes, one step at the noisiest t (with noise) and the
+    t = 0 step (x0 / sqrt(abar_0): network error undamped), against the oracle run eagerly on the GPU with TF32 off:
+      configs[2]  unconditional generation, batch 64, 1000 timesteps (generation_ddpm_x0, spec == -1)
+      configs[3]  inpainting, 50 % of the frames masked, 8 rolls per GPU (batch 32 over 4 GPUs)
+      configs[4]  one 32-roll shard of the 256-roll job, here with the cfdg_ddpm_x0 sampler (test.py's default)"""
+    import diffroll_b200 as M
+    from oracle.diffroll_oracle import OracleDiffRoll
+    kw, B = {
+        "configs2_generation_b64_1000": (dict(timesteps=1000, sampling_type="generation_ddpm_x0"), 64),
+        "configs3_inpaint_shard_b8": (dict(inpainting_t=[0, 320]), 8),
+        "configs4_shard_b32_cfdg": (dict(sampling_type="cfdg_ddpm_x0"), 32),
+    }[case]
+    hp = default_hparams(**kw)
+    sd = make_state_dict(hp)
+    T = hp["timesteps"]
+    x_T, wav, noise = make_inputs(B, T, seed=321, n_noise=1)
+    x, w, nz = x_T.cuda(), wav.cuda(), noise.cuda()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        orc = OracleDiffRoll(hp, sd, device="cuda")
+        with torch.no_grad():
+            ref_hi, ref_spec = orc.reverse_diffusion(x, w, T - 1, noise=nz[0])
+            ref_0, _ = orc.reverse_diffusion(x, w, 0)
+        del orc
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    torch.cuda.empty_cache()
+    m = M.ClassifierFreeDiffRoll(**hp, precision="f16e5")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    a_hi, spec = m.reverse_diffusion(x, w, T - 1, noise=nz[0])
+    a_0, _ = m.reverse_diffusion(x, w, 0)
+    torch.cuda.synchronize()
+    e_hi, e_0 = float((a_hi - ref_hi).abs().max()), float((a_0 - ref_0).abs().max())
+    e_spec = float((spec - ref_spec).abs().max())
+    print(f"{case}: step t={T - 1} max|delta| {e_hi:.3e}, t=0 {e_0:.3e}, spec {e_spec:.3e}")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_numbers.log"), "a") as f:
+        f.write(f"full-size {case} vs GPU-eager oracle: t={T - 1} {e_hi:.3e}, t=0 {e_0:.3e}, spec {e_spec:.3e}\n")
+    assert e_spec < 2e-4 and max(e_hi, e_0) < 5e-4, (case, e_hi, e_0, e_spec)
+    if "inpaint" in case:
+        assert float(spec[:, :, :320].max()) == -1.0
+    if "generation" in case:
+        assert float(spec.max()) == -1.0
+    for e, _ in m._engines.values():
+        e.close()
