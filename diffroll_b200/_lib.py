@@ -18,7 +18,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f
 
 EXPORTS = [
     "drb_version", "drb_last_error", "drb_plan_workspace_bytes", "drb_plan_create", "drb_plan_destroy",
-    "drb_plan_set_branches", "drb_plan_set_steps", "drb_time_tables", "drb_mel_forward", "drb_in_proj", "drb_resblock_forward",
+    "drb_plan_set_branches", "drb_plan_set_steps", "drb_time_tables", "drb_mel_forward", "drb_cond_tables", "drb_plan_use_cond_tables", "drb_in_proj", "drb_resblock_forward",
     "drb_head_posterior_step", "drb_sample_step", "drb_sample_loop", "drb_launch_count", "drb_plan_buffer",
     "drb_plan_profile", "drb_plan_profile_read", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",

@@ -98,6 +98,8 @@ struct drb_plan {
   int NB, n_cond;      // active branches
   bool zero_spec;      // second branch = conditional forward on an all-zero spectrogram (cfdg_ddim_x0)
   bool tables_ready, spec_ready;
+  bool cond_ready = false;   // cond tables hold the conditioner projections of the CURRENT spectrogram
+  bool cond_use = true;      // drb_plan_use_cond_tables: steps read the tables when they are ready
   int pair = 1;        // CTA pairs (cta_group::2); DRB_NO_PAIR=1 selects the single-CTA kernels, for A/B runs
   std::vector<int> dil;
   // weight pointers used in place (caller keeps them alive)
@@ -321,21 +323,34 @@ int drb_mel_forward(drb_plan* p, const float* waveform, float* spec_out, int32_t
   int r = mel_forward(p->mel, waveform, spec_out, p->at<float>(p->lay.spec32), tensor ? p->ws + p->lay.sh : nullptr,
                       tensor ? p->ws + p->lay.sl : nullptr, p->fmt(), p->lay.Mp, p->cfg.frames, it0, it1, if0, if1,
                       (cudaStream_t)stream);
-  if (r == 0 && p->condpre) {
-    // conditioner_projection_l(spec) (model/diffwave.py:143) does not depend on the timestep: computed here once per
-    // clip, in fp32, for every layer; the gate kernel adds it in its epilogue
-    const drb_config& c = p->cfg;
-    const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)c.batch * c.frames * C2;
-    for (int l = 0; l < c.residual_layers && r == 0; ++l) {
-      SimtGemm g;
-      g.A = p->at<float>(p->lay.spec32); g.lda = p->lay.Mp; g.T = c.frames; g.Ck = p->lay.Mp;
-      g.W = p->at<float>(p->lay.wcpad) + (size_t)l * C2 * p->lay.Mp; g.ldw = p->lay.Mp;
-      g.C = p->at<float>(p->lay.cond) + (size_t)l * per; g.ldc = (int)C2; g.M = c.batch * c.frames; g.N = (int)C2;
-      r = launch_simt_gemm(g, (cudaStream_t)stream);
-    }
-  }
+  p->cond_ready = false;   // built lazily: drb_cond_tables / drb_sample_loop (a single forward is cheaper without them)
   if (r == 0) p->spec_ready = true;
   return r;
+}
+
+int drb_cond_tables(drb_plan* p, void* stream) {
+  if (!p) return DRB_E_INVALID;
+  if (!p->condpre || p->cond_ready) return 0;
+  if (!p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
+  // conditioner_projection_l(spec) (model/diffwave.py:143) does not depend on the timestep: computed once per clip, in
+  // fp32, for every layer; the gate kernel then adds it in its epilogue instead of contracting it every step
+  const drb_config& c = p->cfg;
+  const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)c.batch * c.frames * C2;
+  for (int l = 0; l < c.residual_layers; ++l) {
+    SimtGemm g;
+    g.A = p->at<float>(p->lay.spec32); g.lda = p->lay.Mp; g.T = c.frames; g.Ck = p->lay.Mp;
+    g.W = p->at<float>(p->lay.wcpad) + (size_t)l * C2 * p->lay.Mp; g.ldw = p->lay.Mp;
+    g.C = p->at<float>(p->lay.cond) + (size_t)l * per; g.ldc = (int)C2; g.M = c.batch * c.frames; g.N = (int)C2;
+    int r = launch_simt_gemm(g, (cudaStream_t)stream); if (r) return r;
+  }
+  p->cond_ready = true;
+  return 0;
+}
+
+int drb_plan_use_cond_tables(drb_plan* p, int32_t enable) {
+  if (!p) return DRB_E_INVALID;
+  p->cond_use = enable != 0;
+  return 0;
 }
 
 int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
@@ -402,7 +417,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
   ug.pair = p->pair; ug.window = p->window; ug.persistent = p->persistent; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
-  if (p->condpre && nc > 0) {
+  if (p->condpre && p->cond_ready && p->cond_use && nc > 0) {
     ug.cond = p->at<float>(p->lay.cond) + (size_t)layer * B * T * 2 * C;
     if (first && p->share0 && NB == 2 * B && nc == B) ug.dual_B = B;
   }
@@ -475,6 +490,7 @@ int drb_sample_loop(drb_plan* p, float* x, const float* noise, const drb_update*
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)p->cfg.batch * p->cfg.frames * p->cfg.pitches;
   size_t j = 0;
+  if (p->n_cond > 0) { p->cond_use = true; int r = drb_cond_tables(p, stream); if (r) return r; }
   if (!trajectory) {
     for (int t = t_start - 1, i = 0; t >= t_stop; --t, ++i) {
       const drb_update* u = &updates_host[i];

@@ -158,6 +158,13 @@ class Engine:
         if out is None:
             out = torch.empty_like(x_t)
         s = _stream()
+        # The per-clip conditioner tables cost about one forward.  A sampler step is one of a chain over the same clip
+        # (task/diffusion.py:528-529): build them (no-op when ready) and use them.  A plain forward (UPD_NONE: forward(),
+        # the validation step) runs without them, whether or not they happen to be ready: results never depend on history.
+        sampler_step = upd.mode != _lib.UPD_NONE and self.branches != _lib.BRANCH_UNCOND
+        if sampler_step:
+            _lib.check(self.lib.drb_cond_tables(self.plan, s), "drb_cond_tables")
+        _lib.check(self.lib.drb_plan_use_cond_tables(self.plan, 1 if sampler_step else 0), "drb_plan_use_cond_tables")
         if net_out is None:
             _lib.check(self.lib.drb_sample_step(self.plan, _ptr(x_t), _ptr(noise), _ptr(out), int(t_index),
                                                 C.byref(upd), s), "drb_sample_step")

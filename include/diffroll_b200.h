@@ -148,6 +148,15 @@ int drb_time_tables(drb_plan* plan, const float* emb_table, void* stream);
 int drb_mel_forward(drb_plan* plan, const float* waveform, float* spec_out,
                     int32_t it0, int32_t it1, int32_t if0, int32_t if1, void* stream);
 
+/* Optional, once per clip after drb_mel_forward: conditioner_projection_l(spec) of every layer (model/diffwave.py:143,
+ * step-invariant) in fp32, added by the gate kernel's epilogue from then on instead of being contracted as extra
+ * K-slabs every step.  Costs about as much as one network forward, so it pays off from the second step on the same
+ * clip: drb_sample_loop always builds and uses the tables; a lone forward is cheaper without them.  Results with and
+ * without differ by fp32-vs-operand-pair rounding of that term only (~1e-6); drb_plan_use_cond_tables(plan, 0) makes
+ * the following steps ignore tables that happen to be ready, so a result never depends on call history. */
+int drb_cond_tables(drb_plan* plan, void* stream);
+int drb_plan_use_cond_tables(drb_plan* plan, int32_t enable);
+
 /* input_projection + ReLU (model/diffwave.py:640,667-668) for timestep t_index. x_t [B,1,T,88]. */
 int drb_in_proj(drb_plan* plan, const float* x_t, int32_t t_index, void* stream);
 
