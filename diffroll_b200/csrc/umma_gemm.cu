@@ -999,7 +999,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
 // ---------------------------------------------------------------------------------------------
 constexpr int RP_STAGE = 65536;
 constexpr int RP_STAGES = 2;
-constexpr int RP_XBOXES = 4;
+constexpr int RP_XBOXES = 4;    // 16 KB boxes after the operand stages: 2 landing boxes (x loads) + 2 store-staging boxes (x')
+constexpr int RP_LANDING = 2;
 constexpr int RP_RING = RP_STAGES * RP_STAGE + RP_XBOXES * CHUNK_BYTES;   // 192 KB
 constexpr int RP_SMEM = RP_RING + 2 * CHUNK_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;   // 231,680 <= 227 KB
 
@@ -1046,7 +1047,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
       mbar_init(&full[i], 2); mbar_init(&empty[i], 1);
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16);
     }
-    for (int i = 0; i < RP_XBOXES; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+    for (int i = 0; i < RP_XBOXES; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 4); }   // 4 warps read a landing box
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
@@ -1084,8 +1085,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
       for (int item = pair_id; item < n_items; item += n_pairs) {
         const Tile ti = tile_of(item);
         for (int c = 0; c < 8; ++c, ++gb) {
-          const int sl = gb % RP_XBOXES;
-          mbar_wait(&xempty[sl], ((gb / RP_XBOXES) & 1) ^ 1);
+          const int sl = gb % RP_LANDING;
+          mbar_wait(&xempty[sl], ((gb / RP_LANDING) & 1) ^ 1);
           mbar_expect_tx(&xfull[sl], CHUNK_BYTES);
           tma_load_3d(xring + sl * CHUNK_BYTES, &p.out32, &xfull[sl], ti.n_base + c * 32, ti.t0, ti.nb);
         }
@@ -1130,6 +1131,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
     const bool issuer = (warp == 4) && (lane == 0);
     const uint32_t stg = smem_u32(staging);
     const float rsqrt2 = 0.70710678118654752f;
+    // x pipeline: the fp32 x tile arrives by TMA in a landing box (one per 4-warp group), is pulled into registers one
+    // iteration AHEAD and the box handed straight back to the x producer, so the next load has a whole iteration to
+    // arrive (ncu: 22 % of this kernel's stall samples sat on the x barrier when a box stayed occupied until its TMA
+    // store had drained).  x' and the next layer's operand pair leave through separate store-staging boxes.
+    uint8_t* const xstage = xring + RP_LANDING * CHUNK_BYTES;
+    const uint32_t land = smem_u32(xring + hc * CHUNK_BYTES);
+    const uint32_t xst = smem_u32(xstage + hc * CHUNK_BYTES);
+    const int my_tiles = pair_id < n_items ? (n_items - pair_id + n_pairs - 1) / n_pairs : 0;
+    const int total_it = 4 * my_tiles;
+    float xc[32];
+    auto fetch_x = [&](int g) {                     // x values of global iteration g -> registers, landing box released
+      mbar_wait(&xfull[hc], g & 1);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const float4 t = lds128(land + sw128_off(row, v));
+        xc[4 * v] = t.x; xc[4 * v + 1] = t.y; xc[4 * v + 2] = t.z; xc[4 * v + 3] = t.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xempty[hc]);
+    };
+    if (total_it > 0) fetch_x(0);
     int tcnt = 0, git = 0;
     for (int item = pair_id; item < n_items; item += n_pairs, ++tcnt) {
       const Tile ti = tile_of(item);
@@ -1137,11 +1159,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
 #pragma unroll 1
       for (int it = 0; it < 4; ++it, ++git) {
-        // Everything up to the staging writes (TMEM load, x tile update in its own ring slot, operand split into
-        // registers) overlaps the TMA stores of the previous iteration, which are still reading the staging area and the
-        // previous two ring slots; only then does the issuer wait for those reads.  (Measured alternative: writing x' and
-        // the operand pair straight from registers to global memory, no staging and no barriers, is 50 % SLOWER --
-        // 1.84 vs 1.23 ms per step: per-row 16-byte stores cost more than the synchronisation they remove.)
+        // Everything up to the staging writes (TMEM load, residual update, operand split, all in registers) overlaps the
+        // TMA stores of the previous iteration, which are still reading the staging boxes; only then does the issuer
+        // wait for those reads.  (Measured alternative: writing x' and the operand pair straight from registers to
+        // global memory, no staging and no barriers, is 50 % SLOWER -- 1.84 vs 1.23 ms per step: per-row 16-byte stores
+        // cost more than the synchronisation they remove.)
         if (it == 0) {
           // every thread has passed the last barrier of the previous tile, i.e. finished reading its sbias
           sbias[etid] = __ldg(p.bias + ti.n_base + etid);
@@ -1149,9 +1171,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
           mbar_wait(&tfull[as], (tcnt >> 1) & 1);
           tc_fence_after();
         }
-        const int gb = 2 * git + hc;
-        const int sl = gb % RP_XBOXES;
-        mbar_wait(&xfull[sl], (gb / RP_XBOXES) & 1);
         const int cbox = it * 2 + hc;
         float o[32];
         load_acc32<P>(taddr + cbox * 32, 0.f, o);
@@ -1160,7 +1179,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
         }
-        const uint32_t box = smem_u32(xring + sl * CHUNK_BYTES);
         const float* bs = sbias + cbox * 32;
         // warp-uniform addresses: L1 broadcast, off the critical path
         const float* dn = p.dnext + (size_t)(p.steps ? __ldg(p.steps + ti.nb % p.bsamp) : p.t_uniform) * p.C + ti.n_base + cbox * 32;
@@ -1170,25 +1188,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
           float xin[16];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int v = g16 * 4 + u, i = v * 4;
-            const uint32_t xa = box + sw128_off(row, v);
-            float4 x = lds128(xa);
-            x.x = (x.x + (o[i + 0] + bs[i + 0])) * rsqrt2;
-            x.y = (x.y + (o[i + 1] + bs[i + 1])) * rsqrt2;
-            x.z = (x.z + (o[i + 2] + bs[i + 2])) * rsqrt2;
-            x.w = (x.w + (o[i + 3] + bs[i + 3])) * rsqrt2;
-            sts128(xa, x);
+            const int i = (g16 * 4 + u) * 4;
             const float4 d4 = __ldg(reinterpret_cast<const float4*>(dn + i));
-            xin[u * 4 + 0] = x.x + d4.x; xin[u * 4 + 1] = x.y + d4.y;
-            xin[u * 4 + 2] = x.z + d4.z; xin[u * 4 + 3] = x.w + d4.w;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xc[i + e] = (xc[i + e] + (o[i + e] + bs[i + e])) * rsqrt2;   // (x + residual) / sqrt(2.0)   diffwave.py:151
+            xin[u * 4 + 0] = xc[i + 0] + d4.x; xin[u * 4 + 1] = xc[i + 1] + d4.y;
+            xin[u * 4 + 2] = xc[i + 2] + d4.z; xin[u * 4 + 3] = xc[i + 3] + d4.w;
           }
           pack16<P>(xin, pm[g16], pa[g16]);
         }
-        if (issuer) {
-          tma_store_wait_read<0>();                 // the previous iteration's stores no longer read smem
-          if (git > 0) { mbar_arrive(&xempty[(2 * (git - 1)) % RP_XBOXES]); mbar_arrive(&xempty[(2 * (git - 1) + 1) % RP_XBOXES]); }
-        }
-        named_bar_sync(EPI_BAR, EPI_THREADS);       // the staging area may be overwritten
+        if (issuer) tma_store_wait_read<0>();       // the previous iteration's stores no longer read the staging boxes
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) sts128(xst + sw128_off(row, v), make_float4(xc[4 * v], xc[4 * v + 1], xc[4 * v + 2], xc[4 * v + 3]));
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
           const int chn = hc * 32 + g16 * 16;
@@ -1206,12 +1218,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
         named_bar_sync(EPI_BAR, EPI_THREADS);
         if (issuer) {
           const int c0 = ti.n_base + it * 64;
-          tma_store_3d(&p.out32, xring + ((2 * git) % RP_XBOXES) * CHUNK_BYTES, c0, ti.t0, ti.nb);
-          tma_store_3d(&p.out32, xring + ((2 * git + 1) % RP_XBOXES) * CHUNK_BYTES, c0 + 32, ti.t0, ti.nb);
+          tma_store_3d(&p.out32, xstage, c0, ti.t0, ti.nb);
+          tma_store_3d(&p.out32, xstage + CHUNK_BYTES, c0 + 32, ti.t0, ti.nb);
           tma_store_3d(&p.xh, staging, c0, ti.t0, ti.nb);
           tma_store_3d(&p.xl, staging + CHUNK_BYTES, AM * c0, ti.t0, ti.nb);
           tma_store_commit();
         }
+        if (git + 1 < total_it) fetch_x(git + 1);   // next iteration's x: usually landed long ago
       }
     }
     if (issuer) tma_store_wait_read<0>();
