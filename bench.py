@@ -343,6 +343,8 @@ def run_b200(args, rank, world, local):
                    "l2": "per-step working set (weights 0.6 GB + activations 0.6 GB) exceeds the 126 MB L2; no flush needed",
                    "parallelism": f"dp{world} (independent batch shards, no data-path collective; one all-gather of the "
                                   "finished rolls inside the e2e region when N>1)"},
+        "sample_steps_per_s": value * args.batch,                 # B x steps/s, whole job
+        "chain_wall_s": TIMESTEPS / (value / world),              # one 200-step chain of a 32-roll shard
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "ms_per_step": ms_e2e / Ke},

@@ -14,7 +14,7 @@
 namespace drb {
 
 __global__ void notes_mark_kernel(const float* __restrict__ onsets, const float* __restrict__ frames, int16_t* __restrict__ endmark,
-                                  int B, int T, int P, float on_thr, float fr_thr) {
+                                  int B, int T, int P, float on_thr, float fr_thr, int rule) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * P) return;
   const int b = idx / P, p = idx - b * P;
@@ -27,8 +27,8 @@ __global__ void notes_mark_kernel(const float* __restrict__ onsets, const float*
     const bool f_cur = fr[(size_t)t * P] > fr_thr;
     const bool o_prev = t > 0 ? (on[(size_t)(t - 1) * P] > on_thr) : false;
     if (!(o_cur || f_cur)) end = t;
-    // onset_diff: onsets[t] - onsets[t-1] == 1 (first row: onsets[0] == 1), rule1: and frames[t] == 1
-    const bool edge = o_cur && !o_prev && f_cur;
+    // onset_diff: onsets[t] - onsets[t-1] == 1 (first row: onsets[0] == 1); rule1: and frames[t] == 1; rule2: nothing more
+    const bool edge = o_cur && !o_prev && (f_cur || rule == 2);
     em[(size_t)t * P] = edge ? (int16_t)end : (int16_t)-1;   // edge implies o_cur, so end > t
     o_cur = o_prev;
   }
@@ -104,16 +104,16 @@ extern "C" size_t drb_extract_notes_scratch_bytes(int32_t B, int32_t T, int32_t 
 }
 
 extern "C" int drb_extract_notes(const float* onsets, const float* frames, int32_t B, int32_t T, int32_t P, float onset_threshold,
-                                 float frame_threshold, void* scratch, int32_t* pitches, int32_t* intervals, int32_t* counts,
-                                 int32_t max_notes, void* stream) {
+                                 float frame_threshold, int32_t rule, void* scratch, int32_t* pitches, int32_t* intervals,
+                                 int32_t* counts, int32_t max_notes, void* stream) {
   if (!onsets || !frames || !scratch || !pitches || !intervals || !counts || B <= 0 || T <= 0 || P <= 0 || P > 128 || T > 32767 ||
-      max_notes <= 0) {
-    set_error("extract_notes: bad argument (need 0 < P <= 128, 0 < T <= 32767)");
+      max_notes <= 0 || (rule != 1 && rule != 2)) {
+    set_error("extract_notes: bad argument (need 0 < P <= 128, 0 < T <= 32767, rule 1 or 2)");
     return DRB_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
   const int n = B * P;
-  notes_mark_kernel<<<(n + 127) / 128, 128, 0, s>>>(onsets, frames, (int16_t*)scratch, B, T, P, onset_threshold, frame_threshold);
+  notes_mark_kernel<<<(n + 127) / 128, 128, 0, s>>>(onsets, frames, (int16_t*)scratch, B, T, P, onset_threshold, frame_threshold, rule);
   DRB_LAUNCH_CHECK();
   notes_compact_kernel<<<B, 128, 0, s>>>((const int16_t*)scratch, pitches, intervals, counts, T, P, max_notes);
   DRB_LAUNCH_CHECK();

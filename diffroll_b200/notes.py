@@ -17,9 +17,7 @@ from . import _lib
 
 
 def extract_notes_batch(onsets, frames, onset_threshold=0.5, frame_threshold=0.5, rule="rule1"):
-    if rule == "rule2":
-        raise NotImplementedError("rule2 is not built (the reference's sampling path uses rule1)")
-    if rule != "rule1":
+    if rule not in ("rule1", "rule2"):
         raise NameError("Please enter the correct rule name")
     if not (torch.is_tensor(onsets) and onsets.is_cuda and torch.is_tensor(frames) and frames.is_cuda):
         raise _lib.DrbError("extract_notes: CUDA tensors required (no CPU path)")
@@ -37,7 +35,8 @@ def extract_notes_batch(onsets, frames, onset_threshold=0.5, frame_threshold=0.5
     counts = torch.empty(B, dtype=torch.int32, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(lib.drb_extract_notes(C.c_void_p(on.data_ptr()), C.c_void_p(fr.data_ptr()), B, T, P, float(onset_threshold),
-                                     float(frame_threshold), C.c_void_p(scratch.data_ptr()), C.c_void_p(pitches.data_ptr()),
+                                     float(frame_threshold), 1 if rule == "rule1" else 2, C.c_void_p(scratch.data_ptr()),
+                                     C.c_void_p(pitches.data_ptr()),
                                      C.c_void_p(intervals.data_ptr()), C.c_void_p(counts.data_ptr()), max_notes, stream),
                "drb_extract_notes")
     n = counts.cpu().numpy()

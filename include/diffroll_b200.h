@@ -184,15 +184,16 @@ int drb_sample_loop(drb_plan* plan, float* x, const float* noise, const drb_upda
 /* Number of kernels launched by this library on the calling thread since the last reset. */
 int64_t drb_launch_count(int32_t reset);
 
-/* Post-loop decode: extract_notes_wo_velocity(onsets, frames, ...) with rule1,
+/* Post-loop decode: extract_notes_wo_velocity(onsets, frames, ..., rule) with rule = 1
+ * ('rule1': an onset also needs its frame activation, the sampling path's default) or 2 ('rule2': rising onset edges only),
  * task/utils.py:4-54, as called on every finished roll at task/diffusion.py:599-602.  onsets/frames [B,T,P] fp32 (may be
  * the same pointer); outputs per roll b: counts[b] notes in the reference's order (frame-major, then pitch),
  * pitches[b*max_notes + i], intervals[(b*max_notes + i)*2 + {0,1}] = (onset frame, offset frame).  Notes beyond
  * max_notes are counted but not stored (T*P/2 + P is always enough).  scratch: drb_extract_notes_scratch_bytes. */
 size_t drb_extract_notes_scratch_bytes(int32_t B, int32_t T, int32_t P);
 int drb_extract_notes(const float* onsets, const float* frames, int32_t B, int32_t T, int32_t P, float onset_threshold,
-                      float frame_threshold, void* scratch, int32_t* pitches, int32_t* intervals, int32_t* counts,
-                      int32_t max_notes, void* stream);
+                      float frame_threshold, int32_t rule, void* scratch, int32_t* pitches, int32_t* intervals,
+                      int32_t* counts, int32_t max_notes, void* stream);
 
 /* Frame-level confusion counts behind test_step's precision_recall_fscore_support(label.flatten(),
  * pred.flatten() > threshold, average='binary'), task/diffusion.py:378-380: counts3 (device) = {TP, FP, FN} with

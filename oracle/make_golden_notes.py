@@ -42,6 +42,8 @@ def main():
     p, i = ref_fn(on, fr, onset_threshold=0.7, frame_threshold=0.4)
     res["two_on"], res["two_fr"] = on, fr
     res["two_p"], res["two_i"] = np.asarray(p, dtype=np.int64), np.asarray(i, dtype=np.int64).reshape(-1, 2)
+    p, i = ref_fn(on, fr, onset_threshold=0.7, frame_threshold=0.4, rule="rule2")
+    res["rule2_p"], res["rule2_i"] = np.asarray(p, dtype=np.int64), np.asarray(i, dtype=np.int64).reshape(-1, 2)
     # frame-level precision / recall / F1 as test_step computes them (task/diffusion.py:378-380), sklearn's own outputs
     import warnings
     from sklearn.metrics import precision_recall_fscore_support

@@ -133,3 +133,36 @@ def test_full_size_other_configs_vs_gpu_eager_oracle(case):
         assert float(spec.max()) == -1.0
     for e, _ in m._engines.values():
         e.close()
+
+
+def test_config0_single_clip_chain_wall_clock():
+    """BASELINE configs[0]: ONE 20 s clip, the whole 200-step transcription chain.  The reference's CPU run of exactly this
+    chain took the seconds stored in the golden file (8 container cores); here it is timed on the GPU through the public
+    API (predict_step's loop incl. the mel front-end and the per-step host copy), after the parity check against it."""
+    import time
+    import diffroll_b200 as M
+    from conftest import golden
+    g = golden("chain_transcription_b1_200.npz")
+    hp = default_hparams()
+    m = M.ClassifierFreeDiffRoll(**hp)
+    m.load_state_dict(make_state_dict(hp))
+    m = m.cuda().eval()
+    x_T, wav, noise = make_inputs(1, 200, seed=123)
+    x, w, nz = x_T.cuda(), wav.cuda(), noise.cuda()
+    m.sample_loop(x, w, noise=nz, keep_trajectory=True)          # warm-up: plan, pinned trajectory buffer
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x0, _, traj = m.sample_loop(x, w.clone(), noise=nz, keep_trajectory=True)   # a fresh waveform object: mel is recomputed
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    err = float((x0.cpu() - torch.from_numpy(g["final"])).abs().max())
+    assert err < 1e-3
+    res = {"config": "configs[0]: batch 1, 640x88, 200 steps, inpainting_ddpm_x0 w=0.5", "b200_chain_wall_s": dt,
+           "b200_steps_per_s": 200.0 / dt, "reference_cpu_chain_wall_s_container_8_cores": float(g["seconds"]),
+           "final_maxabs_vs_reference": err}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "config0_chain.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res))
+    for e, _ in m._engines.values():
+        e.close()

@@ -25,6 +25,8 @@ def test_oracle_two_inputs_and_thresholds():
     g = golden("notes.npz")
     p, i = oracle_notes(g["two_on"], g["two_fr"], onset_threshold=0.7, frame_threshold=0.4)
     assert _same(p, g["two_p"]) and _same(i, g["two_i"])
+    p, i = oracle_notes(g["two_on"], g["two_fr"], onset_threshold=0.7, frame_threshold=0.4, rule="rule2")
+    assert _same(p, g["rule2_p"]) and _same(i, g["rule2_i"]) and len(g["rule2_p"]) > len(g["two_p"])
     with pytest.raises(NameError):
         oracle_notes(g["two_on"], g["two_fr"], rule="rule3")
 
@@ -45,6 +47,10 @@ def test_cuda_notes_two_inputs_batch_and_full_size():
     g = golden("notes.npz")
     p, i = extract_notes_wo_velocity(torch.from_numpy(g["two_on"]).cuda(), torch.from_numpy(g["two_fr"]).cuda(), 0.7, 0.4)
     assert _same(p, g["two_p"]) and _same(i, g["two_i"])
+    p, i = extract_notes_wo_velocity(torch.from_numpy(g["two_on"]).cuda(), torch.from_numpy(g["two_fr"]).cuda(), 0.7, 0.4, rule="rule2")
+    assert _same(p, g["rule2_p"]) and _same(i, g["rule2_i"])
+    with pytest.raises(NameError):
+        extract_notes_wo_velocity(torch.from_numpy(g["two_on"]).cuda(), torch.from_numpy(g["two_fr"]).cuda(), rule="rule3")
     # BASELINE configs[1] size: 32 rolls of 640 x 88, against the oracle roll by roll
     rng = np.random.default_rng(3)
     rolls = rng.random((32, 640, 88)).astype(np.float32)
