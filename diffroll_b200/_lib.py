@@ -97,8 +97,18 @@ def load():
     lib.drb_plan_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.drb_extract_notes_scratch_bytes.restype = C.c_size_t
     lib.drb_extract_notes_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-    lib.drb_extract_notes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.drb_extract_notes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.drb_frame_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
+    lib.drb_plan_set_steps.argtypes = [C.c_void_p, C.c_void_p]
+    lib.drb_cond_tables.argtypes = [C.c_void_p, C.c_void_p]
+    lib.drb_plan_use_cond_tables.argtypes = [C.c_void_p, C.c_int32]
+    for fn in (lib.drb_q_sample, lib.drb_extract_x0):
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+    lib.drb_p_losses_scratch_bytes.restype = C.c_size_t
+    lib.drb_p_losses_scratch_bytes.argtypes = []
+    lib.drb_p_losses.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.drb_normalize_imagewise.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("drb_version",):
