@@ -202,9 +202,15 @@ def run_b200(args, rank, world, local):
     import torch
     import torch.distributed as dist
     import diffroll_b200 as M
-    from diffroll_b200 import _lib
+    from diffroll_b200 import _lib, build as _build
     from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dict
 
+    if not os.path.exists(_build.LIB):       # a checkout without the (git-ignored) built library: compile it once
+        if local == 0:
+            _build.build()
+        if world > 1:
+            import torch.distributed as _d
+            _d.barrier()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     K, W = args.steps, max(args.warmup, 0)

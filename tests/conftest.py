@@ -42,3 +42,11 @@ def lib_built():
     """Make sure libdiffroll_b200.so exists (nvcc cross-compiles without a GPU)."""
     from diffroll_b200 import build
     return build.build()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_present():
+    """A checkout without the built artefact (the .so is git-ignored) compiles it once; an existing one is used as is."""
+    from diffroll_b200 import build
+    if not os.path.exists(build.LIB):
+        build.build()
