@@ -2,9 +2,9 @@
 // (model/diffwave.py:134-151, 680-684), sm_100a only.
 //
 //   gate kernel  : y[t, n] = sum_{tap, c} xin[t + (tap-k/2)*dil, c] * Wd[n, tap, c]  (+ spec[t, :] . Wc[n, :])  + bias1[n]
-//                  z_l[t, c] = sigmoid(y[t, c]) * tanh(y[t, C + c])                     -> bf16 hi/lo, kept for every layer l
+//                  z_l[t, c] = sigmoid(y[t, c]) * tanh(y[t, C + c])                     -> operand pair, kept for every layer l
 //   zgemm RES    : o[t, c] = sum_k z_l[t, k] * Wo_l[c, k] + bo_l[c]            (residual half of output_projection)
-//                  x[t, c] = (x[t, c] + o[t, c]) / sqrt(2)    -> fp32, and bf16 hi/lo of (x + d_{l+1})
+//                  x[t, c] = (x[t, c] + o[t, c]) / sqrt(2)    -> fp32, and the operand pair of (x + d_{l+1})
 //   zgemm HEAD   : h[t, n] = relu( sum_l sum_k z_l[t, k] * Wcomp[n, l*C + k] + bcomp[n] )
 //                  with Wcomp_l = skip_projection . Wo_l[skip half] / sqrt(L): the skip sum (diffwave.py:680), the
 //                  1/sqrt(L) scale and skip_projection (:682-684) are one long-K GEMM over the stored z_l instead of
@@ -15,18 +15,27 @@
 // activation tensor [roll][frame][channel] at frame offset (tap - k/2)*dil; frames outside [0, T) are zero-filled by
 // the TMA unit, which is exactly the conv's zero padding and cannot bleed into the neighbouring roll.
 //
-// fp32 parity (|delta| < 1e-3 after 200 chained steps) needs more than one bf16 product, so
-// activations and weights are kept as bf16 hi + lo pairs and every K-step issues three MMAs into the same TMEM
-// accumulator: hi*hi + lo*hi + hi*lo.
+// fp32 parity (|delta| < 1e-3 after 200 chained steps) needs more than one 16-bit product, so
+// activations and weights are kept as operand PAIRS (2-byte main + 2-byte aux per element, formats in `Cfg` below and
+// DESIGN.md section 2); the default f16e5 issues one fp16 MMA plus one e5m2 correction MMA per K-step into the same
+// TMEM accumulator (bf16x3: three bf16 MMAs; f16f8: an e4m3 correction into a second accumulator).
 //
 // CTA pairs (PAIR = true, the default when the number of M tiles is even): two CTAs of a cluster issue ONE
 // tcgen05.mma.cta_group::2 with M = 256.  Each CTA stages its own 128 activation rows and only HALF of the weight
 // tile (128 of the 256 output rows), so the shared-memory traffic per MMA (operand reads + TMA fills), which bounds
 // the single-CTA kernel, drops by a third and the ring holds 3 stages instead of 2.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
-// (TMEM -> registers -> swizzled smem staging -> TMA store).  smem ring: full/empty mbarriers per stage; after the last
-// MMA retires the ring memory is reused as epilogue staging.
+// Kernels, from the general fallback to the ones the benchmark runs:
+//   umma_gate_kernel<P, PAIR>        one tile per CTA (pair), one TMA box per tap          (odd tile counts, P = 0)
+//   umma_gate_win_kernel<P>          + tap window fetched once per 64-channel chunk        (f16f8: needs 512 TMEM columns)
+//   umma_gate_pers_kernel<P, DUAL>   + persistent pairs, two accumulator stages, conditioner term from the per-clip
+//                                      fp32 table in the epilogue; DUAL = layer-0 conv shared by both guidance branches
+//   umma_zgemm_kernel<P, PAIR>       RES / HEAD, one tile per CTA (pair)
+//   umma_res_pers_kernel<P>          RES, persistent pairs, register-prefetched x tile, TMA-staged stores
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = bias stager /
+// second producer, warps 4-11 = epilogue (TMEM -> registers -> swizzled smem staging -> TMA store).  smem ring:
+// full/empty mbarriers per stage.
 #include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
