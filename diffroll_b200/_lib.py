@@ -20,7 +20,7 @@ EXPORTS = [
     "drb_version", "drb_last_error", "drb_plan_workspace_bytes", "drb_plan_create", "drb_plan_destroy",
     "drb_plan_set_branches", "drb_plan_set_steps", "drb_time_tables", "drb_mel_forward", "drb_cond_tables", "drb_plan_use_cond_tables", "drb_in_proj", "drb_resblock_forward",
     "drb_head_posterior_step", "drb_sample_step", "drb_sample_loop", "drb_launch_count", "drb_plan_buffer",
-    "drb_plan_profile", "drb_plan_profile_read", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
+    "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
 ]
 
@@ -95,6 +95,9 @@ def load():
     lib.drb_plan_buffer.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.drb_plan_profile.argtypes = [C.c_void_p, C.c_int32]
     lib.drb_plan_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.drb_plan_profile_read2.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32,
+                                           C.POINTER(C.c_double), C.c_int32]
+    lib.drb_plan_range_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_void_p]
     lib.drb_extract_notes_scratch_bytes.restype = C.c_size_t
     lib.drb_extract_notes_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.drb_extract_notes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,

@@ -6,10 +6,24 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 #include "kernels.h"
 
 namespace drb {
+
+// Opt-in NVTX ranges (DRB_NVTX=1): one range per sampler step and per residual layer, so a timeline tool shows the
+// loop's structure.  The header-only NVTX v3 costs nothing when no tool is attached; off by default anyway.
+static int g_nvtx = -1;
+struct NvtxRange {
+  bool on;
+  NvtxRange(const char* fmt, int a, int b = 0) {
+    if (g_nvtx < 0) { const char* e = getenv("DRB_NVTX"); g_nvtx = (e && e[0] == '1') ? 1 : 0; }
+    on = g_nvtx == 1;
+    if (on) { char buf[64]; snprintf(buf, sizeof(buf), fmt, a, b); nvtxRangePushA(buf); }
+  }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 static thread_local char g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -28,6 +42,7 @@ struct Layout {  // byte offsets into the workspace
   size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel, xpp;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
+  size_t range;                                         // one word: max |activation operand| (fp32 bits) since the last reset
   size_t wcpad, cond;                                   // fp32 Wc of every layer padded to Mp; conditioner projections of the spectrogram [L][B][T][2C]
   size_t total;
   int NBcap, Mp, KC;
@@ -64,6 +79,7 @@ static Layout make_layout(const drb_config& c) {
   l.wtmp = take(2 * C * k * C * 4);
   l.mel = take(mel_workspace_bytes(c));
   l.xpp = take(B * T * c.pitches * 4);
+  l.range = take(256);
   if (c.precision == DRB_PREC_FP32) {
     l.wd32 = take(L * 2 * C * k * C * 4);
     l.wc32 = take(L * 2 * C * Mp * 4);
@@ -118,7 +134,7 @@ struct drb_plan {
   cudaEvent_t ev_step[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
   bool prof = false;
   std::vector<cudaEvent_t> ev_pool;
-  std::vector<std::pair<int, int>> ev_spans[4];  // 0 gate kernel, 1 out kernel, 2 in_proj+prep, 3 head
+  std::vector<std::pair<int, int>> ev_spans[5];  // 0 gate kernel, 1 out kernel, 2 in_proj+prep, 3 head (GEMM + projection), 4 head projection + posterior alone
   size_t ev_used = 0;
   int ev_mark(cudaStream_t s) {
     if (ev_used == ev_pool.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return -1; ev_pool.push_back(e); }
@@ -216,10 +232,11 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
       PLAN_TRY(launch_repack_conv_fp32(w->dilated_conv_w[i], tmp, 2 * C, C, k, s));
       const int fmt = p->fmt();
       const int dm = fmt >= 2 ? 2 : 0, da = fmt >= 2 ? 3 : 0, am = fmt >= 2 ? 2 : 1;  // tensor-map dtypes, aux width factor
-      if (fmt == 2) {
+      if (fmt >= 2) {   // per-tensor power-of-two weight scales (f16f8: e4m3 range; f16e5: keeps small weights normal in fp16)
+        const float sa = fmt == 2 ? F8_SA : 1.f;
         PLAN_TRY(launch_weight_scale(tmp, (size_t)2 * C * k * C, w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels,
-                                     p->wscale(2 * i), s));
-        PLAN_TRY(launch_weight_scale(w->output_projection_w[i], (size_t)2 * C * C, nullptr, 0, p->wscale(2 * i + 1), s));
+                                     p->wscale(2 * i), sa, s));
+        PLAN_TRY(launch_weight_scale(w->output_projection_w[i], (size_t)2 * C * C, nullptr, 0, p->wscale(2 * i + 1), sa, s));
       }
       char* wdh = p->ws + lay.wdh + (size_t)i * 2 * C * k * C * 2;
       char* wdl = p->ws + lay.wdl + (size_t)i * 2 * C * k * C * 2;
@@ -270,12 +287,14 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
     for (int i = 0; i < L; ++i)
       PLAN_TRY(launch_compose_skip(p->skw, p->wo32[i], p->at<float>(lay.wcomp32), C, L, i, s));
     PLAN_TRY(launch_compose_bias(p->skw, p->skb, p->bo.data(), C, L, p->at<float>(lay.bsum), p->at<float>(lay.bcomp), s));
-    if (fmt == 2) PLAN_TRY(launch_weight_scale(p->at<float>(lay.wcomp32), (size_t)C * L * C, nullptr, 0, p->wscale(2 * L), s));
+    if (fmt >= 2) PLAN_TRY(launch_weight_scale(p->at<float>(lay.wcomp32), (size_t)C * L * C, nullptr, 0, p->wscale(2 * L),
+                                               fmt == 2 ? F8_SA : 1.f, s));
     PLAN_TRY(launch_repack_split(p->at<float>(lay.wcomp32), p->ws + lay.wcomph, p->ws + lay.wcompl, C, L * C, L * C, 0, fmt,
                                  p->wscale(2 * L), s));
     PLAN_TRY(make_tmap_2d(&p->maps.wcomp_h, p->ws + lay.wcomph, C, (uint64_t)L * C, 128, dm));
     PLAN_TRY(make_tmap_2d(&p->maps.wcomp_l, p->ws + lay.wcompl, C, am * L * C, 128, da));
   }
+  if (cudaMemsetAsync(p->ws + lay.range, 0, 256, s) != cudaSuccess) { set_error("plan_create: memset failed"); drb_plan_destroy(p); return DRB_E_INVALID; }
 #undef PLAN_TRY
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { set_error("plan_create sync: %s", cudaGetErrorString(e)); drb_plan_destroy(p); return (int)e; }
@@ -363,7 +382,7 @@ int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
   int r;
   if (tensor) {  // relu(input_projection(x_t)) for every branch copy + operand pair of x + d_0(t), one kernel
     r = launch_in_proj_fused(x_t, p->in_w, p->in_b, p->dvec(0, 0), p->steps, t_index, B * T, T, F, C, p->NB / B, p->fmt(),
-                             p->at<float>(p->lay.x32), p->ws + p->lay.xh, p->ws + p->lay.xl, s);
+                             p->at<float>(p->lay.x32), p->ws + p->lay.xh, p->ws + p->lay.xl, p->at<unsigned int>(p->lay.range), s);
   } else {
     SimtGemm g;  // relu(input_projection(x_t))   model/diffwave.py:667-668 ; x_t [B,1,T,88] is already [B*T][88]
     g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = p->in_w; g.ldw = F; g.bias = p->in_b; g.act = 1;
@@ -381,6 +400,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   if (!p->tables_ready) { set_error("drb_time_tables has not been called"); return DRB_E_STATE; }
   if (p->n_cond > 0 && !p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
+  NvtxRange nv("drb.resblock l=%d t=%d", layer, t_index);
   cudaStream_t s = (cudaStream_t)stream;
   const drb_config& c = p->cfg;
   const int B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size, Mp = p->lay.Mp;
@@ -430,6 +450,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
     uz.inv_scale = p->wscale(2 * layer + 1) + 1;
     uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
     uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, 0); uz.t_uniform = t_index; uz.steps = p->steps; uz.bsamp = B;
+    uz.range_max = p->at<unsigned int>(p->lay.range);
     r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
   }
   if (p->prof) {
@@ -470,13 +491,15 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
     o.A2 = h + (size_t)B * T * C; o.alpha = 1.f + upd->w; o.beta = -upd->w;
   }
   o.C = x_prev; o.ldc = F; o.M = B * T; o.N = F; o.upd = upd; o.x_t = x_t; o.noise = noise; o.net_out = net_out;
+  const int e1 = p->prof ? p->ev_mark(s) : -1;
   r = launch_simt_gemm(o, s);
-  if (p->prof && r == 0) p->ev_spans[3].push_back({e0, p->ev_mark(s)});
+  if (p->prof && r == 0) { const int e2 = p->ev_mark(s); p->ev_spans[3].push_back({e0, e2}); p->ev_spans[4].push_back({e1, e2}); }
   return r;
 }
 
 int drb_sample_step(drb_plan* p, const float* x_t, const float* noise, float* x_prev, int32_t t_index,
                     const drb_update* upd, void* stream) {
+  NvtxRange nv("drb.sample_step t=%d", t_index);
   int r = drb_in_proj(p, x_t, t_index, stream); if (r) return r;
   for (int l = 0; l < p->cfg.residual_layers; ++l) { r = drb_resblock_forward(p, l, t_index, stream); if (r) return r; }
   return drb_head_posterior_step(p, x_t, noise, x_prev, nullptr, upd, stream);
@@ -549,6 +572,41 @@ int drb_plan_profile_read(drb_plan* p, double* ms_total, int64_t* launches) {
       tot += ms;
     }
     ms_total[k] = tot; launches[k] = (int64_t)p->ev_spans[k].size();
+  }
+  return 0;
+}
+
+int drb_plan_range_stats(drb_plan* p, float* max_abs, int32_t reset, void* stream) {
+  if (!p || !max_abs) return DRB_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned int bits = 0;
+  DRB_CUDA(cudaMemcpyAsync(&bits, p->ws + p->lay.range, sizeof(bits), cudaMemcpyDeviceToHost, s));
+  if (reset) DRB_CUDA(cudaMemsetAsync(p->ws + p->lay.range, 0, sizeof(bits), s));
+  DRB_CUDA(cudaStreamSynchronize(s));
+  memcpy(max_abs, &bits, sizeof(bits));   // NaN operands read back as NaN, overflowed ones as inf or > 65504
+  return 0;
+}
+
+int drb_plan_profile_read2(drb_plan* p, double* ms_total, int64_t* launches, int32_t n_classes, double* gate_ms_per_layer,
+                           int32_t n_layers) {
+  if (!p || !ms_total || !launches || n_classes < 1 || n_classes > 5) return DRB_E_INVALID;
+  DRB_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < n_classes; ++k) {
+    double tot = 0.0;
+    for (auto& sp : p->ev_spans[k]) {
+      float ms = 0.f;
+      DRB_CUDA(cudaEventElapsedTime(&ms, p->ev_pool[sp.first], p->ev_pool[sp.second]));
+      tot += ms;
+    }
+    ms_total[k] = tot; launches[k] = (int64_t)p->ev_spans[k].size();
+  }
+  if (gate_ms_per_layer && n_layers == p->cfg.residual_layers) {   // spans are recorded layer 0..L-1 every step
+    for (int l = 0; l < n_layers; ++l) gate_ms_per_layer[l] = 0.0;
+    for (size_t i = 0; i < p->ev_spans[0].size(); ++i) {
+      float ms = 0.f;
+      DRB_CUDA(cudaEventElapsedTime(&ms, p->ev_pool[p->ev_spans[0][i].first], p->ev_pool[p->ev_spans[0][i].second]));
+      gate_ms_per_layer[i % n_layers] += ms;
+    }
   }
   return 0;
 }

@@ -48,15 +48,17 @@ int launch_prep_xin(float* x32, void* xmain, void* xaux, const float* dvec, int 
 // tensor path: relu(input_projection(x_t)) -> fp32 x32 for every branch copy + operand pair of x + dtab0[t] in ONE kernel;
 // t = steps[row / T] when steps != nullptr (per-sample diffusion steps), else the uniform t
 int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, const float* dtab0, const int* steps, int t,
-                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux, cudaStream_t s);
+                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux,
+                         unsigned int* range_max, cudaStream_t s);
 // weight repacks
 int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cudaStream_t s);  // [OC][C][k] -> [OC][k][C]
 // [OC][Kin] fp32 (k index already tap-major) -> operand pair (fmt 1 or 2), rows optionally permuted into 256-wide
-// gate/filter blocks (interleave_C > 0), K padded to Kp; fmt 2 reads SW from scale[0]
+// gate/filter blocks (interleave_C > 0), K padded to Kp; fmt 2 and 3 read SW from scale[0]
 int launch_repack_split(const float* w, void* mainp, void* auxp, int OC, int Kin, int Kp, int interleave_C, int fmt,
                         const float* scale, cudaStream_t s);
-// scale2[0] = SW, scale2[1] = 1/(SA*SW) from max|w| over one or two tensors (scale2 must have 3 floats of space)
-int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, cudaStream_t s);
+// scale2[0] = SW = 2^floor(log2(224 / max|w|)), scale2[1] = 1/(sa*SW) from max|w| over one or two tensors (scale2 must
+// have 3 floats of space).  sa: F8_SA for f16f8 (scale of the activation residual), 1 for f16e5.
+int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, float sa, cudaStream_t s);
 int launch_pad_rows(const float* src, float* dst, int rows, int Kin, int Kp, cudaStream_t s);
 // bias1[n'] (interleaved) = bd[n] + bc[n] (- sum_k Wc[n][k] if uncond)
 int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_cond, float* out_unc,
@@ -119,6 +121,7 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
   int t_uniform = 0;                // row of dnext when steps == nullptr
   const int* steps = nullptr;       // per-sample diffusion steps [bsamp] (device); roll nb uses steps[nb % bsamp]
   int bsamp = 1;
+  unsigned int* range_max = nullptr;  // RES: device word, atomicMax of |x + d_next| (fp32 bits) over the emitted operands
 };
 int umma_init();  // resolves cuTensorMapEncodeTiled
 // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8; the box always spans 128 bytes of the innermost dimension

@@ -347,6 +347,7 @@ struct InProjDev {
   const float* x; const float* W; const float* bias; const float* dtab; const int* steps;
   int t, M, T, F, C, copies, fmt;
   float* x32; void* xmain; void* xaux;
+  unsigned int* range_max;   // device word: atomicMax of |x + d_0| (fp32 bits) over the emitted operands, or nullptr
 };
 // FC: compile-time pitch count (88: every load loop fully unrolled, so all of a thread's global loads are in flight at
 // once instead of one L2 round trip per iteration) or 0 for the generic run-time F.
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
   }
   const int n = n0 + tx * 4;
   const float4 bias = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+  unsigned int umax = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + ty * 8 + i;
@@ -407,15 +409,22 @@ __global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
     const int tsel = g.steps ? __ldg(g.steps + m / g.T) : g.t;
     const float4 d = __ldg(reinterpret_cast<const float4*>(g.dtab + (size_t)tsel * g.C + n));
     const float xin[4] = {v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) umax = max(umax, __float_as_uint(xin[e]) & 0x7fffffffu);
     for (int r = 0; r < g.copies; ++r) {
       const size_t row = (size_t)r * g.M + m;
       *reinterpret_cast<float4*>(g.x32 + row * g.C + n) = v;
       store_operand4(g.xmain, g.xaux, row, n, g.C, xin, g.fmt);
     }
   }
+  if (g.range_max) {   // every thread reaches this point (no early return above)
+    umax = __reduce_max_sync(0xffffffffu, umax);
+    if ((tid & 31) == 0 && umax > *reinterpret_cast<volatile unsigned int*>(g.range_max)) atomicMax(g.range_max, umax);
+  }
 }
 int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, const float* dtab0, const int* steps, int t,
-                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux, cudaStream_t s) {
+                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux,
+                         unsigned int* range_max, cudaStream_t s) {
   if ((F % 4) || (C % IP_BN) || fmt <= 0) { set_error("in_proj_fused: unsupported F=%d C=%d fmt=%d", F, C, fmt); return DRB_E_INVALID; }
   const int smem = F * (IP_BM + 4 + IP_BN + 4) * (int)sizeof(float);
   static int smem_set = 0;
@@ -430,7 +439,7 @@ int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, co
   }
   InProjDev g;
   g.x = x_t; g.W = W; g.bias = bias; g.dtab = dtab0; g.steps = steps; g.t = t; g.M = M; g.T = T; g.F = F; g.C = C;
-  g.copies = copies; g.fmt = fmt; g.x32 = x32; g.xmain = xmain; g.xaux = xaux;
+  g.copies = copies; g.fmt = fmt; g.x32 = x32; g.xmain = xmain; g.xaux = xaux; g.range_max = range_max;
   dim3 grid((M + IP_BM - 1) / IP_BM, C / IP_BN);
   if (F == 88) in_proj_kernel<88><<<grid, 256, smem, s>>>(g);
   else in_proj_kernel<0><<<grid, 256, smem, s>>>(g);
@@ -468,6 +477,7 @@ __global__ void repack_split_kernel(const float* __restrict__ w, void* __restric
   int src = np;
   if (C > 0) { int j = np >> 8, i = np & 255; src = (i < 128) ? (128 * j + i) : (C + 128 * j + (i - 128)); }
   float v = (kk < Kin) ? w[(size_t)src * Kin + kk] : 0.f;
+  if (fmt == 3) v *= scale[0];   // f16e5: per-tensor power-of-two scale, undone in the consuming kernel's epilogue
   if (fmt == 1) {
     __nv_bfloat16 hh, ll;
     split_bf16(v, hh, ll);
@@ -503,22 +513,22 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
-__global__ void wscale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ out) {
+__global__ void wscale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ out, float sa) {
   float m = __uint_as_float(mx[0]);
   float sw = 1.f;
   if (m > 0.f && m < 3.0e38f) sw = exp2f(floorf(log2f(224.f / m)));
   sw = fminf(fmaxf(sw, 9.5367431640625e-07f), 1048576.f);
   out[0] = sw;
-  out[1] = 1.f / (F8_SA * sw);
+  out[1] = 1.f / (sa * sw);
 }
-int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, cudaStream_t s) {
+int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, float sa, cudaStream_t s) {
   unsigned int* tmp = reinterpret_cast<unsigned int*>(scale2 + 2);  // scratch word right behind the two outputs
   cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return (int)e; }
   absmax_kernel<<<148, 256, 0, s>>>(w0, n0, tmp);
   DRB_LAUNCH_CHECK();
   if (w1 && n1) { absmax_kernel<<<148, 256, 0, s>>>(w1, n1, tmp); DRB_LAUNCH_CHECK(); }
-  wscale_kernel<<<1, 1, 0, s>>>(tmp, scale2);
+  wscale_kernel<<<1, 1, 0, s>>>(tmp, scale2, sa);
   DRB_LAUNCH_CHECK();
   return 0;
 }

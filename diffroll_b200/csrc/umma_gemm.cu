@@ -81,7 +81,7 @@ struct alignas(64) GateParams {
   int NB, n_cond, T, C, taps, dil, cond_slabs, tiles_t, n_blocks, z_group0;
   const float* bias_cond;
   const float* bias_unc;
-  const float* inv_scale;  // f16f8: 1 / (SA * SW) of this layer's weights (device scalar)
+  const float* inv_scale;  // f16f8: 1 / (SA * SW), f16e5: 1 / SW of this layer's weights (device scalar)
   // Persistent kernel only.  The conditioner projection is step-invariant, so it is computed once per clip in fp32
   // (cond[roll][t][2C], natural channel order: gate 0..C-1, filter C..2C-1) and ADDED IN THE EPILOGUE of conditional
   // rolls (nb < n_cond) instead of being re-contracted every step as extra K-slabs (those run for nb < n_cond_mma).
@@ -101,6 +101,7 @@ struct alignas(64) ZGemmParams {
   const float* inv_scale;
   const int* steps;        // per-sample diffusion steps (device, [bsamp]) or nullptr: every roll uses row t_uniform
   int t_uniform, bsamp;
+  unsigned int* range_max; // RES: running max |x + d_next| over the emitted operands (fp32 bits), or nullptr
 };
 
 struct SmemView {
@@ -259,11 +260,27 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float inv_scale, floa
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(c[i]), inv_scale, __uint_as_float(r[i]));
+  } else if (P == 3) {   // f16e5: weights were split as W * SW (a power of two, keeps small weights out of the fp16 subnormals)
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * inv_scale;
   } else {
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
   }
+}
+
+// Largest |value| (as fp32 bits; NaN > inf > finite in this order) of the activation operands a kernel emitted: the fp16
+// main part of the f16 formats overflows at 65504, so the host can tell when a run left the format's range.
+__device__ __forceinline__ void range_note(unsigned int& umax, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) umax = max(umax, __float_as_uint(v[i]) & 0x7fffffffu);
+}
+__device__ __forceinline__ void range_publish(unsigned int* dst, unsigned int umax) {
+  if (!dst) return;
+  umax = __reduce_max_sync(0xffffffffu, umax);
+  if ((threadIdx.x & 31) == 0 && umax > *reinterpret_cast<volatile unsigned int*>(dst)) atomicMax(dst, umax);
 }
 
 // Stage 16 consecutive channel values (channel offset ch inside a 64-channel box, multiple of 16) of one row into the
@@ -308,7 +325,7 @@ __device__ __forceinline__ void gate_epilogue(const SmemView& sv, const GatePara
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     // staging: z main boxes 0,1 then z aux boxes 0,1; each [128 frames][128 bytes], 128-byte swizzled
     const uint32_t stg = smem_u32(sv.stage0);
-    const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
+    const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
 #pragma unroll 1
     for (int c2 = 0; c2 < 2; ++c2) {
       const int ch = grp * 2 + c2;         // 32 gate + 32 filter columns; group g fills box g
@@ -743,6 +760,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
     const int etid = (int)threadIdx.x - 128;
     const bool issuer = (warp == 4) && (lane == 0);
     const uint32_t stg = smem_u32(staging);
+    const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
     int tcnt = 0;
     for (int item = pair_id; item < p.n_items; item += n_pairs, ++tcnt) {
       const GateTile ti = tile_of(item);
@@ -765,8 +783,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
       for (int c2 = 0; c2 < 2; ++c2) {
         const int ch = grp * 2 + c2;
         float g[32], f[32];
-        load_acc32<P>(taddr + ch * 32, 0.f, g);
-        load_acc32<P>(taddr + 128 + ch * 32, 0.f, f);
+        load_acc32<P>(taddr + ch * 32, inv, g);
+        load_acc32<P>(taddr + 128 + ch * 32, inv, f);
         if (is_cond && p.cond != nullptr) {   // + conditioner_projection(spec) of this frame, fp32, computed once per clip
           const int tf = ti.t0 + row;
           if (tf < p.T) {
@@ -931,7 +949,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = smem_u32(sv.stage0);
     const float rsqrt2 = 0.70710678118654752f;
-    const float inv = (P == 2) ? __ldg(p.inv_scale) : 0.f;
+    const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
+    unsigned int umax = 0;
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {       // 64 output channels per iteration
       // operand staging of the next layer (x + d_next split): two alternating sets of {main box, aux box}
@@ -964,6 +983,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
             xin[u * 4 + 0] = x.x + dn[i + 0]; xin[u * 4 + 1] = x.y + dn[i + 1];
             xin[u * 4 + 2] = x.z + dn[i + 2]; xin[u * 4 + 3] = x.w + dn[i + 3];
           }
+          range_note(umax, xin);
           stage16<P>(set, set + CHUNK_BYTES, row, hc * 32 + g16 * 16, xin);
         }
       } else {
@@ -993,6 +1013,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
     }
     tc_fence_before();
     if (issuer) tma_store_wait_read<0>();
+    if (res) range_publish(p.range_max, umax);
   }
   teardown<P, PAIR>(tmem_base, warp);
 }
@@ -1140,6 +1161,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
     const bool issuer = (warp == 4) && (lane == 0);
     const uint32_t stg = smem_u32(staging);
     const float rsqrt2 = 0.70710678118654752f;
+    const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
+    unsigned int umax = 0;
     // x pipeline: the fp32 x tile arrives by TMA in a landing box (one per 4-warp group), is pulled into registers one
     // iteration AHEAD and the box handed straight back to the x producer, so the next load has a whole iteration to
     // arrive (ncu: 22 % of this kernel's stall samples sat on the x barrier when a box stayed occupied until its TMA
@@ -1182,7 +1205,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
         }
         const int cbox = it * 2 + hc;
         float o[32];
-        load_acc32<P>(taddr + cbox * 32, 0.f, o);
+        load_acc32<P>(taddr + cbox * 32, inv, o);
         if (it == 3) {                              // last TMEM read of this tile: hand the accumulator stage back
           tc_fence_before();
           __syncwarp();
@@ -1204,6 +1227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
             xin[u * 4 + 0] = xc[i + 0] + d4.x; xin[u * 4 + 1] = xc[i + 1] + d4.y;
             xin[u * 4 + 2] = xc[i + 2] + d4.z; xin[u * 4 + 3] = xc[i + 3] + d4.w;
           }
+          range_note(umax, xin);
           pack16<P>(xin, pm[g16], pa[g16]);
         }
         if (issuer) tma_store_wait_read<0>();       // the previous iteration's stores no longer read the staging boxes
@@ -1237,6 +1261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
       }
     }
     if (issuer) tma_store_wait_read<0>();
+    range_publish(p.range_max, umax);
   }
   __syncthreads();
   cluster_sync_all();
@@ -1399,6 +1424,7 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   p.NB = z.NB; p.T = z.T; p.C = z.C; p.tiles_t = (z.T + TILE_M - 1) / TILE_M; p.n_blocks = z.C / TILE_N;
   p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg; p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
+  p.range_max = z.range_max;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = z.inv_scale;
   const bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);

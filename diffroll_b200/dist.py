@@ -62,12 +62,13 @@ def all_gather_rolls(local: torch.Tensor, n_total: int, group=None) -> torch.Ten
 
 
 @torch.no_grad()
-def sample_sharded(model, x_T, waveform, noise=None, group=None):
+def sample_sharded(model, x_T, waveform, noise=None, group=None, generator=None):
     """Run the sampling loop on this rank's contiguous shard of the global batch and all-gather x_0.
 
     x_T [B,1,T,88], waveform [B,L] and (optional) noise [n,B,1,T,88] are GLOBAL tensors (every rank passes
     the same ones, e.g. drawn from one seeded generator), so an N-rank run returns exactly what a 1-rank
-    run returns, sample for sample.
+    run returns, sample for sample.  Without pre-drawn noise every rank draws each step's noise for the GLOBAL
+    batch (from ``generator``, or its default CUDA generator: seed it alike on every rank) and keeps its slice.
     """
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -76,5 +77,6 @@ def sample_sharded(model, x_T, waveform, noise=None, group=None):
     x_loc = x_T[lo:hi].to(dev, non_blocking=True)
     w_loc = waveform[lo:hi].to(dev, non_blocking=True)
     n_loc = None if noise is None else noise[:, lo:hi].to(dev, non_blocking=True)
-    x0, spec, _ = model.sample_loop(x_loc, w_loc, noise=n_loc)
+    x0, spec, _ = model.sample_loop(x_loc, w_loc, noise=n_loc, generator=generator,
+                                    shard=None if noise is not None else (x_T.shape[0], lo, hi))
     return all_gather_rolls(x0, x_T.shape[0], group), spec

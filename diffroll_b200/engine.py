@@ -13,8 +13,8 @@ from . import _lib
 from ._lib import DrbConfig, DrbUpdate, DrbWeights
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ptr(t):
@@ -85,11 +85,12 @@ class Engine:
             )
             plan = C.c_void_p()
             _lib.check(self.lib.drb_plan_create(C.byref(plan), C.byref(cfg), C.byref(ws),
-                                                C.c_void_p(base + self._ws_off), C.c_size_t(need), _stream()),
+                                                C.c_void_p(base + self._ws_off), C.c_size_t(need), _stream(self.device)),
                        "drb_plan_create")
             self.plan = plan
             self._emb = emb_table.detach().to(device=self.device, dtype=torch.float32).contiguous()
-            _lib.check(self.lib.drb_time_tables(self.plan, _ptr(self._emb), _stream()), "drb_time_tables")
+            _lib.check(self.lib.drb_time_tables(self.plan, _ptr(self._emb), _stream(self.device)), "drb_time_tables")
+        self.workspace_bytes = int(need)
         self.branches = branches
 
     def close(self):
@@ -136,17 +137,18 @@ class Engine:
         if inpainting_t:
             it0, it1, _ = slice(int(inpainting_t[0]), int(inpainting_t[1])).indices(nF)
             it1 = max(it1, it0)
-            if it1 == it0:
-                it0 = it1 = 0
         if inpainting_f:
             if0, if1, _ = slice(int(inpainting_f[0]), int(inpainting_f[1])).indices(self.n_mels)
             if1 = max(if1, if0)
-            if if1 == if0:
-                if0 = if1 = 0
-        # a requested-but-empty range masks nothing, exactly like the reference's empty slice assignment
-        spec = torch.empty(self.batch, self.n_mels, self.frames, device=self.device) if want_spec else None
-        _lib.check(self.lib.drb_mel_forward(self.plan, _ptr(waveform), _ptr(spec), it0, it1, if0, if1, _stream()),
-                   "drb_mel_forward")
+        # The library reads it1 > it0 / if1 > if0 as "this mask was requested".  A requested-but-empty range masks
+        # nothing, like the reference's empty slice assignment (model/diffwave.py:649-654) -- and when BOTH ranges were
+        # requested the masked region is their product (:653), so one empty range empties the whole mask.
+        if (inpainting_t and it1 == it0) or (inpainting_f and if1 == if0):
+            it0 = it1 = if0 = if1 = 0
+        with torch.cuda.device(self.device):
+            spec = torch.empty(self.batch, self.n_mels, self.frames, device=self.device) if want_spec else None
+            _lib.check(self.lib.drb_mel_forward(self.plan, _ptr(waveform), _ptr(spec), it0, it1, if0, if1,
+                                                _stream(self.device)), "drb_mel_forward")
         return spec
 
     def step(self, x_t, noise, t_index, upd: DrbUpdate, out=None, net_out=None):
@@ -157,7 +159,11 @@ class Engine:
             self._check(noise, shape, "noise")
         if out is None:
             out = torch.empty_like(x_t)
-        s = _stream()
+        with torch.cuda.device(self.device):
+            return self._step_on_device(x_t, noise, t_index, upd, out, net_out)
+
+    def _step_on_device(self, x_t, noise, t_index, upd, out, net_out):
+        s = _stream(self.device)
         # The per-clip conditioner tables cost about one forward.  A sampler step is one of a chain over the same clip
         # (task/diffusion.py:528-529): build them (no-op when ready) and use them.  A plain forward (UPD_NONE: forward(),
         # the validation step) runs without them, whether or not they happen to be ready: results never depend on history.
@@ -187,9 +193,18 @@ class Engine:
             if noise.shape[0] < n_noise:
                 raise ValueError(f"need {n_noise} noise slices, got {noise.shape[0]}")
         tp = C.c_void_p(trajectory.data_ptr()) if trajectory is not None else C.c_void_p(0)
-        _lib.check(self.lib.drb_sample_loop(self.plan, _ptr(x), _ptr(noise) if n_noise else C.c_void_p(0), arr,
-                                            int(t_start), int(t_stop), tp, _stream()), "drb_sample_loop")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drb_sample_loop(self.plan, _ptr(x), _ptr(noise) if n_noise else C.c_void_p(0), arr,
+                                                int(t_start), int(t_stop), tp, _stream(self.device)), "drb_sample_loop")
         return x
+
+    def range_max(self, reset=True):
+        """Largest |activation operand| the fp16-based kernels emitted since the last reset (synchronises)."""
+        v = C.c_float()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drb_plan_range_stats(self.plan, C.byref(v), 1 if reset else 0, _stream(self.device)),
+                       "drb_plan_range_stats")
+        return float(v.value)
 
     def buffer(self, name, dtype=torch.float32):
         """Debug view of a plan-owned device buffer."""
@@ -208,6 +223,16 @@ class Engine:
         n = (C.c_int64 * 4)()
         _lib.check(self.lib.drb_plan_profile_read(self.plan, ms, n), "drb_plan_profile_read")
         return {k: (ms[i], int(n[i])) for i, k in enumerate(("gate", "out", "in_proj", "head"))}
+
+    def profile_read_detail(self):
+        """({class: (total_ms, spans)} incl. 'head_out' = the head's projection + posterior kernel alone, gate ms per layer)."""
+        L = self.cfg.residual_layers
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        per = (C.c_double * L)()
+        _lib.check(self.lib.drb_plan_profile_read2(self.plan, ms, n, 5, per, L), "drb_plan_profile_read2")
+        names = ("gate", "out", "in_proj", "head", "head_out")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(names)}, [per[i] for i in range(L)]
 
     def launch_count(self, reset=False):
         return int(self.lib.drb_launch_count(1 if reset else 0))

@@ -99,6 +99,14 @@ class _MelBuffers(nn.Module):
 
 
 class ClassifierFreeDiffRoll(SpecRollDiffusion):
+    MAX_ENGINES = 4   # engines (one per batch/frames/wave_len/device) kept alive at once
+    # Range guard.  The f16e5 / f16f8 formats round activations to fp16 (max 65504); weights are
+    # pre-scaled per tensor by a power of two, activations are not.  Every call reads back the largest |operand| its
+    # kernels emitted; a value that is not finite or above F16_RANGE_LIMIT switches this model to bf16x3 (fp32 exponent
+    # range, same parity grade, ~20 % slower) and re-runs the call.  ``range_check = False`` skips the read-back.
+    F16_RANGE_LIMIT = 3.0e4
+    range_check = True
+
     def __init__(self, residual_channels, unconditional, condition, n_mels, norm_args,
                  residual_layers=30, kernel_size=3, dilation_base=1, dilation_bound=4, spec_args={},
                  spec_dropout=0.5, inpainting_t=None, inpainting_f=None, precision="f16e5", **kwargs):
@@ -152,6 +160,8 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             ent[0].close()
         for k in [k for k, e in self._engines.items() if e[1] != ver]:
             self._engines.pop(k)[0].close()
+        while len(self._engines) >= self.MAX_ENGINES:       # bounded: a workspace is gigabytes; least recently built goes first
+            self._engines.pop(next(iter(self._engines)))[0].close()
         eng = Engine(self.state_dict(), self.hparams, batch, frames, wave_len, self.diffusion_embedding.embedding,
                      precision=self.precision, branches=_lib.BRANCH_COND_UNCOND, device=device)
         self._engines[key] = (eng, ver)
@@ -192,6 +202,22 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         eng.set_branches(branches)
         return eng, xx, spec
 
+    def _range_guarded(self):
+        return self.range_check and self.precision in ("f16e5", "f16f8")
+
+    def _range_ok(self, eng):
+        if not self._range_guarded():
+            return True
+        m = eng.range_max(reset=True)
+        return m == m and m <= self.F16_RANGE_LIMIT
+
+    def _range_fallback(self):
+        import warnings
+        warnings.warn(f"diffroll_b200: activations left the fp16 range of precision='{self.precision}' "
+                      f"(|x| > {self.F16_RANGE_LIMIT:g} or non-finite); re-running in 'bf16x3'", RuntimeWarning, stacklevel=3)
+        self.precision = "bf16x3"
+        self._mel_key = None
+
     def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):
         eng, xx, spec = self._prepare(x, waveform, branches, inpainting_t, inpainting_f)
         if upd.has_noise:
@@ -202,6 +228,9 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         else:
             noise = None
         out = eng.step(xx, noise, t_index, upd)
+        if not self._range_ok(eng):
+            self._range_fallback()
+            return self._step(x, waveform, t_index, upd, branches, noise, inpainting_t, inpainting_f)
         return out, spec
 
     # ---- reference forward ---------------------------------------------------------------------------
@@ -226,12 +255,16 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         branches = _lib.BRANCH_UNCOND if sampling is True else _lib.BRANCH_COND
         eng, xx, spec = self._prepare(x_t, waveform, branches, inpainting_t, inpainting_f)
         if not per_roll:
-            return eng.step(xx, None, t0, _upd(_lib.UPD_NONE)), spec
-        eng.set_steps(steps)
-        try:
             pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
-        finally:
-            eng.set_steps(None)
+        else:
+            eng.set_steps(steps)
+            try:
+                pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
+            finally:
+                eng.set_steps(None)
+        if not self._range_ok(eng):
+            self._range_fallback()
+            return self.forward(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)
         return pred, spec
 
     def train(self, mode=True):

@@ -33,12 +33,13 @@ def extract_notes_batch(onsets, frames, onset_threshold=0.5, frame_threshold=0.5
     pitches = torch.empty(B, max_notes, dtype=torch.int32, device=dev)
     intervals = torch.empty(B, max_notes, 2, dtype=torch.int32, device=dev)
     counts = torch.empty(B, dtype=torch.int32, device=dev)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.drb_extract_notes(C.c_void_p(on.data_ptr()), C.c_void_p(fr.data_ptr()), B, T, P, float(onset_threshold),
-                                     float(frame_threshold), 1 if rule == "rule1" else 2, C.c_void_p(scratch.data_ptr()),
-                                     C.c_void_p(pitches.data_ptr()),
-                                     C.c_void_p(intervals.data_ptr()), C.c_void_p(counts.data_ptr()), max_notes, stream),
-               "drb_extract_notes")
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = lib.drb_extract_notes(C.c_void_p(on.data_ptr()), C.c_void_p(fr.data_ptr()), B, T, P, float(onset_threshold),
+                                   float(frame_threshold), 1 if rule == "rule1" else 2, C.c_void_p(scratch.data_ptr()),
+                                   C.c_void_p(pitches.data_ptr()), C.c_void_p(intervals.data_ptr()),
+                                   C.c_void_p(counts.data_ptr()), max_notes, stream)
+    _lib.check(rc, "drb_extract_notes")
     n = counts.cpu().numpy()
     nmax = int(n.max()) if B else 0
     p_host = pitches[:, :nmax].cpu().numpy().astype(np.int64)
@@ -70,7 +71,7 @@ def frame_precision_recall_f1(label, pred, threshold=0.5):
     la = label.to(torch.float32).contiguous()
     pr = pred.to(torch.float32).contiguous()
     counts = torch.empty(3, dtype=torch.int64, device=pr.device)
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stream = C.c_void_p(torch.cuda.current_stream(pr.device).cuda_stream)
     with torch.cuda.device(pr.device):
         _lib.check(lib.drb_frame_counts(C.c_void_p(pr.data_ptr()), C.c_void_p(la.data_ptr()), C.c_int64(pr.numel()),
                                         C.c_float(threshold), C.c_void_p(counts.data_ptr()), stream), "drb_frame_counts")

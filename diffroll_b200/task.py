@@ -115,7 +115,7 @@ class SpecRollDiffusion(nn.Module):
                                   self.sqrt_one_minus_alphas_cumprod[t_index], sigma], has_noise=not ddim)
 
     def _w(self):
-        return float(self.hparams.sampling.get("w", 0.0) if hasattr(self.hparams.sampling, "get") else self.hparams.sampling.w)
+        return float(self.hparams.sampling.w)   # AttributeError when absent, like the reference's hparams access (:1009)
 
     # ---- samplers: (x, waveform, t_index) -> (x_prev, spec) ----------------------------------
     def inpainting_ddpm_x0(self, x, waveform, t_index, noise=None):
@@ -179,15 +179,25 @@ class SpecRollDiffusion(nn.Module):
             ups.append(probe.capture(t_index))
         return ups, probe.branches, probe.masks
 
-    @torch.no_grad()
-    def sample_loop(self, x_T, waveform, noise=None, keep_trajectory=False, n_steps=None):
-        """The loop body of predict_step / sampling (task/diffusion.py:528-534, 779-788) as ONE library call.
+    # device bytes of pre-drawn noise held at any time by sample_loop (the reference draws one step at a time, :1023)
+    NOISE_CHUNK_BYTES = 1 << 30
+    # trajectories up to this size live in pinned host memory (async copies overlap compute); larger ones are pageable
+    PINNED_TRAJ_BYTES = 8 << 30
 
-        noise: optional pre-drawn [n_noisy_steps, B, 1, T, 88]; by default it is drawn step by step with
-        ``torch.randn_like`` on the roll's device, in the reference's order (descending t, only t with noise).
+    @torch.no_grad()
+    def sample_loop(self, x_T, waveform, noise=None, keep_trajectory=False, n_steps=None, generator=None, shard=None):
+        """The loop body of predict_step / sampling (task/diffusion.py:528-534, 779-788) as a few library calls.
+
+        noise: optional pre-drawn [n_noisy_steps, B, 1, T, 88] (device or host tensor).  By default the noise is drawn
+        step by step with ``torch.randn_like`` on the roll's device (``generator``: a CUDA ``torch.Generator`` to draw
+        from instead of the default one), in the reference's order (descending t, only steps with noise), in chunks
+        of at most NOISE_CHUNK_BYTES so a 1000-step chain does not hold 1000 noise tensors.
+        shard: (global_batch, lo, hi) when x_T holds rows lo:hi of a global batch split over ranks: every step's noise
+        is then drawn for the GLOBAL batch and sliced, so an N-rank run consumes the generator exactly like a 1-rank
+        run and returns the same rolls.
         n_steps: run only the first n_steps of the chain (t = T-1 .. T-n_steps); default the whole chain.
-        Returns (x_0, spec, trajectory) — trajectory is a pinned host tensor [steps, B, 1, T, 88] or None; it is
-        reused by the next call with the same shape (copy it if you need to keep it).
+        Returns (x_0, spec, trajectory) -- trajectory is a host tensor [steps, B, 1, T, 88] or None; it is reused by
+        the next call with the same shape (copy it if you need to keep it).
         """
         ups, branches, masks = self._all_updates()
         T_all = self.hparams.timesteps
@@ -195,29 +205,73 @@ class SpecRollDiffusion(nn.Module):
             if not 0 < n_steps <= T_all:
                 raise ValueError("n_steps must be in [1, timesteps]")
             ups = ups[:n_steps]
-        t_stop = T_all - len(ups)
         eng, x, spec = self._prepare(x_T, waveform, branches, *masks)
         x = x.clone()
-        n_noise = sum(1 for u in ups if u.has_noise)
-        if noise is None and n_noise:
-            noise = torch.empty((n_noise,) + tuple(x.shape), device=x.device)
-            for i in range(n_noise):
-                noise[i] = torch.randn_like(x)      # same generator consumption order as task/diffusion.py:1023
-        elif noise is not None:
-            noise = noise.to(device=x.device, dtype=torch.float32)[..., :x.shape[2], :].contiguous()
+        n_total = sum(1 for u in ups if u.has_noise)
+        rng_state = None
+        if noise is None and self._range_guarded():     # a re-run in the range-safe format must see the same noise
+            rng_state = generator.get_state() if generator is not None else torch.cuda.get_rng_state(x.device)
+        if noise is not None:
+            if noise.shape[0] < n_total:
+                raise ValueError(f"need {n_total} noise slices, got {noise.shape[0]}")
+            resident = noise.is_cuda and noise.dtype == torch.float32 and noise.shape[3] == x.shape[2] and noise.is_contiguous()
+        if shard is not None:
+            gB, lo, hi = (int(v) for v in shard)
+            if hi - lo != x.shape[0] or not 0 <= lo <= hi <= gB:
+                raise ValueError(f"shard {shard} does not describe a batch of {x.shape[0]} rolls")
         traj = None
         if keep_trajectory:
             # pinned host memory is expensive to allocate (~0.5 s per GB): keep one buffer per shape
             shape = (len(ups),) + tuple(x.shape)
             traj = self.__dict__.get("_traj_buf")
             if traj is None or tuple(traj.shape) != shape:
-                traj = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+                self.__dict__["_traj_buf"] = None
+                nbytes = 4
+                for d in shape:
+                    nbytes *= d
+                traj = torch.empty(shape, dtype=torch.float32, pin_memory=nbytes <= self.PINNED_TRAJ_BYTES)
                 self.__dict__["_traj_buf"] = traj
-        eng.loop(x, noise, ups, T_all, t_stop, traj)
+        per_step = x.numel() * 4
+        chunk = max(1, min(len(ups), self.NOISE_CHUNK_BYTES // per_step))
+        k = 0                                            # noisy steps consumed so far
+        for i0 in range(0, len(ups), chunk):
+            cu = ups[i0:i0 + chunk]
+            nn = sum(1 for u in cu if u.has_noise)
+            nz = None
+            if nn and noise is not None:
+                nz = noise[k:k + nn] if resident else noise[k:k + nn].to(device=x.device, dtype=torch.float32)[..., :x.shape[2], :].contiguous()
+            elif nn:
+                nz = torch.empty((nn,) + tuple(x.shape), device=x.device)
+                for j in range(nn):                      # same generator consumption order as task/diffusion.py:1023
+                    if shard is not None:
+                        nz[j] = torch.randn((gB,) + tuple(x.shape[1:]), device=x.device, generator=generator)[lo:hi]
+                    elif generator is not None:
+                        nz[j] = torch.randn(tuple(x.shape), device=x.device, generator=generator)
+                    else:
+                        nz[j] = torch.randn_like(x)
+            k += nn
+            eng.loop(x, nz, cu, T_all - i0, T_all - i0 - len(cu), None if traj is None else traj[i0:i0 + len(cu)])
+        if not self._range_ok(eng):
+            if rng_state is not None:
+                if generator is not None:
+                    generator.set_state(rng_state)
+                else:
+                    torch.cuda.set_rng_state(rng_state, x.device)
+            self._range_fallback()
+            return self.sample_loop(x_T, waveform, noise=noise, keep_trajectory=keep_trajectory, n_steps=n_steps,
+                                    generator=generator, shard=shard)
         return x, spec, traj
 
+    def release_buffers(self):
+        """Drop the cached host trajectory buffer and every engine (device workspaces) of this model."""
+        self.__dict__.pop("_traj_buf", None)
+        for eng, _ in getattr(self, "_engines", {}).values():
+            eng.close()
+        if hasattr(self, "_engines"):
+            self._engines.clear()
+
     @torch.no_grad()
-    def predict_step(self, batch, batch_idx=0):
+    def predict_step(self, batch, batch_idx=0, generator=None, shard=None):
         """task/diffusion.py:513-534.  batch = (x_T [B,1,T,88], waveform [B,L][, roll_label]).
 
         The reference copies every intermediate roll to the host (:530) and then writes figures/MIDI
@@ -227,8 +281,8 @@ class SpecRollDiffusion(nn.Module):
         are views of one pinned host buffer that the next call with the same shape overwrites; ``roll_pred`` is a copy.
         """
         noise, waveform = batch[0], batch[1]
-        x0, spec, traj = self.sample_loop(noise, waveform, keep_trajectory=True)
-        torch.cuda.current_stream().synchronize()
+        x0, spec, traj = self.sample_loop(noise, waveform, keep_trajectory=True, generator=generator, shard=shard)
+        torch.cuda.current_stream(x0.device).synchronize()
         noise_list = [(noise, self.hparams.timesteps)]
         tnp = traj.numpy()
         for i, t_index in enumerate(reversed(range(self.hparams.timesteps))):
@@ -237,14 +291,20 @@ class SpecRollDiffusion(nn.Module):
         return roll_pred, noise_list, spec
 
     @torch.no_grad()
-    def sampling(self, batch, batch_idx=0):
-        """task/diffusion.py:765-790: batch = {'frame': [B,T,88], 'audio': [B,L]} -> (noise_list, spec)."""
+    def sampling(self, batch, batch_idx=0, zero_copy=False):
+        """task/diffusion.py:765-790: batch = {'frame': [B,T,88], 'audio': [B,L]} -> (noise_list, spec).
+
+        The reference returns independent ``.cpu().numpy()`` arrays (:784); so does this method.  ``zero_copy=True``
+        returns views of the single reused host trajectory buffer instead (the next sampling / predict_step / test_step
+        call with the same shape overwrites them)."""
         roll = self.normalize(batch["frame"]).unsqueeze(1)
         waveform = batch["audio"]
         noise = torch.randn_like(roll)
         if self.hparams.debug:
             raise NotImplementedError("debug=True conditions on the label roll (DiffRollDebug); not on this path")
         _, noise_list, spec = self.predict_step((noise, waveform), batch_idx)
+        if not zero_copy:
+            noise_list = [noise_list[0]] + [(a.copy(), t) for a, t in noise_list[1:]]
         return noise_list, spec
 
     @torch.no_grad()
@@ -266,8 +326,8 @@ class SpecRollDiffusion(nn.Module):
         Returns a dict: frame_p, frame_r, frame_f1, counts (tp, fp, fn), notes_est / notes_ref (lists of
         (pitches, intervals) in frames, the reference's order), roll_pred (numpy [B,1,T,88]), spec."""
         from .notes import extract_notes_batch, frame_precision_recall_f1
-        noise_list, spec = self.sampling(batch, batch_idx)
-        roll_pred = noise_list[-1][0]
+        noise_list, spec = self.sampling(batch, batch_idx, zero_copy=True)
+        roll_pred = noise_list[-1][0].copy()   # independent of the reused host trajectory buffer
         thr = self.hparams.frame_threshold
         label = batch["frame"]
         pred_dev = torch.from_numpy(roll_pred).to(label.device)
@@ -343,6 +403,16 @@ class SpecRollDiffusion(nn.Module):
             total_loss = total_loss + losses[k]
             self.log(f"Val/{k}", losses[k])
         return total_loss
+
+    # range guard of the fp16-based operand formats: no-ops here, implemented by the model subclass
+    def _range_guarded(self):
+        return False
+
+    def _range_ok(self, eng):
+        return True
+
+    def _range_fallback(self):
+        raise NotImplementedError
 
     # provided by the model subclass
     def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):

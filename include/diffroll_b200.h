@@ -222,6 +222,19 @@ int drb_normalize_imagewise(const float* x, float* out, int32_t B, int64_t n_per
  * {0: gate kernel, 1: out kernel, 2: in_proj, 3: head}, the summed milliseconds and the number of spans. */
 int drb_plan_profile(drb_plan* plan, int32_t enable);
 int drb_plan_profile_read(drb_plan* plan, double* ms_total4, int64_t* launches4);
+/* Same with n_classes <= 5 classes (4: the head's output projection + guidance + posterior kernel alone, also part of
+ * class 3) and, when gate_ms_per_layer != NULL and n_layers == residual_layers, the gate-kernel milliseconds summed per
+ * layer (layer 0 is the launch shared by both guidance branches). */
+int drb_plan_profile_read2(drb_plan* plan, double* ms_total, int64_t* launches, int32_t n_classes,
+                           double* gate_ms_per_layer, int32_t n_layers);
+
+/* Range guard of the fp16-based operand formats (f16e5, f16f8).  Their main product rounds activations to fp16, which
+ * overflows at 65504; weights are pre-scaled per tensor by a power of two, activations are not.  Every kernel that
+ * emits an activation operand (in_proj, the residual update) folds max |value| into one device word; this call copies
+ * it to *max_abs (synchronises the stream; NaN operands read back as NaN) and optionally resets it.  The Python module
+ * re-runs a call in bf16x3 (fp32 exponent range) when the value is not finite or above 3e4.  No reference counterpart:
+ * the reference computes in fp32 (model/diffwave.py:134-151). */
+int drb_plan_range_stats(drb_plan* plan, float* max_abs, int32_t reset, void* stream);
 
 /* Debug / test access to plan-owned device buffers ("x32","skip","xh","xl","zh","zl","spec_h","dtab","logmel"). */
 int drb_plan_buffer(drb_plan* plan, const char* name, void** ptr, size_t* bytes);

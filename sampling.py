@@ -79,7 +79,11 @@ def main(argv=None):
         a, b = shard_bounds(hi - lo, rank, world)
         if b > a:
             batch = (x[lo + a:lo + b].cuda(non_blocking=True), waveform[lo + a:lo + b].cuda(non_blocking=True))
-            roll_pred, _, _ = model.predict_step(batch, lo // bs)
+            # Step noise (task/diffusion.py:1023) is drawn for the WHOLE batch from a generator seeded per batch and
+            # sliced to this rank's rolls: shards are statistically independent and an N-rank run returns exactly the
+            # rolls of a 1-rank run (every rank seeding its own generator alike would repeat one noise sequence per shard).
+            gen = torch.Generator(device="cuda").manual_seed(int(cfg.seed) + 1 + lo // bs)
+            roll_pred, _, _ = model.predict_step(batch, lo // bs, generator=gen, shard=(hi - lo, a, b))
             part = torch.from_numpy(roll_pred).cuda()
         else:
             part = torch.empty(0, 1, 640, 88, device="cuda")

@@ -33,7 +33,8 @@ def pytest_collection_modifyitems(config, items):
 def golden(name):
     path = os.path.join(GOLDEN, name)
     if not os.path.exists(path):
-        pytest.skip(f"golden fixture {name} missing")
+        # a lost fixture must not silently turn the parity suite into skips
+        pytest.fail(f"golden fixture {name} missing (regenerate with oracle/make_golden.py in the build container)")
     return np.load(path)
 
 

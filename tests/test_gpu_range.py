@@ -1,0 +1,106 @@
+"""Range behaviour of the default f16e5 operand format.
+
+f16e5 rounds activations and weights to fp16 (+ an e5m2 correction).  Weights are pre-scaled per tensor by a power of
+two at plan creation, activations are not: every call reads back the largest |operand| its kernels emitted and the
+module re-runs the call in bf16x3 (fp32 exponent range) when that is not finite or above 3e4 (model.F16_RANGE_LIMIT).
+
+The cases scale ALL weights by {0.01, 10, 100} and the input roll by {10, 1e3, 1e5} and compare one sampler step at the
+noisiest t and the t = 0 step (x0 / sqrt(abar_0): the network error undamped) with the oracle run eagerly on the GPU
+with the same scaled tensors.  The bar is the per-step tolerance of tests/test_gpu_parity.py relative to the output
+scale: |delta|max < 5e-4 * max(1, |ref|max), and every result finite.  x_T * 1e5 overflows fp16 and must take the
+bf16x3 fall-back (with a RuntimeWarning); the other cases must stay on f16e5.
+"""
+import os
+import warnings
+
+import pytest
+import torch
+
+from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dict
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_REL = 5e-4
+
+
+def _record(msg):
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_numbers.log"), "a") as f:
+        f.write(msg + "\n")
+    print(msg)
+
+
+def _oracle_steps(hp, sd, x, w, nz):
+    from oracle.diffroll_oracle import OracleDiffRoll
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        orc = OracleDiffRoll(hp, sd, device="cuda")
+        with torch.no_grad():
+            hi, _ = orc.reverse_diffusion(x, w, hp["timesteps"] - 1, noise=nz)
+            lo, _ = orc.reverse_diffusion(x, w, 0)
+        return hi, lo
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+CASES = [("weights", 0.01, False), ("weights", 10.0, False), ("weights", 100.0, False),
+         ("input", 10.0, False), ("input", 1e3, False), ("input", 1e5, True)]
+
+
+@pytest.mark.parametrize("what,scale,expect_fallback", CASES)
+def test_f16e5_scaled_operands(what, scale, expect_fallback):
+    import diffroll_b200 as M
+    hp = default_hparams()
+    sd = make_state_dict(hp)
+    if what == "weights":
+        sd = type(sd)((k, v * scale if k.endswith(".weight") else v) for k, v in sd.items())
+    x_T, wav, noise = make_inputs(2, 200, seed=9, n_noise=1, T=256, wav_len=131072)
+    x, w, nz = x_T.cuda(), wav.cuda(), noise[0].cuda()
+    if what == "input":
+        x = x * scale
+    ref_hi, ref_lo = _oracle_steps(hp, sd, x, w, nz)
+    m = M.ClassifierFreeDiffRoll(**hp, precision="f16e5")
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        a_hi, _ = m.reverse_diffusion(x, w, hp["timesteps"] - 1, noise=nz)
+        a_lo, _ = m.reverse_diffusion(x, w, 0)
+        torch.cuda.synchronize()
+    fell_back = m.precision == "bf16x3"
+    assert fell_back == expect_fallback, (what, scale, m.precision)
+    assert fell_back == any(issubclass(c.category, RuntimeWarning) and "bf16x3" in str(c.message) for c in caught)
+    assert bool(torch.isfinite(a_hi).all()) and bool(torch.isfinite(a_lo).all())
+    rel = []
+    for a, r in ((a_hi, ref_hi), (a_lo, ref_lo)):
+        rel.append(float((a - r).abs().max()) / max(1.0, float(r.abs().max())))
+    _record(f"range: {what} x {scale:g}: precision used {m.precision}, step t=199 rel. max|delta| {rel[0]:.3e}, "
+            f"t=0 {rel[1]:.3e} (|ref|max {float(ref_hi.abs().max()):.3g} / {float(ref_lo.abs().max()):.3g})")
+    assert max(rel) < TOL_REL, (what, scale, rel)
+    m.release_buffers()
+
+
+def test_range_word_tracks_operand_magnitude():
+    """drb_plan_range_stats (include/diffroll_b200.h) through the engine: the read-back follows the input scale and resets."""
+    import diffroll_b200 as M
+    from diffroll_b200 import _lib
+    from diffroll_b200.task import _upd
+    hp = default_hparams()
+    m = M.ClassifierFreeDiffRoll(**hp, precision="f16e5")
+    m.load_state_dict(make_state_dict(hp))
+    m = m.cuda().eval()
+    m.range_check = False
+    x_T, wav, _ = make_inputs(2, 200, seed=9, n_noise=0, T=128, wav_len=65536)
+    eng, xx, _ = m._prepare(x_T.cuda(), wav.cuda(), _lib.BRANCH_COND)
+    eng.range_max(reset=True)
+    eng.step(xx, None, 100, _upd(_lib.UPD_NONE))
+    m1 = eng.range_max(reset=True)
+    assert 0.5 < m1 < 100.0
+    assert eng.range_max(reset=False) == 0.0
+    eng.step(xx * 50.0, None, 100, _upd(_lib.UPD_NONE))
+    m2 = eng.range_max(reset=True)
+    assert m2 > 10.0 * m1
+    m.release_buffers()
