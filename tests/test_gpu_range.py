@@ -12,8 +12,9 @@ where 5e-4 is the per-step tolerance of tests/test_gpu_parity.py and ``floor`` i
 own fp32 arithmetic (oracle fp32, TF32 off, against the fp64 run).  Scaling every weight by 10 or 100 drives the gates
 into saturation and makes the 15-layer stack amplify ANY rounding difference (measured: the fp32 reference itself
 moves by 1e-4..1e-2 against fp64 there), so an absolute bar would test the network's conditioning, not the format; the
-format's product error is ~2^-16 against fp32's 2^-24, i.e. at most 2^8 x the fp32 floor.  x_T * 1e5 overflows fp16 and
-must take the bf16x3 fall-back (with a RuntimeWarning); the other cases must stay on f16e5.
+format's product error is ~2^-16 against fp32's 2^-24, i.e. at most 2^8 x the fp32 floor.  x_T * 1e5 and weights * 100
+drive activations past the guard (3e4) and must take the bf16x3 fall-back (with a RuntimeWarning); the other cases
+must stay on f16e5.
 """
 import os
 import warnings
@@ -55,7 +56,7 @@ def _rel(a, ref):
     return float((a.double() - ref).abs().max()) / max(1.0, float(ref.abs().max()))
 
 
-CASES = [("weights", 0.01, False), ("weights", 10.0, False), ("weights", 100.0, False),
+CASES = [("weights", 0.01, False), ("weights", 10.0, False), ("weights", 100.0, True),
          ("input", 10.0, False), ("input", 1e3, False), ("input", 1e5, True)]
 
 
