@@ -357,7 +357,8 @@ def gate_roofline(m, peaks, precision, world, K, traffic):
     full = m["gate_layers"][1:]                       # layers 1..L-1: launches that issue every MMA (layer 0 may be shared)
     full_avg_s = sum(full) / max(len(full), 1) / n_prof / 1000.0
     r = {
-        "kernel": {"f16e5": "umma_gate_pers_kernel<3> (f16e5, persistent CTA pairs, tap window)",
+        "kernel": {"f16n4": "umma_gate_n4_kernel (f16n4: fp16 + block-scaled fp4 correction, persistent CTA pairs, tap window)",
+                   "f16e5": "umma_gate_pers_kernel<3> (f16e5, persistent CTA pairs, tap window)",
                    "f16f8": "umma_gate_win_kernel<2> (f16f8, CTA pairs, tap window)",
                    "bf16x3": "umma_gate_pers_kernel<1> (bf16x3, persistent CTA pairs, tap window)"}.get(precision, f"umma_gate_kernel<{precision}>"),
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
@@ -365,7 +366,7 @@ def gate_roofline(m, peaks, precision, world, K, traffic):
         "traffic_source": "static: one ncu --set full capture of this kernel at this shape (profiles/roofline_traffic.json), "
                           "not re-measured by this run",
         "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step); burst {peaks['bf16']}",
-        "mma_multiplicity": {"bf16x3": 3, "f16f8": 2, "f16e5": 2}.get(precision, 1),
+        "mma_multiplicity": {"bf16x3": 3, "f16f8": 2, "f16e5": 2, "f16n4": 1.5}.get(precision, 1),
         "algorithmic_flops_per_launch": gate_flops,
         "avg_launch_ms": gate_avg_s * 1e3, "launches_timed": gate_n,
         "full_launch_avg_ms": full_avg_s * 1e3,
@@ -521,7 +522,9 @@ def run_b200(args, rank, world, local):
         "metric": METRIC if cfg_id == 1 else f"diffusion sampling steps/sec ({cfg['tag']})",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": main["ms"] / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (bf16 hi/lo split, 3 tcgen05 products, fp32 accumulate)",
+        "dtype": {"f16n4": "f16n4 (fp16 tcgen05 product + block-scaled e2m1 correction product, one fp32 accumulator; "
+                           "RES / HEAD GEMMs: f16e5)",
+                  "bf16x3": "bf16x3 (bf16 hi/lo split, 3 tcgen05 products, fp32 accumulate)",
                   "f16f8": "f16f8 (fp16 tcgen05 product + e4m3 correction product, fp32 accumulate)",
                   "f16e5": "f16e5 (fp16 tcgen05 product + e5m2 correction product, one fp32 accumulator)"}.get(args.precision, args.precision),
         "data": "synthetic",
@@ -552,7 +555,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4])
     ap.add_argument("--batch", type=int, default=0, help="override the configuration's (per-GPU or global) batch")
-    ap.add_argument("--precision", default="f16e5", choices=["f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="f16e5", choices=["f16n4", "f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="headline configuration only (no configs2 / strong / eager extras)")
     args = ap.parse_args()

@@ -11,16 +11,17 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffroll_b200.so")
 
-PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16F8, PREC_F16E5 = 0, 1, 2, 3, 4
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16F8, PREC_F16E5, PREC_F16N4 = 0, 1, 2, 3, 4, 5
 BRANCH_COND_UNCOND, BRANCH_COND, BRANCH_UNCOND, BRANCH_COND_ZEROSPEC = 0, 1, 2, 3
 UPD_X0, UPD_X0_FINAL, UPD_EPS_DDPM, UPD_EPS_DDIM, UPD_EPS_FINAL, UPD_NONE = range(6)
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8, "f16e5": PREC_F16E5}
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8, "f16e5": PREC_F16E5,
+              "f16n4": PREC_F16N4}
 
 EXPORTS = [
     "drb_version", "drb_last_error", "drb_plan_workspace_bytes", "drb_plan_create", "drb_plan_destroy",
     "drb_plan_set_branches", "drb_plan_set_steps", "drb_time_tables", "drb_mel_forward", "drb_cond_tables", "drb_plan_use_cond_tables", "drb_in_proj", "drb_resblock_forward",
     "drb_head_posterior_step", "drb_sample_step", "drb_sample_loop", "drb_launch_count", "drb_plan_buffer",
-    "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
+    "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_plan_precision", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
 ]
 
@@ -97,6 +98,7 @@ def load():
     lib.drb_plan_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.drb_plan_profile_read2.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32,
                                            C.POINTER(C.c_double), C.c_int32]
+    lib.drb_plan_precision.argtypes = [C.c_void_p]
     lib.drb_plan_range_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_void_p]
     lib.drb_extract_notes_scratch_bytes.restype = C.c_size_t
     lib.drb_extract_notes_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]

@@ -42,6 +42,7 @@ struct Layout {  // byte offsets into the workspace
   size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel, xpp;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
+  size_t xs, wsf4;                                      // f16n4: activation scale factors [NB][C/64][T][8]; weight scale atoms [L][2C/256][k*C/64][2048]
   size_t range;                                         // one word: max |activation operand| (fp32 bits) since the last reset
   size_t wcpad, cond;                                   // fp32 Wc of every layer padded to Mp; conditioner projections of the spectrogram [L][B][T][2C]
   size_t total;
@@ -53,10 +54,26 @@ static bool cfg_ok(const drb_config& c) {
   if (c.residual_channels <= 0 || c.residual_channels % 256) return false;
   if (c.residual_layers <= 0 || c.kernel_size <= 0 || !(c.kernel_size & 1)) return false;
   if (c.dilation_base <= 0 || c.dilation_bound <= 0 || c.n_mels <= 0 || c.n_fft <= 0 || c.hop_length <= 0) return false;
-  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 4 || c.branches < 0 || c.branches > 3) return false;
+  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 5 || c.branches < 0 || c.branches > 3) return false;
   if (c.wave_len / c.hop_length + 1 < c.frames) return false;
   if (c.wave_len <= c.n_fft / 2) return false;  // reflect padding needs pad < length
   return true;
+}
+
+// f16n4 exists only as persistent CTA-pair kernels: a plan whose M-tile count can be odd (batch * ceil(frames / 128) odd) or
+// that was told not to use pairs / windows / persistence runs as f16e5 (same parity grade, 2 MMA units).
+static drb_config effective_config(const drb_config& in) {
+  drb_config c = in;
+  if (c.precision == DRB_PREC_F16N4) {
+    auto off = [](const char* name) { const char* e = getenv(name); return e && e[0] == '1'; };
+    const int tiles_t = (c.frames + 127) / 128;
+    const bool ok = ((c.batch * tiles_t) % 2 == 0) && !off("DRB_NO_PAIR") && !off("DRB_NO_WINDOW") && !off("DRB_NO_PERSIST") &&
+                    !off("DRB_NO_CONDPRE") && !off("DRB_NO_N4");
+    int win = 0, d = 1;
+    for (int i = 0; i < c.dilation_bound && i < c.residual_layers; ++i) { win = 128 + (c.kernel_size - 1) * d; d *= c.dilation_base; }
+    if (!ok || win > 192) c.precision = DRB_PREC_F16E5;
+  }
+  return c;
 }
 
 static Layout make_layout(const drb_config& c) {
@@ -94,7 +111,11 @@ static Layout make_layout(const drb_config& c) {
     l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
     l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
     l.bcomp = take(C * 4); l.bsum = take(C * 4);
-    l.wscale = take((2 * L + 1) * 4 * 4);  // f16f8: {SW, 1/(SA*SW), scratch, -} per gate / out weight set and the head
+    l.wscale = take((2 * L + 1) * 4 * 4);
+    if (c.precision == DRB_PREC_F16N4) {
+      l.xs = take(NB * (C / 64) * T * 8);
+      l.wsf4 = take(L * (2 * C / 256) * (k * C / 64) * 2048);
+    }  // f16f8: {SW, 1/(SA*SW), scratch, -} per gate / out weight set and the head
     if (c.branches != DRB_BRANCH_UNCOND && c.precision != DRB_PREC_F16F8 && c.precision != DRB_PREC_BF16) {
       l.wcpad = take(L * 2 * C * Mp * 4); l.cond = take(L * B * T * 2 * C * 4);
     }
@@ -125,6 +146,8 @@ struct drb_plan {
   UmmaMaps maps;
   std::vector<UmmaLayer> layers;
   std::vector<CUtensorMap> win_h, win_l;  // per layer: x operand maps whose box covers the layer's whole tap window
+  std::vector<CUtensorMap> win4, wd4, wsf4;   // f16n4 per layer: aux window map, aux weight map, weight scale atoms
+  CUtensorMap xl4;                            // f16n4: RES store map of the 64-byte e2m1 rows
   int window = 1, persistent = 1;
   const int32_t* steps = nullptr;   // per-sample diffusion steps (device, [batch]); nullptr = the t_index arguments
   int condpre = 1;     // conditioner projections precomputed per clip, added in the gate epilogue (DRB_NO_CONDPRE=1: off)
@@ -146,8 +169,11 @@ struct drb_plan {
     return at<float>(lay.bias) + ((size_t)layer * 4 + which) * 2 * cfg.residual_channels;
   }
   // tensor-path arithmetic: kernel template mode (0 bf16, 1 bf16x3, 2 f16f8) and operand format (1 bf16 hi/lo, 2 fp16+e4m3)
-  int prec() const { return cfg.precision == DRB_PREC_BF16X3 ? 1 : cfg.precision == DRB_PREC_F16F8 ? 2 : cfg.precision == DRB_PREC_F16E5 ? 3 : 0; }
-  int fmt() const { return cfg.precision == DRB_PREC_FP32 ? 0 : cfg.precision == DRB_PREC_F16F8 ? 2 : cfg.precision == DRB_PREC_F16E5 ? 3 : 1; }
+  // f16n4: only the gate kernel's activation / weight operands are block-scaled fp4; z operands, RES and HEAD stay f16e5
+  bool n4() const { return cfg.precision == DRB_PREC_F16N4; }
+  int prec() const { return cfg.precision == DRB_PREC_BF16X3 ? 1 : cfg.precision == DRB_PREC_F16F8 ? 2 : (cfg.precision == DRB_PREC_F16E5 || n4()) ? 3 : 0; }
+  int fmt() const { return cfg.precision == DRB_PREC_FP32 ? 0 : cfg.precision == DRB_PREC_F16F8 ? 2 : (cfg.precision == DRB_PREC_F16E5 || n4()) ? 3 : 1; }
+  int xfmt() const { return n4() ? 4 : fmt(); }   // format of the x operand pair (in_proj / RES -> gate kernel)
   float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head
   const float* dvec(int layer, int t) const {
     return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
@@ -162,7 +188,7 @@ int64_t drb_launch_count(int32_t reset) { int64_t v = g_launches; if (reset) g_l
 
 size_t drb_plan_workspace_bytes(const drb_config* cfg) {
   if (!cfg || !cfg_ok(*cfg)) { set_error("invalid drb_config"); return 0; }
-  return make_layout(*cfg).total;
+  return make_layout(effective_config(*cfg)).total;
 }
 
 int drb_plan_set_branches(drb_plan* p, int32_t branches) {
@@ -185,10 +211,14 @@ int drb_plan_set_steps(drb_plan* p, const int32_t* steps_dev) {
   return 0;
 }
 
-int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w, void* workspace, size_t ws_bytes,
+int drb_plan_precision(const drb_plan* p) { return p ? p->cfg.precision : DRB_E_INVALID; }
+
+int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights* w, void* workspace, size_t ws_bytes,
                     void* stream) {
-  if (!out || !cfg || !w || !workspace) { set_error("null argument"); return DRB_E_INVALID; }
-  if (!cfg_ok(*cfg)) { set_error("invalid drb_config"); return DRB_E_INVALID; }
+  if (!out || !cfg_in || !w || !workspace) { set_error("null argument"); return DRB_E_INVALID; }
+  if (!cfg_ok(*cfg_in)) { set_error("invalid drb_config"); return DRB_E_INVALID; }
+  const drb_config cfg_eff = effective_config(*cfg_in);
+  const drb_config* cfg = &cfg_eff;
   cudaStream_t s = (cudaStream_t)stream;
   Layout lay = make_layout(*cfg);
   if (ws_bytes < lay.total || ((uintptr_t)workspace & 255)) {
@@ -234,13 +264,20 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
       const int dm = fmt >= 2 ? 2 : 0, da = fmt >= 2 ? 3 : 0, am = fmt >= 2 ? 2 : 1;  // tensor-map dtypes, aux width factor
       if (fmt >= 2) {   // per-tensor power-of-two weight scales (f16f8: e4m3 range; f16e5: keeps small weights normal in fp16)
         const float sa = fmt == 2 ? F8_SA : 1.f;
-        PLAN_TRY(launch_weight_scale(tmp, (size_t)2 * C * k * C, w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels,
-                                     p->wscale(2 * i), sa, s));
+        if (!p->n4())
+          PLAN_TRY(launch_weight_scale(tmp, (size_t)2 * C * k * C, w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels,
+                                       p->wscale(2 * i), sa, s));
         PLAN_TRY(launch_weight_scale(w->output_projection_w[i], (size_t)2 * C * C, nullptr, 0, p->wscale(2 * i + 1), sa, s));
       }
       char* wdh = p->ws + lay.wdh + (size_t)i * 2 * C * k * C * 2;
       char* wdl = p->ws + lay.wdl + (size_t)i * 2 * C * k * C * 2;
-      PLAN_TRY(launch_repack_split(tmp, wdh, wdl, 2 * C, k * C, k * C, C, fmt, p->wscale(2 * i), s));
+      if (p->n4()) {   // own scale (only the conv weights, up to 2^15), fp16 main + e2m1 aux + scale atoms
+        uint8_t* sfa = p->at<uint8_t>(lay.wsf4) + (size_t)i * (2 * C / 256) * (k * C / 64) * 2048;
+        PLAN_TRY(launch_weight_scale(tmp, (size_t)2 * C * k * C, nullptr, 0, p->wscale(2 * i), 1.f, s, N4_WTARGET));
+        PLAN_TRY(launch_repack_n4(tmp, wdh, wdl, sfa, 2 * C, k * C, C, p->wscale(2 * i), s));
+      } else {
+        PLAN_TRY(launch_repack_split(tmp, wdh, wdl, 2 * C, k * C, k * C, C, fmt, p->wscale(2 * i), s));
+      }
       char* wch = p->ws + lay.wch + (size_t)i * 2 * C * Mp * 2;
       char* wcl = p->ws + lay.wcl + (size_t)i * 2 * C * Mp * 2;
       PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], wch, wcl, 2 * C, cfg->n_mels, Mp, C, fmt, p->wscale(2 * i), s));
@@ -255,6 +292,13 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
       PLAN_TRY(make_tmap_2d(&ul.wo_h, woh, 2 * C, C, 128, dm));
       PLAN_TRY(make_tmap_2d(&ul.wo_l, wol, 2 * C, (uint64_t)am * C, 128, da));
       p->layers.push_back(ul);
+      if (p->n4()) {
+        CUtensorMap m4, ms;
+        PLAN_TRY(make_tmap_2d_bytes(&m4, wdl, 2 * C, (uint64_t)k * C, 128, 64, 64));
+        PLAN_TRY(make_tmap_2d_bytes(&ms, p->at<uint8_t>(lay.wsf4) + (size_t)i * (2 * C / 256) * (k * C / 64) * 2048,
+                                    (uint64_t)(2 * C / 256) * (k * C / 64) * 16, 128, 16, 128, 0));
+        p->wd4.push_back(m4); p->wsf4.push_back(ms);
+      }
     }
   }
   if (p->condpre)   // fp32 conditioner weights, K padded to Mp (the spectrogram rows are zero-padded alike)
@@ -276,7 +320,14 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg, const drb_weights* w,
         PLAN_TRY(make_tmap_3d(&ml, p->ws + lay.xl, NBc, T, am * C, rows, da));
       } else { mh = p->maps.xh; ml = p->maps.xl; }
       p->win_h.push_back(mh); p->win_l.push_back(ml);
+      if (p->n4()) {
+        if (rows > 192) { set_error("f16n4: tap window of layer %d (%d frames) exceeds 192", i, rows); drb_plan_destroy(p); return DRB_E_INVALID; }
+        CUtensorMap m4;
+        PLAN_TRY(make_tmap_3d_bytes(&m4, p->ws + lay.xl, NBc, T, C, rows, 64, 64));
+        p->win4.push_back(m4);
+      }
     }
+    if (p->n4()) PLAN_TRY(make_tmap_3d_bytes(&p->xl4, p->ws + lay.xl, NBc, T, C, 128, 64, 64));
     PLAN_TRY(make_tmap_3d(&p->maps.zh, p->ws + lay.zh, (uint64_t)L * NBc, T, C, 128, dm));
     PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, am * C, 128, da));
     PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, dm));
@@ -381,8 +432,9 @@ int drb_in_proj(drb_plan* p, const float* x_t, int32_t t_index, void* stream) {
   const int e0 = p->prof ? p->ev_mark(s) : -1;
   int r;
   if (tensor) {  // relu(input_projection(x_t)) for every branch copy + operand pair of x + d_0(t), one kernel
-    r = launch_in_proj_fused(x_t, p->in_w, p->in_b, p->dvec(0, 0), p->steps, t_index, B * T, T, F, C, p->NB / B, p->fmt(),
-                             p->at<float>(p->lay.x32), p->ws + p->lay.xh, p->ws + p->lay.xl, p->at<unsigned int>(p->lay.range), s);
+    r = launch_in_proj_fused(x_t, p->in_w, p->in_b, p->dvec(0, 0), p->steps, t_index, B * T, T, F, C, p->NB / B, p->xfmt(),
+                             p->at<float>(p->lay.x32), p->ws + p->lay.xh, p->ws + p->lay.xl,
+                             p->n4() ? p->at<uint8_t>(p->lay.xs) : nullptr, p->at<unsigned int>(p->lay.range), s);
   } else {
     SimtGemm g;  // relu(input_projection(x_t))   model/diffwave.py:667-668 ; x_t [B,1,T,88] is already [B*T][88]
     g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = p->in_w; g.ldw = F; g.bias = p->in_b; g.act = 1;
@@ -437,7 +489,11 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
   ug.pair = p->pair; ug.window = p->window; ug.persistent = p->persistent; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
-  if (p->condpre && p->cond_ready && p->cond_use && nc > 0) {
+  if (p->n4()) {   // the f16n4 kernel has no conditioner K-slabs: the per-clip tables are always used (built on demand)
+    if (nc > 0 && !p->cond_ready) { r = drb_cond_tables(p, stream); if (r) return r; }
+    ug.n4 = 1; ug.xw4 = &p->win4[layer]; ug.wd4 = &p->wd4[layer]; ug.wsf = &p->wsf4[layer]; ug.xs = p->at<uint8_t>(p->lay.xs);
+  }
+  if (p->condpre && p->cond_ready && (p->cond_use || p->n4()) && nc > 0) {
     ug.cond = p->at<float>(p->lay.cond) + (size_t)layer * B * T * 2 * C;
     if (first && p->share0 && NB == 2 * B && nc == B) ug.dual_B = B;
   }
@@ -451,6 +507,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
     uz.group_stride = p->lay.NBcap; uz.w_h = &p->layers[layer].wo_h; uz.w_l = &p->layers[layer].wo_l; uz.out32 = &p->maps.x32;
     uz.bias = p->bo[layer]; uz.dnext = p->dvec(layer + 1, 0); uz.t_uniform = t_index; uz.steps = p->steps; uz.bsamp = B;
     uz.range_max = p->at<unsigned int>(p->lay.range);
+    if (p->n4()) { uz.x_n4 = 1; uz.xl4 = &p->xl4; uz.xs = p->at<uint8_t>(p->lay.xs); }
     r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
   }
   if (p->prof) {

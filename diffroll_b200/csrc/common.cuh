@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
+#include <cuda_fp4.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -99,6 +100,57 @@ __device__ __forceinline__ void split_f16e5_x4(const float (&v)[4], uint32_t& h0
         ((uint32_t)pack_e5m2x2((v[2] - fb.x) * 16.f, (v[3] - fb.y) * 16.f) << 16);
   hi4 = (uint32_t)pack_e5m2x2(fa.x * 0.00390625f, fa.y * 0.00390625f) |
         ((uint32_t)pack_e5m2x2(fb.x * 0.00390625f, fb.y * 0.00390625f) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// "f16n4": fp16 main product + ONE block-scaled fp4 correction product (kind::mxf4nvf4, K = 64 per instruction, half the
+// issue cycles of the e5m2 correction).  Per 64-channel chunk an activation row carries 64 B of e2m1 codes
+// [lo part (64 codes) | hi part (64 codes)] and 8 ue4m3 scales (one per 16 codes); weights carry [hi | lo], so
+//   instruction 0:  (l_a * 2^10) . (h_w * 2^-10)      instruction 1:  (h_a * 2^4) . (l_w * 2^-4)
+// with h = fp16(v), l = v - h and weights pre-multiplied by the per-tensor power of two SW (max |W * SW| in (2^14, 2^15]).
+// The powers of two put every block scale (block max / 6) inside ue4m3's range [2^-9, 448] for |activation| in
+// [2^-6, 2^8]; the scale is rounded UP to the next ue4m3 so the block maximum never saturates.  Emulated on real layer
+// inputs (profiles/experiments/n4_emulation.py) the per-layer rms error is 4.3e-5 (f16e5: 2.1e-5, one fp16 product: 2.9e-4).
+// ---------------------------------------------------------------------------------------------
+constexpr float N4_ALO = 1024.f, N4_AHI = 16.f;              // activation lo / hi part multipliers
+constexpr float N4_WHI = 1.f / 1024.f, N4_WLO = 1.f / 16.f;  // weight hi / lo part multipliers
+constexpr float N4_WTARGET = 32768.f;                         // SW = 2^floor(log2(N4_WTARGET / max|W|))
+
+__device__ __forceinline__ float e4m3_to_float(uint32_t b) {
+  return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3)));
+}
+// 16 values -> 8 bytes of e2m1 codes (value 2i in the low nibble of byte i) and one ue4m3 scale byte >= max|v| / 6
+__device__ __forceinline__ void n4_block16(const float (&v)[16], uint32_t& c0, uint32_t& c1, uint32_t& sf) {
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
+  const float want = amax * (1.f / 6.f);
+  uint32_t b = (uint32_t)__nv_cvt_float_to_fp8(want, __NV_SATFINITE, __NV_E4M3);
+  float q = e4m3_to_float(b);
+  if (q < want && b < 0x7eu) { ++b; q = e4m3_to_float(b); }
+  const float inv = q > 0.f ? __frcp_rn(q) : 0.f;
+  uint32_t w[2] = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t byte = (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(v[2 * i] * inv, v[2 * i + 1] * inv), __NV_E2M1, cudaRoundNearest);
+    w[i >> 2] |= (byte & 0xffu) << (8 * (i & 3));
+  }
+  c0 = w[0]; c1 = w[1]; sf = b;
+}
+// 16 fp32 values -> 8 packed fp16 pairs + the two f16n4 blocks (lo part, hi part) of an ACTIVATION row
+__device__ __forceinline__ void split_f16n4_x16(const float (&v)[16], uint32_t (&h)[8], uint32_t (&lo)[2], uint32_t (&hi)[2],
+                                                uint32_t& sf_lo, uint32_t& sf_hi) {
+  float l[16], g[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __half2 a = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&a);
+    const float2 f = __half22float2(a);
+    l[2 * i] = (v[2 * i] - f.x) * N4_ALO; l[2 * i + 1] = (v[2 * i + 1] - f.y) * N4_ALO;
+    g[2 * i] = f.x * N4_AHI; g[2 * i + 1] = f.y * N4_AHI;
+  }
+  n4_block16(l, lo[0], lo[1], sf_lo);
+  n4_block16(g, hi[0], hi[1], sf_hi);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,6 +406,55 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// K-major, 64-byte-swizzled operand (rows of 64 B = 128 e2m1 codes, 8-row groups 512 B apart).  Row-shifted views work like
+// under SWIZZLE_128B (verified on a B200: profiles/experiments/nv4_probe.cu).
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// Un-swizzled 32 rows x 16 B (one 512-byte scale-factor atom: rows 16 B apart, 8-row groups 128 B apart), source of tcgen05.cp
+__device__ __forceinline__ uint64_t make_sfatom_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(16 >> 4) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// smem -> TMEM copy of one scale-factor atom in BOTH CTAs of a pair (each from its own smem at this offset): 32 lanes x 4
+// columns, replicated over the four lane quarters
+__device__ __forceinline__ void utccp_sf_pair(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// block-scaled fp4 MMA of a CTA pair: e2m1 codes, one ue4m3 scale per 16 codes (scale_vec::4X), K = 64
+__device__ __forceinline__ void umma_nv4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf4nvf4.block_scale.scale_vec::4X [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// instruction descriptor of the block-scaled fp4 MMA: a/b format 1 = e2m1 [7,10) / [10,13), scale format 0 = ue4m3 [23],
+// N>>3 [17,23), M>>4 [24,29), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_nv4(int M, int N) {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// byte offset of (row, 16-byte chunk) inside a 64-byte-swizzled tile whose rows are 64 bytes (base 512-aligned)
+__device__ __forceinline__ uint32_t sw64_off(int row, int chunk16) {
+  return (uint32_t)row * 64u + (uint32_t)((chunk16 ^ ((row >> 1) & 3)) << 4);
 }
 
 // Instruction descriptor, kind::f16: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, both K-major,

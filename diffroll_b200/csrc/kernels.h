@@ -47,9 +47,15 @@ int launch_res_skip(const float* o, float* x, float* skip, int M, int C, int fir
 int launch_prep_xin(float* x32, void* xmain, void* xaux, const float* dvec, int Mb, int C, int copies, int fmt, cudaStream_t s);
 // tensor path: relu(input_projection(x_t)) -> fp32 x32 for every branch copy + operand pair of x + dtab0[t] in ONE kernel;
 // t = steps[row / T] when steps != nullptr (per-sample diffusion steps), else the uniform t
+// fmt 4 (f16n4): xaux = e2m1 bytes [rows][C], xsf = scale factors [roll][C/64][T][8]
 int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, const float* dtab0, const int* steps, int t,
-                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux,
+                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux, uint8_t* xsf,
                          unsigned int* range_max, cudaStream_t s);
+// f16n4 weights: w [OC][K] fp32 (tap-major K, K % 64 == 0), rows permuted into 256-wide gate/filter blocks (C > 0) ->
+// main fp16(W * SW) [OC][K], aux e2m1 bytes [OC][K] ([hi part 32 B | lo part 32 B] per 64-wide K-slab) and the scale atoms
+// [OC / 256][K / 64][2 instructions][2 atoms][512 B]; SW = scale[0]
+int launch_repack_n4(const float* w, void* mainp, void* auxp, uint8_t* sf_atoms, int OC, int K, int interleave_C,
+                     const float* scale, cudaStream_t s);
 // weight repacks
 int launch_repack_conv_fp32(const float* w, float* out, int OC, int C, int k, cudaStream_t s);  // [OC][C][k] -> [OC][k][C]
 // [OC][Kin] fp32 (k index already tap-major) -> operand pair (fmt 1 or 2), rows optionally permuted into 256-wide
@@ -58,7 +64,8 @@ int launch_repack_split(const float* w, void* mainp, void* auxp, int OC, int Kin
                         const float* scale, cudaStream_t s);
 // scale2[0] = SW = 2^floor(log2(224 / max|w|)), scale2[1] = 1/(sa*SW) from max|w| over one or two tensors (scale2 must
 // have 3 floats of space).  sa: F8_SA for f16f8 (scale of the activation residual), 1 for f16e5.
-int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, float sa, cudaStream_t s);
+int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, float sa, cudaStream_t s,
+                        float target = 224.f);
 int launch_pad_rows(const float* src, float* dst, int rows, int Kin, int Kp, cudaStream_t s);
 // bias1[n'] (interleaved) = bd[n] + bc[n] (- sum_k Wc[n][k] if uncond)
 int launch_bias1(const float* bd, const float* bc, const float* wc, float* out_cond, float* out_unc,
@@ -109,6 +116,10 @@ struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filt
   // dual_B > 0 (layer 0, both branches read the same x): conv once over dual_B rolls, two gated outputs per tile.
   const float* cond = nullptr;
   int dual_B = 0;
+  // f16n4 (prec must be 3 for the z output): fp16 main + block-scaled e2m1 correction operands
+  int n4 = 0;
+  const CUtensorMap *xw4 = nullptr, *wd4 = nullptr, *wsf = nullptr;   // aux window map, aux weight map, weight scale atoms
+  const uint8_t* xs = nullptr;                                        // activation scale factors [roll][chunk][frame][8]
 };
 struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
   int pair = 1, persistent = 1;
@@ -122,11 +133,17 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
   const int* steps = nullptr;       // per-sample diffusion steps [bsamp] (device); roll nb uses steps[nb % bsamp]
   int bsamp = 1;
   unsigned int* range_max = nullptr;  // RES: device word, atomicMax of |x + d_next| (fp32 bits) over the emitted operands
+  int x_n4 = 0;                       // RES emits the next layer's operand in the f16n4 format (xl4 = 64-byte-row aux map, xs = scales)
+  const CUtensorMap* xl4 = nullptr;
+  uint8_t* xs = nullptr;
 };
 int umma_init();  // resolves cuTensorMapEncodeTiled
 // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8; the box always spans 128 bytes of the innermost dimension
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int dtype);
 int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, int dtype);
+// byte tensors, explicit inner box width (bytes) and swizzle (128 / 64 / 0)
+int make_tmap_2d_bytes(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+int make_tmap_3d_bytes(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0, int swizzle_bytes);
 int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g, cudaStream_t s);
 int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s);
 

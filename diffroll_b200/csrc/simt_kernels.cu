@@ -348,6 +348,7 @@ struct InProjDev {
   int t, M, T, F, C, copies, fmt;
   float* x32; void* xmain; void* xaux;
   unsigned int* range_max;   // device word: atomicMax of |x + d_0| (fp32 bits) over the emitted operands, or nullptr
+  uint8_t* xsf;              // fmt 4: activation scale factors [roll][C/64][T][8]
 };
 // FC: compile-time pitch count (88: every load loop fully unrolled, so all of a thread's global loads are in flight at
 // once instead of one L2 round trip per iteration) or 0 for the generic run-time F.
@@ -411,10 +412,67 @@ __global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
     const float xin[4] = {v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) umax = max(umax, __float_as_uint(xin[e]) & 0x7fffffffu);
+    if (g.fmt == 4) continue;   // f16n4 needs whole 16-channel blocks: emitted below by converged warps
     for (int r = 0; r < g.copies; ++r) {
       const size_t row = (size_t)r * g.M + m;
       *reinterpret_cast<float4*>(g.x32 + row * g.C + n) = v;
       store_operand4(g.xmain, g.xaux, row, n, g.C, xin, g.fmt);
+    }
+  }
+  if (g.fmt == 4) {
+    // A 16-channel block of one row lives in 4 consecutive lanes (tx & ~3 .. +3): block max and code bytes travel by
+    // shuffles, so every lane takes part for every row (rows past M are computed on zeros and not stored).
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + ty * 8 + i;
+      const bool ok = m < g.M;
+      float4 v;
+      v.x = fmaxf(acc[i][0] + bias.x, 0.f); v.y = fmaxf(acc[i][1] + bias.y, 0.f);
+      v.z = fmaxf(acc[i][2] + bias.z, 0.f); v.w = fmaxf(acc[i][3] + bias.w, 0.f);
+      const int tsel = g.steps ? __ldg(g.steps + (ok ? m : 0) / g.T) : g.t;
+      const float4 d = __ldg(reinterpret_cast<const float4*>(g.dtab + (size_t)tsel * g.C + n));
+      const float xin[4] = {v.x + d.x, v.y + d.y, v.z + d.z, v.w + d.w};
+      const __half2 h01 = __floats2half2_rn(xin[0], xin[1]), h23 = __floats2half2_rn(xin[2], xin[3]);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const float hv[4] = {f01.x, f01.y, f23.x, f23.y};
+      uint32_t code[2], sfb[2];                 // part 0 = lo (residual * 2^10), part 1 = hi (fp16 value * 2^4)
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        float q[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e] = part == 0 ? (xin[e] - hv[e]) * N4_ALO : hv[e] * N4_AHI;
+        float amax = fmaxf(fmaxf(fabsf(q[0]), fabsf(q[1])), fmaxf(fabsf(q[2]), fabsf(q[3])));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        const float want = amax * (1.f / 6.f);
+        uint32_t b = (uint32_t)__nv_cvt_float_to_fp8(want, __NV_SATFINITE, __NV_E4M3);
+        float sq = e4m3_to_float(b);
+        if (sq < want && b < 0x7eu) { ++b; sq = e4m3_to_float(b); }
+        const float inv = sq > 0.f ? __frcp_rn(sq) : 0.f;
+        const uint32_t b0 = (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(q[0] * inv, q[1] * inv), __NV_E2M1, cudaRoundNearest) & 0xffu;
+        const uint32_t b1 = (uint32_t)__nv_cvt_float2_to_fp4x2(make_float2(q[2] * inv, q[3] * inv), __NV_E2M1, cudaRoundNearest) & 0xffu;
+        uint32_t c16 = b0 | (b1 << 8);
+        c16 |= __shfl_down_sync(0xffffffffu, c16, 1) << 16;      // even lanes: 4 code bytes of lanes l, l + 1
+        code[part] = c16;
+        sfb[part] = b;
+      }
+      const uint32_t lo_hi = __shfl_down_sync(0xffffffffu, code[0], 2), hi_hi = __shfl_down_sync(0xffffffffu, code[1], 2);
+      if (!ok) continue;
+      const int blk = (tx >> 2), chunk = n0 / 64;               // this CTA's 64 channels are one K chunk
+      for (int r = 0; r < g.copies; ++r) {
+        const size_t row = (size_t)r * g.M + m;
+        *reinterpret_cast<float4*>(g.x32 + row * g.C + n) = v;
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(g.xmain) + row * g.C + n) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        if ((tx & 3) == 0) {
+          uint8_t* a8 = reinterpret_cast<uint8_t*>(g.xaux) + row * g.C + (size_t)chunk * 64 + blk * 8;
+          *reinterpret_cast<uint2*>(a8) = make_uint2(code[0], lo_hi);
+          *reinterpret_cast<uint2*>(a8 + 32) = make_uint2(code[1], hi_hi);
+          const size_t roll = row / g.T, t = row % g.T;
+          uint8_t* sp = g.xsf + ((roll * (g.C / 64) + chunk) * g.T + t) * 8;
+          sp[blk] = (uint8_t)sfb[0]; sp[4 + blk] = (uint8_t)sfb[1];
+        }
+      }
     }
   }
   if (g.range_max) {   // every thread reaches this point (no early return above)
@@ -423,7 +481,7 @@ __global__ void __launch_bounds__(256) in_proj_kernel(const InProjDev g) {
   }
 }
 int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, const float* dtab0, const int* steps, int t,
-                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux,
+                         int M, int T, int F, int C, int copies, int fmt, float* x32, void* xmain, void* xaux, uint8_t* xsf,
                          unsigned int* range_max, cudaStream_t s) {
   if ((F % 4) || (C % IP_BN) || fmt <= 0) { set_error("in_proj_fused: unsupported F=%d C=%d fmt=%d", F, C, fmt); return DRB_E_INVALID; }
   const int smem = F * (IP_BM + 4 + IP_BN + 4) * (int)sizeof(float);
@@ -439,7 +497,8 @@ int launch_in_proj_fused(const float* x_t, const float* W, const float* bias, co
   }
   InProjDev g;
   g.x = x_t; g.W = W; g.bias = bias; g.dtab = dtab0; g.steps = steps; g.t = t; g.M = M; g.T = T; g.F = F; g.C = C;
-  g.copies = copies; g.fmt = fmt; g.x32 = x32; g.xmain = xmain; g.xaux = xaux; g.range_max = range_max;
+  g.copies = copies; g.fmt = fmt; g.x32 = x32; g.xmain = xmain; g.xaux = xaux; g.range_max = range_max; g.xsf = xsf;
+  if (fmt == 4 && !xsf) { set_error("in_proj_fused: f16n4 needs the scale-factor buffer"); return DRB_E_INVALID; }
   dim3 grid((M + IP_BM - 1) / IP_BM, C / IP_BN);
   if (F == 88) in_proj_kernel<88><<<grid, 256, smem, s>>>(g);
   else in_proj_kernel<0><<<grid, 256, smem, s>>>(g);
@@ -505,6 +564,52 @@ int launch_repack_split(const float* w, void* mainp, void* auxp, int OC, int Kin
   return 0;
 }
 
+// f16n4 weights (common.cuh): one thread per (output row, 64-wide K-slab).
+__global__ void repack_n4_kernel(const float* __restrict__ w, __half* __restrict__ mainp, uint8_t* __restrict__ auxp,
+                                 uint8_t* __restrict__ sf_atoms, int OC, int K, int C, const float* __restrict__ scale) {
+  const int nslab = K / 64;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)OC * nslab) return;
+  const int slab = (int)(idx % nslab), np = (int)(idx / nslab);
+  int src = np;
+  if (C > 0) { int j = np >> 8, i = np & 255; src = (i < 128) ? (128 * j + i) : (C + 128 * j + (i - 128)); }
+  const float sw = scale[0];
+  const float* wr = w + (size_t)src * K + (size_t)slab * 64;
+  __half* mo = mainp + (size_t)np * K + (size_t)slab * 64;
+  uint8_t* ao = auxp + (size_t)np * K + (size_t)slab * 64;            // [hi part codes 32 B | lo part codes 32 B]
+  // scale atoms of this N block / slab: [instruction k][atom h][512]; row n of the 256-row block -> atom n / 128,
+  // byte 16 * (n % 32) + 4 * ((n % 128) / 32) + block
+  const int n = np & 255;
+  uint8_t* so = sf_atoms + ((size_t)(np >> 8) * nslab + slab) * 2048 + (size_t)(n >> 7) * 512 + 16 * (n & 31) + 4 * ((n & 127) >> 5);
+  for (int b = 0; b < 4; ++b) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v = wr[b * 16 + i] * sw;
+      const __half h = __float2half_rn(v);
+      mo[b * 16 + i] = h;
+      const float hf = __half2float(h);
+      hi[i] = hf * N4_WHI; lo[i] = (v - hf) * N4_WLO;
+    }
+    uint32_t c0, c1, sf;
+    n4_block16(hi, c0, c1, sf);
+    *reinterpret_cast<uint2*>(ao + b * 8) = make_uint2(c0, c1);
+    so[b] = (uint8_t)sf;                      // instruction 0 pairs the activation lo part with the weight hi part
+    n4_block16(lo, c0, c1, sf);
+    *reinterpret_cast<uint2*>(ao + 32 + b * 8) = make_uint2(c0, c1);
+    so[1024 + b] = (uint8_t)sf;               // instruction 1: activation hi part x weight lo part
+  }
+}
+int launch_repack_n4(const float* w, void* mainp, void* auxp, uint8_t* sf_atoms, int OC, int K, int interleave_C,
+                     const float* scale, cudaStream_t s) {
+  if ((K % 64) || (OC % 256)) { set_error("repack_n4: unsupported OC=%d K=%d", OC, K); return DRB_E_INVALID; }
+  const size_t n = (size_t)OC * (K / 64);
+  repack_n4_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(w, reinterpret_cast<__half*>(mainp), reinterpret_cast<uint8_t*>(auxp),
+                                                              sf_atoms, OC, K, interleave_C, scale);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
 // f16f8 weight scale: SW = 2^floor(log2(224 / max|w|)) over up to two tensors; out[0] = SW, out[1] = 1 / (SA * SW)
 __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out) {
   unsigned int m = 0;
@@ -513,22 +618,22 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
-__global__ void wscale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ out, float sa) {
+__global__ void wscale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ out, float sa, float target) {
   float m = __uint_as_float(mx[0]);
   float sw = 1.f;
-  if (m > 0.f && m < 3.0e38f) sw = exp2f(floorf(log2f(224.f / m)));
-  sw = fminf(fmaxf(sw, 9.5367431640625e-07f), 1048576.f);
+  if (m > 0.f && m < 3.0e38f) sw = exp2f(floorf(log2f(target / m)));
+  sw = fminf(fmaxf(sw, 9.5367431640625e-07f), 1073741824.f);
   out[0] = sw;
   out[1] = 1.f / (sa * sw);
 }
-int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, float sa, cudaStream_t s) {
+int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, float* scale2, float sa, cudaStream_t s, float target) {
   unsigned int* tmp = reinterpret_cast<unsigned int*>(scale2 + 2);  // scratch word right behind the two outputs
   cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return (int)e; }
   absmax_kernel<<<148, 256, 0, s>>>(w0, n0, tmp);
   DRB_LAUNCH_CHECK();
   if (w1 && n1) { absmax_kernel<<<148, 256, 0, s>>>(w1, n1, tmp); DRB_LAUNCH_CHECK(); }
-  wscale_kernel<<<1, 1, 0, s>>>(tmp, scale2, sa);
+  wscale_kernel<<<1, 1, 0, s>>>(tmp, scale2, sa, target);
   DRB_LAUNCH_CHECK();
   return 0;
 }

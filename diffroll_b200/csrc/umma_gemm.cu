@@ -91,6 +91,10 @@ struct alignas(64) GateParams {
   const float* cond;
   int n_cond_mma;
   int dual_off;
+  // f16n4 kernel only: aux activation window map (64-byte rows of e2m1 codes, SWIZZLE_64B), aux weight map, weight scale-factor
+  // atoms (2 KB per N block and K-slab, un-swizzled), activation scale factors [roll][chunk][frame][8]
+  CUtensorMap xw4, wd4, wsf;
+  const uint8_t* xs;
 };
 
 struct alignas(64) ZGemmParams {
@@ -102,6 +106,7 @@ struct alignas(64) ZGemmParams {
   const int* steps;        // per-sample diffusion steps (device, [bsamp]) or nullptr: every roll uses row t_uniform
   int t_uniform, bsamp;
   unsigned int* range_max; // RES: running max |x + d_next| over the emitted operands (fp32 bits), or nullptr
+  uint8_t* xs;             // f16n4: activation scale factors [roll][chunk][frame][8] (xl then maps the 64-byte e2m1 rows)
 };
 
 struct SmemView {
@@ -865,6 +870,309 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
 }
 
 // ---------------------------------------------------------------------------------------------
+// gate kernel, f16n4 variant: fp16 main product + ONE block-scaled fp4 correction product (1.5 MMA units per K-step
+// instead of 2).  Same persistent CTA pairs, tap window and epilogue as umma_gate_pers_kernel, plus what kind::mxf4nvf4
+// needs (layouts verified by profiles/experiments/nv4_probe.cu on a B200):
+//   * aux operands are 64-byte rows of e2m1 codes [part 0 | part 1] per 64-channel chunk, 64-byte swizzle; a tap is still a
+//     row-shifted descriptor into the window;
+//   * scale factors live in TMEM.  The weight side's 2 KB of atoms per (N block, K-slab) are precomputed and arrive with the
+//     weight stage; the activation side's depend on the tap's row shift, so warp 3 of EACH CTA gathers them per K-slab
+//     from the window's per-row scales into two 512-byte atoms (a 4-slot ring), and the MMA thread copies both sides to
+//     TMEM with tcgen05.cp right before the slab's MMAs (two alternating 24-column sets);
+//   * the scale factors take TMEM columns, so there is ONE accumulator stage: the epilogue warps (224 registers each, taken
+//     from the producer warps with setmaxnreg) drain the whole accumulator into registers and hand it back at once; the
+//     next tile's MMAs wait ~1 us per 22 us tile instead of overlapping the whole epilogue.
+//   smem: 2 windows x (24 + 12 KB) | 3 weight stages x (16 + 8 + 2 KB) | SF atom ring 4 KB | window scales 1.5 KB | 64 KB staging
+// ---------------------------------------------------------------------------------------------
+constexpr int N4_WIN_MAIN = 24576, N4_WIN_AUX = 12288, N4_WIN_BUF = N4_WIN_MAIN + N4_WIN_AUX;
+constexpr int N4_B_MAIN = 16384, N4_B_AUX = 8192, N4_B_SF = 2048, N4_BSTAGE = N4_B_MAIN + N4_B_AUX + N4_B_SF;
+constexpr int N4_BSTAGES = 3, N4_SFSLOTS = 4, N4_SFSLOT = 1024;
+constexpr int N4_OFF_BRING = 2 * N4_WIN_BUF;
+constexpr int N4_OFF_SFRING = N4_OFF_BRING + N4_BSTAGES * N4_BSTAGE;
+constexpr int N4_OFF_SFWIN = N4_OFF_SFRING + N4_SFSLOTS * N4_SFSLOT;
+constexpr int N4_OFF_STAGING = (N4_OFF_SFWIN + 192 * 8 + 1023) / 1024 * 1024;
+constexpr int N4_OFF_BARS = N4_OFF_STAGING + 4 * CHUNK_BYTES;
+constexpr int N4_SMEM = N4_OFF_BARS + 256 /*barriers*/ + 1024 /*bias*/ + 1024 /*align*/;
+static_assert(N4_SMEM <= 232448, "f16n4 gate kernel: shared memory over the 227 KB limit");
+
+template <bool DUAL>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __grid_constant__ GateParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+
+  uint8_t* ring;
+  { uint32_t a = smem_u32(smem_raw); ring = smem_raw + (((a + 1023u) & ~1023u) - a); }
+  uint8_t* const wbuf = ring;
+  uint8_t* const bring = ring + N4_OFF_BRING;
+  uint8_t* const sfring = ring + N4_OFF_SFRING;
+  uint8_t* const sfwin = ring + N4_OFF_SFWIN;
+  uint8_t* const staging = ring + N4_OFF_STAGING;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + N4_OFF_BARS);
+  uint64_t* const bfull = bars;            // [3]
+  uint64_t* const bempty = bars + 3;       // [3]
+  uint64_t* const afull = bars + 6;        // [2]
+  uint64_t* const aempty = bars + 8;       // [2]
+  uint64_t* const sffull = bars + 10;      // [4]
+  uint64_t* const sfempty = bars + 14;     // [4]
+  uint64_t* const tfull = bars + 18;
+  uint64_t* const tempty = bars + 19;
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  float* const sbias = reinterpret_cast<float*>(ring + N4_OFF_BARS + 256);
+
+  const int cpt = p.C / TILE_K;
+  const int half = p.taps / 2;
+  auto tile_of = [&](int item) -> GateTile {
+    GateTile t;
+    t.nblk = item % p.n_blocks;
+    const int pm = item / p.n_blocks;
+    const int mt = pm * 2 + (int)rank;
+    t.nb = mt / p.tiles_t;
+    t.t0 = (mt % p.tiles_t) * TILE_M;
+    t.nchunks = cpt;
+    return t;
+  };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.xwh); tma_prefetch_desc(&p.xw4); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.wd4);
+    tma_prefetch_desc(&p.wsf); tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.zl);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < N4_BSTAGES; ++i) { mbar_init(&bfull[i], 2); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 2); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < N4_SFSLOTS; ++i) { mbar_init(&sffull[i], 2); mbar_init(&sfempty[i], 1); }   // both CTAs' SF warps fill a slot
+    mbar_init(tfull, 1); mbar_init(tempty, 16);    // 8 epilogue warps x 2 CTAs drain the accumulator
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_ptr;
+  // register split: 128 x 64 + 256 x 224 = the SM's 64 K registers
+  if (warp < 4) {
+  setmaxnreg_dec<64>();
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- producer: windows (main + aux) and weight stages (main + aux + scale atoms) ----------------
+      int a_issued = 0;
+      int w_item = pair_id, w_c = 0;
+      GateTile wt = tile_of(w_item < p.n_items ? w_item : 0);
+      auto issue_window = [&]() {
+        const int ai = a_issued & 1;
+        mbar_wait(&aempty[ai], ((a_issued >> 1) & 1) ^ 1);
+        const uint32_t fb = mapa_cluster(smem_u32(&afull[ai]), 0);
+        uint8_t* dst = wbuf + ai * N4_WIN_BUF;
+        mbar_expect_tx_cluster(fb, (uint32_t)p.win_rows * 192u);
+        tma_load_3d_pair(dst, &p.xwh, fb, w_c * TILE_K, wt.t0 - half * p.dil, wt.nb);
+        tma_load_3d_pair(dst + N4_WIN_MAIN, &p.xw4, fb, w_c * TILE_K, wt.t0 - half * p.dil, wt.nb);
+        ++a_issued;
+        if (++w_c == cpt) { w_c = 0; w_item += n_pairs; if (w_item < p.n_items) wt = tile_of(w_item); }
+      };
+      int gidx = 0, bcnt = 0;
+      if (w_item < p.n_items) issue_window();
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const GateTile ti = tile_of(item);
+        const int row0 = ti.nblk * TILE_N + (int)rank * (TILE_N / 2);
+        for (int c = 0; c < cpt; ++c, ++gidx) {
+          for (int j = 0; j < p.taps; ++j) {
+            if (a_issued == gidx + 1 && w_item < p.n_items && j >= (p.taps > 4 ? 4 : p.taps - 1)) issue_window();
+            const int bs = bcnt % N4_BSTAGES;
+            mbar_wait(&bempty[bs], ((bcnt / N4_BSTAGES) & 1) ^ 1);
+            const uint32_t fb = mapa_cluster(smem_u32(&bfull[bs]), 0);
+            uint8_t* dst = bring + bs * N4_BSTAGE;
+            mbar_expect_tx_cluster(fb, N4_BSTAGE);
+            const int slab = j * cpt + c;
+            tma_load_2d_pair(dst, &p.wd_h, fb, slab * TILE_K, row0);
+            tma_load_2d_pair(dst + N4_B_MAIN, &p.wd4, fb, slab * TILE_K, row0);
+            tma_load_2d_pair(dst + N4_B_MAIN + N4_B_AUX, &p.wsf, fb, 0, (ti.nblk * p.taps * cpt + slab) * 16);
+            ++bcnt;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ---------------- MMA issuer (leader CTA) ----------------
+      constexpr uint32_t idesc = make_idesc_fmt0(2 * TILE_M, TILE_N);
+      constexpr uint32_t idesc4 = make_idesc_nv4(2 * TILE_M, TILE_N);
+      int gidx = 0, bcnt = 0, tcnt = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs, ++tcnt) {
+        mbar_wait(tempty, (tcnt & 1) ^ 1);     // both CTAs' epilogues hold the previous tile's accumulator in registers
+        tc_fence_after();
+        bool first = true;
+        for (int c = 0; c < cpt; ++c, ++gidx) {
+          const int ai = gidx & 1;
+          mbar_wait(&afull[ai], (gidx >> 1) & 1);
+          const uint32_t a_main = smem_u32(wbuf + ai * N4_WIN_BUF), a_aux = a_main + N4_WIN_MAIN;
+          for (int j = 0; j < p.taps; ++j, ++bcnt) {
+            const int bs = bcnt % N4_BSTAGES, ss = bcnt % N4_SFSLOTS;
+            mbar_wait(&bfull[bs], (bcnt / N4_BSTAGES) & 1);
+            mbar_wait(&sffull[ss], (bcnt / N4_SFSLOTS) & 1);
+            tc_fence_after();
+            const uint32_t b_main = smem_u32(bring + bs * N4_BSTAGE), b_aux = b_main + N4_B_MAIN, b_sf = b_aux + N4_B_AUX;
+            const uint32_t sfc = tmem_base + 256u + (uint32_t)(bcnt & 1) * 24u;   // SFA 2 x 4 columns, SFB 2 x 8 columns
+            const uint32_t a_sf = smem_u32(sfring + ss * N4_SFSLOT);
+            utccp_sf_pair(sfc, make_sfatom_desc(a_sf));
+            utccp_sf_pair(sfc + 4, make_sfatom_desc(a_sf + 512));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) utccp_sf_pair(sfc + 8 + 4 * i, make_sfatom_desc(b_sf + 512 * i));
+            const uint32_t rshift = (uint32_t)(j * p.dil);
+#pragma unroll
+            for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+              const uint32_t ko = k * UMMA_K * 2;
+              umma_bf16_pair(tmem_base, make_sw128_desc(a_main + rshift * 128u + ko), make_sw128_desc(b_main + ko), idesc,
+                             (first && k == 0) ? 0u : 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_nv4_pair(tmem_base, make_sw64_desc(a_aux + rshift * 64u + 32u * k), make_sw64_desc(b_aux + 32u * k), idesc4, 1u,
+                            sfc + 4 * k, sfc + 8 + 8 * k);
+            first = false;
+            umma_commit_pair(&bempty[bs]);
+            umma_commit_pair(&sfempty[ss]);
+          }
+          umma_commit_pair(&aempty[ai]);
+        }
+        umma_commit_pair(tfull);
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------- scale-factor warp (both CTAs): per-row window scales -> per-tap atoms ----------------
+    const int nch = p.C / TILE_K;
+    auto load_win = [&](const GateTile& t, int c, uint2 (&v)[6]) {
+      const int tw0 = t.t0 - half * p.dil;
+      const uint2* src = reinterpret_cast<const uint2*>(p.xs) + ((size_t)t.nb * nch + c) * p.T;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int wr = lane + 32 * i, tt = tw0 + wr;
+        v[i] = (wr < p.win_rows && tt >= 0 && tt < p.T) ? __ldg(src + tt) : make_uint2(0u, 0u);
+      }
+    };
+    uint2 cur[6], nxt[6];
+    int scnt = 0;
+    if (pair_id < p.n_items) { const GateTile t0 = tile_of(pair_id); load_win(t0, 0, cur); }
+    for (int item = pair_id; item < p.n_items; item += n_pairs) {
+      const GateTile ti = tile_of(item);
+      for (int c = 0; c < cpt; ++c) {
+        __syncwarp();                               // the previous chunk's atoms have all been gathered from sfwin
+#pragma unroll
+        for (int i = 0; i < 6; ++i) *reinterpret_cast<uint2*>(sfwin + (lane + 32 * i) * 8) = cur[i];
+        __syncwarp();
+        // prefetch the next chunk's window scales while this chunk's taps are served
+        if (c + 1 < cpt) load_win(ti, c + 1, nxt);
+        else if (item + n_pairs < p.n_items) { const GateTile tn = tile_of(item + n_pairs); load_win(tn, 0, nxt); }
+        for (int j = 0; j < p.taps; ++j, ++scnt) {
+          const int ss = scnt % N4_SFSLOTS;
+          mbar_wait(&sfempty[ss], ((scnt / N4_SFSLOTS) & 1) ^ 1);
+          uint2 q[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) q[r] = *reinterpret_cast<const uint2*>(sfwin + (32 * r + lane + j * p.dil) * 8);
+          const uint32_t dst = smem_u32(sfring + ss * N4_SFSLOT) + lane * 16;
+          sts128u(dst, q[0].x, q[1].x, q[2].x, q[3].x);          // instruction 0 (lo part): row 32 r + lane -> bytes 4 r .. 4 r + 3
+          sts128u(dst + 512, q[0].y, q[1].y, q[2].y, q[3].y);    // instruction 1 (hi part)
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&sffull[ss]), 0));
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cur[i] = nxt[i];
+      }
+    }
+  }
+  } else {
+    setmaxnreg_inc<224>();
+    // ---------------- epilogue (8 warps): drain the accumulator into registers, release it, then gate / split / store ----------------
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = (int)threadIdx.x - 128;
+    const bool issuer = (warp == 4) && (lane == 0);
+    const uint32_t stg = smem_u32(staging);
+    const float inv = __ldg(p.inv_scale);
+    int tcnt = 0;
+    for (int item = pair_id; item < p.n_items; item += n_pairs, ++tcnt) {
+      const GateTile ti = tile_of(item);
+      mbar_wait(tfull, tcnt & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      uint32_t acc[2][2][32];                        // [c2][gate | filter][column]
+      __syncwarp();
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        tmem_ld32(taddr + (grp * 2 + c2) * 32, acc[c2][0]);
+        tmem_ld32(taddr + 128 + (grp * 2 + c2) * 32, acc[c2][1]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(tempty), 0));
+#pragma unroll 1
+      for (int pass = 0; pass < (DUAL ? 2 : 1); ++pass) {
+        const bool is_cond = DUAL ? (pass == 1) : (ti.nb < p.n_cond);
+        const int zroll = p.z_group0 + ti.nb + ((DUAL && pass == 0) ? p.dual_off : 0);
+        if (issuer) tma_store_wait_read<0>();        // the previous stores no longer read the staging boxes
+        named_bar_sync(EPI_BAR, EPI_THREADS);        // ... and every thread is done with sbias
+        sbias[etid] = __ldg((is_cond ? p.bias_cond : p.bias_unc) + ti.nblk * TILE_N + etid);
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+        const int tf = ti.t0 + row;
+        const bool add_cond = is_cond && p.cond != nullptr && tf < p.T;
+        const uint32_t box = stg + grp * CHUNK_BYTES;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int ch = grp * 2 + c2;
+          const float* cg = p.cond + ((size_t)ti.nb * p.T + (add_cond ? tf : 0)) * (size_t)(2 * p.C) + ti.nblk * (TILE_N / 2) + ch * 32;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float z[16];
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+              if (add_cond) {
+                a = __ldg(reinterpret_cast<const float4*>(cg) + hf * 4 + v4);
+                b = __ldg(reinterpret_cast<const float4*>(cg + p.C) + hf * 4 + v4);
+              }
+              const float ca[4] = {a.x, a.y, a.z, a.w}, cb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = hf * 16 + v4 * 4 + e;
+                const float g = __uint_as_float(acc[c2][0][j]) * inv + ca[e];
+                const float f = __uint_as_float(acc[c2][1][j]) * inv + cb[e];
+                z[v4 * 4 + e] = gate_act(g + sbias[ch * 32 + j], f + sbias[128 + ch * 32 + j]);
+              }
+            }
+            uint32_t zm[8], za[8];
+            pack16<3>(z, zm, za);
+            const int chn = c2 * 32 + hf * 16;
+            sts128u(box + sw128_off(row, chn / 8), zm[0], zm[1], zm[2], zm[3]);
+            sts128u(box + sw128_off(row, chn / 8 + 1), zm[4], zm[5], zm[6], zm[7]);
+            sts128u(box + 2 * CHUNK_BYTES + sw128_off(row, chn / 16), za[0], za[1], za[2], za[3]);
+            sts128u(box + 2 * CHUNK_BYTES + sw128_off(row, 4 + chn / 16), za[4], za[5], za[6], za[7]);
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+        if (issuer) {
+          const int c0 = ti.nblk * (TILE_N / 2);
+          tma_store_3d(&p.zh, staging, c0, ti.t0, zroll);
+          tma_store_3d(&p.zh, staging + CHUNK_BYTES, c0 + 64, ti.t0, zroll);
+          tma_store_3d(&p.zl, staging + 2 * CHUNK_BYTES, 2 * c0, ti.t0, zroll);
+          tma_store_3d(&p.zl, staging + 3 * CHUNK_BYTES, 2 * (c0 + 64), ti.t0, zroll);
+          tma_store_commit();
+        }
+      }   // pass
+    }
+    if (issuer) tma_store_wait_read<0>();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // zgemm kernel: A = stored z of one layer (RES) or of all layers (HEAD)
 // ---------------------------------------------------------------------------------------------
 template <int P, bool PAIR>
@@ -1034,9 +1342,10 @@ constexpr int RP_LANDING = 2;
 constexpr int RP_RING = RP_STAGES * RP_STAGE + RP_XBOXES * CHUNK_BYTES;   // 192 KB
 constexpr int RP_SMEM = RP_RING + 2 * CHUNK_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;   // 231,680 <= 227 KB
 
-template <int P>
+template <int P, int XF>
 __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __grid_constant__ ZGemmParams p) {
   static_assert(P == 1 || P == 3, "needs a single 256-column accumulator");
+  static_assert(XF == 0 || (XF == 4 && P == 3), "f16n4 activations pair with f16e5 z operands");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1215,6 +1524,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
         // warp-uniform addresses: L1 broadcast, off the critical path
         const float* dn = p.dnext + (size_t)(p.steps ? __ldg(p.steps + ti.nb % p.bsamp) : p.t_uniform) * p.C + ti.n_base + cbox * 32;
         uint32_t pm[2][8], pa[2][8];                // packed operand pair of this thread's 32 channels
+        uint32_t sfl[2], sfh[2];                    // f16n4: scale bytes of the two 16-channel blocks (lo part, hi part)
 #pragma unroll
         for (int g16 = 0; g16 < 2; ++g16) {
           float xin[16];
@@ -1228,7 +1538,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
             xin[u * 4 + 2] = xc[i + 2] + d4.z; xin[u * 4 + 3] = xc[i + 3] + d4.w;
           }
           range_note(umax, xin);
-          pack16<P>(xin, pm[g16], pa[g16]);
+          if (XF == 4) {   // pa: [lo codes (2 words) | hi codes (2 words)]
+            uint32_t lo[2], hi[2];
+            split_f16n4_x16(xin, pm[g16], lo, hi, sfl[g16], sfh[g16]);
+            pa[g16][0] = lo[0]; pa[g16][1] = lo[1]; pa[g16][2] = hi[0]; pa[g16][3] = hi[1];
+          } else {
+            pack16<P>(xin, pm[g16], pa[g16]);
+          }
         }
         if (issuer) tma_store_wait_read<0>();       // the previous iteration's stores no longer read the staging boxes
         named_bar_sync(EPI_BAR, EPI_THREADS);
@@ -1239,7 +1555,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
           const int chn = hc * 32 + g16 * 16;
           sts128u(stg + sw128_off(row, chn / 8), pm[g16][0], pm[g16][1], pm[g16][2], pm[g16][3]);
           sts128u(stg + sw128_off(row, chn / 8 + 1), pm[g16][4], pm[g16][5], pm[g16][6], pm[g16][7]);
-          if (P >= 2) {
+          if (XF == 4) {
+            // aux box: 64-byte rows [lo codes 32 B | hi codes 32 B], 64-byte swizzle; this thread owns bytes [16 hc, 16 hc + 16) of each half
+            if (g16 == 1) {
+              sts128u(stg + CHUNK_BYTES + sw64_off(row, hc), pa[0][0], pa[0][1], pa[1][0], pa[1][1]);
+              sts128u(stg + CHUNK_BYTES + sw64_off(row, 2 + hc), pa[0][2], pa[0][3], pa[1][2], pa[1][3]);
+            }
+          } else if (P >= 2) {
             sts128u(stg + CHUNK_BYTES + sw128_off(row, chn / 16), pa[g16][0], pa[g16][1], pa[g16][2], pa[g16][3]);
             sts128u(stg + CHUNK_BYTES + sw128_off(row, 4 + chn / 16), pa[g16][4], pa[g16][5], pa[g16][6], pa[g16][7]);
           } else {
@@ -1254,8 +1576,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
           tma_store_3d(&p.out32, xstage, c0, ti.t0, ti.nb);
           tma_store_3d(&p.out32, xstage + CHUNK_BYTES, c0 + 32, ti.t0, ti.nb);
           tma_store_3d(&p.xh, staging, c0, ti.t0, ti.nb);
-          tma_store_3d(&p.xl, staging + CHUNK_BYTES, AM * c0, ti.t0, ti.nb);
+          tma_store_3d(&p.xl, staging + CHUNK_BYTES, XF == 4 ? c0 : AM * c0, ti.t0, ti.nb);   // f16n4: 64 aux bytes per 64 channels
           tma_store_commit();
+        }
+        if (XF == 4 && ti.t0 + row < p.T) {   // scale factors [roll][chunk][frame][lo x4 | hi x4]: this thread's blocks 2 hc, 2 hc + 1
+          uint8_t* sp = p.xs + (((size_t)ti.nb * (p.C / TILE_K) + (ti.n_base / TILE_K + it)) * p.T + (ti.t0 + row)) * 8 + 2 * hc;
+          *reinterpret_cast<uint16_t*>(sp) = (uint16_t)(sfl[0] | (sfl[1] << 8));
+          *reinterpret_cast<uint16_t*>(sp + 4) = (uint16_t)(sfh[0] | (sfh[1] << 8));
         }
         if (git + 1 < total_it) fetch_x(git + 1);   // next iteration's x: usually landed long ago
       }
@@ -1299,7 +1626,9 @@ int umma_init() {
   set((const void*)umma_gate_win_kernel<3>, Cfg<3, true>::kSmemBytes);
   set((const void*)umma_gate_pers_kernel<1, false>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3, false>, PW_SMEM);
   set((const void*)umma_gate_pers_kernel<1, true>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3, true>, PW_SMEM);
-  set((const void*)umma_res_pers_kernel<1>, RP_SMEM); set((const void*)umma_res_pers_kernel<3>, RP_SMEM);
+  set((const void*)umma_res_pers_kernel<1, 0>, RP_SMEM); set((const void*)umma_res_pers_kernel<3, 0>, RP_SMEM);
+  set((const void*)umma_res_pers_kernel<3, 4>, RP_SMEM);
+  set((const void*)umma_gate_n4_kernel<false>, N4_SMEM); set((const void*)umma_gate_n4_kernel<true>, N4_SMEM);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<2, true>, Cfg<2, false>::kSmemBytes);
@@ -1313,14 +1642,16 @@ int umma_init() {
 }
 
 static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, int dtype) {  // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8
+                  const cuuint32_t* box, int dtype, int swizzle_bytes = 128) {  // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8
   if (!g_encode) { int r = umma_init(); if (r) return r; }
   cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                  : dtype == 3 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = g_encode(m, dt, (cuuint32_t)rank,
                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DRB_E_DRIVER; }
   return 0;
 }
@@ -1343,6 +1674,20 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uin
   cuuint64_t strides[2] = {d0 * es, d1 * d0 * es};
   cuuint32_t box[3] = {(cuuint32_t)(128 / es), box1, 1};
   return encode(m, base, 3, dims, strides, box, dtype);
+}
+
+// byte tensors with an explicit inner box width and swizzle (f16n4: 64-byte e2m1 rows under SWIZZLE_64B, un-swizzled scale atoms)
+int make_tmap_2d_bytes(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode(m, base, 2, dims, strides, box, 3, swizzle_bytes);
+}
+int make_tmap_3d_bytes(CUtensorMap* m, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1, uint32_t box0, int swizzle_bytes) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0, d1 * d0};
+  cuuint32_t box[3] = {box0, box1, 1};
+  return encode(m, base, 3, dims, strides, box, 3, swizzle_bytes);
 }
 
 static int g_pdl = -1;
@@ -1377,7 +1722,7 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   p.cond_slabs = g.Mp / TILE_K; p.tiles_t = (g.T + TILE_M - 1) / TILE_M; p.n_blocks = 2 * g.C / TILE_N;
   p.z_group0 = g.z_group0;
   p.bias_cond = g.bias_cond; p.bias_unc = g.bias_unc;
-  p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0;
+  p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0; p.xs = nullptr;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = g.inv_scale;
   const bool mc = g.pair && ((p.NB * p.tiles_t) % 2 == 0);
@@ -1386,6 +1731,20 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   if (mc && g.window && g.prec != 0 && win_rows <= 192 && g.xwh && g.xwl) {
     p.xwh = *g.xwh; p.xwl = *g.xwl; p.win_rows = win_rows;
     p.n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+    if (g.n4) {   // f16n4: persistent pairs only, conditioner term always from the per-clip table
+      if (!g.persistent || !g.xw4 || !g.wd4 || !g.wsf || !g.xs || (g.n_cond > 0 && !g.cond) || win_rows > 192) {
+        set_error("umma_gate: f16n4 needs the persistent window kernel and the conditioner tables"); return DRB_E_INVALID;
+      }
+      int n_sm = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+      p.xw4 = *g.xw4; p.wd4 = *g.wd4; p.wsf = *g.wsf; p.xs = g.xs;
+      p.cond = g.cond; p.n_cond_mma = 0;
+      const bool dual = g.dual_B > 0 && g.cond && g.NB == 2 * g.dual_B && ((g.dual_B * p.tiles_t) % 2 == 0);
+      if (dual) { p.NB = g.dual_B; p.dual_off = g.dual_B; p.n_items = (p.NB * p.tiles_t / 2) * p.n_blocks; }
+      const int pairs = p.n_items < n_sm / 2 ? p.n_items : n_sm / 2;
+      return dual ? launch_k(umma_gate_n4_kernel<true>, p, 2 * pairs, N4_SMEM, true, s)
+                  : launch_k(umma_gate_n4_kernel<false>, p, 2 * pairs, N4_SMEM, true, s);
+    }
     if (g.persistent && (g.prec == 1 || g.prec == 3)) {   // one CTA pair per SM pair, looping over its tiles
       int n_sm = 148;
       { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
@@ -1406,6 +1765,7 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
          : g.prec == 2 ? launch_k(umma_gate_win_kernel<2>, p, grid, Cfg<2, true>::kSmemBytes, true, s)
                        : launch_k(umma_gate_win_kernel<3>, p, grid, Cfg<3, true>::kSmemBytes, true, s);
   }
+  if (g.n4) { set_error("umma_gate: f16n4 needs CTA pairs (even tile count) and the tap window"); return DRB_E_INVALID; }
   p.xwh = maps.xh; p.xwl = maps.xl; p.win_rows = TILE_M; p.n_items = 0;
   if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
                              : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
@@ -1424,7 +1784,7 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   p.NB = z.NB; p.T = z.T; p.C = z.C; p.tiles_t = (z.T + TILE_M - 1) / TILE_M; p.n_blocks = z.C / TILE_N;
   p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg; p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
-  p.range_max = z.range_max;
+  p.range_max = z.range_max; p.xs = nullptr;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = z.inv_scale;
   const bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);
@@ -1433,9 +1793,15 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     const int n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
     const int pairs = n_items < n_sm / 2 ? n_items : n_sm / 2;
-    return z.prec == 1 ? launch_k(umma_res_pers_kernel<1>, p, 2 * pairs, RP_SMEM, true, s)
-                       : launch_k(umma_res_pers_kernel<3>, p, 2 * pairs, RP_SMEM, true, s);
+    if (z.x_n4) {
+      if (z.prec != 3 || !z.xl4 || !z.xs) { set_error("umma_zgemm: f16n4 activations need f16e5 z operands"); return DRB_E_INVALID; }
+      p.xl = *z.xl4; p.xs = z.xs;
+      return launch_k(umma_res_pers_kernel<3, 4>, p, 2 * pairs, RP_SMEM, true, s);
+    }
+    return z.prec == 1 ? launch_k(umma_res_pers_kernel<1, 0>, p, 2 * pairs, RP_SMEM, true, s)
+                       : launch_k(umma_res_pers_kernel<3, 0>, p, 2 * pairs, RP_SMEM, true, s);
   }
+  if (z.x_n4 && z.mode == 0) { set_error("umma_zgemm: f16n4 needs the persistent CTA-pair kernels (even tile count)"); return DRB_E_INVALID; }
   if (z.prec == 1) return mc ? launch_k(umma_zgemm_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
                              : launch_k(umma_zgemm_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);
   if (z.prec == 2) return mc ? launch_k(umma_zgemm_kernel<2, true>, p, grid, Cfg<2, false>::kSmemBytes, true, s)

@@ -91,6 +91,9 @@ class Engine:
             self._emb = emb_table.detach().to(device=self.device, dtype=torch.float32).contiguous()
             _lib.check(self.lib.drb_time_tables(self.plan, _ptr(self._emb), _stream(self.device)), "drb_time_tables")
         self.workspace_bytes = int(need)
+        # f16n4 is granted only to shapes that run as CTA pairs; otherwise the plan computes in f16e5 (drb_plan_precision)
+        code = int(self.lib.drb_plan_precision(self.plan))
+        self.effective_precision = {v: k for k, v in _lib.PRECISIONS.items()}.get(code, precision)
         self.branches = branches
 
     def close(self):

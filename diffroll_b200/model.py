@@ -105,6 +105,9 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
     # kernels emitted; a value that is not finite or above F16_RANGE_LIMIT switches this model to bf16x3 (fp32 exponent
     # range, same parity grade, ~20 % slower) and re-runs the call.  ``range_check = False`` skips the read-back.
     F16_RANGE_LIMIT = 3.0e4
+    # f16n4 adds block scales stored as ue4m3 (max 448): its activation range ends near 2^7 (csrc/common.cuh); beyond
+    # N4_RANGE_LIMIT the model steps down to f16e5 first.
+    N4_RANGE_LIMIT = 100.0
     range_check = True
 
     def __init__(self, residual_channels, unconditional, condition, n_mels, norm_args,
@@ -203,19 +206,25 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         return eng, xx, spec
 
     def _range_guarded(self):
-        return self.range_check and self.precision in ("f16e5", "f16f8")
+        return self.range_check and self.precision in ("f16n4", "f16e5", "f16f8")
+
+    def _range_limit(self):
+        return self.N4_RANGE_LIMIT if self.precision == "f16n4" else self.F16_RANGE_LIMIT
 
     def _range_ok(self, eng):
         if not self._range_guarded():
             return True
         m = eng.range_max(reset=True)
-        return m == m and m <= self.F16_RANGE_LIMIT
+        self._range_seen = m
+        return m == m and m <= self._range_limit()
 
     def _range_fallback(self):
         import warnings
-        warnings.warn(f"diffroll_b200: activations left the fp16 range of precision='{self.precision}' "
-                      f"(|x| > {self.F16_RANGE_LIMIT:g} or non-finite); re-running in 'bf16x3'", RuntimeWarning, stacklevel=3)
-        self.precision = "bf16x3"
+        m = getattr(self, "_range_seen", float("nan"))
+        nxt = "f16e5" if (self.precision == "f16n4" and m == m and m <= self.F16_RANGE_LIMIT) else "bf16x3"
+        warnings.warn(f"diffroll_b200: activations left the range of precision='{self.precision}' "
+                      f"(max |x| = {m:g}, limit {self._range_limit():g}); re-running in '{nxt}'", RuntimeWarning, stacklevel=3)
+        self.precision = nxt
         self._mel_key = None
 
     def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):

@@ -43,6 +43,9 @@ extern "C" {
 #define DRB_PREC_BF16    2  /* tcgen05, single bf16 product (fast mode, NOT within 1e-3)            */
 #define DRB_PREC_F16F8   3  /* tcgen05, fp16 product + e4m3 correction product (2 MMA units, parity-grade) */
 #define DRB_PREC_F16E5   4  /* tcgen05, fp16 product + e5m2 correction product into the same accumulator   */
+#define DRB_PREC_F16N4   5  /* as F16E5, but the dilated conv's correction product is block-scaled fp4 (kind::mxf4nvf4,
+                               e2m1 codes + one ue4m3 scale per 16 channels): 1.5 instead of 2 MMA units per K-step.
+                               Needs an even number of 128-frame tiles (CTA pairs) and tap windows <= 192 frames. */
 
 /* which network branches one step evaluates */
 #define DRB_BRANCH_COND_UNCOND 0  /* classifier-free pair: (1+w)*cond - w*uncond   task/diffusion.py:1007-1009 */
@@ -227,6 +230,10 @@ int drb_plan_profile_read(drb_plan* plan, double* ms_total4, int64_t* launches4)
  * layer (layer 0 is the launch shared by both guidance branches). */
 int drb_plan_profile_read2(drb_plan* plan, double* ms_total, int64_t* launches, int32_t n_classes,
                            double* gate_ms_per_layer, int32_t n_layers);
+
+/* The DRB_PREC_* a plan actually computes in: DRB_PREC_F16N4 is granted only when every launch can run as CTA pairs
+ * (batch * ceil(frames / 128) even) with tap windows <= 192 frames; otherwise the plan runs as DRB_PREC_F16E5. */
+int drb_plan_precision(const drb_plan* plan);
 
 /* Range guard of the fp16-based operand formats (f16e5, f16f8).  Their main product rounds activations to fp16, which
  * overflows at 65504; weights are pre-scaled per tensor by a power of two, activations are not.  Every kernel that

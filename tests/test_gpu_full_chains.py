@@ -47,13 +47,18 @@ def _oracle_chain(hp, sd, x, w, seed):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+_REF = {}   # the eager oracle chain of a case is computed once per session (40 s .. 3 min each)
+
+
 def _chain_case(B, hp_kw, seed, label, precision="f16e5"):
     import diffroll_b200 as M
     hp = default_hparams(**hp_kw)
     sd = make_state_dict(hp)
     x_T, wav, _ = make_inputs(B, hp["timesteps"], seed=seed, n_noise=0)
     x, w = x_T.cuda(), wav.cuda()
-    ref = _oracle_chain(hp, sd, x, w, seed=seed + 1)
+    if label not in _REF:
+        _REF[label] = _oracle_chain(hp, sd, x, w, seed=seed + 1).cpu()
+    ref = _REF[label].cuda()
     torch.cuda.empty_cache()
     m = M.ClassifierFreeDiffRoll(**hp, precision=precision)
     m.load_state_dict(sd)
@@ -71,8 +76,9 @@ def _chain_case(B, hp_kw, seed, label, precision="f16e5"):
     m.release_buffers()
 
 
-def test_configs1_full_chain_b32_200_vs_gpu_eager_oracle():
-    _chain_case(32, dict(), 123, "configs[1] transcription chain")
+@pytest.mark.parametrize("precision", ["f16e5", "f16n4"])
+def test_configs1_full_chain_b32_200_vs_gpu_eager_oracle(precision):
+    _chain_case(32, dict(), 123, "configs[1] transcription chain", precision)
 
 
 @pytest.mark.slow

@@ -18,9 +18,9 @@ from diffroll_b200.synthetic import default_hparams, make_inputs, make_state_dic
 pytestmark = pytest.mark.gpu
 
 TOL_FINAL = 1e-3
-TOL_STEP = {"fp32": 2e-4, "bf16x3": 5e-4, "f16f8": 5e-4, "f16e5": 5e-4}
+TOL_STEP = {"fp32": 2e-4, "bf16x3": 5e-4, "f16f8": 5e-4, "f16e5": 5e-4, "f16n4": 5e-4}
 TOL_SPEC = 2e-4
-PRECS = ["fp32", "bf16x3", "f16f8", "f16e5"]
+PRECS = ["fp32", "bf16x3", "f16f8", "f16e5", "f16n4"]
 _models = {}
 
 
@@ -124,7 +124,7 @@ def test_sampler_single_steps_vs_golden(name, precision):
         assert maxabs(x_prev, ref) < TOL_STEP[precision] * scale, (name, t_index)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "f16e5"])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "f16e5", "f16n4"])
 def test_chain_transcription_200_vs_golden(precision):
     """configs[0]/[1]: 200-step inpainting_ddpm_x0 (w=0.5, no masks) on a full 640-frame clip, B=1."""
     g = golden("chain_transcription_b1_200.npz")
@@ -151,7 +151,7 @@ def test_chain_fp32_path_first_50_steps():
     assert maxabs(x, g["t150"]) < TOL_FINAL
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "f16e5"])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "f16e5", "f16n4"])
 def test_chain_inpainting_T128_vs_golden(precision):
     """configs[3] shape: 50 % of the frames masked to -1 (model/diffwave.py:649-650)."""
     g = golden("chain_inpaint_b2_200_T128.npz")
@@ -175,7 +175,7 @@ def test_chain_generation_1000_T128_vs_golden(precision):
     assert float(spec.max()) == -1.0
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "f16e5"])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "f16e5", "f16n4"])
 def test_tensor_path_matches_fp32_path_per_layer(precision):
     """tcgen05 kernels against the fp32 CUDA-core kernels, layer by layer, through the C ABI entry points."""
     import ctypes as C
@@ -204,7 +204,7 @@ def test_tensor_path_matches_fp32_path_per_layer(precision):
         if os.environ.get("DRB_TRACE_LAYERS"):
             record(f"  layer {layer} (dil {2 ** (layer % 4)}): x32 err {err:.3e} ref {ref:.3e}")
         else:
-            assert err < 2e-4 * max(ref, 1.0), (layer, "x32", err, ref)
+            assert err < (3e-4 if precision == "f16n4" else 2e-4) * max(ref, 1.0), (layer, "x32", err, ref)
     # head: the fp32 path sums a skip buffer and applies skip_projection; the tensor path runs one long-K GEMM over
     # the stored z of all layers with composed weights.  Both leave relu(skip_projection(...)) in "h".
     outs = []
