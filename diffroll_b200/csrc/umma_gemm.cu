@@ -876,21 +876,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
 //   * aux operands are 64-byte rows of e2m1 codes [part 0 | part 1] per 64-channel chunk, 64-byte swizzle; a tap is still a
 //     row-shifted descriptor into the window;
 //   * scale factors live in TMEM.  The weight side's 2 KB of atoms per (N block, K-slab) are precomputed and arrive with the
-//     weight stage; the activation side's depend on the tap's row shift, so warp 3 of EACH CTA gathers them per K-slab
-//     from the window's per-row scales into two 512-byte atoms (a 4-slot ring), and the MMA thread copies both sides to
-//     TMEM with tcgen05.cp right before the slab's MMAs (two alternating 24-column sets);
-//   * the scale factors take TMEM columns, so there is ONE accumulator stage: the epilogue warps (224 registers each, taken
+//     weight stage.  The activation side's depend on the tap's row shift: an atom holds, at row l, the scales of window rows
+//     s + l, s + 32 + l, s + 64 + l, s + 96 + l (s = tap * dilation).  Warp 3 of EACH CTA therefore writes, once per WINDOW,
+//     an image whose row R is {sf[R], sf[R + 32], sf[R + 64], sf[R + 96]} (16 bytes, all four from the lane's own prefetched
+//     registers): the atom of any tap is then the 512 contiguous bytes starting at image row s, and the MMA thread copies
+//     it (and the weight atoms) to TMEM with tcgen05.cp right before the slab's MMAs (two alternating 24-column sets).
+//     (First version: the warp gathered two atoms PER K-SLAB into a 4-slot ring; ncu showed it spending 71 % of its time
+//     in the membar of the release.cluster arrive, one per slab, which held the tensor pipe at 48 %.)
+//   * the scale factors take TMEM columns, so there is ONE accumulator stage: the epilogue warps (216 registers each, taken
 //     from the producer warps with setmaxnreg) drain the whole accumulator into registers and hand it back at once; the
-//     next tile's MMAs wait ~1 us per 22 us tile instead of overlapping the whole epilogue.
-//   smem: 2 windows x (24 + 12 KB) | 3 weight stages x (16 + 8 + 2 KB) | SF atom ring 4 KB | window scales 1.5 KB | 64 KB staging
+//     next tile's MMAs wait ~1 us per tile instead of overlapping the whole epilogue.
+//   smem: 2 windows x (24 + 12 KB) | 3 weight stages x (16 + 8 + 2 KB) | 2 SF images x 3 KB | 64 KB staging
 // ---------------------------------------------------------------------------------------------
 constexpr int N4_WIN_MAIN = 24576, N4_WIN_AUX = 12288, N4_WIN_BUF = N4_WIN_MAIN + N4_WIN_AUX;
 constexpr int N4_B_MAIN = 16384, N4_B_AUX = 8192, N4_B_SF = 2048, N4_BSTAGE = N4_B_MAIN + N4_B_AUX + N4_B_SF;
-constexpr int N4_BSTAGES = 3, N4_SFSLOTS = 4, N4_SFSLOT = 1024;
+constexpr int N4_BSTAGES = 3;
+constexpr int N4_SFIMG_PART = 96 * 16, N4_SFIMG_BUF = 2 * N4_SFIMG_PART;   // image rows 0 .. win_rows - 97 (<= 96), lo part then hi part
 constexpr int N4_OFF_BRING = 2 * N4_WIN_BUF;
-constexpr int N4_OFF_SFRING = N4_OFF_BRING + N4_BSTAGES * N4_BSTAGE;
-constexpr int N4_OFF_SFWIN = N4_OFF_SFRING + N4_SFSLOTS * N4_SFSLOT;
-constexpr int N4_OFF_STAGING = (N4_OFF_SFWIN + 192 * 8 + 1023) / 1024 * 1024;
+constexpr int N4_OFF_SFIMG = N4_OFF_BRING + N4_BSTAGES * N4_BSTAGE;
+constexpr int N4_OFF_STAGING = (N4_OFF_SFIMG + 2 * N4_SFIMG_BUF + 1023) / 1024 * 1024;
 constexpr int N4_OFF_BARS = N4_OFF_STAGING + 4 * CHUNK_BYTES;
 constexpr int N4_SMEM = N4_OFF_BARS + 256 /*barriers*/ + 1024 /*bias*/ + 1024 /*align*/;
 static_assert(N4_SMEM <= 232448, "f16n4 gate kernel: shared memory over the 227 KB limit");
@@ -906,19 +910,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
   { uint32_t a = smem_u32(smem_raw); ring = smem_raw + (((a + 1023u) & ~1023u) - a); }
   uint8_t* const wbuf = ring;
   uint8_t* const bring = ring + N4_OFF_BRING;
-  uint8_t* const sfring = ring + N4_OFF_SFRING;
-  uint8_t* const sfwin = ring + N4_OFF_SFWIN;
+  uint8_t* const sfimg = ring + N4_OFF_SFIMG;
   uint8_t* const staging = ring + N4_OFF_STAGING;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + N4_OFF_BARS);
   uint64_t* const bfull = bars;            // [3]
   uint64_t* const bempty = bars + 3;       // [3]
   uint64_t* const afull = bars + 6;        // [2]
   uint64_t* const aempty = bars + 8;       // [2]
-  uint64_t* const sffull = bars + 10;      // [4]
-  uint64_t* const sfempty = bars + 14;     // [4]
-  uint64_t* const tfull = bars + 18;
-  uint64_t* const tempty = bars + 19;
-  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* const tfull = bars + 10;
+  uint64_t* const tempty = bars + 11;
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
   float* const sbias = reinterpret_cast<float*>(ring + N4_OFF_BARS + 256);
 
   const int cpt = p.C / TILE_K;
@@ -940,8 +941,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < N4_BSTAGES; ++i) { mbar_init(&bfull[i], 2); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 2); mbar_init(&aempty[i], 1); }
-    for (int i = 0; i < N4_SFSLOTS; ++i) { mbar_init(&sffull[i], 2); mbar_init(&sfempty[i], 1); }   // both CTAs' SF warps fill a slot
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }   // full: 2 producers (TMA bytes) + 2 SF warps
     mbar_init(tfull, 1); mbar_init(tempty, 16);    // 8 epilogue warps x 2 CTAs drain the accumulator
     fence_barrier_init();
   }
@@ -953,7 +953,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
-  // register split: 128 x 64 + 256 x 224 = the SM's 64 K registers
+  // register split inside the CTA's own pool (384 x 168 registers at launch): 128 x 64 + 256 x 216 = 63488 <= 64512.
+  // (setmaxnreg.inc waits for registers freed by THIS CTA's dec: a split summing above the launch allocation hangs.)
   if (warp < 4) {
   setmaxnreg_dec<64>();
   if (warp == 0) {
@@ -1010,18 +1011,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
           mbar_wait(&afull[ai], (gidx >> 1) & 1);
           const uint32_t a_main = smem_u32(wbuf + ai * N4_WIN_BUF), a_aux = a_main + N4_WIN_MAIN;
           for (int j = 0; j < p.taps; ++j, ++bcnt) {
-            const int bs = bcnt % N4_BSTAGES, ss = bcnt % N4_SFSLOTS;
+            const int bs = bcnt % N4_BSTAGES;
             mbar_wait(&bfull[bs], (bcnt / N4_BSTAGES) & 1);
-            mbar_wait(&sffull[ss], (bcnt / N4_SFSLOTS) & 1);
             tc_fence_after();
             const uint32_t b_main = smem_u32(bring + bs * N4_BSTAGE), b_aux = b_main + N4_B_MAIN, b_sf = b_aux + N4_B_AUX;
             const uint32_t sfc = tmem_base + 256u + (uint32_t)(bcnt & 1) * 24u;   // SFA 2 x 4 columns, SFB 2 x 8 columns
-            const uint32_t a_sf = smem_u32(sfring + ss * N4_SFSLOT);
+            const uint32_t rshift = (uint32_t)(j * p.dil);
+            const uint32_t a_sf = smem_u32(sfimg + ai * N4_SFIMG_BUF) + rshift * 16u;   // this tap's atoms start at image row j * dil
             utccp_sf_pair(sfc, make_sfatom_desc(a_sf));
-            utccp_sf_pair(sfc + 4, make_sfatom_desc(a_sf + 512));
+            utccp_sf_pair(sfc + 4, make_sfatom_desc(a_sf + N4_SFIMG_PART));
 #pragma unroll
             for (int i = 0; i < 4; ++i) utccp_sf_pair(sfc + 8 + 4 * i, make_sfatom_desc(b_sf + 512 * i));
-            const uint32_t rshift = (uint32_t)(j * p.dil);
 #pragma unroll
             for (int k = 0; k < TILE_K / UMMA_K; ++k) {
               const uint32_t ko = k * UMMA_K * 2;
@@ -1034,7 +1034,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
                             sfc + 4 * k, sfc + 8 + 8 * k);
             first = false;
             umma_commit_pair(&bempty[bs]);
-            umma_commit_pair(&sfempty[ss]);
           }
           umma_commit_pair(&aempty[ai]);
         }
@@ -1042,7 +1041,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
       }
     }
   } else if (warp == 3) {
-    // ---------------- scale-factor warp (both CTAs): per-row window scales -> per-tap atoms ----------------
+    // ---------------- scale-factor warp (both CTAs): per-row window scales -> one shift-addressable image per window ----------------
     const int nch = p.C / TILE_K;
     auto load_win = [&](const GateTile& t, int c, uint2 (&v)[6]) {
       const int tw0 = t.t0 - half * p.dil;
@@ -1053,39 +1052,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
         v[i] = (wr < p.win_rows && tt >= 0 && tt < p.T) ? __ldg(src + tt) : make_uint2(0u, 0u);
       }
     };
-    uint2 cur[6], nxt[6];
-    int scnt = 0;
+    uint2 cur[6];
+    int wcnt = 0;
     if (pair_id < p.n_items) { const GateTile t0 = tile_of(pair_id); load_win(t0, 0, cur); }
     for (int item = pair_id; item < p.n_items; item += n_pairs) {
       const GateTile ti = tile_of(item);
-      for (int c = 0; c < cpt; ++c) {
-        __syncwarp();                               // the previous chunk's atoms have all been gathered from sfwin
+      for (int c = 0; c < cpt; ++c, ++wcnt) {
+        const int ai = wcnt & 1;
+        mbar_wait(&aempty[ai], ((wcnt >> 1) & 1) ^ 1);          // the MMAs (and scale copies) of the window two back have retired
+        const uint32_t img = smem_u32(sfimg + ai * N4_SFIMG_BUF) + lane * 16;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) *reinterpret_cast<uint2*>(sfwin + (lane + 32 * i) * 8) = cur[i];
-        __syncwarp();
-        // prefetch the next chunk's window scales while this chunk's taps are served
-        if (c + 1 < cpt) load_win(ti, c + 1, nxt);
-        else if (item + n_pairs < p.n_items) { const GateTile tn = tile_of(item + n_pairs); load_win(tn, 0, nxt); }
-        for (int j = 0; j < p.taps; ++j, ++scnt) {
-          const int ss = scnt % N4_SFSLOTS;
-          mbar_wait(&sfempty[ss], ((scnt / N4_SFSLOTS) & 1) ^ 1);
-          uint2 q[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) q[r] = *reinterpret_cast<const uint2*>(sfwin + (32 * r + lane + j * p.dil) * 8);
-          const uint32_t dst = smem_u32(sfring + ss * N4_SFSLOT) + lane * 16;
-          sts128u(dst, q[0].x, q[1].x, q[2].x, q[3].x);          // instruction 0 (lo part): row 32 r + lane -> bytes 4 r .. 4 r + 3
-          sts128u(dst + 512, q[0].y, q[1].y, q[2].y, q[3].y);    // instruction 1 (hi part)
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&sffull[ss]), 0));
+        for (int m = 0; m < 3; ++m) {                            // image rows lane, lane + 32, lane + 64
+          sts128u(img + m * 512, cur[m].x, cur[m + 1].x, cur[m + 2].x, cur[m + 3].x);                   // lo part (instruction 0)
+          sts128u(img + N4_SFIMG_PART + m * 512, cur[m].y, cur[m + 1].y, cur[m + 2].y, cur[m + 3].y);   // hi part (instruction 1)
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) cur[i] = nxt[i];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&afull[ai]), 0));
+        // next window's scales: issued after the arrive (its release fence would wait for them), needed one chunk from now
+        if (c + 1 < cpt) load_win(ti, c + 1, cur);
+        else if (item + n_pairs < p.n_items) { const GateTile tn = tile_of(item + n_pairs); load_win(tn, 0, cur); }
       }
     }
   }
   } else {
-    setmaxnreg_inc<224>();
+    setmaxnreg_inc<216>();
     // ---------------- epilogue (8 warps): drain the accumulator into registers, release it, then gate / split / store ----------------
     const int q = warp & 3, grp = (warp - 4) >> 2;
     const int row = q * 32 + lane;

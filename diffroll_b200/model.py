@@ -21,35 +21,40 @@ from .synthetic import hann_window, melscale_fbanks
 from .task import AttributeDict, SpecRollDiffusion, _upd, to_attr
 
 
+def _minmax_rescale(x, dims, lo, hi, nan_to):
+    """Scale ``x`` so that its minimum / maximum over ``dims`` land on ``lo`` / ``hi``; a constant slice (0/0) becomes ``nan_to``."""
+    top = x.amax(dim=dims, keepdim=True)
+    bottom = x.amin(dim=dims, keepdim=True)
+    unit = (x - bottom) / (top - bottom)
+    if nan_to[0] == "unit":                       # framewise: the NaNs are replaced BEFORE the affine map (model/utils.py:13-15)
+        unit = torch.where(torch.isnan(unit), torch.zeros_like(unit), unit)
+        return unit * (hi - lo) + lo
+    out = unit * (hi - lo) + lo                   # imagewise: replaced after it, by the lower bound (model/utils.py:28-30)
+    return torch.where(torch.isnan(out), torch.full_like(out, lo), out)
+
+
 class Normalization:
-    """model/utils.py:2-38 (min-max scaling of label rolls; host-side, not on the hot path)."""
+    """Min-max scaling of label rolls / spectrograms with the reference's call surface (model/utils.py:2-38):
+    ``Normalization(min, max, mode)(x)``.  'imagewise' scales each batch element over all of its entries, 'framewise' over
+    dim 1 only.  CUDA inputs of the imagewise mode go through one kernel (``drb_normalize_imagewise``); the torch
+    expressions below serve host tensors (labels before they are moved to the GPU) and are not on the hot path."""
+
+    MODES = ("framewise", "imagewise")
 
     def __init__(self, min, max, mode='imagewise'):
-        if mode == 'framewise':
-            def normalize(x):
-                x_max = x.max(1, keepdim=True)[0]
-                x_min = x.min(1, keepdim=True)[0]
-                x_std = (x - x_min) / (x_max - x_min)
-                x_std[torch.isnan(x_std)] = 0
-                return x_std * (max - min) + min
-        elif mode == 'imagewise':
-            def normalize(x):
-                if x.is_cuda:   # label rolls already on the GPU (the validation step): one kernel, model/utils.py:25-32
-                    from .diffusion_ops import normalize_imagewise
-                    return normalize_imagewise(x, min, max)
-                x_max = x.flatten(1).max(1, keepdim=True)[0].unsqueeze(1)
-                x_min = x.flatten(1).min(1, keepdim=True)[0].unsqueeze(1)
-                x_std = (x - x_min) / (x_max - x_min)
-                x_scaled = x_std * (max - min) + min
-                x_scaled[torch.isnan(x_scaled)] = min
-                return x_scaled
-        else:
-            print('please choose the correct mode')
-            normalize = None
-        self.normalize = normalize
+        self.lo, self.hi, self.mode = min, max, mode
+        if mode not in self.MODES:                # the reference prints a hint and fails later at call time; fail at the source
+            raise ValueError(f"Normalization mode must be one of {self.MODES}, got {mode!r}")
 
-    def __call__(self, x):
-        return self.normalize(x)
+    def normalize(self, x):
+        if self.mode == "framewise":
+            return _minmax_rescale(x, (1,), self.lo, self.hi, ("unit",))
+        if x.is_cuda:
+            from .diffusion_ops import normalize_imagewise
+            return normalize_imagewise(x, self.lo, self.hi)
+        return _minmax_rescale(x, tuple(range(1, x.dim())), self.lo, self.hi, ("out",))
+
+    __call__ = normalize
 
 
 def Conv1d(*args, **kwargs):

@@ -235,3 +235,28 @@ def test_config_compose_groups_overrides_interpolation():
     kw = dict(c.model.args); t = dict(c.task); t.pop("name"); kw.update(t); kw["spec_args"] = dict(c.spec.args)
     m = M.ClassifierFreeDiffRoll(**kw)
     assert m.hparams.kernel_size == 9 and m.reverse_diffusion.__name__ == "inpainting_ddpm_x0"
+
+
+def test_compose_reads_a_reference_style_hydra_tree(tmp_path):
+    """config.compose on a directory tree laid out like the reference's config/ (defaults LIST + one file per group option,
+    /root/reference/config/sampling.yaml:23-26): group files land under their group key and win over the primary file
+    (Hydra 1.1 order), `group=option` and dotted overrides work, unresolvable interpolations stay lazy."""
+    from diffroll_b200.config import compose
+    (tmp_path / "task").mkdir()
+    (tmp_path / "model").mkdir()
+    (tmp_path / "sampling.yaml").write_text(
+        "gpus: 1\nhop_length: 512\ntask:\n    frame_threshold: 0.8\n    extra: 7\ntrainer:\n    gpus: ${gpus}\n"
+        "dataloader:\n    batch_size: 4\ndefaults:\n    - model: ClassifierFreeDiffRoll\n    - task: generation\n")
+    (tmp_path / "task" / "generation.yaml").write_text(
+        "name: 'generation'\nlr: ${learning_rate}\ntimesteps: 200\nframe_threshold: 0.5\nsampling:\n    type: 'generation_ddpm_x0'\n")
+    (tmp_path / "task" / "transcription.yaml").write_text(
+        "name: 'inpainting'\ntimesteps: 200\nframe_threshold: 0.5\nsampling:\n    type: 'inpainting_ddpm_x0'\n    w: 0.5\n")
+    (tmp_path / "model" / "ClassifierFreeDiffRoll.yaml").write_text(
+        "name: 'ClassifierFreeDiffRoll'\nargs:\n    kernel_size: 3\n    hop: ${hop_length}\n")
+    cfg = compose(str(tmp_path / "sampling.yaml"))
+    assert cfg.task.sampling.type == "generation_ddpm_x0" and cfg.task.frame_threshold == 0.5 and cfg.task.extra == 7
+    assert cfg.trainer.gpus == 1 and cfg.model.args.hop == 512 and cfg.task.lr == "${learning_rate}"
+    cfg = compose(str(tmp_path / "sampling.yaml"), ["task=transcription", "model.args.kernel_size=9", "dataloader.batch_size=32"])
+    assert cfg.task.sampling.w == 0.5 and cfg.model.args.kernel_size == 9 and cfg.dataloader.batch_size == 32
+    with pytest.raises(KeyError):
+        compose(str(tmp_path / "sampling.yaml"), ["task=nope"])

@@ -57,3 +57,22 @@ def test_sampler_step_and_validation_step_match_live_reference():
     assert abs(float(la["diffusion_loss"]) - float(lb["diffusion_loss"])) < 1e-6
     assert float((ta["pred_roll"] - tb["pred_roll"]).abs().max()) <= 2e-5
     assert np.array_equal(ta["label_roll"].numpy(), tb["label_roll"].numpy())
+
+
+@pytest.mark.parametrize("mode", ["imagewise", "framewise"])
+@pytest.mark.parametrize("bounds", [(0, 1), (-1, 1)])
+def test_normalization_matches_live_reference(mode, bounds):
+    """diffroll_b200.Normalization (host tensors) against the reference's model/utils.py:2-38, incl. the constant-slice NaN rules."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("_ref_model_utils", os.path.join(ref_shim.REFERENCE_ROOT, "model", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from diffroll_b200 import Normalization
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(4, 37, 88, generator=g)
+    x[2] = 0.3              # constant image: 0/0 -> the lower bound (imagewise)
+    x[1, :, 5] = 0.7        # constant frame column: 0/0 -> 0 before the affine map (framewise)
+    a = mod.Normalization(bounds[0], bounds[1], mode)(x.clone())
+    b = Normalization(bounds[0], bounds[1], mode)(x.clone())
+    assert torch.equal(a, b)
