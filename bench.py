@@ -293,7 +293,7 @@ def measure(ctx, cfg_id, K, W, precision, want_e2e=True, want_profile=True, samp
     ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if sampler_started else None
     out = dict(cfg=cfg, hp=hp, batch=batch, global_batch=global_batch, ms=ms, launches=launches, clocks=clocks,
-               workspace_bytes=eng.workspace_bytes, range_max=eng.range_max(reset=True))
+               workspace_bytes=eng.workspace_bytes, range_max=eng.range_max(reset=True), precision=eng.effective_precision)
 
     # ---- per-kernel CUDA-event timing inside a running loop (roofline) ------------------------------
     if want_profile:
@@ -468,13 +468,13 @@ def run_b200(args, rank, world, local):
         Kx = min(K, 20)
         try:
             m2 = measure(ctx, 2, Kx, 3, args.precision)
-            r2 = gate_roofline(m2, peaks, args.precision, world, Kx, None)
+            r2 = gate_roofline(m2, peaks, m2["precision"], world, Kx, None)
             extras["configs2"] = {
                 "workload": f"configs[2]: batch={m2['batch']} per GPU, {CONFIGS[2]['what']}",
                 "value": steps_per_s(m2, world, Kx), "unit": UNIT, "steps": Kx, "ms_per_step": m2["ms"] / Kx,
                 "e2e": {"value": steps_per_s(m2, world, m2["Ke"], "ms_e2e"), "amortised_over": m2["Ke"]},
                 "gate_frac": r2["frac"], "gate_avg_launch_ms": r2["avg_launch_ms"], "per_step_ms": r2["per_step_ms"],
-                "workspace_bytes": m2["workspace_bytes"], "scaling": "weak"}
+                "workspace_bytes": m2["workspace_bytes"], "scaling": "weak", "precision": m2["precision"]}
         except Exception as e:
             extras["configs2"] = {"error": repr(e)}
         strong = {}
@@ -507,7 +507,8 @@ def run_b200(args, rank, world, local):
                 traffic = json.load(f).get("umma_gate_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = gate_roofline(main, peaks, args.precision, world, K, traffic)
+    prec = main["precision"]       # what the plan actually computes in (f16n4 steps down to f16e5 on odd tile counts)
+    roofline = gate_roofline(main, peaks, prec, world, K, traffic)
     cpu = None
     if not args.no_cpu_baseline:
         try:
@@ -526,7 +527,7 @@ def run_b200(args, rank, world, local):
                            "RES / HEAD GEMMs: f16e5)",
                   "bf16x3": "bf16x3 (bf16 hi/lo split, 3 tcgen05 products, fp32 accumulate)",
                   "f16f8": "f16f8 (fp16 tcgen05 product + e4m3 correction product, fp32 accumulate)",
-                  "f16e5": "f16e5 (fp16 tcgen05 product + e5m2 correction product, one fp32 accumulator)"}.get(args.precision, args.precision),
+                  "f16e5": "f16e5 (fp16 tcgen05 product + e5m2 correction product, one fp32 accumulator)"}.get(prec, prec),
         "data": "synthetic",
         "config": {"workload": f"{cfg['tag']}: {per_gpu}, synthetic 640x88 rolls + 229-bin mel, {cfg['what']}, "
                                "ClassifierFreeDiffRoll k=9, random weights",
@@ -555,7 +556,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4])
     ap.add_argument("--batch", type=int, default=0, help="override the configuration's (per-GPU or global) batch")
-    ap.add_argument("--precision", default="f16e5", choices=["f16n4", "f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="f16n4", choices=["f16n4", "f16e5", "f16f8", "bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="headline configuration only (no configs2 / strong / eager extras)")
     args = ap.parse_args()

@@ -24,7 +24,7 @@ def _ptr(t):
 class Engine:
     """One plan = one (batch, frames, wave_len, precision) configuration on one GPU."""
 
-    def __init__(self, state, hp, batch, frames, wave_len, emb_table, precision="f16e5",
+    def __init__(self, state, hp, batch, frames, wave_len, emb_table, precision="f16n4",
                  branches=_lib.BRANCH_COND_UNCOND, device=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():

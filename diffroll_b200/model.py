@@ -117,7 +117,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
 
     def __init__(self, residual_channels, unconditional, condition, n_mels, norm_args,
                  residual_layers=30, kernel_size=3, dilation_base=1, dilation_bound=4, spec_args={},
-                 spec_dropout=0.5, inpainting_t=None, inpainting_f=None, precision="f16e5", **kwargs):
+                 spec_dropout=0.5, inpainting_t=None, inpainting_f=None, precision="f16n4", **kwargs):
         spec_args = to_attr(dict(spec_args))
         self._pending_hparams = AttributeDict(
             residual_channels=residual_channels, unconditional=unconditional, condition=condition, n_mels=n_mels,

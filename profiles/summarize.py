@@ -46,7 +46,8 @@ if os.path.exists(rep) or os.path.exists(rawcsv):
     out = {}
     for r in rr[2:]:
         nm = r[ik].split("(")[0].replace("void ", "").replace("drb::", "")
-        key = ("umma_gate_dual_kernel" if "gate_pers_kernel<3, 1>" in nm or "gate_pers_kernel<1, 1>" in nm else "umma_gate_kernel" if "gate" in nm
+        key = ("umma_gate_dual_kernel" if "gate_pers_kernel<3, 1>" in nm or "gate_pers_kernel<1, 1>" in nm or "gate_n4_kernel<1>" in nm
+               else "umma_gate_n4_kernel" if "gate_n4" in nm else "umma_gate_kernel" if "gate" in nm
                else "umma_res_kernel" if "res_pers" in nm else "umma_zgemm_kernel" if "zgemm" in nm else nm)
         out.setdefault(key + "_dram_bytes_per_launch", []).append(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]))
     out = {k: sum(v) / len(v) for k, v in out.items()}

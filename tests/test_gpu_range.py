@@ -123,3 +123,35 @@ def test_range_word_tracks_operand_magnitude():
     m2 = eng.range_max(reset=True)
     assert m2 > 10.0 * m1
     m.release_buffers()
+
+
+@pytest.mark.parametrize("scale,expect", [(1.0, "f16n4"), (1e3, "f16e5"), (1e5, "bf16x3")])
+def test_f16n4_steps_down_with_operand_range(scale, expect):
+    """The default f16n4 format stores block scales as ue4m3 (activations up to ~2^7, model.N4_RANGE_LIMIT = 100): an input
+    that drives |x + d| beyond it re-runs the call in f16e5, one beyond fp16's range in bf16x3; results stay finite and
+    within the per-step tolerance of the fp64 oracle (same bar as above)."""
+    import diffroll_b200 as M
+    hp = default_hparams()
+    sd = make_state_dict(hp)
+    x_T, wav, noise = make_inputs(2, 200, seed=9, n_noise=1, T=256, wav_len=131072)
+    x, w, nz = x_T.cuda() * scale, wav.cuda(), noise[0].cuda()
+    ref_hi, ref_lo = _oracle_steps(hp, sd, x, w, nz, torch.float64)
+    f32_hi, f32_lo = _oracle_steps(hp, sd, x, w, nz, torch.float32)
+    floor = max(_rel(f32_hi, ref_hi), _rel(f32_lo, ref_lo))
+    m = M.ClassifierFreeDiffRoll(**hp)            # default precision
+    assert m.precision == "f16n4"
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        a_hi, _ = m.reverse_diffusion(x, w, hp["timesteps"] - 1, noise=nz)
+        a_lo, _ = m.reverse_diffusion(x, w, 0)
+        torch.cuda.synchronize()
+    assert m.precision == expect, (scale, m.precision)
+    assert (expect != "f16n4") == any(issubclass(c.category, RuntimeWarning) and expect in str(c.message) for c in caught)
+    assert bool(torch.isfinite(a_hi).all()) and bool(torch.isfinite(a_lo).all())
+    rel = [_rel(a_hi, ref_hi), _rel(a_lo, ref_lo)]
+    _record(f"range[f16n4 default]: input x {scale:g}: precision used {m.precision}, vs fp64 oracle: t=199 {rel[0]:.3e}, t=0 {rel[1]:.3e}; "
+            f"fp32 reference floor {floor:.3e}")
+    assert max(rel) < max(TOL_REL, 300.0 * floor), (scale, rel, floor)
+    m.release_buffers()
