@@ -23,6 +23,8 @@ EXPORTS = [
     "drb_head_posterior_step", "drb_sample_step", "drb_sample_loop", "drb_launch_count", "drb_plan_buffer",
     "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_plan_precision", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
+    "drb_train_workspace_bytes", "drb_train_create", "drb_train_destroy", "drb_train_forward", "drb_train_backward", "drb_loss_grad",
+    "drb_adam_step",
 ]
 
 
@@ -50,6 +52,18 @@ class DrbWeights(C.Structure):
         ("head_projection_w", _FP), ("head_projection_b", _FP),
         ("stft_window", _FP), ("mel_fb", _FP),
     ]
+
+
+class DrbTrainConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "frames", "pitches", "residual_channels", "residual_layers", "kernel_size", "dilation_base", "dilation_bound",
+        "n_mels", "timesteps")]
+
+
+class DrbTrainParams(C.Structure):
+    """Device pointers of the 132 state_dict tensors (or of their gradients), include/diffroll_b200.h drb_train_params."""
+    _fields_ = [(n, _FP) for n in ("in_w", "in_b", "e1w", "e1b", "e2w", "e2b", "skw", "skb", "hdw", "hdb")] + \
+               [(n, _FPP) for n in ("wd", "bd", "wdp", "bdp", "wc", "bc", "wo", "bo")]
 
 
 class DrbUpdate(C.Structure):
@@ -114,6 +128,18 @@ def load():
     lib.drb_p_losses_scratch_bytes.argtypes = []
     lib.drb_p_losses.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.drb_normalize_imagewise.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_void_p]
+    lib.drb_train_workspace_bytes.restype = C.c_size_t
+    lib.drb_train_workspace_bytes.argtypes = [C.POINTER(DrbTrainConfig)]
+    lib.drb_train_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DrbTrainConfig), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.drb_train_destroy.argtypes = [C.c_void_p]
+    lib.drb_train_destroy.restype = None
+    lib.drb_train_forward.argtypes = [C.c_void_p, C.POINTER(DrbTrainParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    lib.drb_train_backward.argtypes = [C.c_void_p, C.POINTER(DrbTrainParams), C.POINTER(DrbTrainParams), C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_void_p, C.c_void_p]
+    lib.drb_loss_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.drb_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_int32, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("drb_version",):

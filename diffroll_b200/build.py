@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiffroll_b200.so")
-SOURCES = ["api.cu", "simt_kernels.cu", "mel.cu", "umma_gemm.cu", "notes.cu", "diffusion_ops.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "mel.cu", "umma_gemm.cu", "notes.cu", "diffusion_ops.cu", "train.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "diffroll_b200.h")]
 
 

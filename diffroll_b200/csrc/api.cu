@@ -111,7 +111,7 @@ static Layout make_layout(const drb_config& c) {
     l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
     l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
     l.bcomp = take(C * 4); l.bsum = take(C * 4);
-    l.wscale = take((2 * L + 1) * 4 * 4);
+    l.wscale = take((3 * L + 1) * 4 * 4);
     if (c.precision == DRB_PREC_F16N4) {
       l.xs = take(NB * (C / 64) * T * 8);
       l.wsf4 = take(L * (2 * C / 256) * (k * C / 64) * 2048);
@@ -174,7 +174,9 @@ struct drb_plan {
   int prec() const { return cfg.precision == DRB_PREC_BF16X3 ? 1 : cfg.precision == DRB_PREC_F16F8 ? 2 : (cfg.precision == DRB_PREC_F16E5 || n4()) ? 3 : 0; }
   int fmt() const { return cfg.precision == DRB_PREC_FP32 ? 0 : cfg.precision == DRB_PREC_F16F8 ? 2 : (cfg.precision == DRB_PREC_F16E5 || n4()) ? 3 : 1; }
   int xfmt() const { return n4() ? 4 : fmt(); }   // format of the x operand pair (in_proj / RES -> gate kernel)
-  float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head
+  float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head, 2L+1+l: Wc (f16n4)
+  int wc_slot(int layer) const { return n4() ? 2 * cfg.residual_layers + 1 + layer : 2 * layer; }   // f16n4 scales the conv weights alone
+  std::vector<CUtensorMap> cond32;   // per layer: fp32 [B][T][2C] map of the conditioner table (tensor-core build)
   const float* dvec(int layer, int t) const {
     return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
   }
@@ -280,7 +282,9 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
       }
       char* wch = p->ws + lay.wch + (size_t)i * 2 * C * Mp * 2;
       char* wcl = p->ws + lay.wcl + (size_t)i * 2 * C * Mp * 2;
-      PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], wch, wcl, 2 * C, cfg->n_mels, Mp, C, fmt, p->wscale(2 * i), s));
+      if (p->n4() && fmt >= 2)   // the f16n4 conv-weight scale targets 2^15 for the e2m1 split: the conditioner weights get their own
+        PLAN_TRY(launch_weight_scale(w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels, nullptr, 0, p->wscale(p->wc_slot(i)), 1.f, s));
+      PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], wch, wcl, 2 * C, cfg->n_mels, Mp, C, fmt, p->wscale(p->wc_slot(i)), s));
       char* woh = p->ws + lay.woh + (size_t)i * 2 * C * C * 2;
       char* wol = p->ws + lay.wol + (size_t)i * 2 * C * C * 2;
       PLAN_TRY(launch_repack_split(w->output_projection_w[i], woh, wol, 2 * C, C, C, 0, fmt, p->wscale(2 * i + 1), s));
@@ -332,6 +336,12 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
     PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, am * C, 128, da));
     PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, dm));
     PLAN_TRY(make_tmap_3d(&p->maps.sl, p->ws + lay.sl, cfg->batch, T, am * Mp, 128, da));
+    if (lay.cond)   // conditioner tables built on the tensor cores (drb_cond_tables): one fp32 map per layer
+      for (int i = 0; i < L; ++i) {
+        CUtensorMap mc;
+        PLAN_TRY(make_tmap_3d(&mc, p->at<float>(lay.cond) + (size_t)i * cfg->batch * T * 2 * C, cfg->batch, T, 2 * (uint64_t)C, 128, 1));
+        p->cond32.push_back(mc);
+      }
     PLAN_TRY(make_tmap_3d(&p->maps.x32, p->ws + lay.x32, NBc, T, C, 128, 1));
     PLAN_TRY(make_tmap_3d(&p->maps.h32, p->ws + lay.hbuf, NBc, T, C, 128, 1));
     // skip sum + 1/sqrt(L) + skip_projection composed into one [C][L*C] weight over the stored z of all layers
@@ -406,6 +416,25 @@ int drb_cond_tables(drb_plan* p, void* stream) {
   // fp32, for every layer; the gate kernel then adds it in its epilogue instead of contracting it every step
   const drb_config& c = p->cfg;
   const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)c.batch * c.frames * C2;
+  static int tc_cond = -1;
+  if (tc_cond < 0) { const char* e = getenv("DRB_COND_TC"); tc_cond = (e && e[0] == '1') ? 1 : 0; }
+  if (tc_cond && (p->prec() == 1 || p->prec() == 3) && (int)p->cond32.size() == c.residual_layers) {
+    // OPT-IN tensor-core build (DRB_COND_TC=1): the spectrogram operand pair [B][T][Mp] against the conditioner weights in the
+    // plan's pair format, K = Mp, plain fp32 result in natural channel order: 15 short tcgen05 launches instead of 15 x 0.37 ms
+    // of fp32 FMA per clip.  Measured (B200, configs[1]): per-clip work 5.5 -> 0.9 ms, i.e. +3.6 % on a 20-step e2e run and
+    // +0.3 % on a real 200-step chain, but the tables then carry the pair format's rounding into EVERY step: 200-step B=32
+    // chain error 2.9e-4 -> 3.6e-4 (f16n4), 2.0e-4 -> 2.5e-4 (f16e5).  The default keeps the exact fp32 tables: parity first.
+    for (int l = 0; l < c.residual_layers; ++l) {
+      UmmaZGemm uz;
+      uz.pair = p->pair; uz.persistent = 0; uz.NB = c.batch; uz.T = c.frames; uz.C = (int)C2; uz.prec = p->prec(); uz.mode = 2;
+      uz.inv_scale = p->wscale(p->wc_slot(l)) + 1; uz.groups = 1; uz.z_group0 = 0; uz.group_stride = 0;
+      uz.w_h = &p->layers[l].wc_h; uz.w_l = &p->layers[l].wc_l; uz.out32 = &p->cond32[l]; uz.bias = nullptr; uz.dnext = nullptr;
+      uz.a_h = &p->maps.sh; uz.a_l = &p->maps.sl; uz.nslabs64 = p->lay.Mp / 64;
+      int r = launch_umma_zgemm(p->maps, uz, (cudaStream_t)stream); if (r) return r;
+    }
+    p->cond_ready = true;
+    return 0;
+  }
   for (int l = 0; l < c.residual_layers; ++l) {
     SimtGemm g;
     g.A = p->at<float>(p->lay.spec32); g.lda = p->lay.Mp; g.T = c.frames; g.Ck = p->lay.Mp;

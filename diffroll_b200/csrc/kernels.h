@@ -123,7 +123,10 @@ struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filt
 };
 struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32 output tile through `out32`
   int pair = 1, persistent = 1;
-  int NB, T, C, prec, mode;         // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h
+  int NB, T, C, prec, mode;         // mode 0: residual update (x32 in place, xh/xl of x + dnext); 1: relu -> h;
+                                    // 2: conditioner tables: A = spectrogram pair (K = nslabs64 * 64), N = 2C gate-interleaved weight
+                                    //    rows, plain fp32 result stored in NATURAL channel order [gate 0..C-1 | filter C..2C-1]
+  int nslabs64 = 0;                 // mode 2: K-slabs (Mp / 64)
   const float* inv_scale;
   int groups, z_group0, group_stride;
   const CUtensorMap *w_h, *w_l, *out32;
@@ -133,6 +136,7 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
   const int* steps = nullptr;       // per-sample diffusion steps [bsamp] (device); roll nb uses steps[nb % bsamp]
   int bsamp = 1;
   unsigned int* range_max = nullptr;  // RES: device word, atomicMax of |x + d_next| (fp32 bits) over the emitted operands
+  const CUtensorMap *a_h = nullptr, *a_l = nullptr;   // mode 2: A operand maps (the spectrogram pair) instead of the stored z
   int x_n4 = 0;                       // RES emits the next layer's operand in the f16n4 format (xl4 = 64-byte-row aux map, xs = scales)
   const CUtensorMap* xl4 = nullptr;
   uint8_t* xs = nullptr;

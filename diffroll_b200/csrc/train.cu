@@ -1,0 +1,695 @@
+// Row f3 of SURVEY.md section 8: the TRAINING step of ClassifierFreeDiffRoll, forward with saved activations and the
+// full backward pass to every one of the 132 state_dict tensors, plus Adam.
+//   reference: SpecRollDiffusion.step / training_step   task/diffusion.py:258-270, 651-763
+//              ClassifierFreeDiffRoll.forward            model/diffwave.py:637-686   (training mode: spec dropout :646-647, 689-693)
+//              ResidualBlock.forward                     model/diffwave.py:134-151
+//              DiffusionEmbedding.forward                model/diffwave.py:66-75
+//              configure_optimizers (torch.optim.Adam)   task/diffusion.py:1057-1067
+//
+// Arithmetic: fp32 on the CUDA cores, like the reference trains.  The contractions reuse the generic fp32 GEMM of the
+// validation path (simt_kernels.cu: NT form with the dilated-tap gather) for the forward and for every "gradient with
+// respect to the input" product (dgrad: the same gather with flipped taps over a transposed weight copy), and one new
+// kernel for every "gradient with respect to a weight" product (wgrad: contraction over rolls x frames, TN form, the
+// same tap gather on the activation side, split over the row range with fp32 atomics).  This is the functional
+// version of the row: parity-exact against fp32 autograd; moving dgrad / wgrad onto tcgen05 is the follow-up.
+//
+// Memory (one drb_train plan, caller-provided workspace): the inputs x_l, pre-activations y_l and gated activations z_l
+// of every layer are kept for the backward pass (L x M x 4C floats, 2.5 GB at 32 rolls x 640 frames).
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/diffroll_b200.h"
+
+namespace drb {
+
+// ---------------------------------------------------------------------------------------------
+// wgrad:  dW[n][c][tap] (+)= sum_m G[m][n] * Aeff(m, tap, c)
+//   Aeff(m, tap, c) = X[(seg*T + t')*ldx + c] + addvec[seg][c]   with m = seg*T + t, t' = t + (tap - taps/2)*dil, 0 <= t' < T
+//   (else 0): exactly the operand the forward GEMM contracted with W[n][tap*Ck + c].
+// 128 x 128 output tile per block, 16 rows of m per stage, 8 x 8 outputs per thread; blockIdx.z splits the m range and
+// the partial tiles are accumulated with atomicAdd (dW is zeroed, or holds the gradient being accumulated, beforehand).
+// Output address: dW + n*sn + c*sc + tap*st  (PyTorch conv weights are [out][in][k]: sn = Ck*k, sc = k, st = 1).
+// ---------------------------------------------------------------------------------------------
+struct WgradDev {
+  const float* G; int ldg; const float* X; int ldx; const float* addvec; int av_stride;
+  int M, T, N, Ck, taps, dil, rows_per_split;
+  float* dW; long long sn, sc, st; float out_scale;
+};
+
+__global__ void __launch_bounds__(256, 2) simt_wgrad_kernel(const WgradDev g) {
+  constexpr int WK = 16;
+  __shared__ __align__(16) float Gs[2][WK][128 + 4];
+  __shared__ __align__(16) float Xs[2][WK][128 + 4];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * 128;
+  const int cblocks = (g.Ck + 127) / 128;
+  const int tap = blockIdx.y / cblocks, c0 = (blockIdx.y - tap * cblocks) * 128;
+  const int m_lo = blockIdx.z * g.rows_per_split, m_hi = min(g.M, m_lo + g.rows_per_split);
+  const int shift = (tap - g.taps / 2) * g.dil;
+  // loader: thread -> (row r = tid / 16 of the stage, 8 consecutive columns starting at (tid % 16) * 8)
+  const int lr = tid >> 4, lc = (tid & 15) * 8;
+  float4 rg[2], rx[2];
+  auto load = [&](int m0) {
+    const int m = m0 + lr;
+    const bool m_ok = m < m_hi;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int n = n0 + lc + q * 4;
+      if (m_ok && n < g.N) {
+        const float* p = g.G + (size_t)m * g.ldg + n;
+        if (n + 3 < g.N) v = *reinterpret_cast<const float4*>(p);
+        else { v.x = p[0]; if (n + 1 < g.N) v.y = p[1]; if (n + 2 < g.N) v.z = p[2]; }
+      }
+      rg[q] = v;
+    }
+    int seg = 0, t2 = -1;
+    if (m_ok) { seg = m / g.T; t2 = m - seg * g.T + shift; }
+    const bool x_ok = m_ok && t2 >= 0 && t2 < g.T;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = c0 + lc + q * 4;
+      if (x_ok && c < g.Ck) {
+        const float* p = g.X + (size_t)(seg * g.T + t2) * g.ldx + c;
+        if (c + 3 < g.Ck) v = *reinterpret_cast<const float4*>(p);
+        else { v.x = p[0]; if (c + 1 < g.Ck) v.y = p[1]; if (c + 2 < g.Ck) v.z = p[2]; }
+        if (g.addvec) {
+          const float* a = g.addvec + (size_t)seg * g.av_stride + c;
+          v.x += a[0]; if (c + 1 < g.Ck) v.y += a[1]; if (c + 2 < g.Ck) v.z += a[2]; if (c + 3 < g.Ck) v.w += a[3];
+        }
+      }
+      rx[q] = v;
+    }
+  };
+  auto store = [&](int buf) {
+    *reinterpret_cast<float4*>(&Gs[buf][lr][lc]) = rg[0]; *reinterpret_cast<float4*>(&Gs[buf][lr][lc + 4]) = rg[1];
+    *reinterpret_cast<float4*>(&Xs[buf][lr][lc]) = rx[0]; *reinterpret_cast<float4*>(&Xs[buf][lr][lc + 4]) = rx[1];
+  };
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int nk = (m_hi - m_lo + WK - 1) / WK;
+  if (nk <= 0) return;
+  load(m_lo); store(0);
+  __syncthreads();
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) load(m_lo + (kb + 1) * WK);
+#pragma unroll
+    for (int k = 0; k < WK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Gs[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Gs[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Xs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Xs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) { store(buf ^ 1); __syncthreads(); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (n >= g.N) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (c >= g.Ck) continue;
+      atomicAdd(g.dW + (long long)n * g.sn + (long long)c * g.sc + (long long)tap * g.st, acc[i][j] * g.out_scale);
+    }
+  }
+}
+
+struct Wgrad {
+  const float* G = nullptr; int ldg = 0; const float* X = nullptr; int ldx = 0; const float* addvec = nullptr; int av_stride = 0;
+  int M = 0, T = 1, N = 0, Ck = 0, taps = 1, dil = 1;
+  float* dW = nullptr; long long sn = 0, sc = 1, st = 0;
+  float out_scale = 1.f;   // dW += out_scale * (G^T Aeff): the forward's division of the GEMM input (skip / sqrt(L))
+};
+static int launch_wgrad(const Wgrad& w, cudaStream_t s) {
+  WgradDev g;
+  g.G = w.G; g.ldg = w.ldg; g.X = w.X; g.ldx = w.ldx; g.addvec = w.addvec; g.av_stride = w.av_stride;
+  g.M = w.M; g.T = w.T; g.N = w.N; g.Ck = w.Ck; g.taps = w.taps; g.dil = w.dil; g.dW = w.dW; g.sn = w.sn; g.sc = w.sc; g.st = w.st; g.out_scale = w.out_scale;
+  if (w.M <= 0 || w.N <= 0 || w.Ck <= 0 || (w.ldg & 3) || (w.ldx & 3) || ((uintptr_t)w.G & 15) || ((uintptr_t)w.X & 15)) {
+    set_error("wgrad: unsupported shape M=%d N=%d Ck=%d ldg=%d ldx=%d", w.M, w.N, w.Ck, w.ldg, w.ldx);
+    return DRB_E_INVALID;
+  }
+  const int nb = (w.N + 127) / 128, cb = (w.Ck + 127) / 128 * w.taps;
+  // enough blocks to fill the machine a few times over; every split covers a multiple of 16 rows
+  int splits = (4 * 148 + nb * cb - 1) / (nb * cb);
+  const int max_splits = (w.M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  g.rows_per_split = ((w.M + splits - 1) / splits + 15) / 16 * 16;
+  splits = (w.M + g.rows_per_split - 1) / g.rows_per_split;
+  dim3 grid(nb, cb, splits);
+  simt_wgrad_kernel<<<grid, 256, 0, s>>>(g);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise / reduction kernels of the training step
+// ---------------------------------------------------------------------------------------------
+// out[seg][n] (+)= sum over the rows of segment seg of G[row][n]   (rows_per_seg = M: one segment = a plain column sum)
+__global__ void colsum_kernel(const float* __restrict__ G, int ldg, int N, int rows_per_seg, int chunk, float* __restrict__ out, int ldo) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int seg = blockIdx.z;
+  const int r0 = blockIdx.y * chunk, r1 = min(rows_per_seg, r0 + chunk);
+  if (n >= N) return;
+  const float* p = G + ((size_t)seg * rows_per_seg + r0) * ldg + n;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4, p += 4 * (size_t)ldg) { s0 += p[0]; s1 += p[ldg]; s2 += p[2 * (size_t)ldg]; s3 += p[3 * (size_t)ldg]; }
+  for (; r < r1; ++r, p += ldg) s0 += p[0];
+  atomicAdd(out + (size_t)seg * ldo + n, (s0 + s1) + (s2 + s3));
+}
+static int launch_colsum(const float* G, int ldg, int N, int segs, int rows_per_seg, float* out, int ldo, cudaStream_t s) {
+  const int chunk = 64;
+  dim3 grid((N + 127) / 128, (rows_per_seg + chunk - 1) / chunk, segs);
+  colsum_kernel<<<grid, 128, 0, s>>>(G, ldg, N, rows_per_seg, chunk, out, ldo);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// x_out = (x_in + o[:, :C]) / sqrt(2)  (skipped for the last layer) ; skip (+)= o[:, C:]      model/diffwave.py:150-151, 680
+__global__ void res_skip_fwd_kernel(const float* __restrict__ o, const float* __restrict__ x_in, float* __restrict__ x_out,
+                                    float* __restrict__ skip, size_t M, int C, int first, int do_res) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C / 4) return;
+  const size_t m = (i * 4) / C; const int c = (int)((i * 4) % C);
+  const float rs2 = 1.41421356237309515f;
+  if (do_res) {
+    const float4 r = *reinterpret_cast<const float4*>(o + m * 2 * C + c);
+    float4 xv = *reinterpret_cast<const float4*>(x_in + m * C + c);
+    xv.x = (xv.x + r.x) / rs2; xv.y = (xv.y + r.y) / rs2; xv.z = (xv.z + r.z) / rs2; xv.w = (xv.w + r.w) / rs2;
+    *reinterpret_cast<float4*>(x_out + m * C + c) = xv;
+  }
+  float4 sk = *reinterpret_cast<const float4*>(o + m * 2 * C + C + c);
+  if (!first) {
+    const float4 p = *reinterpret_cast<const float4*>(skip + m * C + c);
+    sk.x += p.x; sk.y += p.y; sk.z += p.z; sk.w += p.w;
+  }
+  *reinterpret_cast<float4*>(skip + m * C + c) = sk;
+}
+
+// g_o[m] = [ g_x[m] / sqrt(2)  (zeros for the last layer) | g_skip[m] ]      gradient of the layer's output_projection output
+__global__ void make_go_kernel(const float* __restrict__ gx, const float* __restrict__ gskip, float* __restrict__ go, size_t M, int C,
+                               int has_res) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C / 4) return;
+  const size_t m = (i * 4) / C; const int c = (int)((i * 4) % C);
+  const float rs2 = 1.41421356237309515f;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_res) { r = *reinterpret_cast<const float4*>(gx + m * C + c); r.x /= rs2; r.y /= rs2; r.z /= rs2; r.w /= rs2; }
+  *reinterpret_cast<float4*>(go + m * 2 * C + c) = r;
+  *reinterpret_cast<float4*>(go + m * 2 * C + C + c) = *reinterpret_cast<const float4*>(gskip + m * C + c);
+}
+
+// z = sigmoid(y_g) * tanh(y_f):  g_yg = g_z * tanh(y_f) * s (1 - s),  g_yf = g_z * s * (1 - tanh(y_f)^2)      model/diffwave.py:146-147
+__global__ void gate_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gz, float* __restrict__ gy, size_t M, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C / 4) return;
+  const size_t m = (i * 4) / C; const int c = (int)((i * 4) % C);
+  const float4 g4 = *reinterpret_cast<const float4*>(y + m * 2 * C + c);
+  const float4 f4 = *reinterpret_cast<const float4*>(y + m * 2 * C + C + c);
+  const float4 z4 = *reinterpret_cast<const float4*>(gz + m * C + c);
+  const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ff[4] = {f4.x, f4.y, f4.z, f4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+  float og[4], of[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float sg = 1.f / (1.f + expf(-gg[e])), th = tanhf(ff[e]);
+    og[e] = zz[e] * th * sg * (1.f - sg);
+    of[e] = zz[e] * sg * (1.f - th * th);
+  }
+  *reinterpret_cast<float4*>(gy + m * 2 * C + c) = make_float4(og[0], og[1], og[2], og[3]);
+  *reinterpret_cast<float4*>(gy + m * 2 * C + C + c) = make_float4(of[0], of[1], of[2], of[3]);
+}
+
+// g_x_l = g_u (+ g_x_{l+1} / sqrt(2)) in place on gu ; the dead gradient of the last layer's residual output is skipped
+__global__ void add_res_grad_kernel(float* __restrict__ gu, const float* __restrict__ gx_next, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float rs2 = 1.41421356237309515f;
+  float4 a = reinterpret_cast<float4*>(gu)[i];
+  const float4 b = reinterpret_cast<const float4*>(gx_next)[i];
+  a.x += b.x / rs2; a.y += b.y / rs2; a.z += b.z / rs2; a.w += b.w / rs2;
+  reinterpret_cast<float4*>(gu)[i] = a;
+}
+
+// g *= (act > 0)  (ReLU backward, from the saved post-activation), optionally scaled
+__global__ void relu_bwd_kernel(float* __restrict__ g, const float* __restrict__ act, size_t n4, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = reinterpret_cast<float4*>(g)[i];
+  const float4 h = reinterpret_cast<const float4*>(act)[i];
+  a.x = h.x > 0.f ? a.x * scale : 0.f; a.y = h.y > 0.f ? a.y * scale : 0.f;
+  a.z = h.z > 0.f ? a.z * scale : 0.f; a.w = h.w > 0.f ? a.w * scale : 0.f;
+  reinterpret_cast<float4*>(g)[i] = a;
+}
+__global__ void scale_kernel(float* __restrict__ g, size_t n, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] *= scale;
+}
+// silu(p) = p * sigmoid(p);  g_p = g * (s + p s (1 - s))      model/diffwave.py:53-55
+__global__ void silu_bwd_kernel(float* __restrict__ g, const float* __restrict__ p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = p[i], s = 1.f / (1.f + expf(-v));
+  g[i] *= s + v * s * (1.f - s);
+}
+// out[b][:] = table[steps[b]][:]   (DiffusionEmbedding lookup, model/diffwave.py:67-68)
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int* __restrict__ steps, float* __restrict__ out, int B, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * W) return;
+  const int b = i / W, j = i - b * W;
+  out[i] = table[(size_t)steps[b] * W + j];
+}
+__global__ void iota_kernel(int* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; }
+
+// dst[c][r] = src[r][c]  (weights: [rows][cols] -> [cols][rows]); 32 x 32 tiles through shared memory
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+static int launch_transpose(const float* src, float* dst, int rows, int cols, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(src, dst, rows, cols);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+// Dilated-conv weight for the dgrad GEMM: out[c][tap'*OC + n] = w[n][c][k-1-tap']   (w: PyTorch [OC][C][k])
+// The dgrad is the same tap gather as the forward over g_y with the taps mirrored: g_u[t] = sum_tap g_y[t - (tap-k/2) dil] . w[:, :, tap]
+__global__ void repack_dgrad_kernel(const float* __restrict__ w, float* __restrict__ out, int OC, int C, int k) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)OC * C * k) return;
+  const int n = (int)(i % OC); const size_t r = i / OC; const int tp = (int)(r % k); const int c = (int)(r / k);
+  out[i] = w[((size_t)n * C + c) * k + (k - 1 - tp)];
+}
+// spec [B][n_mels][T] (the module's layout) -> [B*T][Mp] time-major, zero padded to Mp columns
+__global__ void spec_to_rows_kernel(const float* __restrict__ spec, float* __restrict__ out, int B, int nm, int T, int Mp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (m < nm && t < T) ? spec[((size_t)b * nm + m) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, m = m0 + threadIdx.x;
+    if (t < T && m < Mp) out[((size_t)b * T + t) * Mp + m] = tile[threadIdx.x][i];
+  }
+}
+
+// Adam, torch.optim.Adam semantics (amsgrad=False, maximize=False; weight_decay adds wd * p to the gradient):
+//   m = b1 m + (1 - b1) g ; v = b2 v + (1 - b2) g^2 ; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+                            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  const float pi = p[i];
+  if (wd != 0.f) gi = fmaf(wd, pi, gi);
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+// d loss / d prediction for the mean l1 / l2 / smooth-l1 losses of p_losses (task/diffusion.py:792-802), times a per-roll factor
+// (training mode 'ex_0': pred_roll = (x_t - s1[t] eps) / sa[t]  ->  d pred_roll / d eps = -s1[t] / sa[t])
+__global__ void loss_grad_kernel(const float* __restrict__ label, const float* __restrict__ pred, float* __restrict__ g, size_t n,
+                                 size_t per_roll, int loss_type, const float* __restrict__ roll_scale, float inv_n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = pred[i] - label[i];
+  float r;
+  if (loss_type == 0) r = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);      // l1
+  else if (loss_type == 1) r = 2.f * d;                                 // l2
+  else r = fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f);                 // huber = smooth_l1_loss, beta = 1
+  r *= inv_n;
+  if (roll_scale) r *= roll_scale[i / per_roll];
+  g[i] = r;
+}
+
+}  // namespace drb
+
+using namespace drb;
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct drb_train {
+  drb_train_config cfg;
+  char* ws;
+  int Mp;
+  std::vector<int> dil;
+  // workspace offsets (bytes)
+  size_t xs, ys, zs, skip, hbuf, obuf, spec, e0, p1, s1, p2, emb, dl, iota, wtmp, gskip, gx, gu, gz, gemb, gd, gsmall, total;
+  bool fwd_done = false;
+  template <class Tp> Tp* at(size_t off) const { return reinterpret_cast<Tp*>(ws + off); }
+};
+
+static size_t train_layout(drb_train& p) {
+  const drb_train_config& c = p.cfg;
+  const size_t B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size, M = B * T;
+  p.Mp = (c.n_mels + 3) / 4 * 4;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) / 256 * 256; return r; };
+  p.xs = take(L * M * C * 4); p.ys = take(L * M * 2 * C * 4); p.zs = take(L * M * C * 4);
+  p.skip = take(M * C * 4); p.hbuf = take(M * C * 4); p.obuf = take(M * 2 * C * 4);
+  p.spec = take(M * (size_t)p.Mp * 4);
+  p.e0 = take(B * 128 * 4); p.p1 = take(B * 512 * 4); p.s1 = take(B * 512 * 4); p.p2 = take(B * 512 * 4); p.emb = take(B * 512 * 4);
+  p.dl = take(L * B * C * 4); p.iota = take(B * 4);
+  size_t wmax = 2 * C * k * C;                       // repacked / transposed weight scratch (largest: the dilated conv)
+  if (wmax < 2 * C * (size_t)p.Mp) wmax = 2 * C * (size_t)p.Mp;
+  p.wtmp = take(wmax * 4);
+  p.gskip = take(M * C * 4); p.gx = take(M * C * 4); p.gu = take(M * C * 4); p.gz = take(M * C * 4);
+  p.gemb = take(B * 512 * 4); p.gd = take(B * C * 4); p.gsmall = take(B * 512 * 4);
+  p.total = off;
+  return off;
+}
+
+static bool train_cfg_ok(const drb_train_config& c) {
+  return c.batch > 0 && c.frames > 0 && c.pitches > 0 && (c.pitches % 4) == 0 && c.residual_channels > 0 && (c.residual_channels % 16) == 0 &&
+         c.residual_layers > 0 && c.kernel_size > 0 && (c.kernel_size & 1) && c.dilation_base > 0 && c.dilation_bound > 0 && c.n_mels > 0 &&
+         c.timesteps > 0;
+}
+
+static bool params_ok(const drb_train_params* q, int L) {
+  if (!q || !q->in_w || !q->in_b || !q->e1w || !q->e1b || !q->e2w || !q->e2b || !q->skw || !q->skb || !q->hdw || !q->hdb) return false;
+  if (!q->wd || !q->bd || !q->wdp || !q->bdp || !q->wc || !q->bc || !q->wo || !q->bo) return false;
+  for (int l = 0; l < L; ++l)
+    if (!q->wd[l] || !q->bd[l] || !q->wdp[l] || !q->bdp[l] || !q->wc[l] || !q->bc[l] || !q->wo[l] || !q->bo[l]) return false;
+  return true;
+}
+
+#define TR(expr) do { int _r = (expr); if (_r) return _r; } while (0)
+
+static inline unsigned nblk(size_t n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" {
+
+size_t drb_train_workspace_bytes(const drb_train_config* cfg) {
+  if (!cfg || !train_cfg_ok(*cfg)) { set_error("invalid drb_train_config"); return 0; }
+  drb_train tmp; tmp.cfg = *cfg;
+  return train_layout(tmp);
+}
+
+int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspace, size_t ws_bytes, void* stream) {
+  if (!out || !cfg || !workspace) { set_error("null argument"); return DRB_E_INVALID; }
+  if (!train_cfg_ok(*cfg)) { set_error("invalid drb_train_config"); return DRB_E_INVALID; }
+  drb_train* p = new drb_train();
+  p->cfg = *cfg; p->ws = (char*)workspace;
+  if (ws_bytes < train_layout(*p) || ((uintptr_t)workspace & 255)) {
+    set_error("train workspace: need %zu bytes 256-aligned, got %zu", p->total, ws_bytes);
+    delete p; return DRB_E_WORKSPACE;
+  }
+  for (int i = 0; i < cfg->residual_layers; ++i) {   // dilation_base ** (i % dilation_bound)   model/diffwave.py:624
+    int d = 1;
+    for (int j = 0; j < i % cfg->dilation_bound; ++j) d *= cfg->dilation_base;
+    p->dil.push_back(d);
+  }
+  iota_kernel<<<nblk(cfg->batch), 256, 0, (cudaStream_t)stream>>>(p->at<int>(p->iota), cfg->batch);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("train_create: %s", cudaGetErrorString(e)); delete p; return (int)e; }
+  *out = p;
+  return 0;
+}
+
+void drb_train_destroy(drb_train* p) { delete p; }
+
+// Forward pass in training form.  x_t [B][T][F]; spec [B][n_mels][T] exactly as the network sees it (normalised log-mel with the
+// spec-dropout rows and masks already set to -1); steps [B] int32; emb_table [timesteps][128].  pred [B][T][F].
+int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t, const float* spec, const int32_t* steps,
+                      const float* emb_table, float* pred, void* stream) {
+  if (!p || !x_t || !spec || !steps || !emb_table || !pred || !params_ok(w, p->cfg.residual_layers)) {
+    set_error("train_forward: null argument"); return DRB_E_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const drb_train_config& c = p->cfg;
+  const int B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size, F = c.pitches, Mp = p->Mp;
+  const size_t M = (size_t)B * T;
+  float* wtmp = p->at<float>(p->wtmp);
+  {  // spectrogram to time-major rows
+    dim3 grid((T + 31) / 32, (Mp + 31) / 32, B), block(32, 8);
+    spec_to_rows_kernel<<<grid, block, 0, s>>>(spec, p->at<float>(p->spec), B, c.n_mels, T, Mp);
+    DRB_LAUNCH_CHECK();
+  }
+  {  // diffusion embedding: table lookup, silu(projection1), silu(projection2)      model/diffwave.py:66-75
+    gather_rows_kernel<<<nblk((size_t)B * 128), 256, 0, s>>>(emb_table, steps, p->at<float>(p->e0), B, 128);
+    DRB_LAUNCH_CHECK();
+    SimtGemm g;
+    g.A = p->at<float>(p->e0); g.lda = 128; g.T = 1; g.Ck = 128; g.W = w->e1w; g.ldw = 128; g.bias = w->e1b; g.C = p->at<float>(p->p1); g.ldc = 512; g.M = B; g.N = 512;
+    TR(launch_simt_gemm(g, s));
+    g.act = 2; g.C = p->at<float>(p->s1);
+    TR(launch_simt_gemm(g, s));
+    SimtGemm h;
+    h.A = p->at<float>(p->s1); h.lda = 512; h.T = 1; h.Ck = 512; h.W = w->e2w; h.ldw = 512; h.bias = w->e2b; h.C = p->at<float>(p->p2); h.ldc = 512; h.M = B; h.N = 512;
+    TR(launch_simt_gemm(h, s));
+    h.act = 2; h.C = p->at<float>(p->emb);
+    TR(launch_simt_gemm(h, s));
+  }
+  {  // x_0 = relu(input_projection(x_t))      model/diffwave.py:667-668
+    SimtGemm g;
+    g.A = x_t; g.lda = F; g.T = T; g.Ck = F; g.W = w->in_w; g.ldw = F; g.bias = w->in_b; g.act = 1;
+    g.C = p->at<float>(p->xs); g.ldc = C; g.M = (int)M; g.N = C;
+    TR(launch_simt_gemm(g, s));
+  }
+  for (int l = 0; l < L; ++l) {
+    float* x_l = p->at<float>(p->xs) + (size_t)l * M * C;
+    float* y_l = p->at<float>(p->ys) + (size_t)l * M * 2 * C;
+    float* z_l = p->at<float>(p->zs) + (size_t)l * M * C;
+    float* d_l = p->at<float>(p->dl) + (size_t)l * B * C;
+    SimtGemm d;  // diffusion_projection(emb)   model/diffwave.py:137
+    d.A = p->at<float>(p->emb); d.lda = 512; d.T = 1; d.Ck = 512; d.W = w->wdp[l]; d.ldw = 512; d.bias = w->bdp[l]; d.C = d_l; d.ldc = C; d.M = B; d.N = C;
+    TR(launch_simt_gemm(d, s));
+    TR(launch_repack_conv_fp32(w->wd[l], wtmp, 2 * C, C, k, s));   // [2C][C][k] -> tap-major [2C][k*C]
+    SimtGemm g;  // dilated_conv(x + d)   :138-139
+    g.A = x_l; g.lda = C; g.T = T; g.taps = k; g.dil = p->dil[l]; g.Ck = C; g.addvec = d_l; g.addvec_steps = p->at<int>(p->iota);
+    g.addvec_mod = B; g.addvec_stride = C; g.W = wtmp; g.ldw = k * C; g.bias = w->bd[l]; g.C = y_l; g.ldc = 2 * C; g.M = (int)M; g.N = 2 * C;
+    TR(launch_simt_gemm(g, s));
+    TR(launch_pad_rows(w->wc[l], wtmp, 2 * C, c.n_mels, Mp, s));
+    SimtGemm q;  // + conditioner_projection(spec)   :143-144
+    q.A = p->at<float>(p->spec); q.lda = Mp; q.T = T; q.Ck = Mp; q.W = wtmp; q.ldw = Mp; q.bias = w->bc[l]; q.accumulate = 1;
+    q.C = y_l; q.ldc = 2 * C; q.M = (int)M; q.N = 2 * C;
+    TR(launch_simt_gemm(q, s));
+    TR(launch_gate(y_l, z_l, (int)M, C, s));
+    SimtGemm o;  // output_projection(z)   :149
+    o.A = z_l; o.lda = C; o.T = T; o.Ck = C; o.W = w->wo[l]; o.ldw = C; o.bias = w->bo[l]; o.C = p->at<float>(p->obuf); o.ldc = 2 * C; o.M = (int)M; o.N = 2 * C;
+    TR(launch_simt_gemm(o, s));
+    const int do_res = l < L - 1;
+    res_skip_fwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(p->at<float>(p->obuf), x_l, do_res ? x_l + M * C : nullptr, p->at<float>(p->skip), M, C,
+                                                        l == 0, do_res);
+    DRB_LAUNCH_CHECK();
+  }
+  {  // h = relu(skip_projection(skip / sqrt(L))) ; pred = output_projection(h)      :680-685
+    SimtGemm g;
+    g.A = p->at<float>(p->skip); g.lda = C; g.T = T; g.Ck = C; g.a_div = sqrtf((float)L); g.W = w->skw; g.ldw = C; g.bias = w->skb; g.act = 1;
+    g.C = p->at<float>(p->hbuf); g.ldc = C; g.M = (int)M; g.N = C;
+    TR(launch_simt_gemm(g, s));
+    SimtGemm o;
+    o.A = p->at<float>(p->hbuf); o.lda = C; o.T = T; o.Ck = C; o.W = w->hdw; o.ldw = C; o.bias = w->hdb; o.C = pred; o.ldc = F; o.M = (int)M; o.N = F;
+    TR(launch_simt_gemm(o, s));
+  }
+  p->fwd_done = true;
+  return 0;
+}
+
+// Backward pass of the last drb_train_forward.  g_pred [B][T][F] = d loss / d pred.  Every tensor of `grads` (same shapes as the
+// parameters) receives its gradient; accumulate != 0 adds to what is there (second forward of a two-dataset batch).
+// g_x_t (optional) [B][T][F] = d loss / d x_t.  The saved pre-activations y_l are overwritten (one backward per forward).
+int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_params* gr, const float* x_t, const float* g_pred,
+                       int32_t accumulate, float* g_x_t, void* stream) {
+  if (!p || !x_t || !g_pred || !params_ok(w, p->cfg.residual_layers) || !params_ok(gr, p->cfg.residual_layers)) {
+    set_error("train_backward: null argument"); return DRB_E_INVALID;
+  }
+  if (!p->fwd_done) { set_error("train_backward: no forward pass to differentiate"); return DRB_E_STATE; }
+  p->fwd_done = false;
+  cudaStream_t s = (cudaStream_t)stream;
+  const drb_train_config& c = p->cfg;
+  const int B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size, F = c.pitches, Mp = p->Mp;
+  const size_t M = (size_t)B * T;
+  float* wtmp = p->at<float>(p->wtmp);
+  if (!accumulate) {
+    auto zero = [&](float* q, size_t n) { return cudaMemsetAsync(q, 0, n * 4, s); };
+    DRB_CUDA(zero(gr->in_w, (size_t)C * F)); DRB_CUDA(zero(gr->in_b, C));
+    DRB_CUDA(zero(gr->e1w, 512 * 128)); DRB_CUDA(zero(gr->e1b, 512)); DRB_CUDA(zero(gr->e2w, 512 * 512)); DRB_CUDA(zero(gr->e2b, 512));
+    DRB_CUDA(zero(gr->skw, (size_t)C * C)); DRB_CUDA(zero(gr->skb, C)); DRB_CUDA(zero(gr->hdw, (size_t)F * C)); DRB_CUDA(zero(gr->hdb, F));
+    for (int l = 0; l < L; ++l) {
+      DRB_CUDA(zero(gr->wd[l], (size_t)2 * C * C * k)); DRB_CUDA(zero(gr->bd[l], 2 * C));
+      DRB_CUDA(zero(gr->wdp[l], (size_t)C * 512)); DRB_CUDA(zero(gr->bdp[l], C));
+      DRB_CUDA(zero(gr->wc[l], (size_t)2 * C * c.n_mels)); DRB_CUDA(zero(gr->bc[l], 2 * C));
+      DRB_CUDA(zero(gr->wo[l], (size_t)2 * C * C)); DRB_CUDA(zero(gr->bo[l], 2 * C));
+    }
+  }
+  float* h = p->at<float>(p->hbuf);
+  float* gx = p->at<float>(p->gx);        // g_x_{l+1}
+  float* gu = p->at<float>(p->gu);        // g_h, then g_u of the current layer
+  float* gz = p->at<float>(p->gz);
+  float* gskip = p->at<float>(p->gskip);
+  float* go = p->at<float>(p->obuf);      // [M][2C]
+  float* emb = p->at<float>(p->emb);
+  float* gemb = p->at<float>(p->gemb);
+  float* gd = p->at<float>(p->gd);
+  const float sqrtL = sqrtf((float)L);
+  // ---- head: output_projection, ReLU, skip_projection(skip / sqrt(L))      model/diffwave.py:680-685 ----
+  {
+    Wgrad a;
+    a.G = g_pred; a.ldg = F; a.X = h; a.ldx = C; a.M = (int)M; a.T = T; a.N = F; a.Ck = C; a.dW = gr->hdw; a.sn = C;
+    TR(launch_wgrad(a, s));
+    TR(launch_colsum(g_pred, F, F, 1, (int)M, gr->hdb, F, s));
+    TR(launch_transpose(w->hdw, wtmp, F, C, s));                    // [F][C] -> [C][F]
+    SimtGemm g;                                                     // g_h = g_pred . W_out
+    g.A = g_pred; g.lda = F; g.T = T; g.Ck = F; g.W = wtmp; g.ldw = F; g.C = gu; g.ldc = C; g.M = (int)M; g.N = C;
+    TR(launch_simt_gemm(g, s));
+    relu_bwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gu, h, M * C / 4, 1.f);
+    DRB_LAUNCH_CHECK();
+    Wgrad b;
+    b.G = gu; b.ldg = C; b.X = p->at<float>(p->skip); b.ldx = C; b.M = (int)M; b.T = T; b.N = C; b.Ck = C; b.dW = gr->skw; b.sn = C;
+    b.out_scale = 1.f / sqrtL;
+    TR(launch_wgrad(b, s));
+    TR(launch_colsum(gu, C, C, 1, (int)M, gr->skb, C, s));
+    TR(launch_transpose(w->skw, wtmp, C, C, s));
+    SimtGemm q;                                                     // g_skip = (g_hp . W_sp) / sqrt(L), the same for every layer
+    q.A = gu; q.lda = C; q.T = T; q.Ck = C; q.a_div = sqrtL; q.W = wtmp; q.ldw = C; q.C = gskip; q.ldc = C; q.M = (int)M; q.N = C;
+    TR(launch_simt_gemm(q, s));
+  }
+  // ---- residual layers, last to first      model/diffwave.py:134-151 ----
+  for (int l = L - 1; l >= 0; --l) {
+    float* x_l = p->at<float>(p->xs) + (size_t)l * M * C;
+    float* y_l = p->at<float>(p->ys) + (size_t)l * M * 2 * C;       // becomes g_y in place
+    float* z_l = p->at<float>(p->zs) + (size_t)l * M * C;
+    float* d_l = p->at<float>(p->dl) + (size_t)l * B * C;
+    const int has_res = l < L - 1;                                   // the last layer's residual output is never used (:676-680)
+    make_go_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gx, gskip, go, M, C, has_res);
+    DRB_LAUNCH_CHECK();
+    Wgrad a;                                                         // output_projection: weight [2C][C][1], bias
+    a.G = go; a.ldg = 2 * C; a.X = z_l; a.ldx = C; a.M = (int)M; a.T = T; a.N = 2 * C; a.Ck = C; a.dW = gr->wo[l]; a.sn = C;
+    TR(launch_wgrad(a, s));
+    TR(launch_colsum(go, 2 * C, 2 * C, 1, (int)M, gr->bo[l], 2 * C, s));
+    TR(launch_transpose(w->wo[l], wtmp, 2 * C, C, s));               // [2C][C] -> [C][2C]
+    SimtGemm g;                                                      // g_z = g_o . W_o
+    g.A = go; g.lda = 2 * C; g.T = T; g.Ck = 2 * C; g.W = wtmp; g.ldw = 2 * C; g.C = gz; g.ldc = C; g.M = (int)M; g.N = C;
+    TR(launch_simt_gemm(g, s));
+    gate_bwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(y_l, gz, y_l, M, C);
+    DRB_LAUNCH_CHECK();
+    const float* gy = y_l;
+    TR(launch_colsum(gy, 2 * C, 2 * C, 1, (int)M, gr->bd[l], 2 * C, s));     // dilated_conv.bias
+    TR(launch_colsum(gy, 2 * C, 2 * C, 1, (int)M, gr->bc[l], 2 * C, s));     // conditioner_projection.bias (added to the same y)
+    Wgrad cw;                                                        // conditioner_projection.weight [2C][n_mels][1]
+    cw.G = gy; cw.ldg = 2 * C; cw.X = p->at<float>(p->spec); cw.ldx = Mp; cw.M = (int)M; cw.T = T; cw.N = 2 * C; cw.Ck = c.n_mels;
+    cw.dW = gr->wc[l]; cw.sn = c.n_mels;
+    TR(launch_wgrad(cw, s));
+    Wgrad dw;                                                        // dilated_conv.weight [2C][C][k]: the forward's tap gather of x + d
+    dw.G = gy; dw.ldg = 2 * C; dw.X = x_l; dw.ldx = C; dw.addvec = d_l; dw.av_stride = C; dw.M = (int)M; dw.T = T; dw.N = 2 * C; dw.Ck = C;
+    dw.taps = k; dw.dil = p->dil[l]; dw.dW = gr->wd[l]; dw.sn = (long long)C * k; dw.sc = k; dw.st = 1;
+    TR(launch_wgrad(dw, s));
+    {                                                                // g_u = transposed dilated conv of g_y
+      const size_t n = (size_t)2 * C * C * k;
+      repack_dgrad_kernel<<<nblk(n), 256, 0, s>>>(w->wd[l], wtmp, 2 * C, C, k);
+      DRB_LAUNCH_CHECK();
+      SimtGemm u;
+      u.A = gy; u.lda = 2 * C; u.T = T; u.taps = k; u.dil = p->dil[l]; u.Ck = 2 * C; u.W = wtmp; u.ldw = k * 2 * C; u.C = gu; u.ldc = C;
+      u.M = (int)M; u.N = C;
+      TR(launch_simt_gemm(u, s));
+    }
+    // diffusion_projection: d enters only through the conv input x + d (broadcast over the frames of a roll)
+    DRB_CUDA(cudaMemsetAsync(gd, 0, (size_t)B * C * 4, s));
+    TR(launch_colsum(gu, C, C, B, T, gd, C, s));
+    Wgrad pw;
+    pw.G = gd; pw.ldg = C; pw.X = emb; pw.ldx = 512; pw.M = B; pw.T = 1; pw.N = C; pw.Ck = 512; pw.dW = gr->wdp[l]; pw.sn = 512;
+    TR(launch_wgrad(pw, s));
+    TR(launch_colsum(gd, C, C, 1, B, gr->bdp[l], C, s));
+    TR(launch_transpose(w->wdp[l], wtmp, C, 512, s));                // [C][512] -> [512][C]
+    SimtGemm e;
+    e.A = gd; e.lda = C; e.T = 1; e.Ck = C; e.W = wtmp; e.ldw = C; e.C = gemb; e.ldc = 512; e.M = B; e.N = 512; e.accumulate = l < L - 1;
+    TR(launch_simt_gemm(e, s));
+    if (has_res) {
+      add_res_grad_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gu, gx, M * C / 4);
+      DRB_LAUNCH_CHECK();
+    }
+    float* t = gx; gx = gu; gu = t;                                  // gx now holds g_x_l
+  }
+  // ---- input projection + ReLU      model/diffwave.py:667-668 ----
+  {
+    relu_bwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gx, p->at<float>(p->xs), M * C / 4, 1.f);
+    DRB_LAUNCH_CHECK();
+    Wgrad a;
+    a.G = gx; a.ldg = C; a.X = x_t; a.ldx = F; a.M = (int)M; a.T = T; a.N = C; a.Ck = F; a.dW = gr->in_w; a.sn = F;
+    TR(launch_wgrad(a, s));
+    TR(launch_colsum(gx, C, C, 1, (int)M, gr->in_b, C, s));
+    if (g_x_t) {
+      TR(launch_transpose(w->in_w, wtmp, C, F, s));                  // [C][F] -> [F][C]
+      SimtGemm g;
+      g.A = gx; g.lda = C; g.T = T; g.Ck = C; g.W = wtmp; g.ldw = C; g.C = g_x_t; g.ldc = F; g.M = (int)M; g.N = F;
+      TR(launch_simt_gemm(g, s));
+    }
+  }
+  // ---- diffusion embedding MLP      model/diffwave.py:66-75 ----
+  {
+    float* gs = p->at<float>(p->gsmall);
+    silu_bwd_kernel<<<nblk((size_t)B * 512), 256, 0, s>>>(gemb, p->at<float>(p->p2), (size_t)B * 512);
+    DRB_LAUNCH_CHECK();
+    Wgrad a;
+    a.G = gemb; a.ldg = 512; a.X = p->at<float>(p->s1); a.ldx = 512; a.M = B; a.T = 1; a.N = 512; a.Ck = 512; a.dW = gr->e2w; a.sn = 512;
+    TR(launch_wgrad(a, s));
+    TR(launch_colsum(gemb, 512, 512, 1, B, gr->e2b, 512, s));
+    TR(launch_transpose(w->e2w, wtmp, 512, 512, s));
+    SimtGemm g;
+    g.A = gemb; g.lda = 512; g.T = 1; g.Ck = 512; g.W = wtmp; g.ldw = 512; g.C = gs; g.ldc = 512; g.M = B; g.N = 512;
+    TR(launch_simt_gemm(g, s));
+    silu_bwd_kernel<<<nblk((size_t)B * 512), 256, 0, s>>>(gs, p->at<float>(p->p1), (size_t)B * 512);
+    DRB_LAUNCH_CHECK();
+    Wgrad b;
+    b.G = gs; b.ldg = 512; b.X = p->at<float>(p->e0); b.ldx = 128; b.M = B; b.T = 1; b.N = 512; b.Ck = 128; b.dW = gr->e1w; b.sn = 128;
+    TR(launch_wgrad(b, s));
+    TR(launch_colsum(gs, 512, 512, 1, B, gr->e1b, 512, s));
+  }
+  return 0;
+}
+
+// d loss / d prediction of p_losses (task/diffusion.py:792-802; loss_type 0 l1, 1 l2, 2 huber), mean over all n elements, optionally
+// times a per-roll factor (training mode 'ex_0').  label, pred, g_pred: n floats; roll_scale: n / per_roll floats or NULL.
+int drb_loss_grad(const float* label, const float* pred, float* g_pred, size_t n, size_t per_roll, int32_t loss_type,
+                  const float* roll_scale, void* stream) {
+  if (!label || !pred || !g_pred || n == 0 || per_roll == 0 || loss_type < 0 || loss_type > 2) { set_error("loss_grad: bad argument"); return DRB_E_INVALID; }
+  loss_grad_kernel<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(label, pred, g_pred, n, per_roll, loss_type, roll_scale, 1.f / (float)n);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// One Adam update of a parameter tensor (torch.optim.Adam defaults: betas (0.9, 0.999), eps 1e-8, weight_decay 0, amsgrad off).
+// step = 1 for the first update.  task/diffusion.py:1057-1059
+int drb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int32_t step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) { set_error("adam: bad argument"); return DRB_E_INVALID; }
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                         (float)sqrt(bc2));
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
   }
   if (warp == 3) {
     for (int i = lane; i < TILE_N; i += 32) {
-      sv.sbias[i] = __ldg(p.bias + n_base + i);
+      sv.sbias[i] = p.bias ? __ldg(p.bias + n_base + i) : 0.f;
       if (res) sv.sdn[i] = __ldg(p.dnext + (size_t)(p.steps ? __ldg(p.steps + nb % p.bsamp) : p.t_uniform) * p.C + n_base + i);
     }
   }
@@ -1290,17 +1290,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
         for (int v = 0; v < 8; ++v) {
           const int i = v * 4;
           float4 h;
-          h.x = fmaxf(o[i + 0] + bs[i + 0], 0.f);
-          h.y = fmaxf(o[i + 1] + bs[i + 1], 0.f);
-          h.z = fmaxf(o[i + 2] + bs[i + 2], 0.f);
-          h.w = fmaxf(o[i + 3] + bs[i + 3], 0.f);
+          const float floor_ = p.mode == 2 ? -INFINITY : 0.f;   // HEAD: ReLU; conditioner tables: linear
+          h.x = fmaxf(o[i + 0] + bs[i + 0], floor_);
+          h.y = fmaxf(o[i + 1] + bs[i + 1], floor_);
+          h.z = fmaxf(o[i + 2] + bs[i + 2], floor_);
+          h.w = fmaxf(o[i + 3] + bs[i + 3], floor_);
           sts128(box + sw128_off(row, v), h);
         }
       }
       fence_proxy_async();
       named_bar_sync(EPI_BAR, EPI_THREADS);
       if (issuer) {
-        const int c0 = n_base + it * 64;
+        // mode 2: the weight rows of an N block are [128 gate | 128 filter] channels; the table keeps the natural order
+        const int c0 = p.mode == 2 ? (it < 2 ? nblk * (TILE_N / 2) + it * 64 : p.C / 2 + nblk * (TILE_N / 2) + (it - 2) * 64)
+                                   : n_base + it * 64;
         tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2), c0, t0, nb);
         tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2 + 1), c0 + 32, t0, nb);
         if (res) {
@@ -1773,7 +1776,11 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   ZGemmParams p;
   p.zh = maps.zh; p.zl = maps.zl; p.w_h = *z.w_h; p.w_l = *z.w_l; p.out32 = *z.out32; p.xh = maps.xh; p.xl = maps.xl;
   p.NB = z.NB; p.T = z.T; p.C = z.C; p.tiles_t = (z.T + TILE_M - 1) / TILE_M; p.n_blocks = z.C / TILE_N;
-  p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg; p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
+  p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg;
+  if (z.mode == 2) {   // conditioner tables: A = spectrogram pair, C counts the 2C output channels, K = nslabs64 slabs
+    if (!z.a_h || !z.a_l || z.nslabs64 <= 0) { set_error("umma_zgemm: mode 2 needs the spectrogram maps"); return DRB_E_INVALID; }
+    p.zh = *z.a_h; p.zl = *z.a_l; p.spg = z.nslabs64; p.nslabs = z.nslabs64;
+  } p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
   p.range_max = z.range_max; p.xs = nullptr;
   const int grid = p.NB * p.tiles_t * p.n_blocks;

@@ -158,10 +158,12 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
     def _weights_version(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
-    def _engine(self, batch, frames, wave_len, device):
+    def _engine(self, batch, frames, wave_len, device, any_version=False):
         key = (batch, frames, wave_len, self.precision, str(device))
-        ver = self._weights_version()
         ent = self._engines.get(key)
+        if ent is not None and any_version:      # mel front-end only (training step): it has no trainable tensors
+            return ent[0]
+        ver = self._weights_version()
         if ent is not None and ent[1] == ver:
             return ent[0]
         if ent is not None:
@@ -176,8 +178,9 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         self._mel_key = None
         return eng
 
-    def _prepare(self, x, waveform, branches, inpainting_t=None, inpainting_f=None):
-        """Pick the engine for these shapes, run the (cached) mel front-end, select branches."""
+    def _prepare(self, x, waveform, branches, inpainting_t=None, inpainting_f=None, mel_only=False):
+        """Pick the engine for these shapes, run the (cached) mel front-end, select branches.  mel_only: the caller wants
+        the spectrogram alone (training step), so an engine built from older parameter values is good enough."""
         if not x.is_cuda:
             raise _lib.DrbError("ClassifierFreeDiffRoll (diffroll_b200) runs on CUDA tensors only; there is no CPU path")
         B, _, T, Fp = x.shape
@@ -187,7 +190,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         wave_len = waveform.shape[-1]
         n_frames = wave_len // sa["hop_length"] + 1
         T_min = min(T, n_frames)                                  # trim_spec_roll, model/diffwave.py:30-39,662
-        eng = self._engine(B, T_min, wave_len, x.device)
+        eng = self._engine(B, T_min, wave_len, x.device, any_version=mel_only)
         xx = x.to(torch.float32)
         if T_min != T:
             xx = xx[:, :, :T_min, :]
@@ -253,7 +256,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         """model/diffwave.py:637-686.  ``diffusion_step``: int64[B]; the samplers pass one value repeated
         (``tensor(t).repeat(B)``), the training / validation step a different one per roll (task/diffusion.py:667)."""
         if self.training:
-            raise NotImplementedError("training-mode forward (spec dropout, autograd) is outside the sampling hot path; call .eval()")
+            return self._forward_training(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)
         if torch.is_tensor(diffusion_step):
             if diffusion_step.dtype not in (torch.int32, torch.int64):
                 raise NotImplementedError("fractional diffusion steps (_lerp_embedding) are not on the sampling path")
@@ -280,6 +283,24 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             self._range_fallback()
             return self.forward(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)
         return pred, spec
+
+    def _forward_training(self, x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f, dropout_mask=None):
+        """model/diffwave.py:637-686 with ``self.training`` set: spec dropout (:646-647), then the fp32 training forward that
+        keeps its activations for ``TrainEngine.backward`` (csrc/train.cu).  No autograd graph is attached to the result."""
+        if not torch.is_tensor(diffusion_step) or diffusion_step.dtype not in (torch.int32, torch.int64):
+            raise NotImplementedError("fractional diffusion steps (_lerp_embedding) are not built")
+        _, _, spec = self._prepare(x_t, waveform, _lib.BRANCH_COND, inpainting_t, inpainting_f, mel_only=True)
+        if spec.shape[-1] != x_t.shape[2]:
+            raise NotImplementedError("training forward: the clip must cover the whole roll (trim_spec_roll would shorten it)")
+        spec = self.uncon_dropout(spec.clone(), self.hparams.spec_dropout, mask=dropout_mask)
+        if inpainting_t or inpainting_f:     # the masks were applied before the dropout in the cached spectrogram; re-apply (:649-654)
+            t0, t1 = (int(inpainting_t[0]), int(inpainting_t[1])) if inpainting_t else (0, spec.shape[2])
+            f0, f1 = (int(inpainting_f[0]), int(inpainting_f[1])) if inpainting_f else (0, spec.shape[1])
+            spec[:, f0:f1, t0:t1] = -1
+        if sampling is True:
+            spec = torch.full_like(spec, -1.0)
+        eng = self._train_engine(x_t.shape[0], x_t.shape[2])
+        return eng.forward(x_t, spec, diffusion_step.flatten()), spec
 
     def train(self, mode=True):
         return super().train(mode)

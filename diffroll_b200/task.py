@@ -269,6 +269,8 @@ class SpecRollDiffusion(nn.Module):
             eng.close()
         if hasattr(self, "_engines"):
             self._engines.clear()
+        for eng in self.__dict__.pop("_train_engines", {}).values():
+            eng.close()
 
     @torch.no_grad()
     def predict_step(self, batch, batch_idx=0, generator=None, shard=None):
@@ -394,6 +396,110 @@ class SpecRollDiffusion(nn.Module):
         tensors.update(pred_roll=pred_roll, label_roll=roll, spec=spec)
         return losses, tensors
 
+    # ---- training step ------------------------------------------------------------------
+    def fixed_dropout(self, x, p, masked_value=-1, mask=None):
+        """model/diffwave.py:689-693: every roll's conditioning is replaced by ``masked_value`` with probability ``p``.
+        The reference samples ``torch.distributions.Bernoulli(probs=p).sample((B,))``, i.e. B draws from the CPU generator;
+        ``torch.bernoulli`` over a CPU vector of p consumes the generator identically.  ``mask`` ([B], nonzero = drop)
+        overrides the draw (parity tests)."""
+        if mask is None:
+            mask = torch.bernoulli(torch.full((x.shape[0],), float(p)))
+        drop = mask.to(device=x.device).bool()
+        x[drop] = masked_value
+        return x
+
+    uncon_dropout = fixed_dropout        # condition == 'fixed' (model/diffwave.py:617)
+
+    def _train_engine(self, batch, frames):
+        from .train import TrainEngine
+        key = (int(batch), int(frames), str(next(self.parameters()).device))
+        cache = self.__dict__.setdefault("_train_engines", {})
+        eng = cache.get(key)
+        if eng is None:
+            for old in list(cache.values()):      # one training shape at a time: a workspace is gigabytes
+                old.close()
+            cache.clear()
+            eng = cache[key] = TrainEngine(self, batch, frames)
+        return eng
+
+    @torch.no_grad()
+    def training_step(self, batch, batch_idx=0, t=None, noise=None, dropout_mask=None, want_input_grad=False):
+        """task/diffusion.py:258-270 + ``step`` :651-763 in training mode: draw a diffusion step per roll, ``q_sample`` the
+        normalised label roll, the network forward WITH spec dropout (model/diffwave.py:646-647), the losses of
+        ``hparams.loss_keys`` -- and, because there is no autograd graph here, the whole backward pass: on return every
+        parameter's ``.grad`` holds d(total loss)/d(parameter) (added to an existing gradient, like ``loss.backward()``).
+        Returns the total loss (0-dim CUDA tensor).  ``t`` / ``noise`` / ``dropout_mask`` default to the reference's draws
+        and can be injected for parity tests; the last step's (losses, tensors) are kept in ``self.last_step``."""
+        from .diffusion_ops import extract_x0, q_sample
+        from .train import loss_grad
+        two = isinstance(batch, list)
+        first = batch[0] if two else batch
+        roll = self.normalize(first["frame"]).unsqueeze(1)
+        waveform = first["audio"]
+        B, _, T, _ = roll.shape
+        device = roll.device
+        if t is None:
+            t = torch.randint(0, self.hparams.timesteps, (B,), device=device).long()
+        if noise is None:
+            noise = torch.randn_like(roll)
+        sa, s1 = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
+        x_t = q_sample(roll, t, sa, s1, noise)
+        mode = self.hparams.training.mode
+        if self.hparams.debug:
+            raise NotImplementedError("debug=True conditions on the label roll (DiffRollDebug); not on this path")
+        if mode not in ("epsilon", "x_0", "ex_0"):
+            raise ValueError(f"training mode {mode} is not supported. Please either use 'x_0' or 'epsilon'.")
+        from . import _lib
+        _, _, spec = self._prepare(x_t, waveform, _lib.BRANCH_COND, self.hparams.inpainting_t, self.hparams.inpainting_f, mel_only=True)
+        if spec.shape[-1] != T:
+            raise NotImplementedError("training step: the clip must cover the whole roll (trim_spec_roll would shorten it)")
+        spec = spec.clone()
+        if self.training:                                  # model/diffwave.py:646-647
+            spec = self.uncon_dropout(spec, self.hparams.spec_dropout, mask=dropout_mask)
+        eng = self._train_engine(B, T)
+        keys = list(self.hparams.loss_keys)
+        losses, tensors = {}, {}
+        net = eng.forward(x_t, spec, t)
+        acc = any(q.grad is not None for q in self.parameters())
+        if mode == "epsilon":
+            losses["diffusion_loss"] = self.p_losses(noise, net, loss_type=self.hparams.loss_type)
+            g = loss_grad(noise, net, self.hparams.loss_type)
+            pred_roll = extract_x0(x_t, net, t, sa, s1)
+        elif mode == "x_0":
+            pred_roll = net
+            losses["diffusion_loss"] = self.p_losses(roll, pred_roll, loss_type=self.hparams.loss_type)
+            g = loss_grad(roll, pred_roll, self.hparams.loss_type)
+        else:                                              # 'ex_0': the loss is taken on x0 extracted from the predicted noise
+            pred_roll = extract_x0(x_t, net, t, sa, s1)
+            losses["diffusion_loss"] = self.p_losses(roll, pred_roll, loss_type=self.hparams.loss_type)
+            scale = -(s1.to(device)[t] / sa.to(device)[t])
+            g = loss_grad(roll, pred_roll, self.hparams.loss_type, roll_scale=scale)
+        gx = None
+        if "diffusion_loss" in keys:
+            gx = eng.backward(g, accumulate=acc, want_input_grad=want_input_grad)
+            acc = True
+        tensors.update(pred_roll=pred_roll, label_roll=roll, spec=spec)
+        if two and mode == "x_0":                          # second dataset: one more, unconditional, forward (:707-719)
+            roll2 = self.normalize(batch[1]["frame"]).unsqueeze(1)
+            x_t2 = q_sample(roll2, t, sa, s1, noise)
+            spec2 = torch.full_like(spec, -1.0)            # sampling=True, model/diffwave.py:656-660
+            pred_roll2 = eng.forward(x_t2, spec2, t)
+            losses["unconditional_diffusion_loss"] = self.p_losses(roll2, pred_roll2, loss_type=self.hparams.loss_type)
+            if "unconditional_diffusion_loss" in keys:
+                eng.backward(loss_grad(roll2, pred_roll2, self.hparams.loss_type), accumulate=acc)
+            tensors.update(spec2=spec2, label_roll2=roll2, pred_roll2=pred_roll2)
+        total_loss = 0
+        for k in keys:
+            total_loss = total_loss + losses[k]
+            self.log(f"Train/{k}", losses[k])
+        self.last_step = (losses, tensors, gx)
+        return total_loss
+
+    def configure_optimizers(self):
+        """task/diffusion.py:1057-1067: ``torch.optim.Adam(self.parameters(), lr=self.hparams.lr)`` as fused CUDA updates."""
+        from .train import Adam
+        return [Adam(self.parameters(), lr=self.hparams.lr)]
+
     @torch.no_grad()
     def validation_step(self, batch, batch_idx=0):
         """task/diffusion.py:271-276 without the figure logging: returns the summed loss over ``hparams.loss_keys``."""
@@ -418,7 +524,7 @@ class SpecRollDiffusion(nn.Module):
     def _step(self, x, waveform, t_index, upd, branches, noise=None, inpainting_t=None, inpainting_f=None):
         raise NotImplementedError
 
-    def _prepare(self, x, waveform, branches, inpainting_t=None, inpainting_f=None):
+    def _prepare(self, x, waveform, branches, inpainting_t=None, inpainting_f=None, mel_only=False):
         raise NotImplementedError
 
 

@@ -220,6 +220,52 @@ int drb_p_losses(const float* label, const float* prediction, int64_t n, int32_t
                  float* loss_out, void* stream);
 int drb_normalize_imagewise(const float* x, float* out, int32_t B, int64_t n_per, float lo, float hi, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step, SURVEY section 8 row f3: forward with saved activations, backward to all 132 state_dict tensors, Adam.
+ *   reference: SpecRollDiffusion.step / training_step   task/diffusion.py:258-270, 651-763   (loss: p_losses :792-802)
+ *              ClassifierFreeDiffRoll.forward, training mode (spec dropout)   model/diffwave.py:637-699
+ *              configure_optimizers = torch.optim.Adam(lr)                    task/diffusion.py:1057-1059
+ * fp32 CUDA-core arithmetic (the reference trains in fp32).  The parameter / gradient structs hold DEVICE pointers to
+ * tensors in the reference's own state_dict layout (conv weights [out][in][k], linear weights [out][in]); the arrays
+ * wd ... bo are HOST arrays of residual_layers device pointers.  Gradients are accumulated with fp32 atomics (the
+ * summation order, hence the last bits, can differ from run to run). */
+typedef struct drb_train_config {
+  int32_t batch, frames, pitches, residual_channels, residual_layers, kernel_size, dilation_base, dilation_bound, n_mels,
+          timesteps;
+} drb_train_config;
+
+typedef struct drb_train_params {
+  float *in_w, *in_b;                 /* input_projection            [C][88][1], [C]            model/diffwave.py:597  */
+  float *e1w, *e1b, *e2w, *e2b;       /* diffusion_embedding.projection1 [512][128], projection2 [512][512]  :62-63 */
+  float *skw, *skb;                   /* skip_projection             [C][C][1], [C]                          :628   */
+  float *hdw, *hdb;                   /* output_projection           [88][C][1], [88]                        :629   */
+  float *const *wd, *const *bd;       /* residual_layers.l.dilated_conv          [2C][C][k], [2C]            :112   */
+  float *const *wdp, *const *bdp;     /* residual_layers.l.diffusion_projection  [C][512], [C]               :118   */
+  float *const *wc, *const *bc;       /* residual_layers.l.conditioner_projection [2C][n_mels][1], [2C]      :120   */
+  float *const *wo, *const *bo;       /* residual_layers.l.output_projection     [2C][C][1], [2C]            :124   */
+} drb_train_params;
+
+typedef struct drb_train drb_train;
+
+size_t drb_train_workspace_bytes(const drb_train_config* cfg);
+int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspace, size_t workspace_bytes, void* stream);
+void drb_train_destroy(drb_train* plan);
+/* x_t [B][T][88]; spec [B][n_mels][T] exactly as the network sees it (normalised log-mel, spec-dropout rolls and masks
+ * already -1); steps int32[B]; emb_table [timesteps][128] (DiffusionEmbedding._build_embedding); pred [B][T][88]. */
+int drb_train_forward(drb_train* plan, const drb_train_params* params, const float* x_t, const float* spec,
+                      const int32_t* steps, const float* emb_table, float* pred, void* stream);
+/* Backward of the last drb_train_forward: g_pred = d loss / d pred [B][T][88]; every tensor of grads receives its gradient
+ * (accumulate != 0: added to its content); g_x_t (optional) = d loss / d x_t. */
+int drb_train_backward(drb_train* plan, const drb_train_params* params, const drb_train_params* grads, const float* x_t,
+                       const float* g_pred, int32_t accumulate, float* g_x_t, void* stream);
+/* d p_losses / d prediction (loss_type 0 l1, 1 l2, 2 huber; mean over n), times roll_scale[i / per_roll] when given
+ * (training mode 'ex_0': d extract_x0 / d epsilon = -sqrt_one_minus_alphas_cumprod[t] / sqrt_alphas_cumprod[t]). */
+int drb_loss_grad(const float* label, const float* pred, float* g_pred, size_t n, size_t per_roll, int32_t loss_type,
+                  const float* roll_scale, void* stream);
+/* One torch.optim.Adam update of one tensor (amsgrad off); step = 1 for the first update. */
+int drb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
 /* Measurement hooks (bench.py): with profiling enabled every step records CUDA events on the launching stream
  * around each kernel class; drb_plan_profile_read synchronises and returns, for class k in
  * {0: gate kernel, 1: out kernel, 2: in_proj, 3: head}, the summed milliseconds and the number of spans. */

@@ -110,11 +110,14 @@ class OracleDiffRoll:
         spec = torch.log(spec + 1e-6)
         return normalize_imagewise(spec, 0.0, 1.0)
 
-    def forward(self, x_t, waveform, diffusion_step, sampling=False, inpainting_t=None, inpainting_f=None):
-        """model/diffwave.py:637-686."""
+    def forward(self, x_t, waveform, diffusion_step, sampling=False, inpainting_t=None, inpainting_f=None, dropout_mask=None):
+        """model/diffwave.py:637-686.  dropout_mask ([B], nonzero = drop): the training-mode spec dropout of :646-647 /
+        fixed_dropout :689-693 with the Bernoulli draw injected."""
         sd = self.sd
         x_t = x_t.to(self.dtype).squeeze(1).transpose(1, 2)
         spec = self.spec_frontend(waveform)
+        if dropout_mask is not None:
+            spec[dropout_mask.to(spec.device).bool()] = -1
         if inpainting_t and inpainting_f is None:
             spec[:, :, int(inpainting_t[0]):int(inpainting_t[1])] = -1
         elif inpainting_t is None and inpainting_f:
@@ -288,6 +291,50 @@ class OracleDiffRoll:
             raise ValueError(mode)
         tensors.update(pred_roll=pred_roll, label_roll=roll, spec=spec)
         return losses, tensors
+
+    # ---- training step with autograd: task/diffusion.py:258-270 over step :651-763 in training mode ---------------
+    def train_step(self, batch, t, noise, dropout_mask=None, want_input_grad=False):
+        """Total loss over hp['loss_keys'] and its gradient with respect to every parameter tensor (torch autograd over the
+        restated forward), with t / noise / the spec-dropout mask injected.  Returns (losses, grads: name -> tensor, g_x_t)."""
+        hp, s = self.hp, self.sched
+        two = isinstance(batch, list)
+        first = batch[0] if two else batch
+        lo, hi = hp["norm_args"][0], hp["norm_args"][1]
+        with torch.no_grad():
+            roll = normalize_imagewise(first["frame"].to(self.dtype), lo, hi).unsqueeze(1)
+            a = s.sqrt_alphas_cumprod[t][:, None, None, None].to(device=roll.device, dtype=self.dtype)
+            b = s.sqrt_one_minus_alphas_cumprod[t][:, None, None, None].to(device=roll.device, dtype=self.dtype)
+            nz = noise.to(self.dtype)
+            x_t = a * roll + b * nz
+        names = [k for k in self.sd if not k.startswith("mel_layer.")]
+        saved = {k: self.sd[k] for k in names}
+        leaves = {k: saved[k].detach().clone().requires_grad_(True) for k in names}
+        self.sd.update(leaves)
+        x_in = x_t.clone().requires_grad_(want_input_grad)
+        fn = {"l1": F.l1_loss, "l2": F.mse_loss, "huber": F.smooth_l1_loss}[hp["loss_type"]]
+        try:
+            with torch.enable_grad():
+                mode = hp["training"]["mode"]
+                losses = {}
+                net, _ = self(x_in, first["audio"], t, dropout_mask=dropout_mask)
+                if mode == "epsilon":
+                    losses["diffusion_loss"] = fn(nz, net)
+                elif mode == "x_0":
+                    losses["diffusion_loss"] = fn(roll, net)
+                    if two:
+                        roll2 = normalize_imagewise(batch[1]["frame"].to(self.dtype), lo, hi).unsqueeze(1)
+                        net2, _ = self(a * roll2 + b * nz, batch[1]["audio"], t, sampling=True)
+                        losses["unconditional_diffusion_loss"] = fn(roll2, net2)
+                elif mode == "ex_0":
+                    losses["diffusion_loss"] = fn(roll, (x_in - b * net) / a)
+                else:
+                    raise ValueError(mode)
+                total = sum(losses[k] for k in hp["loss_keys"])
+                total.backward()
+        finally:
+            self.sd.update(saved)
+        grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+        return {k: v.detach() for k, v in losses.items()}, grads, (x_in.grad if want_input_grad else None)
 
     # ---- the loop (task/diffusion.py:513-534), noise[i] used at the i-th step with t>0 -------
     @torch.no_grad()
