@@ -439,6 +439,65 @@ def gpu_eager_baseline(ctx):
     return res
 
 
+def train_step_extra(ctx, B=16, iters=3):
+    """SURVEY.md section 8 row f3, measured beside the headline: one training step (training_step + fused Adam; fp32 CUDA-core
+    forward + hand-written backward, csrc/train.cu) on B rolls x 640 frames, against torch autograd over the oracle +
+    torch.optim.Adam run eagerly on this GPU (cuDNN / cuBLAS) in fp32 with TF32 off (same arithmetic grade) and on."""
+    torch = ctx.torch
+    import diffroll_b200 as M
+    from diffroll_b200.synthetic import default_hparams, make_labelled_batch, make_state_dict
+    from oracle.diffroll_oracle import OracleDiffRoll
+    hp = default_hparams(); hp["lr"] = 1e-4
+    frame, audio, _, noise = make_labelled_batch(B=B, T=FRAMES, wav_len=WAVE_LEN, seed=5)
+    t = ((torch.arange(B) * 37) % hp["timesteps"]).to(ctx.dev)
+    batch = {"frame": frame.to(ctx.dev), "audio": audio.to(ctx.dev)}
+    nz = noise.to(ctx.dev)
+    mask = (torch.arange(B) % 4 == 1).long()
+    res = {"what": f"one training step (forward with spec dropout, backward to 130 tensors, Adam) on {B} rolls x {FRAMES} frames; "
+                   "ours = fp32 CUDA cores; eager = torch autograd over the oracle + torch.optim.Adam on this GPU",
+           "batch": B, "algorithmic_tflop_per_step": 3 * FLOP_BRANCH * B / 1e12}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    m = M.ClassifierFreeDiffRoll(**hp); m.load_state_dict(make_state_dict(hp)); m = m.to(ctx.dev).train()
+    opt = m.configure_optimizers()[0]
+
+    def ours():
+        opt.zero_grad(); m.training_step(batch, 0, t=t, noise=nz, dropout_mask=mask); opt.step()
+    res["ours_ms"] = timed(ours)
+    res["ours_steps_per_s"] = 1000.0 / res["ours_ms"]
+    res["workspace_bytes"] = list(m._train_engines.values())[0].workspace_bytes
+    m.release_buffers(); del m, opt
+    torch.cuda.empty_cache()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, flag in (("eager_fp32_ms", False), ("eager_tf32_ms", True)):
+            torch.backends.cudnn.allow_tf32 = flag; torch.backends.cuda.matmul.allow_tf32 = flag
+            orc = OracleDiffRoll(hp, make_state_dict(hp), device=ctx.dev)
+            params = {k: torch.nn.Parameter(v.clone()) for k, v in orc.sd.items() if not k.startswith("mel_layer.")}
+            ropt = torch.optim.Adam(params.values(), lr=hp["lr"])
+
+            def ref():
+                orc.sd.update({k: q.data for k, q in params.items()})
+                _, grads, _ = orc.train_step(batch, t.cpu(), nz, dropout_mask=mask)
+                for k, q in params.items():
+                    q.grad = grads[k]
+                ropt.step()
+            res[name] = timed(ref)
+            del orc, params, ropt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return res
+
+
 def run_b200(args, rank, world, local):
     import torch
     from diffroll_b200 import build as _build
@@ -495,6 +554,10 @@ def run_b200(args, rank, world, local):
                 extras["gpu_eager_baseline"] = gpu_eager_baseline(ctx)
             except Exception as e:
                 extras["gpu_eager_baseline"] = {"error": repr(e)}
+            try:
+                extras["train_step"] = train_step_extra(ctx)
+            except Exception as e:
+                extras["train_step"] = {"error": repr(e)}
         ctx.barrier()
 
     if rank != 0:

@@ -886,16 +886,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_pers_kernel(const __
 //   * the scale factors take TMEM columns, so there is ONE accumulator stage: the epilogue warps (216 registers each, taken
 //     from the producer warps with setmaxnreg) drain the whole accumulator into registers and hand it back at once; the
 //     next tile's MMAs wait ~1 us per tile instead of overlapping the whole epilogue.
-//   smem: 2 windows x (24 + 12 KB) | 3 weight stages x (16 + 8 + 2 KB) | 2 SF images x 3 KB | 64 KB staging
+//   * FOUR weight stages: a K-slab is only 768 MMA cycles, so the 3-stage ring of the f16e5 kernel (3072 cycles of cover
+//     there) would cover 2304 cycles of TMA round trip; the staging area shrinks to two boxes (main boxes, then aux
+//     boxes from registers) to make room.
+//   smem: 2 windows x (24 + 12 KB) | 4 weight stages x (16 + 8 + 2 KB) | 2 SF images x 3 KB | 32 KB staging
 // ---------------------------------------------------------------------------------------------
 constexpr int N4_WIN_MAIN = 24576, N4_WIN_AUX = 12288, N4_WIN_BUF = N4_WIN_MAIN + N4_WIN_AUX;
 constexpr int N4_B_MAIN = 16384, N4_B_AUX = 8192, N4_B_SF = 2048, N4_BSTAGE = N4_B_MAIN + N4_B_AUX + N4_B_SF;
-constexpr int N4_BSTAGES = 3;
+constexpr int N4_BSTAGES = 4;
 constexpr int N4_SFIMG_PART = 96 * 16, N4_SFIMG_BUF = 2 * N4_SFIMG_PART;   // image rows 0 .. win_rows - 97 (<= 96), lo part then hi part
 constexpr int N4_OFF_BRING = 2 * N4_WIN_BUF;
 constexpr int N4_OFF_SFIMG = N4_OFF_BRING + N4_BSTAGES * N4_BSTAGE;
 constexpr int N4_OFF_STAGING = (N4_OFF_SFIMG + 2 * N4_SFIMG_BUF + 1023) / 1024 * 1024;
-constexpr int N4_OFF_BARS = N4_OFF_STAGING + 4 * CHUNK_BYTES;
+constexpr int N4_OFF_BARS = N4_OFF_STAGING + 2 * CHUNK_BYTES;
 constexpr int N4_SMEM = N4_OFF_BARS + 256 /*barriers*/ + 1024 /*bias*/ + 1024 /*align*/;
 static_assert(N4_SMEM <= 232448, "f16n4 gate kernel: shared memory over the 227 KB limit");
 
@@ -913,13 +916,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
   uint8_t* const sfimg = ring + N4_OFF_SFIMG;
   uint8_t* const staging = ring + N4_OFF_STAGING;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + N4_OFF_BARS);
-  uint64_t* const bfull = bars;            // [3]
-  uint64_t* const bempty = bars + 3;       // [3]
-  uint64_t* const afull = bars + 6;        // [2]
-  uint64_t* const aempty = bars + 8;       // [2]
-  uint64_t* const tfull = bars + 10;
-  uint64_t* const tempty = bars + 11;
-  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* const bfull = bars;            // [4]
+  uint64_t* const bempty = bars + 4;       // [4]
+  uint64_t* const afull = bars + 8;        // [2]
+  uint64_t* const aempty = bars + 10;      // [2]
+  uint64_t* const tfull = bars + 12;
+  uint64_t* const tempty = bars + 13;
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
   float* const sbias = reinterpret_cast<float*>(ring + N4_OFF_BARS + 256);
 
   const int cpt = p.C / TILE_K;
@@ -1112,6 +1115,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
         const int tf = ti.t0 + row;
         const bool add_cond = is_cond && p.cond != nullptr && tf < p.T;
         const uint32_t box = stg + grp * CHUNK_BYTES;
+        uint32_t zak[2][2][8];                       // aux words, staged after the main boxes have left
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
           const int ch = grp * 2 + c2;
@@ -1135,23 +1139,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_n4_kernel(const __gr
                 z[v4 * 4 + e] = gate_act(g + sbias[ch * 32 + j], f + sbias[128 + ch * 32 + j]);
               }
             }
-            uint32_t zm[8], za[8];
-            pack16<3>(z, zm, za);
+            uint32_t zm[8];
+            pack16<3>(z, zm, zak[c2][hf]);
             const int chn = c2 * 32 + hf * 16;
             sts128u(box + sw128_off(row, chn / 8), zm[0], zm[1], zm[2], zm[3]);
             sts128u(box + sw128_off(row, chn / 8 + 1), zm[4], zm[5], zm[6], zm[7]);
-            sts128u(box + 2 * CHUNK_BYTES + sw128_off(row, chn / 16), za[0], za[1], za[2], za[3]);
-            sts128u(box + 2 * CHUNK_BYTES + sw128_off(row, 4 + chn / 16), za[4], za[5], za[6], za[7]);
           }
         }
         fence_proxy_async();
         named_bar_sync(EPI_BAR, EPI_THREADS);
+        const int c0 = ti.nblk * (TILE_N / 2);
         if (issuer) {
-          const int c0 = ti.nblk * (TILE_N / 2);
           tma_store_3d(&p.zh, staging, c0, ti.t0, zroll);
           tma_store_3d(&p.zh, staging + CHUNK_BYTES, c0 + 64, ti.t0, zroll);
-          tma_store_3d(&p.zl, staging + 2 * CHUNK_BYTES, 2 * c0, ti.t0, zroll);
-          tma_store_3d(&p.zl, staging + 3 * CHUNK_BYTES, 2 * (c0 + 64), ti.t0, zroll);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int chn = c2 * 32 + hf * 16;
+            sts128u(box + sw128_off(row, chn / 16), zak[c2][hf][0], zak[c2][hf][1], zak[c2][hf][2], zak[c2][hf][3]);
+            sts128u(box + sw128_off(row, 4 + chn / 16), zak[c2][hf][4], zak[c2][hf][5], zak[c2][hf][6], zak[c2][hf][7]);
+          }
+        fence_proxy_async();
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+        if (issuer) {
+          tma_store_3d(&p.zl, staging, 2 * c0, ti.t0, zroll);
+          tma_store_3d(&p.zl, staging + CHUNK_BYTES, 2 * (c0 + 64), ti.t0, zroll);
           tma_store_commit();
         }
       }   // pass
