@@ -42,6 +42,7 @@ struct Layout {  // byte offsets into the workspace
   size_t dtab, emb1, emb2, x32, skip, hbuf, spec32, bias, wtmp, mel, xpp;
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
+  size_t wouth, woutl;                                  // output_projection rows padded to 256, operand pair (tensor-core head)
   size_t xs, wsf4;                                      // f16n4: activation scale factors [NB][C/64][T][8]; weight scale atoms [L][2C/256][k*C/64][2048]
   size_t range;                                         // one word: max |activation operand| (fp32 bits) since the last reset
   size_t wcpad, cond;                                   // fp32 Wc of every layer padded to Mp; conditioner projections of the spectrogram [L][B][T][2C]
@@ -111,7 +112,8 @@ static Layout make_layout(const drb_config& c) {
     l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
     l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
     l.bcomp = take(C * 4); l.bsum = take(C * 4);
-    l.wscale = take((3 * L + 1) * 4 * 4);
+    l.wscale = take((3 * L + 2) * 4 * 4);
+    l.wouth = take(256 * C * 2); l.woutl = take(256 * C * 2);
     if (c.precision == DRB_PREC_F16N4) {
       l.xs = take(NB * (C / 64) * T * 8);
       l.wsf4 = take(L * (2 * C / 256) * (k * C / 64) * 2048);
@@ -176,6 +178,10 @@ struct drb_plan {
   int xfmt() const { return n4() ? 4 : fmt(); }   // format of the x operand pair (in_proj / RES -> gate kernel)
   float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head, 2L+1+l: Wc (f16n4)
   int wc_slot(int layer) const { return n4() ? 2 * cfg.residual_layers + 1 + layer : 2 * layer; }   // f16n4 scales the conv weights alone
+  int wout_slot() const { return 3 * cfg.residual_layers + 1; }
+  // tensor-core head: HEAD leaves relu(skip_projection) as an operand pair, output_projection + guidance + posterior run as
+  // one tcgen05 kernel (DRB_NO_HEAD_TC=1: fp32 h + the CUDA-core projection kernel, for A/B runs)
+  int head_tc = 0;
   std::vector<CUtensorMap> cond32;   // per layer: fp32 [B][T][2C] map of the conditioner table (tensor-core build)
   const float* dvec(int layer, int t) const {
     return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
@@ -244,6 +250,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
   int rc = drb_plan_set_branches(p, cfg->branches);
   if (rc) { delete p; return rc; }
 #define PLAN_TRY(expr) do { int _r = (expr); if (_r) { drb_plan_destroy(p); return _r; } } while (0)
+#define PLAN_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error("%s -> %s", #expr, cudaGetErrorString(_e)); drb_plan_destroy(p); return (int)_e; } } while (0)
   const bool tensor = cfg->precision != DRB_PREC_FP32;
   if (tensor) PLAN_TRY(umma_init());
   PLAN_TRY(mel_create(&p->mel, *cfg, w->stft_window, w->mel_fb, p->ws + lay.mel, mel_workspace_bytes(*cfg), s));
@@ -344,6 +351,22 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
       }
     PLAN_TRY(make_tmap_3d(&p->maps.x32, p->ws + lay.x32, NBc, T, C, 128, 1));
     PLAN_TRY(make_tmap_3d(&p->maps.h32, p->ws + lay.hbuf, NBc, T, C, 128, 1));
+    {   // the same storage seen as an operand pair [NB][T][C] (2 + 2 bytes per element) and the padded output_projection
+      const size_t rows_all = (size_t)NBc * T;
+      PLAN_TRY(make_tmap_3d(&p->maps.hh, p->ws + lay.hbuf, NBc, T, C, 128, dm));
+      PLAN_TRY(make_tmap_3d(&p->maps.hl, p->ws + lay.hbuf + rows_all * C * 2, NBc, T, am * C, 128, da));
+      const char* e = getenv("DRB_NO_HEAD_TC");
+      p->head_tc = (p->prec() == 1 || p->prec() == 3) && cfg->pitches <= 256 && (cfg->pitches % 4) == 0 && !(e && e[0] == '1');
+      if (p->head_tc) {
+        float* tmp = p->at<float>(lay.wtmp);
+        PLAN_CUDA(cudaMemsetAsync(tmp, 0, (size_t)256 * C * 4, s));
+        PLAN_CUDA(cudaMemcpyAsync(tmp, p->hdw, (size_t)cfg->pitches * C * 4, cudaMemcpyDeviceToDevice, s));
+        if (fmt >= 2) PLAN_TRY(launch_weight_scale(tmp, (size_t)256 * C, nullptr, 0, p->wscale(p->wout_slot()), fmt == 2 ? F8_SA : 1.f, s));
+        PLAN_TRY(launch_repack_split(tmp, p->ws + lay.wouth, p->ws + lay.woutl, 256, C, C, 0, fmt, p->wscale(p->wout_slot()), s));
+        PLAN_TRY(make_tmap_2d(&p->maps.wout_h, p->ws + lay.wouth, 256, C, 128, dm));
+        PLAN_TRY(make_tmap_2d(&p->maps.wout_l, p->ws + lay.woutl, 256, am * C, 128, da));
+      }
+    }
     // skip sum + 1/sqrt(L) + skip_projection composed into one [C][L*C] weight over the stored z of all layers
     for (int i = 0; i < L; ++i)
       PLAN_TRY(launch_compose_skip(p->skw, p->wo32[i], p->at<float>(lay.wcomp32), C, L, i, s));
@@ -565,11 +588,25 @@ int drb_head_posterior_step(drb_plan* p, const float* x_t, const float* noise, f
     r = launch_simt_gemm(g, s); if (r) return r;
   } else {  // one long-K tensor-core GEMM over the stored z of all layers (skip sum, 1/sqrt(L), skip_projection, ReLU)
     UmmaZGemm uz;
-    uz.pair = p->pair; uz.NB = p->NB; uz.T = T; uz.C = C; uz.prec = p->prec(); uz.mode = 1; uz.groups = c.residual_layers;
+    uz.pair = p->pair; uz.persistent = p->persistent; uz.NB = p->NB; uz.T = T; uz.C = C; uz.prec = p->prec(); uz.mode = 1; uz.groups = c.residual_layers;
     uz.inv_scale = p->wscale(2 * c.residual_layers) + 1;
     uz.z_group0 = 0; uz.group_stride = p->lay.NBcap; uz.w_h = &p->maps.wcomp_h; uz.w_l = &p->maps.wcomp_l; uz.out32 = &p->maps.h32;
     uz.bias = p->at<float>(p->lay.bcomp); uz.dnext = nullptr;
+    const bool tc = p->head_tc && (p->NB == B || (p->NB == 2 * B && p->pair));
+    if (tc) { uz.hp_h = &p->maps.hh; uz.hp_l = &p->maps.hl; }
     r = launch_umma_zgemm(p->maps, uz, s); if (r) return r;
+    if (tc) {   // output_projection + guidance combine + posterior update on the tensor cores (one N block of padded rows)
+      UmmaZGemm uo;
+      uo.pair = p->pair; uo.persistent = 0; uo.NB = p->NB; uo.T = T; uo.C = C; uo.prec = p->prec(); uo.mode = 3; uo.groups = 1;
+      uo.inv_scale = p->wscale(p->wout_slot()) + 1; uo.z_group0 = 0; uo.group_stride = 0;
+      uo.w_h = &p->maps.wout_h; uo.w_l = &p->maps.wout_l; uo.out32 = &p->maps.h32; uo.bias = p->hdb; uo.dnext = nullptr;
+      uo.a_h = &p->maps.hh; uo.a_l = &p->maps.hl; uo.dual_B = p->NB == 2 * B ? B : 0; uo.F = F; uo.upd = upd;
+      uo.x_t = x_t; uo.noise = noise; uo.x_prev = x_prev; uo.net_out = net_out;
+      const int e1 = p->prof ? p->ev_mark(s) : -1;
+      r = launch_umma_zgemm(p->maps, uo, s);
+      if (p->prof && r == 0) { const int e2 = p->ev_mark(s); p->ev_spans[3].push_back({e0, e2}); p->ev_spans[4].push_back({e1, e2}); }
+      return r;
+    }
   }
   SimtGemm o;  // output_projection + guidance combine + posterior update
   o.A = h; o.lda = C; o.T = T; o.Ck = C; o.W = p->hdw; o.ldw = C; o.bias = p->hdb;
@@ -706,7 +743,10 @@ int drb_plan_buffer(drb_plan* p, const char* name, void** ptr, size_t* bytes) {
   size_t off = 0, sz = 0; bool ok = true;
   if (n == "x32") { off = p->lay.x32; sz = rows * C * 4; }
   else if (n == "skip") { off = p->lay.skip; sz = rows * C * 4; }
-  else if (n == "h") { off = p->lay.hbuf; sz = rows * C * 4; }
+  else if (n == "h") {
+    if (tensor && p->head_tc) { set_error("'h' is kept as an operand pair by the tensor-core head (DRB_NO_HEAD_TC=1 keeps fp32)"); return DRB_E_STATE; }
+    off = p->lay.hbuf; sz = rows * C * 4;
+  }
   else if (n == "dtab") { off = p->lay.dtab; sz = (size_t)c.residual_layers * c.timesteps * C * 4; }
   else if (n == "spec32") { off = p->lay.spec32; sz = (size_t)c.batch * c.frames * p->lay.Mp * 4; }
   else if (n == "y" && !tensor) { off = p->lay.ybuf; sz = rows * 2 * C * 4; }

@@ -95,12 +95,37 @@ struct UmmaLayer {
   CUtensorMap wc_h, wc_l;  // [2C][Mp]
   CUtensorMap wo_h, wo_l;  // [2C][C]
 };
+// Posterior update of one element, same operation order as the reference's fp32 tensor expressions (DRB_UPD_* in diffroll_b200.h).
+#ifdef __CUDACC__
+__device__ __forceinline__ float posterior_update(const drb_update& u, float net, float x, float n) {
+  switch (u.mode) {
+    case DRB_UPD_X0: {
+      float r = u.s[0] * net + u.s[1] * (x - u.s[2] * net) / u.s[3];
+      return u.has_noise ? r + u.s[4] * n : r;
+    }
+    case DRB_UPD_X0_FINAL: return net / u.s[0];
+    case DRB_UPD_EPS_DDPM: {
+      float r = u.s[0] * (x - u.s[1] * net / u.s[2]);
+      return u.has_noise ? r + u.s[3] * n : r;
+    }
+    case DRB_UPD_EPS_DDIM: {
+      float r = u.s[0] * ((x - u.s[1] * net) / u.s[2]) + u.s[3] * net;
+      return u.has_noise ? r + u.s[4] * n : r;
+    }
+    case DRB_UPD_EPS_FINAL: return (x - u.s[0] * net) / u.s[1];
+    default: return net;
+  }
+}
+#endif
+
 struct UmmaMaps {
   CUtensorMap xh, xl;      // [NB][T][C]
   CUtensorMap zh, zl;      // [L*NB][T][C]: gated activations of every layer
   CUtensorMap x32, h32;    // fp32 [NB][T][C], box 32 channels x 128 frames
   CUtensorMap wcomp_h, wcomp_l;  // [C][L*C] composed skip/head weights
   CUtensorMap sh, sl;      // [B][T][Mp]
+  CUtensorMap hh, hl;      // [NB][T][C]: operand pair of the head's hidden activations relu(skip_projection(...)) (tensor-core head)
+  CUtensorMap wout_h, wout_l;  // [256][C]: output_projection rows padded to one N block
 };
 struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filter) -> zh/zl[z_group0 + roll]
   int NB, n_cond, T, C, taps, dil, Mp, prec, z_group0;  // prec: 0 bf16, 1 bf16x3, 2 f16f8
@@ -127,6 +152,7 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
                                     // 2: conditioner tables: A = spectrogram pair (K = nslabs64 * 64), N = 2C gate-interleaved weight
                                     //    rows, plain fp32 result stored in NATURAL channel order [gate 0..C-1 | filter C..2C-1]
   int nslabs64 = 0;                 // mode 2: K-slabs (Mp / 64)
+                                    // 3: head output projection, see below
   const float* inv_scale;
   int groups, z_group0, group_stride;
   const CUtensorMap *w_h, *w_l, *out32;
@@ -136,7 +162,15 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
   const int* steps = nullptr;       // per-sample diffusion steps [bsamp] (device); roll nb uses steps[nb % bsamp]
   int bsamp = 1;
   unsigned int* range_max = nullptr;  // RES: device word, atomicMax of |x + d_next| (fp32 bits) over the emitted operands
-  const CUtensorMap *a_h = nullptr, *a_l = nullptr;   // mode 2: A operand maps (the spectrogram pair) instead of the stored z
+  const CUtensorMap *a_h = nullptr, *a_l = nullptr;   // mode 2 / 3: A operand maps (spectrogram pair / head hidden pair) instead of the stored z
+  // mode 1 with h_pair: the ReLU output leaves as an operand pair through xh/xl-style maps instead of fp32 through out32
+  const CUtensorMap *hp_h = nullptr, *hp_l = nullptr;
+  // mode 3: output_projection (N = pitches <= 256 padded) + guidance combine + posterior update     model/diffwave.py:685, task/diffusion.py:1009-1023
+  //   dual_B > 0: CTA pair = (conditional roll b, unconditional roll b + dual_B) of the same frames; the pair's second CTA hands
+  //   its accumulator to the first one through distributed shared memory and the first one writes x_prev.
+  int dual_B = 0, F = 0;
+  const drb_update* upd = nullptr;    // host pointer, copied by value
+  const float* x_t = nullptr; const float* noise = nullptr; float* x_prev = nullptr; float* net_out = nullptr;
   int x_n4 = 0;                       // RES emits the next layer's operand in the f16n4 format (xl4 = 64-byte-row aux map, xs = scales)
   const CUtensorMap* xl4 = nullptr;
   uint8_t* xs = nullptr;

@@ -24,27 +24,6 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ float posterior_update(const drb_update& u, float net, float x, float n) {
-  // Same operation order as the reference's fp32 tensor expressions (see DRB_UPD_* in diffroll_b200.h).
-  switch (u.mode) {
-    case DRB_UPD_X0: {
-      float r = u.s[0] * net + u.s[1] * (x - u.s[2] * net) / u.s[3];
-      return u.has_noise ? r + u.s[4] * n : r;
-    }
-    case DRB_UPD_X0_FINAL: return net / u.s[0];
-    case DRB_UPD_EPS_DDPM: {
-      float r = u.s[0] * (x - u.s[1] * net / u.s[2]);
-      return u.has_noise ? r + u.s[3] * n : r;
-    }
-    case DRB_UPD_EPS_DDIM: {
-      float r = u.s[0] * ((x - u.s[1] * net) / u.s[2]) + u.s[3] * net;
-      return u.has_noise ? r + u.s[4] * n : r;
-    }
-    case DRB_UPD_EPS_FINAL: return (x - u.s[0] * net) / u.s[1];
-    default: return net;
-  }
-}
-
 // TBM = rows per block: 128 (8x8 outputs per thread) or 64 (4x8; used when N is small so that the grid still fills the SMs)
 template <int TBM>
 __global__ void __launch_bounds__(256, 2) simt_gemm_kernel(const SimtGemmDev g) {

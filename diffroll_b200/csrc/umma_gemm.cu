@@ -107,6 +107,10 @@ struct alignas(64) ZGemmParams {
   int t_uniform, bsamp;
   unsigned int* range_max; // RES: running max |x + d_next| over the emitted operands (fp32 bits), or nullptr
   uint8_t* xs;             // f16n4: activation scale factors [roll][chunk][frame][8] (xl then maps the 64-byte e2m1 rows)
+  // mode 1 with h_pair: relu output as an operand pair through xh / xl.  mode 3: head output projection + guidance + posterior
+  int h_pair, dual_B, F;
+  drb_update upd;
+  const float* x_t; const float* noise; float* x_prev; float* net_out;
 };
 
 struct SmemView {
@@ -1193,9 +1197,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nblk = cid % p.n_blocks; cid /= p.n_blocks;
-  const int mt = PAIR ? cid * 2 + (int)rank : cid;
+  // mode 3 with a guidance pair: the two CTAs of a pair take the SAME frames of roll b (conditional) and roll b + dual_B
+  const bool dual3 = PAIR && p.mode == 3 && p.dual_B > 0;
+  const int mt = dual3 ? cid : (PAIR ? cid * 2 + (int)rank : cid);
   const int tt = mt % p.tiles_t;
-  const int nb = mt / p.tiles_t;
+  const int nb = mt / p.tiles_t + (dual3 ? (int)rank * p.dual_B : 0);
   const int t0 = tt * TILE_M;
   const int n_base = nblk * TILE_N;
   const bool res = p.mode == 0;
@@ -1207,7 +1213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
   }
   if (warp == 3) {
     for (int i = lane; i < TILE_N; i += 32) {
-      sv.sbias[i] = p.bias ? __ldg(p.bias + n_base + i) : 0.f;
+      sv.sbias[i] = (p.bias && (p.mode != 3 || i < p.F)) ? __ldg(p.bias + n_base + i) : 0.f;
       if (res) sv.sdn[i] = __ldg(p.dnext + (size_t)(p.steps ? __ldg(p.steps + nb % p.bsamp) : p.t_uniform) * p.C + n_base + i);
     }
   }
@@ -1255,23 +1261,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) mma_loop<P, PAIR>(sv, tmem_base, p.nslabs, nst);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && p.mode != 3) {
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int hc = (warp - 4) >> 2;        // two groups of 4 warps: each takes one 32-channel fp32 box per iteration
     const int row = q * 32 + lane;
     const bool issuer = (warp == 4) && (lane == 0);
+    const bool hpair = p.mode == 1 && p.h_pair;   // HEAD: the ReLU output leaves as an operand pair (input of the tensor-core projection)
     mbar_wait(sv.tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t stg = smem_u32(sv.stage0);
     const float rsqrt2 = 0.70710678118654752f;
     const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
+    const uint32_t pset_off = hpair ? 0u : set_off;
     unsigned int umax = 0;
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {       // 64 output channels per iteration
-      // operand staging of the next layer (x + d_next split): two alternating sets of {main box, aux box}
-      const uint32_t set = stg + set_off + (it & 1) * 2 * CHUNK_BYTES;
-      if (res && it >= 2) {                // the TMA stores of iteration it-2 must have finished reading this set
+      // operand staging of the next GEMM (x + d_next split, or h): two alternating sets of {main box, aux box}
+      const uint32_t set = stg + pset_off + (it & 1) * 2 * CHUNK_BYTES;
+      if ((res || hpair) && it >= 2) {     // the TMA stores of iteration it-2 must have finished reading this set
         if (issuer) tma_store_wait_read<1>();
         named_bar_sync(EPI_BAR, EPI_THREADS);
       }
@@ -1302,6 +1310,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
           range_note(umax, xin);
           stage16<P>(set, set + CHUNK_BYTES, row, hc * 32 + g16 * 16, xin);
         }
+      } else if (hpair) {
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          float hv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hv[i] = fmaxf(o[g16 * 16 + i] + bs[g16 * 16 + i], 0.f);   // F.relu(skip_projection(.))   diffwave.py:683-684
+          stage16<P>(set, set + CHUNK_BYTES, row, hc * 32 + g16 * 16, hv);
+        }
       } else {
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
@@ -1321,11 +1337,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
         // mode 2: the weight rows of an N block are [128 gate | 128 filter] channels; the table keeps the natural order
         const int c0 = p.mode == 2 ? (it < 2 ? nblk * (TILE_N / 2) + it * 64 : p.C / 2 + nblk * (TILE_N / 2) + (it - 2) * 64)
                                    : n_base + it * 64;
-        tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2), c0, t0, nb);
-        tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2 + 1), c0 + 32, t0, nb);
-        if (res) {
-          tma_store_3d(&p.xh, sv.stage0 + set_off + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
-          if (CF::kAux) tma_store_3d(&p.xl, sv.stage0 + set_off + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, AM * c0, t0, nb);
+        if (!hpair) {
+          tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2), c0, t0, nb);
+          tma_store_3d(&p.out32, sv.stage0 + xbox_off(it * 2 + 1), c0 + 32, t0, nb);
+        }
+        if (res || hpair) {
+          tma_store_3d(&p.xh, sv.stage0 + pset_off + (it & 1) * 2 * CHUNK_BYTES, c0, t0, nb);
+          if (CF::kAux) tma_store_3d(&p.xl, sv.stage0 + pset_off + (it & 1) * 2 * CHUNK_BYTES + CHUNK_BYTES, AM * c0, t0, nb);
         }
         tma_store_commit();
       }
@@ -1333,6 +1351,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
     tc_fence_before();
     if (issuer) tma_store_wait_read<0>();
     if (res) range_publish(p.range_max, umax);
+  }
+  // ---- mode 3: output_projection + guidance combine + posterior update (model/diffwave.py:685, task/diffusion.py:1009-1023) ----
+  // Both CTAs park their projection tile [row][pitch] (fp32, row stride 92 floats) in the first CTA's idle operand ring -- the
+  // second one through distributed shared memory --; after a cluster barrier the first CTA's epilogue threads walk the tile in
+  // float4 steps along the pitches, so x_t / noise / x_prev rows are read and written fully coalesced.  The walk is a ROLLED
+  // loop on purpose: the first version kept the 64 columns of a row in registers and unrolled the update per column, ~150 KB
+  // of straight-line code executed once per CTA, and ran at instruction-fetch speed (50 us per wave, 'no_inst' stalls).
+  if (p.mode == 3) {
+    constexpr int RS = 92;                 // row stride in floats: 16-byte aligned rows, at most 4-way conflicts on the column-wise writes
+    const bool epi = warp >= 4;
+    float* const tile_c = reinterpret_cast<float*>(sv.stage0);                        // this CTA's own tile (conditional branch when dual)
+    float* const tile_u = reinterpret_cast<float*>(sv.stage0) + TILE_M * RS;          // the pair's second CTA's tile (unconditional branch)
+    if (epi) {
+      const int q = warp & 3, hc = (warp - 4) >> 2;
+      const int row = q * 32 + lane;
+      mbar_wait(sv.tmem_full, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)hc * 64u;
+      const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
+      const bool remote = dual3 && rank == 1;
+      const uint32_t dst = remote ? mapa_cluster(smem_u32(tile_u), 0) : smem_u32(tile_c);
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        float a[32];
+        load_acc32<P>(taddr + hlf * 32, inv, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = hc * 64 + hlf * 32 + i;
+          if (c < p.F) {
+            const uint32_t ad = dst + (uint32_t)(row * RS + c) * 4u;
+            if (remote) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ad), "f"(a[i]) : "memory");
+            else asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(a[i]) : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    if (dual3) cluster_sync_all();         // every thread of both CTAs: both tiles are complete and visible in the first CTA
+    else __syncthreads();
+    if (epi && (!dual3 || rank == 0)) {
+      const int etid = (int)threadIdx.x - 128;
+      const int g_per_row = p.F >> 2;
+      const float w = p.upd.w;
+      const bool needs_x = !(p.upd.mode == DRB_UPD_X0_FINAL || p.upd.mode == DRB_UPD_NONE);
+#pragma unroll 1
+      for (int i = etid; i < TILE_M * g_per_row; i += EPI_THREADS) {
+        const int row = i / g_per_row, c = (i - row * g_per_row) * 4;
+        const int t = t0 + row;
+        if (t >= p.T) continue;
+        const size_t base = ((size_t)nb * p.T + t) * (size_t)p.F + c;
+        const float4 cv = *reinterpret_cast<const float4*>(tile_c + row * RS + c);
+        const float4 bv = *reinterpret_cast<const float4*>(sv.sbias + c);
+        float net[4] = {cv.x + bv.x, cv.y + bv.y, cv.z + bv.z, cv.w + bv.w};
+        if (dual3) {                                     // (1 + w) * x0_c - w * x0_0     task/diffusion.py:1009
+          const float4 uv = *reinterpret_cast<const float4*>(tile_u + row * RS + c);
+          net[0] = (1.f + w) * net[0] - w * (uv.x + bv.x); net[1] = (1.f + w) * net[1] - w * (uv.y + bv.y);
+          net[2] = (1.f + w) * net[2] - w * (uv.z + bv.z); net[3] = (1.f + w) * net[3] - w * (uv.w + bv.w);
+        }
+        if (p.net_out) *reinterpret_cast<float4*>(p.net_out + base) = make_float4(net[0], net[1], net[2], net[3]);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), nz = x;
+        if (needs_x) x = *reinterpret_cast<const float4*>(p.x_t + base);
+        if (p.upd.has_noise) nz = *reinterpret_cast<const float4*>(p.noise + base);
+        float4 o;
+        o.x = posterior_update(p.upd, net[0], x.x, nz.x); o.y = posterior_update(p.upd, net[1], x.y, nz.y);
+        o.z = posterior_update(p.upd, net[2], x.z, nz.z); o.w = posterior_update(p.upd, net[3], x.w, nz.w);
+        *reinterpret_cast<float4*>(p.x_prev + base) = o;
+      }
+    }
   }
   teardown<P, PAIR>(tmem_base, warp);
 }
@@ -1607,6 +1693,189 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_res_pers_kernel(const __g
 }
 
 // ---------------------------------------------------------------------------------------------
+// zgemm HEAD, persistent variant (CTA pairs; bf16x3 / f16e5; output = operand pair of relu(.) for the tensor-core projection).
+// The one-tile-per-CTA kernel pays ~40 us per wave around an 80 us K loop (prologue, first TMA round trip, four store
+// iterations, teardown): here one CTA pair per SM pair loops over its tiles with two TMEM accumulator stages, so the
+// epilogue of tile i runs under the 120 K-slabs of tile i+1.
+//   smem: 3 operand stages x 64 KB | one staging set (main + aux box, 32 KB)
+// ---------------------------------------------------------------------------------------------
+constexpr int HP_STAGE = 65536, HP_STAGES = 3;
+constexpr int HP_RING = HP_STAGES * HP_STAGE;
+constexpr int HP_SMEM = HP_RING + 2 * CHUNK_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
+
+template <int P>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_head_pers_kernel(const __grid_constant__ ZGemmParams p) {
+  static_assert(P == 1 || P == 3, "needs a single 256-column accumulator");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  constexpr int AM = P >= 2 ? 2 : 1;
+
+  uint8_t* ring;
+  { uint32_t a = smem_u32(smem_raw); ring = smem_raw + (((a + 1023u) & ~1023u) - a); }
+  uint8_t* const staging = ring + HP_RING;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ring + HP_RING + 2 * CHUNK_BYTES);
+  uint64_t* const full = bars;             // [3]
+  uint64_t* const empty = bars + 3;        // [3]
+  uint64_t* const tfull = bars + 6;        // [2]
+  uint64_t* const tempty = bars + 8;       // [2]
+  uint32_t* const tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  float* const sbias = reinterpret_cast<float*>(ring + HP_RING + 2 * CHUNK_BYTES + 256);
+
+  struct Tile { int n_base, nb, t0; };
+  auto tile_of = [&](int item) -> Tile {
+    Tile t;
+    t.n_base = (item % p.n_blocks) * TILE_N;
+    const int mt = (item / p.n_blocks) * 2 + (int)rank;
+    t.nb = mt / p.tiles_t;
+    t.t0 = (mt % p.tiles_t) * TILE_M;
+    return t;
+  };
+  const int n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.zh); tma_prefetch_desc(&p.zl); tma_prefetch_desc(&p.w_h); tma_prefetch_desc(&p.w_l);
+    tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.xl);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < HP_STAGES; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(tmem_ptr, 512); tmem_relinquish_pair(); }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {          // operand producer
+      int cnt = 0;
+      for (int item = pair_id; item < n_items; item += n_pairs) {
+        const Tile ti = tile_of(item);
+        const int row0 = ti.n_base + (int)rank * (TILE_N / 2);
+        for (int s = 0; s < p.nslabs; ++s, ++cnt) {
+          const int st_i = cnt % HP_STAGES;
+          mbar_wait(&empty[st_i], ((cnt / HP_STAGES) & 1) ^ 1);
+          uint8_t* st = ring + st_i * HP_STAGE;
+          const uint32_t fb = mapa_cluster(smem_u32(&full[st_i]), 0);
+          mbar_expect_tx_cluster(fb, HP_STAGE);
+          const int grp = s / p.spg, cc = s - grp * p.spg;
+          const int zrow = p.z_group0 + grp * p.group_stride + ti.nb;
+          tma_load_3d_pair(st, &p.zh, fb, cc * TILE_K, ti.t0, zrow);
+          tma_load_3d_pair(st + A_TILE_BYTES, &p.zl, fb, AM * cc * TILE_K, ti.t0, zrow);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES, &p.w_h, fb, s * TILE_K, row0);
+          tma_load_2d_pair(st + 2 * A_TILE_BYTES + B_TILE_BYTES / 2, &p.w_l, fb, AM * s * TILE_K, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {   // MMA issuer
+      constexpr uint32_t idesc = P >= 2 ? make_idesc_fmt0(2 * TILE_M, TILE_N) : make_idesc_bf16(2 * TILE_M, TILE_N);
+      constexpr uint32_t idesc_e5 = make_idesc_bf16(2 * TILE_M, TILE_N);
+      int cnt = 0, tcnt = 0;
+      for (int item = pair_id; item < n_items; item += n_pairs, ++tcnt) {
+        const int as = tcnt & 1;
+        mbar_wait(&tempty[as], ((tcnt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * 256u;
+        for (int s = 0; s < p.nslabs; ++s, ++cnt) {
+          const int st_i = cnt % HP_STAGES;
+          mbar_wait(&full[st_i], (cnt / HP_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_main = smem_u32(ring + st_i * HP_STAGE), a_aux = a_main + A_TILE_BYTES;
+          const uint32_t b_main = a_main + 2 * A_TILE_BYTES, b_aux = b_main + B_TILE_BYTES / 2;
+#pragma unroll
+          for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+            const uint32_t ko = k * UMMA_K * 2;
+            const uint64_t da = make_sw128_desc(a_main + ko), db = make_sw128_desc(b_main + ko);
+            umma_bf16_pair(tmem_d, da, db, idesc, (s == 0 && k == 0) ? 0u : 1u);
+            if (P == 1) {
+              umma_bf16_pair(tmem_d, make_sw128_desc(a_aux + ko), db, idesc, 1u);
+              umma_bf16_pair(tmem_d, da, make_sw128_desc(b_aux + ko), idesc, 1u);
+            }
+            if (P == 3) umma_f8_pair(tmem_d, make_sw128_desc(a_aux + ko), make_sw128_desc(b_aux + ko), idesc_e5, 1u);
+          }
+          umma_commit_pair(&empty[st_i]);
+        }
+        umma_commit_pair(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, hc = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const int etid = (int)threadIdx.x - 128;
+    const bool issuer = (warp == 4) && (lane == 0);
+    const uint32_t stg = smem_u32(staging);
+    const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
+    int tcnt = 0;
+    for (int item = pair_id; item < n_items; item += n_pairs, ++tcnt) {
+      const Tile ti = tile_of(item);
+      const int as = tcnt & 1;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u;
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        if (it == 0) {
+          named_bar_sync(EPI_BAR, EPI_THREADS);       // every thread is done with the previous tile's sbias
+          sbias[etid] = p.bias ? __ldg(p.bias + ti.n_base + etid) : 0.f;
+          named_bar_sync(EPI_BAR, EPI_THREADS);
+          mbar_wait(&tfull[as], (tcnt >> 1) & 1);
+          tc_fence_after();
+        }
+        const int cbox = it * 2 + hc;
+        float o[32];
+        load_acc32<P>(taddr + cbox * 32, inv, o);
+        if (it == 3) {                                // last TMEM read of this tile: hand the accumulator stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
+        }
+        const float* bs = sbias + cbox * 32;
+        uint32_t pm[2][8], pa[2][8];
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          float hv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hv[i] = fmaxf(o[g16 * 16 + i] + bs[g16 * 16 + i], 0.f);   // F.relu(skip_projection(.))   diffwave.py:683-684
+          pack16<P>(hv, pm[g16], pa[g16]);
+        }
+        if (issuer) tma_store_wait_read<0>();         // the previous iteration's stores no longer read the staging boxes
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          const int chn = hc * 32 + g16 * 16;
+          sts128u(stg + sw128_off(row, chn / 8), pm[g16][0], pm[g16][1], pm[g16][2], pm[g16][3]);
+          sts128u(stg + sw128_off(row, chn / 8 + 1), pm[g16][4], pm[g16][5], pm[g16][6], pm[g16][7]);
+          if (P >= 2) {
+            sts128u(stg + CHUNK_BYTES + sw128_off(row, chn / 16), pa[g16][0], pa[g16][1], pa[g16][2], pa[g16][3]);
+            sts128u(stg + CHUNK_BYTES + sw128_off(row, 4 + chn / 16), pa[g16][4], pa[g16][5], pa[g16][6], pa[g16][7]);
+          } else {
+            sts128u(stg + CHUNK_BYTES + sw128_off(row, chn / 8), pa[g16][0], pa[g16][1], pa[g16][2], pa[g16][3]);
+            sts128u(stg + CHUNK_BYTES + sw128_off(row, chn / 8 + 1), pa[g16][4], pa[g16][5], pa[g16][6], pa[g16][7]);
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(EPI_BAR, EPI_THREADS);
+        if (issuer) {
+          const int c0 = ti.n_base + it * 64;
+          tma_store_3d(&p.xh, staging, c0, ti.t0, ti.nb);
+          tma_store_3d(&p.xl, staging + CHUNK_BYTES, AM * c0, ti.t0, ti.nb);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read<0>();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1639,6 +1908,7 @@ int umma_init() {
   set((const void*)umma_gate_pers_kernel<1, true>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3, true>, PW_SMEM);
   set((const void*)umma_res_pers_kernel<1, 0>, RP_SMEM); set((const void*)umma_res_pers_kernel<3, 0>, RP_SMEM);
   set((const void*)umma_res_pers_kernel<3, 4>, RP_SMEM);
+  set((const void*)umma_head_pers_kernel<1>, HP_SMEM); set((const void*)umma_head_pers_kernel<3>, HP_SMEM);
   set((const void*)umma_gate_n4_kernel<false>, N4_SMEM); set((const void*)umma_gate_n4_kernel<true>, N4_SMEM);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
@@ -1800,9 +2070,23 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   } p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
   p.range_max = z.range_max; p.xs = nullptr;
-  const int grid = p.NB * p.tiles_t * p.n_blocks;
+  p.h_pair = 0; p.dual_B = 0; p.F = 0; p.x_t = nullptr; p.noise = nullptr; p.x_prev = nullptr; p.net_out = nullptr;
+  p.upd.mode = DRB_UPD_NONE; p.upd.has_noise = 0; p.upd.w = 0.f;
+  if (z.mode == 1 && z.hp_h && z.hp_l) { p.h_pair = 1; p.xh = *z.hp_h; p.xl = *z.hp_l; }
+  int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = z.inv_scale;
-  const bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  bool mc = z.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  if (z.mode == 3) {   // head output projection: A = h pair (K = C), one N block of padded output rows
+    if (!z.a_h || !z.a_l || !z.upd || !z.x_prev || z.F <= 0 || z.F > TILE_N || (z.F & 3)) { set_error("umma_zgemm: mode 3 arguments"); return DRB_E_INVALID; }
+    p.zh = *z.a_h; p.zl = *z.a_l; p.n_blocks = 1; p.z_group0 = 0; p.group_stride = 0;
+    p.F = z.F; p.upd = *z.upd; p.x_t = z.x_t; p.noise = z.noise; p.x_prev = z.x_prev; p.net_out = z.net_out;
+    if (z.dual_B > 0) {   // pair = (conditional roll, unconditional roll) of the same frames
+      if (!z.pair || z.NB != 2 * z.dual_B) { set_error("umma_zgemm: mode 3 guidance pair needs CTA pairs"); return DRB_E_INVALID; }
+      p.dual_B = z.dual_B; mc = true; grid = 2 * z.dual_B * p.tiles_t;
+    } else {
+      grid = p.NB * p.tiles_t;
+    }
+  }
   if (mc && z.persistent && z.mode == 0 && (z.prec == 1 || z.prec == 3)) {
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
@@ -1815,6 +2099,14 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
     }
     return z.prec == 1 ? launch_k(umma_res_pers_kernel<1, 0>, p, 2 * pairs, RP_SMEM, true, s)
                        : launch_k(umma_res_pers_kernel<3, 0>, p, 2 * pairs, RP_SMEM, true, s);
+  }
+  if (mc && z.persistent && z.mode == 1 && p.h_pair && (z.prec == 1 || z.prec == 3)) {   // persistent HEAD (operand-pair output)
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+    const int pairs = n_items < n_sm / 2 ? n_items : n_sm / 2;
+    return z.prec == 1 ? launch_k(umma_head_pers_kernel<1>, p, 2 * pairs, HP_SMEM, true, s)
+                       : launch_k(umma_head_pers_kernel<3>, p, 2 * pairs, HP_SMEM, true, s);
   }
   if (z.x_n4 && z.mode == 0) { set_error("umma_zgemm: f16n4 needs the persistent CTA-pair kernels (even tile count)"); return DRB_E_INVALID; }
   if (z.prec == 1) return mc ? launch_k(umma_zgemm_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
