@@ -82,14 +82,24 @@ def test_n_rank_sharded_run_equals_single_rank(tmp_path, world, B):
         parts_g.append(m.sample_loop(x_T[lo:hi].cuda(), wav[lo:hi].cuda(), generator=g, shard=(B, lo, hi))[0].cpu())
     assert torch.equal(got["pre"], torch.cat(parts, 0))
     assert torch.equal(got["gen"], torch.cat(parts_g, 0))
-    # and against ONE rank holding the whole batch (other tile shapes: tolerance, not bits)
+    # and against ONE rank holding the whole batch.  Every roll's arithmetic is independent of its neighbours, but the
+    # operand FORMAT is chosen per plan: f16n4 needs an even number of 128-frame tiles (CTA pairs), so a 1-roll shard runs
+    # in f16e5 while the whole batch runs in f16n4 (or the other way round for an odd batch).  Equal formats -> equal bits;
+    # different formats -> both within the parity bar of the fp32 reference, i.e. within 1e-3 of each other.
+    precs = set()
+    for eng, _ in m._engines.values():
+        precs.add(eng.effective_precision)
     whole = m.sample_loop(x_T.cuda(), wav.cuda(), noise=noise.cuda())[0].cpu()
     g = torch.Generator(device="cuda").manual_seed(4242)
     whole_g = m.sample_loop(x_T.cuda(), wav.cuda(), generator=g)[0].cpu()
+    for eng, _ in m._engines.values():
+        precs.add(eng.effective_precision)
     e1, e2 = float((got["pre"] - whole).abs().max()), float((got["gen"] - whole_g).abs().max())
     _record(f"dist: {world} ranks x global batch {B} (NCCL all-gather): bit-identical to per-shard 1-rank runs; "
-            f"vs one rank holding the whole batch max|delta| = {e1:.2e} (pre-drawn noise), {e2:.2e} (generator-drawn)")
-    assert e1 < 1e-5 and e2 < 1e-5
+            f"vs one rank holding the whole batch max|delta| = {e1:.2e} (pre-drawn noise), {e2:.2e} (generator-drawn); "
+            f"operand formats in play: {sorted(precs)}")
+    tol = 0.0 if len(precs) == 1 else 1e-3 * max(1.0, float(whole.abs().max()))
+    assert e1 <= tol and e2 <= tol, (e1, e2, sorted(precs))
 
 
 def _run_sampling(tmp_path, world, tag):
@@ -113,6 +123,7 @@ def test_sampling_entry_point_torchrun_equals_single_process(tmp_path):
     assert one.shape == two.shape == (6, 1, 640, 88)
     err = float((one - two).abs().max())
     _record(f"sampling.py: torchrun 2 ranks vs 1 process, 6 rolls x 5 steps: max|delta| = {err:.2e}")
-    assert err < 1e-5
+    # the second batch (2 rolls) is split 1 + 1: one-roll shards compute in f16e5, the single process in f16n4 (see above)
+    assert err < 1e-3 * max(1.0, float(one.abs().max()))
     # shards must not repeat one noise sequence: rolls of different shards differ
     assert float((two[0] - two[2]).abs().max()) > 1e-3
