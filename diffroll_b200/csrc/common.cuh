@@ -102,6 +102,17 @@ __device__ __forceinline__ void split_f16e5_x4(const float (&v)[4], uint32_t& h0
         ((uint32_t)pack_e5m2x2(fb.x * 0.00390625f, fb.y * 0.00390625f) << 16);
 }
 
+// the B-side ("weight") form of the same split: [e5m2(h * 2^-4) | e5m2(l * 2^8)], pairing with the activation form above
+__device__ __forceinline__ void split_f16e5w_x4(const float (&v)[4], uint32_t& h01, uint32_t& h23, uint32_t& first4, uint32_t& second4) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  h01 = *reinterpret_cast<const uint32_t*>(&a);
+  h23 = *reinterpret_cast<const uint32_t*>(&b);
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  first4 = (uint32_t)pack_e5m2x2(fa.x * 0.0625f, fa.y * 0.0625f) | ((uint32_t)pack_e5m2x2(fb.x * 0.0625f, fb.y * 0.0625f) << 16);
+  second4 = (uint32_t)pack_e5m2x2((v[0] - fa.x) * 256.f, (v[1] - fa.y) * 256.f) |
+            ((uint32_t)pack_e5m2x2((v[2] - fb.x) * 256.f, (v[3] - fb.y) * 256.f) << 16);
+}
+
 // ---------------------------------------------------------------------------------------------
 // "f16n4": fp16 main product + ONE block-scaled fp4 correction product (kind::mxf4nvf4, K = 64 per instruction, half the
 // issue cycles of the e5m2 correction).  Per 64-channel chunk an activation row carries 64 B of e2m1 codes

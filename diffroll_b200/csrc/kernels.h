@@ -153,6 +153,8 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
                                     //    rows, plain fp32 result stored in NATURAL channel order [gate 0..C-1 | filter C..2C-1]
   int nslabs64 = 0;                 // mode 2: K-slabs (Mp / 64)
                                     // 3: head output projection, see below
+                                    // 4: plain GEMM out32[row][n] = sum_k A[row][k] W[n][k] (A = a_h/a_l maps [NB][T rows][K], C = output
+                                    //    columns, K = nslabs64 * 64), natural column order, no activation (training: weight gradients)
   const float* inv_scale;
   int groups, z_group0, group_stride;
   const CUtensorMap *w_h, *w_l, *out32;
@@ -175,6 +177,28 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
   const CUtensorMap* xl4 = nullptr;
   uint8_t* xs = nullptr;
 };
+struct UmmaConvLin {  // out[roll][t][n] = sum_{tap,c} A[roll][t + (tap - taps/2) dil][c] W[n][tap*Cin + c] (+ sum_m S[roll][t][m] Wc[n][m]) + bias[n]
+  const CUtensorMap *ah = nullptr, *al = nullptr;    // activation pair [NB][T][Cin] (f16e5)
+  const CUtensorMap *wh = nullptr, *wl = nullptr;    // weight pair [Nout][taps*Cin], natural row order
+  const CUtensorMap *sh = nullptr, *sl = nullptr, *wch = nullptr, *wcl = nullptr;   // optional 1x1 term: [NB][T][Mp] and [Nout][Mp]
+  int NB = 0, T = 0, Cin = 0, Nout = 0, taps = 1, dil = 1, Mp = 0, pair = 1;
+  int tap_lo = 0, tap_n = 0, accumulate = 0;          // taps [tap_lo, tap_lo + tap_n) only (0: all); out += result
+  int prec = 3;                                      // 3 f16e5 pairs (aux = bytes [.][2C]); 4 f16x3 (aux = fp16 lo [.][C]): fp32-grade
+  const float* inv_scale = nullptr;                  // device scalar: 1 / (product of the operand scales)
+  const float* bias = nullptr;                       // [Nout] or nullptr
+  float* out = nullptr; int ldo = 0;
+};
+int launch_umma_conv_lin(const UmmaConvLin& c, cudaStream_t s);
+// fp32 rows (+ optional per-segment addvec, * optional device scale) -> f16e5 operand pair [M][C] (main fp16, aux bytes [M][2C])
+// fmt 3: f16e5; fmt 5: f16x3 (fp16 hi + fp16 lo, aux [M][C] halves)
+int launch_split_pair(const float* src, int ld, const float* addvec, int av_stride, int T, const float* scale, void* mainp, void* auxp,
+                      int M, int C, cudaStream_t s, int fmt = 3);
+// fp32 rows -> TRANSPOSED f16e5 operand pair (training weight gradients contract over rolls x frames): out row tap*C + c holds
+// src[m + (tap - taps/2) * dil][c] (+ addvec[roll][c]) * scale for m = 0..M-1, zero outside the roll; main [taps*C][M] fp16,
+// aux [taps*C][2M] bytes ([lo x 64 | hi x 64] per 64 rows m).  M % 64 == 0, C % 64 == 0, T % 64 == 0.
+// bside: the pair is the GEMM's B ("weight") operand ([hi * 2^-4 | lo * 2^8]) instead of the A form ([lo * 2^4 | hi * 2^-8]).
+int launch_split_pair_T(const float* src, int ld, const float* addvec, int av_stride, int T, int taps, int dil, const float* scale,
+                        void* mainp, void* auxp, int M, int C, int bside, cudaStream_t s);
 int umma_init();  // resolves cuTensorMapEncodeTiled
 // dtype: 0 bf16, 1 fp32, 2 fp16, 3 uint8; the box always spans 128 bytes of the innermost dimension
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int dtype);

@@ -280,6 +280,14 @@ __device__ __forceinline__ void store_operand4(void* mainp, void* auxp, size_t r
     split_pack2(v[2], v[3], h1, l1);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(mainp) + row * C + c) = make_uint2(h0, h1);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(auxp) + row * C + c) = make_uint2(l0, l1);
+  } else if (fmt == 5) {   // f16x3: fp16 hi, fp16 lo = fp16(v - hi)
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    const __half2 la = __floats2half2_rn(v[0] - fa.x, v[1] - fa.y), lb = __floats2half2_rn(v[2] - fb.x, v[3] - fb.y);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(mainp) + row * C + c) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(auxp) + row * C + c) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
   } else if (fmt >= 2) {
     uint32_t h01, h23, lo4, hi4;
     if (fmt == 2) split_f16f8_x4(v, h01, h23, lo4, hi4); else split_f16e5_x4(v, h01, h23, lo4, hi4);
@@ -288,6 +296,79 @@ __device__ __forceinline__ void store_operand4(void* mainp, void* auxp, size_t r
     *reinterpret_cast<uint32_t*>(a8) = lo4;
     *reinterpret_cast<uint32_t*>(a8 + 64) = hi4;
   }
+}
+
+// training (csrc/train.cu): any fp32 activation / gradient tensor -> f16e5 operand pair, with the per-roll diffusion_projection
+// vector added (x + d) or a power-of-two scale applied (gradients are far below fp16's normal range)
+__global__ void split_pair_kernel(const float* __restrict__ src, int ld, const float* __restrict__ addvec, int av_stride, int T,
+                                  const float* __restrict__ scale, void* __restrict__ mainp, void* __restrict__ auxp, size_t M, int C, int fmt) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C / 4) return;
+  const size_t row = (i * 4) / C; const int c = (int)((i * 4) % C);
+  const float4 v = *reinterpret_cast<const float4*>(src + row * ld + c);
+  float x[4] = {v.x, v.y, v.z, v.w};
+  if (addvec) {
+    const float4 d = *reinterpret_cast<const float4*>(addvec + (row / T) * av_stride + c);
+    x[0] += d.x; x[1] += d.y; x[2] += d.z; x[3] += d.w;
+  }
+  if (scale) { const float sc = scale[0]; x[0] *= sc; x[1] *= sc; x[2] *= sc; x[3] *= sc; }
+  store_operand4(mainp, auxp, row, c, C, x, fmt);
+}
+int launch_split_pair(const float* src, int ld, const float* addvec, int av_stride, int T, const float* scale, void* mainp, void* auxp,
+                      int M, int C, cudaStream_t s, int fmt) {
+  if ((C & 63) || (ld & 3)) { set_error("split_pair: unsupported C=%d ld=%d", C, ld); return DRB_E_INVALID; }
+  const size_t n = (size_t)M * C / 4;
+  split_pair_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, ld, addvec, av_stride, T > 0 ? T : 1, scale, mainp, auxp, (size_t)M, C, fmt);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+// 64 rows m x 64 channels per block: coalesced fp32 reads along the channels, transposed through shared memory, every output
+// row (one channel of one tap) leaves as 128 contiguous bytes of fp16 and 128 of e5m2 [lo | hi]
+__global__ void __launch_bounds__(256) split_pair_T_kernel(const float* __restrict__ src, int ld, const float* __restrict__ addvec, int av_stride,
+                                                            int T, int taps, int dil, const float* __restrict__ scale,
+                                                            __half* __restrict__ mainp, uint8_t* __restrict__ auxp, int M, int C, int bside) {
+  __shared__ float tile[64][65];
+  const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64, tap = blockIdx.z;
+  const int shift = (tap - taps / 2) * dil;
+  const float sc = scale ? scale[0] : 1.f;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int m = m0 + ty * 16 + i;
+    const int roll = m / T, t2 = m - roll * T + shift;
+    float v = 0.f;
+    if (t2 >= 0 && t2 < T) {
+      v = src[(size_t)(roll * T + t2) * ld + c0 + tx];
+      if (addvec) v += addvec[(size_t)roll * av_stride + c0 + tx];
+      v *= sc;
+    }
+    tile[ty * 16 + i][tx] = v;
+  }
+  __syncthreads();
+  const int c = threadIdx.x >> 2, seg = threadIdx.x & 3;          // output row c0 + c, rows m0 + 16 seg .. + 15
+  const size_t orow = (size_t)tap * C + c0 + c;
+  uint32_t h[8], lo[4], hi[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float t4[4] = {tile[seg * 16 + 4 * q][c], tile[seg * 16 + 4 * q + 1][c], tile[seg * 16 + 4 * q + 2][c], tile[seg * 16 + 4 * q + 3][c]};
+    if (bside) split_f16e5w_x4(t4, h[2 * q], h[2 * q + 1], lo[q], hi[q]);   // B operand of the GEMM: [hi * 2^-4 | lo * 2^8]
+    else split_f16e5_x4(t4, h[2 * q], h[2 * q + 1], lo[q], hi[q]);         // A operand: [lo * 2^4 | hi * 2^-8]
+  }
+  uint4* mp = reinterpret_cast<uint4*>(mainp + orow * M + m0 + seg * 16);
+  mp[0] = make_uint4(h[0], h[1], h[2], h[3]); mp[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  uint8_t* ap = auxp + orow * 2 * (size_t)M + (size_t)(m0 >> 6) * 128 + seg * 16;
+  *reinterpret_cast<uint4*>(ap) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(ap + 64) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+}
+int launch_split_pair_T(const float* src, int ld, const float* addvec, int av_stride, int T, int taps, int dil, const float* scale,
+                        void* mainp, void* auxp, int M, int C, int bside, cudaStream_t s) {
+  if ((M & 63) || (C & 63) || (T & 63) || taps < 1) { set_error("split_pair_T: unsupported M=%d C=%d T=%d", M, C, T); return DRB_E_INVALID; }
+  dim3 grid(M / 64, C / 64, taps);
+  split_pair_T_kernel<<<grid, 256, 0, s>>>(src, ld, addvec, av_stride, T, taps, dil, scale, reinterpret_cast<__half*>(mainp),
+                                           reinterpret_cast<uint8_t*>(auxp), M, C, bside);
+  DRB_LAUNCH_CHECK();
+  return 0;
 }
 
 __global__ void prep_xin_kernel(float* __restrict__ x32, void* __restrict__ xmain, void* __restrict__ xaux,
@@ -515,8 +596,12 @@ __global__ void repack_split_kernel(const float* __restrict__ w, void* __restric
   int src = np;
   if (C > 0) { int j = np >> 8, i = np & 255; src = (i < 128) ? (128 * j + i) : (C + 128 * j + (i - 128)); }
   float v = (kk < Kin) ? w[(size_t)src * Kin + kk] : 0.f;
-  if (fmt == 3) v *= scale[0];   // f16e5: per-tensor power-of-two scale, undone in the consuming kernel's epilogue
-  if (fmt == 1) {
+  if (fmt == 3 || fmt == 5) v *= scale[0];   // f16e5 / f16x3: per-tensor power-of-two scale, undone in the consuming kernel's epilogue
+  if (fmt == 5) {   // f16x3: fp16 hi / fp16 lo
+    const __half hh = __float2half_rn(v);
+    reinterpret_cast<__half*>(mainp)[idx] = hh;
+    reinterpret_cast<__half*>(auxp)[idx] = __float2half_rn(v - __half2float(hh));
+  } else if (fmt == 1) {
     __nv_bfloat16 hh, ll;
     split_bf16(v, hh, ll);
     reinterpret_cast<__nv_bfloat16*>(mainp)[idx] = hh; reinterpret_cast<__nv_bfloat16*>(auxp)[idx] = ll;
@@ -592,8 +677,18 @@ int launch_repack_n4(const float* w, void* mainp, void* auxp, uint8_t* sf_atoms,
 // f16f8 weight scale: SW = 2^floor(log2(224 / max|w|)) over up to two tensors; out[0] = SW, out[1] = 1 / (SA * SW)
 __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out) {
   unsigned int m = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    m = max(m, __float_as_uint(fabsf(w[i])));
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(w) & 15) == 0) {          // 16-byte loads over the aligned bulk, scalars for the tail
+    const size_t n4 = n / 4;
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = w4[i];
+      m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, __float_as_uint(fabsf(w[i])));
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, __float_as_uint(fabsf(w[i])));
+  }
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
@@ -609,9 +704,9 @@ int launch_weight_scale(const float* w0, size_t n0, const float* w1, size_t n1, 
   unsigned int* tmp = reinterpret_cast<unsigned int*>(scale2 + 2);  // scratch word right behind the two outputs
   cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return (int)e; }
-  absmax_kernel<<<148, 256, 0, s>>>(w0, n0, tmp);
+  absmax_kernel<<<148 * 8, 256, 0, s>>>(w0, n0, tmp);
   DRB_LAUNCH_CHECK();
-  if (w1 && n1) { absmax_kernel<<<148, 256, 0, s>>>(w1, n1, tmp); DRB_LAUNCH_CHECK(); }
+  if (w1 && n1) { absmax_kernel<<<148 * 8, 256, 0, s>>>(w1, n1, tmp); DRB_LAUNCH_CHECK(); }
   wscale_kernel<<<1, 1, 0, s>>>(tmp, scale2, sa, target);
   DRB_LAUNCH_CHECK();
   return 0;

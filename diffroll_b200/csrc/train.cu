@@ -16,6 +16,7 @@
 // Memory (one drb_train plan, caller-provided workspace): the inputs x_l, pre-activations y_l and gated activations z_l
 // of every layer are kept for the backward pass (L x M x 4C floats, 2.5 GB at 32 rolls x 640 frames).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -319,6 +320,20 @@ __global__ void spec_to_rows_kernel(const float* __restrict__ spec, float* __res
   }
 }
 
+// grad[n][c][tap] += dwt[n][tap * C + c]   (tap-major GEMM result -> PyTorch conv weight layout [out][in][k])
+__global__ void untap_add_kernel(const float* __restrict__ dwt, float* __restrict__ grad, int OC, int C, int k) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)OC * C * k) return;
+  const int tap = (int)(i % k); const size_t r = i / k; const int c = (int)(r % C); const size_t n = r / C;
+  grad[i] += dwt[n * ((size_t)k * C) + (size_t)tap * C + c];
+}
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+// inverse scale of a product of two scaled operands: out[0] = a[1] * b[1]   (slots as written by launch_weight_scale: {S, 1/S})
+__global__ void mul_inv_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out) { out[0] = a[1] * b[1]; }
+
 // Adam, torch.optim.Adam semantics (amsgrad=False, maximize=False; weight_decay adds wd * p to the gradient):
 //   m = b1 m + (1 - b1) g ; v = b2 v + (1 - b2) g^2 ; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
@@ -366,13 +381,27 @@ struct drb_train {
   // workspace offsets (bytes)
   size_t xs, ys, zs, skip, hbuf, obuf, spec, e0, p1, s1, p2, emb, dl, iota, wtmp, gskip, gx, gu, gz, gemb, gd, gsmall, total;
   bool fwd_done = false;
+  // tensor-core path of the two dilated-conv products that carry 2/3 of the step's FLOPs (forward conv, its transposed form):
+  // f16e5 operand pairs staged per layer, umma_gate_kernel with the linear epilogue (DRB_TRAIN_TC=0: everything on the CUDA cores)
+  bool tc = false;
+  // DRB_TRAIN_TC bits: 1 forward conv, 2 dgrad conv, 4 wgrad conv, 8 the 1x1 output_projection (forward and dgrad) on the tensor cores
+  // (default all).  Products that are linear in a gradient use f16e5 pairs (2 MMA units; their 2^-15 operand rounding stays a ~5e-5
+  // relative error of that gradient).  FORWARD products use f16x3 (fp16 hi + fp16 lo, 3 units, 22 mantissa bits): an f16e5 forward
+  // moved the activations by 1e-4 and with them ReLU / gate / L1-loss derivatives (measured worst gradient error 9e-4 .. 1.5e-2
+  // instead of 6e-5), so the forward gets fp32-grade operands.
+  int tc_mask = 15;
+  size_t uh, ul, gh, gl, sph, spl, wh, wl, wch, wcl, bnat, scal, gth, gtl, uth, utl;
+  CUtensorMap m_uh, m_ul, m_gh, m_gl, m_sh, m_sl, m_wfh, m_wfl, m_wgh, m_wgl, m_wch, m_wcl;
+  CUtensorMap m_ul5, m_sl5, m_wfl5, m_wcl5, m_woh, m_wol5, m_woTh, m_woTl;   // f16x3 aux views (fp16 lo) and the output_projection weights
+  CUtensorMap m_gth, m_gtl, m_uth, m_utl, m_dwt;   // transposed pairs g_y^T [2C][M], im2col(x + d)^T [k*C][M]; tap-major weight gradient [2C][k*C]
+  bool tc_wgrad = false;
   template <class Tp> Tp* at(size_t off) const { return reinterpret_cast<Tp*>(ws + off); }
 };
 
 static size_t train_layout(drb_train& p) {
   const drb_train_config& c = p.cfg;
   const size_t B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size, M = B * T;
-  p.Mp = (c.n_mels + 3) / 4 * 4;
+  p.Mp = (c.n_mels + 63) / 64 * 64;   // one K padding for the CUDA-core and the tensor-core conditioner products
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) / 256 * 256; return r; };
   p.xs = take(L * M * C * 4); p.ys = take(L * M * 2 * C * 4); p.zs = take(L * M * C * 4);
@@ -385,6 +414,12 @@ static size_t train_layout(drb_train& p) {
   p.wtmp = take(wmax * 4);
   p.gskip = take(M * C * 4); p.gx = take(M * C * 4); p.gu = take(M * C * 4); p.gz = take(M * C * 4);
   p.gemb = take(B * 512 * 4); p.gd = take(B * C * 4); p.gsmall = take(B * 512 * 4);
+  // operand pairs (2 + 2 bytes per element): x + d [M][C], g_y [M][2C], spectrogram [M][Mp], one layer's conv weights, conditioner weights
+  p.uh = take(M * C * 2); p.ul = take(M * C * 2); p.gh = take(M * 2 * C * 2); p.gl = take(M * 2 * C * 2);
+  p.sph = take(M * (size_t)p.Mp * 2); p.spl = take(M * (size_t)p.Mp * 2);
+  p.wh = take(2 * C * k * C * 2); p.wl = take(2 * C * k * C * 2); p.wch = take(2 * C * (size_t)p.Mp * 2); p.wcl = take(2 * C * (size_t)p.Mp * 2);
+  p.bnat = take(2 * C * 4); p.scal = take(16 * 4 * 4);
+  p.gth = take(2 * C * M * 2); p.gtl = take(2 * C * M * 2); p.uth = take(k * C * M * 2); p.utl = take(k * C * M * 2);
   p.total = off;
   return off;
 }
@@ -433,6 +468,37 @@ int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspa
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("train_create: %s", cudaGetErrorString(e)); delete p; return (int)e; }
+  {
+    const char* env = getenv("DRB_TRAIN_TC");
+    const int C = cfg->residual_channels, B = cfg->batch, T = cfg->frames, k = cfg->kernel_size, Mp = p->Mp;
+    p->tc = (C % 256) == 0 && !(env && env[0] == '0');
+    if (env && env[0] >= '1' && env[0] <= '9') p->tc_mask = atoi(env);
+    if (p->tc) {
+      int r = 0;
+      auto mk3 = [&](CUtensorMap* m, size_t off, int d0, int dtype) { if (!r) r = make_tmap_3d(m, p->ws + off, B, T, d0, 128, dtype); };
+      auto mk2 = [&](CUtensorMap* m, size_t off, int rows, uint64_t cols, int dtype) { if (!r) r = make_tmap_2d(m, p->ws + off, rows, cols, 128, dtype); };
+      mk3(&p->m_uh, p->uh, C, 2); mk3(&p->m_ul, p->ul, 2 * C, 3);
+      mk3(&p->m_gh, p->gh, 2 * C, 2); mk3(&p->m_gl, p->gl, 4 * C, 3);
+      mk3(&p->m_sh, p->sph, Mp, 2); mk3(&p->m_sl, p->spl, 2 * Mp, 3);
+      mk2(&p->m_wfh, p->wh, 2 * C, (uint64_t)k * C, 2); mk2(&p->m_wfl, p->wl, 2 * C, (uint64_t)2 * k * C, 3);
+      mk2(&p->m_wgh, p->wh, C, (uint64_t)k * 2 * C, 2); mk2(&p->m_wgl, p->wl, C, (uint64_t)2 * k * 2 * C, 3);
+      mk2(&p->m_wch, p->wch, 2 * C, Mp, 2); mk2(&p->m_wcl, p->wcl, 2 * C, (uint64_t)2 * Mp, 3);
+      mk3(&p->m_ul5, p->ul, C, 2); mk3(&p->m_sl5, p->spl, Mp, 2);
+      mk2(&p->m_wfl5, p->wl, 2 * C, (uint64_t)k * C, 2); mk2(&p->m_wcl5, p->wcl, 2 * C, Mp, 2);
+      mk2(&p->m_woh, p->wh, 2 * C, C, 2); mk2(&p->m_wol5, p->wl, 2 * C, C, 2);
+      mk2(&p->m_woTh, p->wh, C, 2 * C, 2); mk2(&p->m_woTl, p->wl, C, (uint64_t)4 * C, 3);
+      const uint64_t Mr = (uint64_t)B * T;
+      p->tc_wgrad = (T % 64) == 0 && ((uint64_t)k * C) % 256 == 0;
+      if (p->tc_wgrad) {
+        if (!r) r = make_tmap_3d(&p->m_gth, p->ws + p->gth, 1, 2 * C, Mr, 128, 2);
+        if (!r) r = make_tmap_3d(&p->m_gtl, p->ws + p->gtl, 1, 2 * C, 2 * Mr, 128, 3);
+        if (!r) r = make_tmap_2d(&p->m_uth, p->ws + p->uth, (uint64_t)k * C, Mr, 128, 2);
+        if (!r) r = make_tmap_2d(&p->m_utl, p->ws + p->utl, (uint64_t)k * C, 2 * Mr, 128, 3);
+        if (!r) r = make_tmap_3d(&p->m_dwt, p->ws + p->wtmp, 1, 2 * C, (uint64_t)k * C, 128, 1);
+      }
+      if (r) { delete p; return r; }
+    }
+  }
   *out = p;
   return 0;
 }
@@ -455,6 +521,8 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
     dim3 grid((T + 31) / 32, (Mp + 31) / 32, B), block(32, 8);
     spec_to_rows_kernel<<<grid, block, 0, s>>>(spec, p->at<float>(p->spec), B, c.n_mels, T, Mp);
     DRB_LAUNCH_CHECK();
+    if (p->tc && (p->tc_mask & 1))
+      TR(launch_split_pair(p->at<float>(p->spec), Mp, nullptr, 0, T, nullptr, p->ws + p->sph, p->ws + p->spl, (int)M, Mp, s, 5));
   }
   {  // diffusion embedding: table lookup, silu(projection1), silu(projection2)      model/diffwave.py:66-75
     gather_rows_kernel<<<nblk((size_t)B * 128), 256, 0, s>>>(emb_table, steps, p->at<float>(p->e0), B, 128);
@@ -485,6 +553,30 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
     d.A = p->at<float>(p->emb); d.lda = 512; d.T = 1; d.Ck = 512; d.W = w->wdp[l]; d.ldw = 512; d.bias = w->bdp[l]; d.C = d_l; d.ldc = C; d.M = B; d.N = C;
     TR(launch_simt_gemm(d, s));
     TR(launch_repack_conv_fp32(w->wd[l], wtmp, 2 * C, C, k, s));   // [2C][C][k] -> tap-major [2C][k*C]
+    if (p->tc && (p->tc_mask & 1)) {
+      // dilated_conv(x + d) + conditioner_projection(spec) (:138-144) as ONE tcgen05 implicit GEMM: 9 x C/64 tap slabs + Mp/64
+      // conditioner slabs into the same accumulator, fp32 pre-activations out
+      float* sw = p->at<float>(p->scal);
+      TR(launch_split_pair(x_l, C, d_l, C, T, nullptr, p->ws + p->uh, p->ws + p->ul, (int)M, C, s, 5));
+      TR(launch_weight_scale(wtmp, (size_t)2 * C * k * C, w->wc[l], (size_t)2 * C * c.n_mels, sw, 1.f, s));
+      TR(launch_repack_split(wtmp, p->ws + p->wh, p->ws + p->wl, 2 * C, k * C, k * C, 0, 5, sw, s));
+      TR(launch_repack_split(w->wc[l], p->ws + p->wch, p->ws + p->wcl, 2 * C, c.n_mels, Mp, 0, 5, sw, s));
+      add2_kernel<<<nblk(2 * C), 256, 0, s>>>(w->bd[l], w->bc[l], p->at<float>(p->bnat), 2 * C);
+      DRB_LAUNCH_CHECK();
+      UmmaConvLin cv;
+      cv.ah = &p->m_uh; cv.al = &p->m_ul5; cv.wh = &p->m_wfh; cv.wl = &p->m_wfl5; cv.sh = &p->m_sh; cv.sl = &p->m_sl5; cv.wch = &p->m_wch; cv.wcl = &p->m_wcl5;
+      cv.prec = 4;
+      cv.NB = B; cv.T = T; cv.Cin = C; cv.Nout = 2 * C; cv.taps = k; cv.dil = p->dil[l]; cv.Mp = Mp; cv.inv_scale = sw + 1;
+      cv.bias = p->at<float>(p->bnat); cv.out = y_l; cv.ldo = 2 * C;
+      // one launch per tap (the first carries the bias, the last the conditioner slabs): accumulation chains of C (+ Mp) instead
+      // of k*C + Mp terms, summed across launches in exact fp32
+      for (int tap = 0; tap < k; ++tap) {
+        cv.tap_lo = tap; cv.tap_n = 1; cv.accumulate = tap > 0;
+        cv.bias = tap == 0 ? p->at<float>(p->bnat) : nullptr;
+        cv.Mp = tap == k - 1 ? Mp : 0;
+        TR(launch_umma_conv_lin(cv, s));
+      }
+    } else {
     SimtGemm g;  // dilated_conv(x + d)   :138-139
     g.A = x_l; g.lda = C; g.T = T; g.taps = k; g.dil = p->dil[l]; g.Ck = C; g.addvec = d_l; g.addvec_steps = p->at<int>(p->iota);
     g.addvec_mod = B; g.addvec_stride = C; g.W = wtmp; g.ldw = k * C; g.bias = w->bd[l]; g.C = y_l; g.ldc = 2 * C; g.M = (int)M; g.N = 2 * C;
@@ -494,10 +586,23 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
     q.A = p->at<float>(p->spec); q.lda = Mp; q.T = T; q.Ck = Mp; q.W = wtmp; q.ldw = Mp; q.bias = w->bc[l]; q.accumulate = 1;
     q.C = y_l; q.ldc = 2 * C; q.M = (int)M; q.N = 2 * C;
     TR(launch_simt_gemm(q, s));
+    }
     TR(launch_gate(y_l, z_l, (int)M, C, s));
+    if (p->tc && (p->tc_mask & 8)) {   // output_projection(z) (:149) = the conv kernel with one tap, f16x3 operands
+      float* sw = p->at<float>(p->scal);
+      TR(launch_split_pair(z_l, C, nullptr, 0, T, nullptr, p->ws + p->uh, p->ws + p->ul, (int)M, C, s, 5));
+      TR(launch_weight_scale(w->wo[l], (size_t)2 * C * C, nullptr, 0, sw, 1.f, s));
+      TR(launch_repack_split(w->wo[l], p->ws + p->wh, p->ws + p->wl, 2 * C, C, C, 0, 5, sw, s));
+      UmmaConvLin cv;
+      cv.ah = &p->m_uh; cv.al = &p->m_ul5; cv.wh = &p->m_woh; cv.wl = &p->m_wol5; cv.prec = 4;
+      cv.NB = B; cv.T = T; cv.Cin = C; cv.Nout = 2 * C; cv.taps = 1; cv.dil = 1; cv.Mp = 0; cv.inv_scale = sw + 1;
+      cv.bias = w->bo[l]; cv.out = p->at<float>(p->obuf); cv.ldo = 2 * C;
+      TR(launch_umma_conv_lin(cv, s));
+    } else {
     SimtGemm o;  // output_projection(z)   :149
     o.A = z_l; o.lda = C; o.T = T; o.Ck = C; o.W = w->wo[l]; o.ldw = C; o.bias = w->bo[l]; o.C = p->at<float>(p->obuf); o.ldc = 2 * C; o.M = (int)M; o.N = 2 * C;
     TR(launch_simt_gemm(o, s));
+    }
     const int do_res = l < L - 1;
     res_skip_fwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(p->at<float>(p->obuf), x_l, do_res ? x_l + M * C : nullptr, p->at<float>(p->skip), M, C,
                                                         l == 0, do_res);
@@ -589,9 +694,24 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     TR(launch_wgrad(a, s));
     TR(launch_colsum(go, 2 * C, 2 * C, 1, (int)M, gr->bo[l], 2 * C, s));
     TR(launch_transpose(w->wo[l], wtmp, 2 * C, C, s));               // [2C][C] -> [C][2C]
+    if (p->tc && (p->tc_mask & 8)) {                                 // g_z = g_o . W_o: one-tap conv kernel over scaled f16e5 pairs
+      float* so = p->at<float>(p->scal) + 4; float* sw = p->at<float>(p->scal) + 8; float* sc = p->at<float>(p->scal) + 12;
+      TR(launch_weight_scale(go, M * 2 * C, nullptr, 0, so, 1.f, s));
+      TR(launch_split_pair(go, 2 * C, nullptr, 0, T, so, p->ws + p->gh, p->ws + p->gl, (int)M, 2 * C, s));
+      TR(launch_weight_scale(wtmp, (size_t)2 * C * C, nullptr, 0, sw, 1.f, s));
+      TR(launch_repack_split(wtmp, p->ws + p->wh, p->ws + p->wl, C, 2 * C, 2 * C, 0, 3, sw, s));
+      mul_inv_kernel<<<1, 1, 0, s>>>(so, sw, sc);
+      DRB_LAUNCH_CHECK();
+      UmmaConvLin cv;
+      cv.ah = &p->m_gh; cv.al = &p->m_gl; cv.wh = &p->m_woTh; cv.wl = &p->m_woTl;
+      cv.NB = B; cv.T = T; cv.Cin = 2 * C; cv.Nout = C; cv.taps = 1; cv.dil = 1; cv.Mp = 0; cv.inv_scale = sc;
+      cv.bias = nullptr; cv.out = gz; cv.ldo = C;
+      TR(launch_umma_conv_lin(cv, s));
+    } else {
     SimtGemm g;                                                      // g_z = g_o . W_o
     g.A = go; g.lda = 2 * C; g.T = T; g.Ck = 2 * C; g.W = wtmp; g.ldw = 2 * C; g.C = gz; g.ldc = C; g.M = (int)M; g.N = C;
     TR(launch_simt_gemm(g, s));
+    }
     gate_bwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(y_l, gz, y_l, M, C);
     DRB_LAUNCH_CHECK();
     const float* gy = y_l;
@@ -601,18 +721,54 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     cw.G = gy; cw.ldg = 2 * C; cw.X = p->at<float>(p->spec); cw.ldx = Mp; cw.M = (int)M; cw.T = T; cw.N = 2 * C; cw.Ck = c.n_mels;
     cw.dW = gr->wc[l]; cw.sn = c.n_mels;
     TR(launch_wgrad(cw, s));
+    float* sg = p->at<float>(p->scal) + 4;                           // {S_g, 1 / S_g}: power-of-two scale that lifts g_y into fp16's range
+    const bool tc_w = p->tc && p->tc_wgrad && (p->tc_mask & 4), tc_d = p->tc && (p->tc_mask & 2);
+    if (tc_w || tc_d) TR(launch_weight_scale(gy, M * 2 * C, nullptr, 0, sg, 1.f, s));
+    if (tc_w) {
+      // dilated_conv.weight on the tensor cores: one plain GEMM  dW[n][tap*C + c] = sum_m g_y^T[n][m] * im2col(x + d)^T[tap*C + c][m]
+      // over transposed f16e5 operand pairs (K = rolls x frames), fp32 result in tap-major order, then added into [2C][C][k]
+      TR(launch_split_pair_T(gy, 2 * C, nullptr, 0, T, 1, 1, sg, p->ws + p->gth, p->ws + p->gtl, (int)M, 2 * C, 0, s));
+      TR(launch_split_pair_T(x_l, C, d_l, C, T, k, p->dil[l], nullptr, p->ws + p->uth, p->ws + p->utl, (int)M, C, 1, s));
+      UmmaZGemm zg;
+      zg.pair = 1; zg.persistent = 0; zg.NB = 1; zg.T = 2 * C; zg.C = k * C; zg.prec = 3; zg.mode = 4; zg.groups = 1; zg.z_group0 = 0; zg.group_stride = 0;
+      zg.inv_scale = sg + 1; zg.w_h = &p->m_uth; zg.w_l = &p->m_utl; zg.out32 = &p->m_dwt; zg.bias = nullptr; zg.dnext = nullptr;
+      zg.a_h = &p->m_gth; zg.a_l = &p->m_gtl; zg.nslabs64 = (int)(M / 64);
+      UmmaMaps dummy;
+      dummy.xh = p->m_gth; dummy.xl = p->m_gtl; dummy.zh = p->m_gth; dummy.zl = p->m_gtl;
+      TR(launch_umma_zgemm(dummy, zg, s));
+      const size_t n = (size_t)2 * C * C * k;
+      untap_add_kernel<<<nblk(n), 256, 0, s>>>(wtmp, gr->wd[l], 2 * C, C, k);
+      DRB_LAUNCH_CHECK();
+    } else {
     Wgrad dw;                                                        // dilated_conv.weight [2C][C][k]: the forward's tap gather of x + d
     dw.G = gy; dw.ldg = 2 * C; dw.X = x_l; dw.ldx = C; dw.addvec = d_l; dw.av_stride = C; dw.M = (int)M; dw.T = T; dw.N = 2 * C; dw.Ck = C;
     dw.taps = k; dw.dil = p->dil[l]; dw.dW = gr->wd[l]; dw.sn = (long long)C * k; dw.sc = k; dw.st = 1;
     TR(launch_wgrad(dw, s));
+    }
     {                                                                // g_u = transposed dilated conv of g_y
       const size_t n = (size_t)2 * C * C * k;
       repack_dgrad_kernel<<<nblk(n), 256, 0, s>>>(w->wd[l], wtmp, 2 * C, C, k);
       DRB_LAUNCH_CHECK();
+      if (tc_d) {
+        // the same tcgen05 kernel with 2C input channels: g_y is scaled into fp16's range by a per-tensor power of two first
+        // (gradients of a mean loss sit around 1e-6), the weights by theirs; the epilogue divides by the product
+        float* sw = p->at<float>(p->scal) + 8; float* sc = p->at<float>(p->scal) + 12;
+        TR(launch_split_pair(gy, 2 * C, nullptr, 0, T, sg, p->ws + p->gh, p->ws + p->gl, (int)M, 2 * C, s));
+        TR(launch_weight_scale(wtmp, n, nullptr, 0, sw, 1.f, s));
+        TR(launch_repack_split(wtmp, p->ws + p->wh, p->ws + p->wl, C, k * 2 * C, k * 2 * C, 0, 3, sw, s));
+        mul_inv_kernel<<<1, 1, 0, s>>>(sg, sw, sc);
+        DRB_LAUNCH_CHECK();
+        UmmaConvLin cv;
+        cv.ah = &p->m_gh; cv.al = &p->m_gl; cv.wh = &p->m_wgh; cv.wl = &p->m_wgl;
+        cv.NB = B; cv.T = T; cv.Cin = 2 * C; cv.Nout = C; cv.taps = k; cv.dil = p->dil[l]; cv.Mp = 0; cv.inv_scale = sc;
+        cv.bias = nullptr; cv.out = gu; cv.ldo = C;
+        TR(launch_umma_conv_lin(cv, s));
+      } else {
       SimtGemm u;
       u.A = gy; u.lda = 2 * C; u.T = T; u.taps = k; u.dil = p->dil[l]; u.Ck = 2 * C; u.W = wtmp; u.ldw = k * 2 * C; u.C = gu; u.ldc = C;
       u.M = (int)M; u.N = C;
       TR(launch_simt_gemm(u, s));
+      }
     }
     // diffusion_projection: d enters only through the conv input x + d (broadcast over the frames of a roll)
     DRB_CUDA(cudaMemsetAsync(gd, 0, (size_t)B * C * 4, s));

@@ -59,6 +59,8 @@ constexpr int EPI_THREADS = 256;
 //   2  f16f8    fp16 product + e4m3 correction product          aux = e4m3 tiles [lo*SA | hi] / [hi*SW | lo*SA*SW],
 //                                                                second accumulator (TMEM columns 256..511)
 //   3  f16e5    fp16 product + e5m2 correction product          aux = e5m2 tiles, unit total scale: same accumulator
+//   4  f16x3    fp16 hi/lo (lo = fp16(v - hi): 22 mantissa bits), 3 products into one accumulator: fp32-grade, used by the
+//               TRAINING forward (csrc/train.cu), whose rounding would otherwise move ReLU / gate / loss derivatives
 template <int P, bool PAIR>
 struct Cfg {
   static constexpr bool kAux = P != 0;
@@ -68,7 +70,7 @@ struct Cfg {
   static constexpr int kStages = kRingBytes / kStageBytes;                 // 2 (single) / 3 (pair) with aux operands
   static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*bias, d_next*/;
   static constexpr uint32_t kTmemCols = P == 2 ? 512 : 256;
-  static constexpr int kAuxMul = P >= 2 ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
+  static constexpr int kAuxMul = (P == 2 || P == 3) ? 2 : 1;  // aux element coordinate = kAuxMul * main element coordinate
   static constexpr int kAOff = 0, kAAuxOff = A_TILE_BYTES;
   static constexpr int kBOff = (kAux ? 2 : 1) * A_TILE_BYTES, kBAuxOff = kBOff + kBBytes;
   static constexpr int kMaxStages = 6;
@@ -95,6 +97,14 @@ struct alignas(64) GateParams {
   // atoms (2 KB per N block and K-slab, un-swizzled), activation scale factors [roll][chunk][frame][8]
   CUtensorMap xw4, wd4, wsf;
   const uint8_t* xs;
+  // Linear epilogue (training, csrc/train.cu): instead of the gate, every accumulator column leaves as fp32
+  // out[(roll * T + t) * ldo + nblk * 256 + column] = acc / scale + bias[column]  (weights in natural row order).
+  float* lin_out;
+  int ldo;
+  // A launch may cover only the taps [tap_lo, tap_lo + tap_n) (tap_n == 0: all) and ADD its result to lin_out (lin_acc): the tensor
+  // core's fp32 accumulation loses ~1e-8 of the running sum per K-step, which a 4608-long chain turns into 4e-5 -- short chains summed
+  // in exact fp32 in global memory keep the training forward at the fp32 floor (csrc/train.cu)
+  int tap_lo, tap_n, lin_acc;
 };
 
 struct alignas(64) ZGemmParams {
@@ -216,7 +226,7 @@ __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool fi
     const uint32_t acc = k == 0 ? acc0 : 1u;
     if (PAIR) {
       umma_bf16_pair(tmem_d, da_hi, db_hi, idesc, acc);   // kind::f16: bf16 or fp16 per idesc
-      if (P == 1) {
+      if (P == 1 || P == 4) {
         umma_bf16_pair(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
         umma_bf16_pair(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
       }
@@ -224,7 +234,7 @@ __device__ __forceinline__ void issue_slab(uint8_t* st, uint32_t tmem_d, bool fi
       if (P == 3) umma_f8_pair(tmem_d, make_sw128_desc(a_lo + ko), make_sw128_desc(b_lo + ko), idesc_e5, 1u);
     } else {
       umma_bf16(tmem_d, da_hi, db_hi, idesc, acc);
-      if (P == 1) {
+      if (P == 1 || P == 4) {
         umma_bf16(tmem_d, make_sw128_desc(a_lo + ko), db_hi, idesc, 1u);
         umma_bf16(tmem_d, da_hi, make_sw128_desc(b_lo + ko), idesc, 1u);
       }
@@ -269,7 +279,7 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float inv_scale, floa
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(c[i]), inv_scale, __uint_as_float(r[i]));
-  } else if (P == 3) {   // f16e5: weights were split as W * SW (a power of two, keeps small weights out of the fp16 subnormals)
+  } else if (P == 3 || P == 4) {   // f16e5 / f16x3: weights were split as W * SW (a power of two, keeps small weights out of the fp16 subnormals)
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * inv_scale;
@@ -332,6 +342,40 @@ __device__ __forceinline__ void gate_epilogue(const SmemView& sv, const GatePara
     mbar_wait(sv.tmem_full, 0);  // every MMA has retired: accumulator complete, ring memory free
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.lin_out) {                       // training: plain fp32 result, natural column order, straight from registers
+      const float inv_l = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
+      const int t = t0 + row;
+      float* dst = p.lin_out + ((size_t)nb * p.T + (t < p.T ? t : 0)) * (size_t)p.ldo + nblk * TILE_N + grp * 128;
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float v[32];
+        load_acc32<P>(taddr + grp * 128 + c4 * 32, inv_l, v);
+        if (t < p.T) {
+          // the bias is read from global memory HERE, after griddepcontrol.wait: in training it is produced by the kernel launched
+          // just before this one, and the shared-memory copy staged in the prologue may predate it (programmatic dependent launch).
+          // Accumulating launches fetch their 8 float4 of old values BEFORE the first store of the chunk: interleaved load/store
+          // pairs on the same row ran 9x slower (570 vs 66 us per launch), every load queued behind the previous store.
+          float4 o4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias_cond) o4[i] = *reinterpret_cast<const float4*>(p.bias_cond + nblk * TILE_N + grp * 128 + c4 * 32 + i * 4);
+          }
+          if (p.lin_acc) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = __ldcg(reinterpret_cast<const float4*>(dst + c4 * 32 + i * 4));
+              o4[i].x += q.x; o4[i].y += q.y; o4[i].z += q.z; o4[i].w += q.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(dst + c4 * 32 + i * 4) = make_float4(v[4 * i] + o4[i].x, v[4 * i + 1] + o4[i].y, v[4 * i + 2] + o4[i].z, v[4 * i + 3] + o4[i].w);
+        }
+      }
+      tc_fence_before();
+      return;
+    }
     // staging: z main boxes 0,1 then z aux boxes 0,1; each [128 frames][128 bytes], 128-byte swizzled
     const uint32_t stg = smem_u32(sv.stage0);
     const float inv = (P >= 2) ? __ldg(p.inv_scale) : 0.f;
@@ -388,7 +432,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_kernel(const __grid_
   const int nb = mt / p.tiles_t;
   const int t0 = tt * TILE_M;
   const int cpt = p.C / TILE_K;  // K-slabs per tap
-  const int conv_slabs = p.taps * cpt;
+  const int conv_slabs = (p.tap_n > 0 ? p.tap_n : p.taps) * cpt;
   // Both CTAs of a cluster run the same slab list.  If only the first tile of the pair is conditional, the second
   // one runs the conditioner slabs too: its spectrogram coordinate (roll >= n_cond) is out of bounds, so TMA feeds zeros.
   const int nb_first = PAIR ? (cid * 2) / p.tiles_t : nb;
@@ -401,8 +445,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_kernel(const __grid_
     if (CF::kAux) { tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l); tma_prefetch_desc(&p.zl); }
   }
   if (warp == 3) {  // this tile's 256 bias values -> smem (the epilogue reads them as warp-wide broadcasts)
-    const float* bsrc = (nb < p.n_cond ? p.bias_cond : p.bias_unc) + nblk * TILE_N;
-    for (int i = lane; i < TILE_N; i += 32) sv.sbias[i] = __ldg(bsrc + i);
+    const float* bsrc = (nb < p.n_cond ? p.bias_cond : p.bias_unc);
+    for (int i = lane; i < TILE_N; i += 32) sv.sbias[i] = bsrc ? __ldg(bsrc + nblk * TILE_N + i) : 0.f;
   }
   prologue<P, PAIR>(sv, warp);
   const uint32_t tmem_base = *sv.tmem_ptr;
@@ -417,7 +461,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_kernel(const __grid_
         const uint32_t fb = PAIR ? mapa_cluster(smem_u32(fl), 0) : 0u;
         prod_expect<PAIR>(fl, fb, CF::kStageBytes);
         if (s < conv_slabs) {
-          const int tap = s / cpt, cc = s - tap * cpt;
+          const int tap = p.tap_lo + s / cpt, cc = s % cpt;
           const int trow = t0 + (tap - half) * p.dil;
           load_a<PAIR>(st + CF::kAOff, &p.xh, fl, fb, cc * TILE_K, trow, nb);
           load_b<PAIR>(st + CF::kBOff, &p.wd_h, fl, fb, tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
@@ -1323,7 +1367,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
         for (int v = 0; v < 8; ++v) {
           const int i = v * 4;
           float4 h;
-          const float floor_ = p.mode == 2 ? -INFINITY : 0.f;   // HEAD: ReLU; conditioner tables: linear
+          const float floor_ = (p.mode == 2 || p.mode == 4) ? -INFINITY : 0.f;   // HEAD: ReLU; conditioner tables / plain GEMM: linear
           h.x = fmaxf(o[i + 0] + bs[i + 0], floor_);
           h.y = fmaxf(o[i + 1] + bs[i + 1], floor_);
           h.z = fmaxf(o[i + 2] + bs[i + 2], floor_);
@@ -1902,6 +1946,7 @@ int umma_init() {
   set((const void*)umma_gate_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_gate_kernel<1, true>, Cfg<1, false>::kSmemBytes);
   set((const void*)umma_gate_kernel<2, false>, Cfg<2, false>::kSmemBytes); set((const void*)umma_gate_kernel<2, true>, Cfg<2, false>::kSmemBytes);
   set((const void*)umma_gate_kernel<3, false>, Cfg<3, false>::kSmemBytes); set((const void*)umma_gate_kernel<3, true>, Cfg<3, false>::kSmemBytes);
+  set((const void*)umma_gate_kernel<4, false>, Cfg<4, false>::kSmemBytes); set((const void*)umma_gate_kernel<4, true>, Cfg<4, false>::kSmemBytes);
   set((const void*)umma_gate_win_kernel<1>, Cfg<1, true>::kSmemBytes); set((const void*)umma_gate_win_kernel<2>, Cfg<2, true>::kSmemBytes);
   set((const void*)umma_gate_win_kernel<3>, Cfg<3, true>::kSmemBytes);
   set((const void*)umma_gate_pers_kernel<1, false>, PW_SMEM); set((const void*)umma_gate_pers_kernel<3, false>, PW_SMEM);
@@ -2003,7 +2048,8 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   p.cond_slabs = g.Mp / TILE_K; p.tiles_t = (g.T + TILE_M - 1) / TILE_M; p.n_blocks = 2 * g.C / TILE_N;
   p.z_group0 = g.z_group0;
   p.bias_cond = g.bias_cond; p.bias_unc = g.bias_unc;
-  p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0; p.xs = nullptr;
+  p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0; p.xs = nullptr; p.lin_out = nullptr; p.ldo = 0;
+  p.tap_lo = 0; p.tap_n = 0; p.lin_acc = 0;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = g.inv_scale;
   const bool mc = g.pair && ((p.NB * p.tiles_t) % 2 == 0);
@@ -2058,14 +2104,42 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
             : launch_k(umma_gate_kernel<0, false>, p, grid, Cfg<0, false>::kSmemBytes, false, s);
 }
 
+// Dilated conv (+ optional 1x1 conditioner term as extra K-slabs) with a linear fp32 epilogue: the training forward and its
+// transposed form (dgrad), csrc/train.cu.  f16e5 operand pairs, one tile per CTA (pair).
+int launch_umma_conv_lin(const UmmaConvLin& c, cudaStream_t s) {
+  if ((c.Nout % TILE_N) || (c.Cin % TILE_K) || (c.taps & 1) == 0 || (c.Mp % TILE_K) || !c.out || (c.ldo & 3)) {
+    set_error("umma_conv_lin: unsupported Cin=%d Nout=%d taps=%d Mp=%d", c.Cin, c.Nout, c.taps, c.Mp);
+    return DRB_E_INVALID;
+  }
+  GateParams p;
+  memset(&p, 0, sizeof(p));
+  p.xh = *c.ah; p.xl = *c.al; p.wd_h = *c.wh; p.wd_l = *c.wl;
+  p.zh = *c.ah; p.zl = *c.al; p.xwh = *c.ah; p.xwl = *c.al;      // never used by this epilogue; valid descriptors for the prefetch
+  if (c.Mp > 0) { p.sh = *c.sh; p.sl = *c.sl; p.wc_h = *c.wch; p.wc_l = *c.wcl; }
+  else { p.sh = *c.ah; p.sl = *c.al; p.wc_h = *c.wh; p.wc_l = *c.wl; }
+  p.NB = c.NB; p.n_cond = c.Mp > 0 ? c.NB : 0; p.T = c.T; p.C = c.Cin; p.taps = c.taps; p.dil = c.dil;
+  p.cond_slabs = c.Mp / TILE_K; p.tiles_t = (c.T + TILE_M - 1) / TILE_M; p.n_blocks = c.Nout / TILE_N; p.z_group0 = 0;
+  p.bias_cond = c.bias; p.bias_unc = c.bias; p.inv_scale = c.inv_scale;
+  p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0; p.xs = nullptr; p.win_rows = TILE_M; p.n_items = 0;
+  p.lin_out = c.out; p.ldo = c.ldo;
+  p.tap_lo = c.tap_lo; p.tap_n = c.tap_n; p.lin_acc = c.accumulate;
+  if (c.tap_n < 0 || c.tap_lo < 0 || c.tap_lo + c.tap_n > c.taps) { set_error("umma_conv_lin: bad tap range"); return DRB_E_INVALID; }
+  const int grid = p.NB * p.tiles_t * p.n_blocks;
+  const bool mc = c.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  if (c.prec == 4) return mc ? launch_k(umma_gate_kernel<4, true>, p, grid, Cfg<4, false>::kSmemBytes, true, s)
+                             : launch_k(umma_gate_kernel<4, false>, p, grid, Cfg<4, false>::kSmemBytes, false, s);
+  return mc ? launch_k(umma_gate_kernel<3, true>, p, grid, Cfg<3, false>::kSmemBytes, true, s)
+            : launch_k(umma_gate_kernel<3, false>, p, grid, Cfg<3, false>::kSmemBytes, false, s);
+}
+
 int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) {
   if (z.C % TILE_N) { set_error("umma_zgemm: unsupported C=%d", z.C); return DRB_E_INVALID; }
   ZGemmParams p;
   p.zh = maps.zh; p.zl = maps.zl; p.w_h = *z.w_h; p.w_l = *z.w_l; p.out32 = *z.out32; p.xh = maps.xh; p.xl = maps.xl;
   p.NB = z.NB; p.T = z.T; p.C = z.C; p.tiles_t = (z.T + TILE_M - 1) / TILE_M; p.n_blocks = z.C / TILE_N;
   p.spg = z.C / TILE_K; p.nslabs = z.groups * p.spg;
-  if (z.mode == 2) {   // conditioner tables: A = spectrogram pair, C counts the 2C output channels, K = nslabs64 slabs
-    if (!z.a_h || !z.a_l || z.nslabs64 <= 0) { set_error("umma_zgemm: mode 2 needs the spectrogram maps"); return DRB_E_INVALID; }
+  if (z.mode == 2 || z.mode == 4) {   // A = caller's operand pair (2: spectrogram; 4: any), C counts the output columns, K = nslabs64 slabs
+    if (!z.a_h || !z.a_l || z.nslabs64 <= 0) { set_error("umma_zgemm: mode %d needs the A operand maps", z.mode); return DRB_E_INVALID; }
     p.zh = *z.a_h; p.zl = *z.a_l; p.spg = z.nslabs64; p.nslabs = z.nslabs64;
   } p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
