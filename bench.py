@@ -454,7 +454,8 @@ def train_step_extra(ctx, B=16, iters=3):
     nz = noise.to(ctx.dev)
     mask = (torch.arange(B) % 4 == 1).long()
     res = {"what": f"one training step (forward with spec dropout, backward to 130 tensors, Adam) on {B} rolls x {FRAMES} frames; "
-                   "ours = fp32 CUDA cores; eager = torch autograd over the oracle + torch.optim.Adam on this GPU",
+                   "ours = csrc/train.cu (tcgen05 products at fp32-grade gradient parity; fp32 CUDA-core variant beside it); "
+                   "eager = torch autograd over the oracle + torch.optim.Adam on this GPU",
            "batch": B, "algorithmic_tflop_per_step": 3 * FLOP_BRANCH * B / 1e12}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -466,16 +467,30 @@ def train_step_extra(ctx, B=16, iters=3):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
-    m = M.ClassifierFreeDiffRoll(**hp); m.load_state_dict(make_state_dict(hp)); m = m.to(ctx.dev).train()
-    opt = m.configure_optimizers()[0]
+    # default: tensor-core products (f16x3 forward with per-tap fp32 accumulation, f16e5 backward); then everything in fp32 on the CUDA cores
+    for key, env in (("ours_ms", None), ("ours_fp32_cuda_cores_ms", "0")):
+        old_env = os.environ.get("DRB_TRAIN_TC")
+        if env is not None:
+            os.environ["DRB_TRAIN_TC"] = env
+        try:
+            m = M.ClassifierFreeDiffRoll(**hp); m.load_state_dict(make_state_dict(hp)); m = m.to(ctx.dev).train()
+            opt = m.configure_optimizers()[0]
 
-    def ours():
-        opt.zero_grad(); m.training_step(batch, 0, t=t, noise=nz, dropout_mask=mask); opt.step()
-    res["ours_ms"] = timed(ours)
-    res["ours_steps_per_s"] = 1000.0 / res["ours_ms"]
-    res["workspace_bytes"] = list(m._train_engines.values())[0].workspace_bytes
-    m.release_buffers(); del m, opt
-    torch.cuda.empty_cache()
+            def ours():
+                opt.zero_grad(); m.training_step(batch, 0, t=t, noise=nz, dropout_mask=mask); opt.step()
+            res[key] = timed(ours)
+            if env is None:
+                res["ours_steps_per_s"] = 1000.0 / res[key]
+                res["ours_algorithmic_tflops"] = res["algorithmic_tflop_per_step"] / (res[key] / 1000.0)
+                res["workspace_bytes"] = list(m._train_engines.values())[0].workspace_bytes
+            m.release_buffers(); del m, opt
+            torch.cuda.empty_cache()
+        finally:
+            if env is not None:
+                if old_env is None:
+                    os.environ.pop("DRB_TRAIN_TC", None)
+                else:
+                    os.environ["DRB_TRAIN_TC"] = old_env
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     try:
         for name, flag in (("eager_fp32_ms", False), ("eager_tf32_ms", True)):

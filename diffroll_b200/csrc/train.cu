@@ -6,12 +6,14 @@
 //              DiffusionEmbedding.forward                model/diffwave.py:66-75
 //              configure_optimizers (torch.optim.Adam)   task/diffusion.py:1057-1067
 //
-// Arithmetic: fp32 on the CUDA cores, like the reference trains.  The contractions reuse the generic fp32 GEMM of the
-// validation path (simt_kernels.cu: NT form with the dilated-tap gather) for the forward and for every "gradient with
-// respect to the input" product (dgrad: the same gather with flipped taps over a transposed weight copy), and one new
-// kernel for every "gradient with respect to a weight" product (wgrad: contraction over rolls x frames, TN form, the
-// same tap gather on the activation side, split over the row range with fp32 atomics).  This is the functional
-// version of the row: parity-exact against fp32 autograd; moving dgrad / wgrad onto tcgen05 is the follow-up.
+// Arithmetic.  DRB_TRAIN_TC=0: fp32 on the CUDA cores throughout, like the reference trains -- the contractions reuse the
+// generic fp32 GEMM of the validation path (simt_kernels.cu: NT form with the dilated-tap gather) for the forward and for
+// every "gradient with respect to the input" product (dgrad: the same gather with mirrored taps over a transposed weight
+// copy), and simt_wgrad_kernel for every "gradient with respect to a weight" product (contraction over rolls x frames, TN
+// form, the same tap gather on the activation side, fp32 atomics).  Default: the five products that carry 97 % of the
+// FLOPs run on the tensor cores (umma_gemm.cu): the forward conv and output_projection in f16x3 (fp16 hi + lo, fp32-grade)
+// with one launch per tap and exact fp32 accumulation across launches, conv dgrad and the 1x1 dgrad through the same
+// kernel over scaled f16e5 pairs, conv wgrad as one plain GEMM over transposed im2col pairs.  DESIGN.md section 8.
 //
 // Memory (one drb_train plan, caller-provided workspace): the inputs x_l, pre-activations y_l and gated activations z_l
 // of every layer are kept for the backward pass (L x M x 4C floats, 2.5 GB at 32 rolls x 640 frames).
@@ -390,6 +392,7 @@ struct drb_train {
   // moved the activations by 1e-4 and with them ReLU / gate / L1-loss derivatives (measured worst gradient error 9e-4 .. 1.5e-2
   // instead of 6e-5), so the forward gets fp32-grade operands.
   int tc_mask = 15;
+  int taps_per_launch = 1;   // DRB_TRAIN_TAPS: taps of the forward conv per tensor-core launch (accumulation chain = taps * C terms)
   size_t uh, ul, gh, gl, sph, spl, wh, wl, wch, wcl, bnat, scal, gth, gtl, uth, utl;
   CUtensorMap m_uh, m_ul, m_gh, m_gl, m_sh, m_sl, m_wfh, m_wfl, m_wgh, m_wgl, m_wch, m_wcl;
   CUtensorMap m_ul5, m_sl5, m_wfl5, m_wcl5, m_woh, m_wol5, m_woTh, m_woTl;   // f16x3 aux views (fp16 lo) and the output_projection weights
@@ -473,6 +476,8 @@ int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspa
     const int C = cfg->residual_channels, B = cfg->batch, T = cfg->frames, k = cfg->kernel_size, Mp = p->Mp;
     p->tc = (C % 256) == 0 && !(env && env[0] == '0');
     if (env && env[0] >= '1' && env[0] <= '9') p->tc_mask = atoi(env);
+    const char* et = getenv("DRB_TRAIN_TAPS");
+    if (et && atoi(et) >= 1) p->taps_per_launch = atoi(et);
     if (p->tc) {
       int r = 0;
       auto mk3 = [&](CUtensorMap* m, size_t off, int d0, int dtype) { if (!r) r = make_tmap_3d(m, p->ws + off, B, T, d0, 128, dtype); };
@@ -570,10 +575,11 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
       cv.bias = p->at<float>(p->bnat); cv.out = y_l; cv.ldo = 2 * C;
       // one launch per tap (the first carries the bias, the last the conditioner slabs): accumulation chains of C (+ Mp) instead
       // of k*C + Mp terms, summed across launches in exact fp32
-      for (int tap = 0; tap < k; ++tap) {
-        cv.tap_lo = tap; cv.tap_n = 1; cv.accumulate = tap > 0;
+      for (int tap = 0; tap < k; tap += p->taps_per_launch) {
+        const int tn = tap + p->taps_per_launch <= k ? p->taps_per_launch : k - tap;
+        cv.tap_lo = tap; cv.tap_n = tn; cv.accumulate = tap > 0;
         cv.bias = tap == 0 ? p->at<float>(p->bnat) : nullptr;
-        cv.Mp = tap == k - 1 ? Mp : 0;
+        cv.Mp = tap + tn == k ? Mp : 0;
         TR(launch_umma_conv_lin(cv, s));
       }
     } else {
