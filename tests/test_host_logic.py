@@ -131,8 +131,10 @@ def test_no_cpu_fallback_and_training_mode_guard():
     from diffroll_b200._lib import DrbError
     m, hp = _model()
     x, w = torch.randn(1, 1, 128, 88), torch.randn(1, 65536)
-    with pytest.raises(NotImplementedError):
-        m(x, w, torch.tensor([3]))                 # training mode: spec dropout is not on this path
+    with pytest.raises(DrbError):
+        m(x, w, torch.tensor([3]))                 # training mode (spec dropout + saved activations) is CUDA-only as well
+    with pytest.raises(DrbError):
+        m.training_step({"frame": torch.zeros(1, 128, 88), "audio": w}, 0)
     m.eval()
     with pytest.raises(DrbError):
         m(x, w, torch.tensor([3]))                 # CPU tensors: no fallback
