@@ -582,7 +582,8 @@ def run_b200(args, rank, world, local):
     if cfg_id == 1 and os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("umma_gate_kernel_dram_bytes_per_launch")
+                tj = json.load(f)
+                traffic = tj.get("umma_gate_n4_kernel_dram_bytes_per_launch", tj.get("umma_gate_kernel_dram_bytes_per_launch"))
         except Exception:
             traffic = None
     prec = main["precision"]       # what the plan actually computes in (f16n4 steps down to f16e5 on odd tile counts)

@@ -43,6 +43,7 @@ struct Layout {  // byte offsets into the workspace
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
   size_t wouth, woutl;                                  // output_projection rows padded to 256, operand pair (tensor-core head)
+  size_t sp5h, sp5l, wc5h, wc5l;                        // f16x3 (fp16 hi + fp16 lo) pairs of the spectrogram and the conditioner weights (tables)
   size_t xs, wsf4;                                      // f16n4: activation scale factors [NB][C/64][T][8]; weight scale atoms [L][2C/256][k*C/64][2048]
   size_t range;                                         // one word: max |activation operand| (fp32 bits) since the last reset
   size_t wcpad, cond;                                   // fp32 Wc of every layer padded to Mp; conditioner projections of the spectrogram [L][B][T][2C]
@@ -112,7 +113,7 @@ static Layout make_layout(const drb_config& c) {
     l.woh = take(L * 2 * C * C * 2); l.wol = take(L * 2 * C * C * 2);
     l.wcomp32 = take(C * L * C * 4); l.wcomph = take(C * L * C * 2); l.wcompl = take(C * L * C * 2);
     l.bcomp = take(C * 4); l.bsum = take(C * 4);
-    l.wscale = take((3 * L + 2) * 4 * 4);
+    l.wscale = take((4 * L + 2) * 4 * 4);
     l.wouth = take(256 * C * 2); l.woutl = take(256 * C * 2);
     if (c.precision == DRB_PREC_F16N4) {
       l.xs = take(NB * (C / 64) * T * 8);
@@ -120,6 +121,7 @@ static Layout make_layout(const drb_config& c) {
     }  // f16f8: {SW, 1/(SA*SW), scratch, -} per gate / out weight set and the head
     if (c.branches != DRB_BRANCH_UNCOND && c.precision != DRB_PREC_F16F8 && c.precision != DRB_PREC_BF16) {
       l.wcpad = take(L * 2 * C * Mp * 4); l.cond = take(L * B * T * 2 * C * 4);
+      l.sp5h = take(B * T * Mp * 2); l.sp5l = take(B * T * Mp * 2); l.wc5h = take(L * 2 * C * Mp * 2); l.wc5l = take(L * 2 * C * Mp * 2);
     }
   }
   l.total = off;
@@ -179,6 +181,12 @@ struct drb_plan {
   float* wscale(int slot) const { return at<float>(lay.wscale) + 4 * slot; }  // slot 2l: gate weights, 2l+1: Wo, 2L: head, 2L+1+l: Wc (f16n4)
   int wc_slot(int layer) const { return n4() ? 2 * cfg.residual_layers + 1 + layer : 2 * layer; }   // f16n4 scales the conv weights alone
   int wout_slot() const { return 3 * cfg.residual_layers + 1; }
+  int wc5_slot(int layer) const { return 3 * cfg.residual_layers + 2 + layer; }
+  // conditioner tables on the tensor cores at fp32 grade: f16x3 operands (22 mantissa bits) and K = Mp = 256 per accumulation
+  // chain, i.e. at the floor of the tensor core's fp32 accumulation (8e-6 on the network output, csrc/train.cu)
+  CUtensorMap sp5h, sp5l;
+  std::vector<CUtensorMap> wc5h, wc5l;
+  int cond_tc = 0;
   // tensor-core head: HEAD leaves relu(skip_projection) as an operand pair, output_projection + guidance + posterior run as
   // one tcgen05 kernel (DRB_NO_HEAD_TC=1: fp32 h + the CUDA-core projection kernel, for A/B runs)
   int head_tc = 0;
@@ -343,6 +351,24 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
     PLAN_TRY(make_tmap_3d(&p->maps.zl, p->ws + lay.zl, (uint64_t)L * NBc, T, am * C, 128, da));
     PLAN_TRY(make_tmap_3d(&p->maps.sh, p->ws + lay.sh, cfg->batch, T, Mp, 128, dm));
     PLAN_TRY(make_tmap_3d(&p->maps.sl, p->ws + lay.sl, cfg->batch, T, am * Mp, 128, da));
+    if (lay.cond) {   // f16x3 operands of the per-clip conditioner tables (DRB_COND_SIMT=1: fp32 CUDA-core build, for A/B runs)
+      const char* e = getenv("DRB_COND_SIMT");
+      p->cond_tc = (2 * C) % 256 == 0 && Mp % 64 == 0 && !(e && e[0] == '1');
+      if (p->cond_tc) {
+        PLAN_TRY(make_tmap_3d(&p->sp5h, p->ws + lay.sp5h, cfg->batch, T, Mp, 128, 2));
+        PLAN_TRY(make_tmap_3d(&p->sp5l, p->ws + lay.sp5l, cfg->batch, T, Mp, 128, 2));
+        for (int i = 0; i < L; ++i) {
+          char* h5 = p->ws + lay.wc5h + (size_t)i * 2 * C * Mp * 2;
+          char* l5 = p->ws + lay.wc5l + (size_t)i * 2 * C * Mp * 2;
+          PLAN_TRY(launch_weight_scale(w->conditioner_projection_w[i], (size_t)2 * C * cfg->n_mels, nullptr, 0, p->wscale(p->wc5_slot(i)), 1.f, s));
+          PLAN_TRY(launch_repack_split(w->conditioner_projection_w[i], h5, l5, 2 * C, cfg->n_mels, Mp, 0, 5, p->wscale(p->wc5_slot(i)), s));
+          CUtensorMap mh, ml;
+          PLAN_TRY(make_tmap_2d(&mh, h5, 2 * C, Mp, 128, 2));
+          PLAN_TRY(make_tmap_2d(&ml, l5, 2 * C, Mp, 128, 2));
+          p->wc5h.push_back(mh); p->wc5l.push_back(ml);
+        }
+      }
+    }
     if (lay.cond)   // conditioner tables built on the tensor cores (drb_cond_tables): one fp32 map per layer
       for (int i = 0; i < L; ++i) {
         CUtensorMap mc;
@@ -439,6 +465,22 @@ int drb_cond_tables(drb_plan* p, void* stream) {
   // fp32, for every layer; the gate kernel then adds it in its epilogue instead of contracting it every step
   const drb_config& c = p->cfg;
   const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)c.batch * c.frames * C2;
+  if (p->cond_tc && p->cfg.precision != DRB_PREC_FP32) {
+    // default: tcgen05 with f16x3 operands (fp16 hi + fp16 lo) and a single K = Mp chain per output -- fp32-grade, 15 short
+    // launches instead of 15 x 0.37 ms of fp32 FMA per clip
+    int r = launch_split_pair(p->at<float>(p->lay.spec32), p->lay.Mp, nullptr, 0, c.frames, nullptr, p->ws + p->lay.sp5h, p->ws + p->lay.sp5l,
+                              c.batch * c.frames, p->lay.Mp, (cudaStream_t)stream, 5);
+    if (r) return r;
+    for (int l = 0; l < c.residual_layers; ++l) {
+      UmmaConvLin cv;
+      cv.ah = &p->sp5h; cv.al = &p->sp5l; cv.wh = &p->wc5h[l]; cv.wl = &p->wc5l[l]; cv.prec = 4; cv.pair = p->pair;
+      cv.NB = c.batch; cv.T = c.frames; cv.Cin = p->lay.Mp; cv.Nout = (int)C2; cv.taps = 1; cv.dil = 1; cv.Mp = 0;
+      cv.inv_scale = p->wscale(p->wc5_slot(l)) + 1; cv.bias = nullptr; cv.out = p->at<float>(p->lay.cond) + (size_t)l * per; cv.ldo = (int)C2;
+      r = launch_umma_conv_lin(cv, (cudaStream_t)stream); if (r) return r;
+    }
+    p->cond_ready = true;
+    return 0;
+  }
   static int tc_cond = -1;
   if (tc_cond < 0) { const char* e = getenv("DRB_COND_TC"); tc_cond = (e && e[0] == '1') ? 1 : 0; }
   if (tc_cond && (p->prec() == 1 || p->prec() == 3) && (int)p->cond32.size() == c.residual_layers) {
