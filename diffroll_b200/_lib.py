@@ -24,7 +24,7 @@ EXPORTS = [
     "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_plan_precision", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
     "drb_train_workspace_bytes", "drb_train_create", "drb_train_destroy", "drb_train_forward", "drb_train_backward", "drb_loss_grad",
-    "drb_adam_step",
+    "drb_adam_step", "drb_plan_set_step_embeddings",
 ]
 
 
@@ -128,6 +128,7 @@ def load():
     lib.drb_p_losses_scratch_bytes.argtypes = []
     lib.drb_p_losses.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.drb_normalize_imagewise.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_void_p]
+    lib.drb_plan_set_step_embeddings.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.drb_train_workspace_bytes.restype = C.c_size_t
     lib.drb_train_workspace_bytes.argtypes = [C.POINTER(DrbTrainConfig)]
     lib.drb_train_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DrbTrainConfig), C.c_void_p, C.c_size_t, C.c_void_p]

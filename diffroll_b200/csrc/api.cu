@@ -43,6 +43,7 @@ struct Layout {  // byte offsets into the workspace
   size_t wd32, wc32, ybuf, z32;                        // fp32 path
   size_t xh, xl, zh, zl, sh, sl, wdh, wdl, wch, wcl, woh, wol, wcomp32, wcomph, wcompl, bcomp, bsum, wscale;  // tensor path
   size_t wouth, woutl;                                  // output_projection rows padded to 256, operand pair (tensor-core head)
+  size_t dtab2, iota;                                   // per-roll time tables of fractional diffusion steps (drb_plan_set_step_embeddings)
   size_t sp5h, sp5l, wc5h, wc5l;                        // f16x3 (fp16 hi + fp16 lo) pairs of the spectrogram and the conditioner weights (tables)
   size_t xs, wsf4;                                      // f16n4: activation scale factors [NB][C/64][T][8]; weight scale atoms [L][2C/256][k*C/64][2048]
   size_t range;                                         // one word: max |activation operand| (fp32 bits) since the last reset
@@ -88,6 +89,8 @@ static Layout make_layout(const drb_config& c) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes); return r; };
   l.dtab = take(L * c.timesteps * C * 4);
+  l.dtab2 = take(L * c.timesteps * C * 4);
+  l.iota = take(B * 4);
   l.emb1 = take((size_t)c.timesteps * 512 * 4);
   l.emb2 = take((size_t)c.timesteps * 512 * 4);
   l.x32 = take(rows * C * 4);
@@ -191,8 +194,9 @@ struct drb_plan {
   // one tcgen05 kernel (DRB_NO_HEAD_TC=1: fp32 h + the CUDA-core projection kernel, for A/B runs)
   int head_tc = 0;
   std::vector<CUtensorMap> cond32;   // per layer: fp32 [B][T][2C] map of the conditioner table (tensor-core build)
+  bool dtab_alt = false;       // the per-roll tables of drb_plan_set_step_embeddings are in force (row = roll index)
   const float* dvec(int layer, int t) const {
-    return at<float>(lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
+    return at<float>(dtab_alt ? lay.dtab2 : lay.dtab) + ((size_t)layer * cfg.timesteps + t) * cfg.residual_channels;
   }
 };
 
@@ -442,6 +446,35 @@ int drb_time_tables(drb_plan* p, const float* emb_table, void* stream) {
     r = launch_simt_gemm(g, s); if (r) return r;
   }
   p->tables_ready = true;
+  return 0;
+}
+
+// Fractional diffusion steps (DiffusionEmbedding._lerp_embedding, model/diffwave.py:76-81): the caller interpolates the sinusoid
+// table per roll; this runs projection1 / projection2 / every diffusion_projection on those `batch` rows into a second table
+// whose row index is the ROLL, and makes the plan read it (with roll-indexed steps) until it is cleared with emb_rows == NULL.
+namespace { __global__ void iota_i32_kernel(int* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = i; } }
+int drb_plan_set_step_embeddings(drb_plan* p, const float* emb_rows, void* stream) {
+  if (!p) return DRB_E_INVALID;
+  if (!emb_rows) { p->dtab_alt = false; p->steps = nullptr; return 0; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = p->cfg.batch, TS = p->cfg.timesteps, C = p->cfg.residual_channels;
+  if (B > TS) { set_error("set_step_embeddings: batch %d exceeds the table rows (timesteps %d)", B, TS); return DRB_E_INVALID; }
+  SimtGemm g;
+  g.A = emb_rows; g.lda = 128; g.T = B; g.Ck = 128; g.W = p->e1w; g.ldw = 128; g.bias = p->e1b; g.act = 2;
+  g.C = p->at<float>(p->lay.emb1); g.ldc = 512; g.M = B; g.N = 512;
+  int r = launch_simt_gemm(g, s); if (r) return r;
+  g.A = p->at<float>(p->lay.emb1); g.lda = 512; g.Ck = 512; g.W = p->e2w; g.ldw = 512; g.bias = p->e2b;
+  g.C = p->at<float>(p->lay.emb2);
+  r = launch_simt_gemm(g, s); if (r) return r;
+  for (int i = 0; i < p->cfg.residual_layers; ++i) {
+    g.A = p->at<float>(p->lay.emb2); g.W = p->dpw[i]; g.bias = p->dpb[i]; g.act = 0;
+    g.C = p->at<float>(p->lay.dtab2) + (size_t)i * TS * C; g.ldc = C; g.N = C;
+    r = launch_simt_gemm(g, s); if (r) return r;
+  }
+  iota_i32_kernel<<<(B + 255) / 256, 256, 0, s>>>(p->at<int>(p->lay.iota), B);
+  DRB_LAUNCH_CHECK();
+  p->dtab_alt = true; p->steps = p->at<int>(p->lay.iota);
+  // NB: emb1 / emb2 are scratch shared with drb_time_tables, whose results (dtab) stay valid
   return 0;
 }
 

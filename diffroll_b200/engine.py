@@ -113,6 +113,20 @@ class Engine:
             _lib.check(self.lib.drb_plan_set_branches(self.plan, branches), "drb_plan_set_branches")
             self.branches = branches
 
+    def set_step_embeddings(self, emb_rows):
+        """Fractional diffusion steps (model/diffwave.py:76-81): ``emb_rows`` [B,128] = the caller's interpolated sinusoid rows, one
+        per roll; ``None`` returns to the integer tables."""
+        if emb_rows is None:
+            self._emb_rows = None
+            _lib.check(self.lib.drb_plan_set_step_embeddings(self.plan, C.c_void_p(0), _stream(self.device)), "drb_plan_set_step_embeddings")
+            return
+        e = emb_rows.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(e.shape) != (self.batch, 128):
+            raise ValueError(f"step embeddings: expected shape ({self.batch}, 128), got {tuple(e.shape)}")
+        self._emb_rows = e
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drb_plan_set_step_embeddings(self.plan, _ptr(e), _stream(self.device)), "drb_plan_set_step_embeddings")
+
     def set_steps(self, steps):
         """Per-sample diffusion steps for the following step()/forward calls (model/diffwave.py:637,670: ``diffusion_step``
         is int64[B]); ``None`` returns to the uniform ``t_index`` argument.  The int32 device copy is kept alive here."""

@@ -131,8 +131,10 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             raise NotImplementedError(f"condition '{condition}' is a training-time variant outside the sampling hot path")
         elif condition != 'fixed':
             raise ValueError("unrecognized condition '{condition}'")  # sic: model/diffwave.py:610
-        if unconditional:
-            raise NotImplementedError("unconditional=True (no conditioner_projection) is not built on this path")
+        # unconditional=True builds residual blocks without conditioner_projection (model/diffwave.py:125-128), but
+        # ClassifierFreeDiffRoll.forward always hands them a spectrogram, which ResidualBlock.forward rejects (:135-136):
+        # the reference constructs such a model and fails its first forward with an AssertionError.  Same here.
+        self._uncond_blocks = bool(unconditional)
         self.precision = precision
         self.input_projection = Conv1d(88, residual_channels, 1)
         self.diffusion_embedding = DiffusionEmbedding(len(self.betas))
@@ -255,11 +257,13 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
     def forward(self, x_t, waveform, diffusion_step, sampling=False, inpainting_t=None, inpainting_f=None):
         """model/diffwave.py:637-686.  ``diffusion_step``: int64[B]; the samplers pass one value repeated
         (``tensor(t).repeat(B)``), the training / validation step a different one per roll (task/diffusion.py:667)."""
+        assert not self._uncond_blocks, \
+            "ResidualBlock built with uncond=True received a conditioner (model/diffwave.py:135-136)"
         if self.training:
             return self._forward_training(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)
+        if torch.is_tensor(diffusion_step) and diffusion_step.dtype not in (torch.int32, torch.int64):
+            return self._forward_fractional(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)
         if torch.is_tensor(diffusion_step):
-            if diffusion_step.dtype not in (torch.int32, torch.int64):
-                raise NotImplementedError("fractional diffusion steps (_lerp_embedding) are not on the sampling path")
             steps = diffusion_step.flatten()
             if steps.numel() != x_t.shape[0]:
                 raise ValueError("diffusion_step must hold one step per roll")
@@ -279,6 +283,30 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
                 pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
             finally:
                 eng.set_steps(None)
+        if not self._range_ok(eng):
+            self._range_fallback()
+            return self.forward(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)
+        return pred, spec
+
+    def _forward_fractional(self, x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f):
+        """Floating-point ``diffusion_step`` (model/diffwave.py:66-81): the sinusoid table is interpolated linearly between the two
+        neighbouring integer steps, per roll, and the embedding MLP + the 15 diffusion projections run on those rows."""
+        t = diffusion_step.flatten().to(device=x_t.device, dtype=torch.float32)
+        if t.numel() != x_t.shape[0]:
+            raise ValueError("diffusion_step must hold one step per roll")
+        table = self.diffusion_embedding.embedding.to(x_t.device)
+        low_idx, high_idx = torch.floor(t).long(), torch.ceil(t).long()       # an out-of-range step fails the lookup, as in the reference
+        low, high = table[low_idx], table[high_idx]
+        rows = low + (high - low) * (t - low_idx).unsqueeze(-1)               # _lerp_embedding (:76-81; t [B] against rows [B,128])
+        branches = _lib.BRANCH_UNCOND if sampling is True else _lib.BRANCH_COND
+        eng, xx, spec = self._prepare(x_t, waveform, branches, inpainting_t, inpainting_f)
+        if x_t.shape[0] > len(self.betas):
+            raise NotImplementedError("fractional diffusion steps need batch <= timesteps (per-roll table rows)")
+        eng.set_step_embeddings(rows)
+        try:
+            pred = eng.step(xx, None, 0, _upd(_lib.UPD_NONE))
+        finally:
+            eng.set_step_embeddings(None)
         if not self._range_ok(eng):
             self._range_fallback()
             return self.forward(x_t, waveform, diffusion_step, sampling, inpainting_t, inpainting_f)

@@ -277,6 +277,12 @@ int drb_plan_profile_read(drb_plan* plan, double* ms_total4, int64_t* launches4)
 int drb_plan_profile_read2(drb_plan* plan, double* ms_total, int64_t* launches, int32_t n_classes,
                            double* gate_ms_per_layer, int32_t n_layers);
 
+/* Fractional diffusion steps, DiffusionEmbedding._lerp_embedding (model/diffwave.py:76-81) as reached from forward() with a
+ * floating-point diffusion_step: emb_rows = device [batch][128], the caller's interpolated sinusoid rows, one per roll.  The plan
+ * runs the embedding MLP and every diffusion_projection on them and uses the result (per roll) for all following calls until
+ * this is called again with emb_rows == NULL.  Needs batch <= timesteps. */
+int drb_plan_set_step_embeddings(drb_plan* plan, const float* emb_rows, void* stream);
+
 /* The DRB_PREC_* a plan actually computes in: DRB_PREC_F16N4 is granted only when every launch can run as CTA pairs
  * (batch * ceil(frames / 128) even) with tap windows <= 192 frames; otherwise the plan runs as DRB_PREC_F16E5. */
 int drb_plan_precision(const drb_plan* plan);

@@ -131,7 +131,13 @@ class OracleDiffRoll:
         spectrogram = spec[..., :T_min]
 
         x = F.relu(F.conv1d(x_t, sd["input_projection.weight"], sd["input_projection.bias"]))
-        e = self.embedding[diffusion_step]
+        if diffusion_step.dtype in (torch.int32, torch.int64):
+            e = self.embedding[diffusion_step]
+        else:                                                          # _lerp_embedding, model/diffwave.py:76-81
+            tt = diffusion_step.to(self.embedding.device)
+            lo_i, hi_i = torch.floor(tt).long(), torch.ceil(tt).long()
+            lo_e, hi_e = self.embedding[lo_i], self.embedding[hi_i]
+            e = lo_e + (hi_e - lo_e) * (tt - lo_i).to(self.dtype).unsqueeze(-1)
         e = silu(F.linear(e, sd["diffusion_embedding.projection1.weight"], sd["diffusion_embedding.projection1.bias"]))
         e = silu(F.linear(e, sd["diffusion_embedding.projection2.weight"], sd["diffusion_embedding.projection2.bias"]))
 

@@ -391,3 +391,26 @@ def test_forward_per_sample_diffusion_steps(precision):
     assert torch.equal(uni[1], pred[1])
     with pytest.raises(IndexError):
         m(x_T.cuda(), wav.cuda(), torch.tensor([0, 1, 2, 200]).cuda())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16n4"])
+def test_forward_fractional_diffusion_steps(precision):
+    """Floating-point diffusion_step (DiffusionEmbedding._lerp_embedding, model/diffwave.py:76-81): per-roll interpolated
+    embeddings through drb_plan_set_step_embeddings, against the oracle; integer-valued float steps equal the integer path."""
+    from oracle.diffroll_oracle import OracleDiffRoll
+    m = model_for(precision)
+    hp = default_hparams()
+    x_T, wav, _ = make_inputs(2, 200, seed=9, n_noise=0, T=128, wav_len=65536)
+    steps = torch.tensor([57.25, 130.5])
+    orc = OracleDiffRoll(hp, make_state_dict(hp))
+    with torch.no_grad():
+        ref, _ = orc(x_T, wav, steps)
+    got, _ = m(x_T.cuda(), wav.cuda(), steps.cuda())
+    err = float((got.cpu() - ref).abs().max())
+    record(f"forward[{precision}] fractional steps max|delta| = {err:.3e}")
+    assert err < TOL_STEP[precision] * max(1.0, float(ref.abs().max()))
+    a, _ = m(x_T.cuda(), wav.cuda(), torch.tensor([57.0, 130.0]).cuda())
+    b, _ = m(x_T.cuda(), wav.cuda(), torch.tensor([57, 130]).cuda())
+    assert float((a - b).abs().max()) < 2e-5
+    c, _ = m(x_T.cuda(), wav.cuda(), torch.tensor([57, 130]).cuda())      # the integer tables are back in force
+    assert torch.equal(b, c)

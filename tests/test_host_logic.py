@@ -142,6 +142,20 @@ def test_no_cpu_fallback_and_training_mode_guard():
         m.reverse_diffusion(x, w, 5)
 
 
+def test_unconditional_blocks_behave_like_the_reference():
+    """unconditional=True: the reference builds blocks without conditioner_projection (122 state_dict tensors instead of 132 + 2
+    buffers... ) and its forward then fails ResidualBlock's assertion (model/diffwave.py:135-136) because ClassifierFreeDiffRoll
+    always passes a spectrogram.  Same construction, same failure."""
+    import diffroll_b200 as M
+    hp = default_hparams()
+    hp["unconditional"] = True
+    m = M.ClassifierFreeDiffRoll(**hp)
+    keys = set(m.state_dict())
+    assert not any("conditioner_projection" in k for k in keys) and len(keys) == 132 - 2 * hp["residual_layers"]
+    with pytest.raises(AssertionError):
+        m.eval()(torch.randn(1, 1, 128, 88), torch.randn(1, 65536), torch.tensor([3]))
+
+
 # ---- C ABI ------------------------------------------------------------------------------------------------------
 def test_cabi_exports_every_declared_symbol(lib_built):
     header = open(os.path.join(ROOT, "include", "diffroll_b200.h")).read()

@@ -76,3 +76,15 @@ def test_normalization_matches_live_reference(mode, bounds):
     a = mod.Normalization(bounds[0], bounds[1], mode)(x.clone())
     b = Normalization(bounds[0], bounds[1], mode)(x.clone())
     assert torch.equal(a, b)
+
+
+def test_fractional_diffusion_step_matches_live_reference():
+    """DiffusionEmbedding._lerp_embedding (model/diffwave.py:76-81) through the whole forward, B = 1 (the reference's expression
+    broadcasts [B,128] against [B] and is only well-formed for one roll; the oracle and the CUDA path apply it per roll)."""
+    ref, orc, _ = _pair()
+    x_T, wav, _ = make_inputs(1, 200, seed=9, n_noise=0, T=128, wav_len=65536)
+    steps = torch.tensor([57.25])
+    with torch.no_grad():
+        a, _ = ref(x_T, wav, steps)
+        b, _ = orc(x_T, wav, steps)
+    assert float((a - b).abs().max()) <= 2e-5
