@@ -173,10 +173,22 @@ class SpecRollDiffusion(nn.Module):
     # ---- loops ----------------------------------------------------------------------------------
     def _all_updates(self):
         """The drb_update of every step t = T-1 .. 0 for the configured sampler, without running it."""
+        # 10 ms of host work for a 200-step chain (torch scalar arithmetic per step) during which the GPU would idle at the
+        # head of every sample_loop call: memoised on everything the sampler methods read.
+        hp = self.hparams
+        sched = (self.betas, self.alphas, self.sqrt_recip_alphas, self.sqrt_alphas_cumprod,
+                 self.sqrt_one_minus_alphas_cumprod, self.posterior_variance)
+        key = (hp.sampling.type, repr(hp.sampling.get("w", None)), hp.timesteps, repr(hp.get("inpainting_t", None)),
+               repr(hp.get("inpainting_f", None)), getattr(self.reverse_diffusion, "__func__", self.reverse_diffusion),
+               tuple((id(t), t._version) for t in sched))
+        hit = self.__dict__.get("_updates_memo")
+        if hit is not None and hit[0] == key:
+            return hit[1]
         probe = _UpdateProbe(self)
         ups = []
-        for t_index in reversed(range(self.hparams.timesteps)):
+        for t_index in reversed(range(hp.timesteps)):
             ups.append(probe.capture(t_index))
+        self.__dict__["_updates_memo"] = (key, (ups, probe.branches, probe.masks), sched)   # sched kept alive: ids stay unique
         return ups, probe.branches, probe.masks
 
     # device bytes of pre-drawn noise held at any time by sample_loop (the reference draws one step at a time, :1023)
@@ -245,10 +257,8 @@ class SpecRollDiffusion(nn.Module):
                 for j in range(nn):                      # same generator consumption order as task/diffusion.py:1023
                     if shard is not None:
                         nz[j] = torch.randn((gB,) + tuple(x.shape[1:]), device=x.device, generator=generator)[lo:hi]
-                    elif generator is not None:
-                        nz[j] = torch.randn(tuple(x.shape), device=x.device, generator=generator)
-                    else:
-                        nz[j] = torch.randn_like(x)
+                    else:                                # drawn in place: the same Philox consumption as randn_like(x)
+                        torch.randn(tuple(x.shape), generator=generator, out=nz[j])
             k += nn
             eng.loop(x, nz, cu, T_all - i0, T_all - i0 - len(cu), None if traj is None else traj[i0:i0 + len(cu)])
         if not self._range_ok(eng):
