@@ -575,13 +575,9 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
       cv.bias = p->at<float>(p->bnat); cv.out = y_l; cv.ldo = 2 * C;
       // one launch per tap (the first carries the bias, the last the conditioner slabs): accumulation chains of C (+ Mp) instead
       // of k*C + Mp terms, summed across launches in exact fp32
-      for (int tap = 0; tap < k; tap += p->taps_per_launch) {
-        const int tn = tap + p->taps_per_launch <= k ? p->taps_per_launch : k - tap;
-        cv.tap_lo = tap; cv.tap_n = tn; cv.accumulate = tap > 0;
-        cv.bias = tap == 0 ? p->at<float>(p->bnat) : nullptr;
-        cv.Mp = tap + tn == k ? Mp : 0;
-        TR(launch_umma_conv_lin(cv, s));
-      }
+      // (one kernel: the persistent linear conv runs the passes of a tile back to back; DRB_LIN_PERS=0 launches once per pass)
+      cv.tap_lo = 0; cv.tap_n = p->taps_per_launch < k ? p->taps_per_launch : k; cv.tap_span = k; cv.accumulate = 0;
+      TR(launch_umma_conv_lin(cv, s));
     } else {
     SimtGemm g;  // dilated_conv(x + d)   :138-139
     g.A = x_l; g.lda = C; g.T = T; g.taps = k; g.dil = p->dil[l]; g.Ck = C; g.addvec = d_l; g.addvec_steps = p->at<int>(p->iota);

@@ -105,6 +105,7 @@ struct alignas(64) GateParams {
   // core's fp32 accumulation loses ~1e-8 of the running sum per K-step, which a 4608-long chain turns into 4e-5 -- short chains summed
   // in exact fp32 in global memory keep the training forward at the fp32 floor (csrc/train.cu)
   int tap_lo, tap_n, lin_acc;
+  int tap_span;   // persistent linear kernel: taps [tap_lo, tap_lo + tap_span) in passes of tap_n, summed in out[] (0: one pass)
 };
 
 struct alignas(64) ZGemmParams {
@@ -487,6 +488,185 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_gate_kernel(const __grid_
     gate_epilogue<P>(sv, p, tmem_base, warp, lane, nb, nblk, t0);
   }
   teardown<P, PAIR>(tmem_base, warp);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Linear conv, persistent form (training forward, conditioner tables).  The one-tile-per-CTA kernel above with the linear epilogue
+// spent two thirds of a launch outside the MMAs (prologue + a serialised epilogue per tile, 66 us for 7 us of tensor work at one tap
+// per launch).  Here one CTA pair per SM pair walks its (tile, tap pass) units: two TMEM accumulator stages, so the epilogue of unit
+// i overlaps the MMAs of unit i + 1; the tap passes of a tile run back to back in the same CTA (the exact-fp32 sum across passes
+// goes through the tile's 128 KB of out[] while it is still in L2: a thread re-reads only addresses it wrote itself); and the
+// epilogue transposes each 32x32 accumulator block through a private 4 KB of shared memory so that every global load / store
+// instruction of a warp covers four whole 128-byte lines (thread = row gave 32 lines x 16 bytes per instruction).
+//   passes: taps [tap_lo, tap_lo + span) in groups of tap_n; pass 0 carries the bias (and lin_acc), the last one the 1x1 slabs.
+//   smem: 3 stages x 64 KB | barriers | 8 x 4 KB transposition buffers
+// ---------------------------------------------------------------------------------------------
+constexpr int CLP_SMEM = 196608 + 1024 /*align*/ + 256 /*barriers*/ + 8 * 4096;
+static_assert(CLP_SMEM <= 232448, "linear conv kernel: shared memory over the 227 KB limit");
+
+template <int P>
+__global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(const __grid_constant__ GateParams p) {
+  static_assert(P == 3 || P == 4, "single 256-column accumulator formats");
+  constexpr bool PAIR = true;
+  using CF = Cfg<P, PAIR>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const SmemView sv = carve<P, PAIR>(smem_raw);
+  uint64_t* const tfull = sv.afull;      // [2] accumulator stage complete (one per CTA, multicast commit)
+  uint64_t* const tempty = sv.aempty;    // [2] leader: 8 epilogue warps x 2 CTAs have read the stage
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair_id = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  constexpr int AM = CF::kAuxMul;
+  const int cpt = p.C / TILE_K;
+  const int half = p.taps / 2;
+  const int per_pass = p.tap_n > 0 ? p.tap_n : p.taps;
+  const int span = p.tap_span > 0 ? p.tap_span : per_pass;
+  const int n_pass = (span + per_pass - 1) / per_pass;
+  const int cslabs = p.n_cond > 0 ? p.cond_slabs : 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < CF::kStages; ++i) { mbar_init(&sv.full[i], 2); mbar_init(&sv.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(sv.tmem_ptr, 512); tmem_relinquish_pair(); }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *sv.tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- producer (each CTA: its 128 frames and its half of the weight tile) ----------------
+      int stage = 0; uint32_t phase = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        const int nblk = item % p.n_blocks;
+        const int mt = (item / p.n_blocks) * 2 + (int)rank;
+        const int nb = mt / p.tiles_t, t0 = (mt % p.tiles_t) * TILE_M;
+        for (int ps = 0; ps < n_pass; ++ps) {
+          const int tap0 = p.tap_lo + ps * per_pass;
+          const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
+          const int conv_slabs = ntap * cpt;
+          const int nslabs = conv_slabs + (ps == n_pass - 1 ? cslabs : 0);
+          for (int sl = 0; sl < nslabs; ++sl) {
+            mbar_wait(&sv.empty[stage], phase ^ 1);
+            uint8_t* st = sv.stage0 + stage * CF::kStageBytes;
+            uint64_t* fl = &sv.full[stage];
+            const uint32_t fb = mapa_cluster(smem_u32(fl), 0);
+            prod_expect<PAIR>(fl, fb, CF::kStageBytes);
+            if (sl < conv_slabs) {
+              const int tap = tap0 + sl / cpt, cc = sl % cpt;
+              const int trow = t0 + (tap - half) * p.dil;
+              load_a<PAIR>(st + CF::kAOff, &p.xh, fl, fb, cc * TILE_K, trow, nb);
+              load_b<PAIR>(st + CF::kBOff, &p.wd_h, fl, fb, tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
+              load_a<PAIR>(st + CF::kAAuxOff, &p.xl, fl, fb, AM * cc * TILE_K, trow, nb);
+              load_b<PAIR>(st + CF::kBAuxOff, &p.wd_l, fl, fb, AM * (tap * p.C + cc * TILE_K), nblk * TILE_N, rank);
+            } else {
+              const int cc = sl - conv_slabs;
+              load_a<PAIR>(st + CF::kAOff, &p.sh, fl, fb, cc * TILE_K, t0, nb);
+              load_b<PAIR>(st + CF::kBOff, &p.wc_h, fl, fb, cc * TILE_K, nblk * TILE_N, rank);
+              load_a<PAIR>(st + CF::kAAuxOff, &p.sl, fl, fb, AM * cc * TILE_K, t0, nb);
+              load_b<PAIR>(st + CF::kBAuxOff, &p.wc_l, fl, fb, AM * cc * TILE_K, nblk * TILE_N, rank);
+            }
+            if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      // ---------------- MMA issuer (leader CTA) ----------------
+      int stage = 0; uint32_t phase = 0;
+      int ucnt = 0;
+      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+        for (int ps = 0; ps < n_pass; ++ps, ++ucnt) {
+          const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
+          const int nslabs = ntap * cpt + (ps == n_pass - 1 ? cslabs : 0);
+          const int as = ucnt & 1;
+          mbar_wait(&tempty[as], ((ucnt >> 1) & 1) ^ 1);   // both CTAs' epilogues have read this accumulator stage
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)as * 256u;
+          for (int sl = 0; sl < nslabs; ++sl) {
+            mbar_wait(&sv.full[stage], phase);
+            tc_fence_after();
+            issue_slab<P, PAIR>(sv.stage0 + stage * CF::kStageBytes, tmem_d, sl == 0);
+            umma_commit_pair(&sv.empty[stage]);
+            if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_pair(&tfull[as]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (8 warps), overlapped with the next unit's MMAs ----------------
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    const uint32_t sbuf = smem_u32(sv.sbias) + (uint32_t)(warp - 4) * 4096u;   // this warp's 32 rows x 128 bytes
+    const float inv_l = __ldg(p.inv_scale);
+    const int l8 = lane & 7, lr = lane >> 3;
+    int ucnt = 0;
+    for (int item = pair_id; item < p.n_items; item += n_pairs) {
+      const int nblk = item % p.n_blocks;
+      const int mt = (item / p.n_blocks) * 2 + (int)rank;
+      const int nb = mt / p.tiles_t, t0 = (mt % p.tiles_t) * TILE_M;
+      const int tq = t0 + q * 32;                                    // first frame of this warp's 32 rows
+      const int colb = nblk * TILE_N + grp * 128 + l8 * 4;           // this lane's 4 columns of every 32-column block
+      float* const dst = p.lin_out + ((size_t)nb * p.T + tq) * (size_t)p.ldo + colb;
+      for (int ps = 0; ps < n_pass; ++ps, ++ucnt) {
+        const int as = ucnt & 1;
+        const bool acc = ps > 0 || p.lin_acc != 0;
+        const float* bias = ps == 0 ? p.bias_cond : nullptr;
+        mbar_wait(&tfull[as], (ucnt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u + (uint32_t)grp * 128u;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float v[32];
+          load_acc32<P>(taddr + c4 * 32, inv_l, v);
+          if (c4 == 3) {   // this warp's last TMEM read of the stage: hand it back to the MMA issuer (leader CTA)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)   // thread = row: 8 x 16 bytes into the row, 16-byte units XOR-swizzled by the row
+            sts128(sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          __syncwarp();
+          // 8 lanes per row: instruction k moves rows 4k .. 4k+3 as four whole 128-byte lines.  All loads of the block before its
+          // first store (a load queued behind a store to the same row was 9x slower in the one-tile kernel).
+          float4 o4[8];
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) b4 = *reinterpret_cast<const float4*>(bias + colb + c4 * 32);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = 4 * k + lr;
+            o4[k] = b4;
+            if (acc && tq + r < p.T) {
+              const float4 qv = __ldcg(reinterpret_cast<const float4*>(dst + (size_t)r * p.ldo + c4 * 32));
+              o4[k].x += qv.x; o4[k].y += qv.y; o4[k].z += qv.z; o4[k].w += qv.w;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = 4 * k + lr;
+            const float4 a = lds128(sbuf + (uint32_t)r * 128u + (uint32_t)((l8 ^ (r & 7)) << 4));
+            if (tq + r < p.T)
+              *reinterpret_cast<float4*>(dst + (size_t)r * p.ldo + c4 * 32) = make_float4(a.x + o4[k].x, a.y + o4[k].y, a.z + o4[k].z, a.w + o4[k].w);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
 
@@ -1954,6 +2134,7 @@ int umma_init() {
   set((const void*)umma_res_pers_kernel<1, 0>, RP_SMEM); set((const void*)umma_res_pers_kernel<3, 0>, RP_SMEM);
   set((const void*)umma_res_pers_kernel<3, 4>, RP_SMEM);
   set((const void*)umma_head_pers_kernel<1>, HP_SMEM); set((const void*)umma_head_pers_kernel<3>, HP_SMEM);
+  set((const void*)umma_conv_lin_pers_kernel<3>, CLP_SMEM); set((const void*)umma_conv_lin_pers_kernel<4>, CLP_SMEM);
   set((const void*)umma_gate_n4_kernel<false>, N4_SMEM); set((const void*)umma_gate_n4_kernel<true>, N4_SMEM);
   set((const void*)umma_zgemm_kernel<0, false>, Cfg<0, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<0, true>, Cfg<0, false>::kSmemBytes);
   set((const void*)umma_zgemm_kernel<1, false>, Cfg<1, false>::kSmemBytes); set((const void*)umma_zgemm_kernel<1, true>, Cfg<1, false>::kSmemBytes);
@@ -2122,10 +2303,36 @@ int launch_umma_conv_lin(const UmmaConvLin& c, cudaStream_t s) {
   p.bias_cond = c.bias; p.bias_unc = c.bias; p.inv_scale = c.inv_scale;
   p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0; p.xs = nullptr; p.win_rows = TILE_M; p.n_items = 0;
   p.lin_out = c.out; p.ldo = c.ldo;
-  p.tap_lo = c.tap_lo; p.tap_n = c.tap_n; p.lin_acc = c.accumulate;
-  if (c.tap_n < 0 || c.tap_lo < 0 || c.tap_lo + c.tap_n > c.taps) { set_error("umma_conv_lin: bad tap range"); return DRB_E_INVALID; }
+  p.tap_lo = c.tap_lo; p.tap_n = c.tap_n; p.lin_acc = c.accumulate; p.tap_span = c.tap_span;
+  if (c.tap_n < 0 || c.tap_lo < 0 || c.tap_span < 0 || c.tap_lo + (c.tap_span > 0 ? c.tap_span : c.tap_n) > c.taps) {
+    set_error("umma_conv_lin: bad tap range"); return DRB_E_INVALID;
+  }
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   const bool mc = c.pair && ((p.NB * p.tiles_t) % 2 == 0);
+  static int pers = -1;   // DRB_LIN_PERS=0: the one-tile-per-CTA kernel (A/B runs)
+  if (pers < 0) { const char* e = getenv("DRB_LIN_PERS"); pers = (e && e[0] == '0') ? 0 : 1; }
+  if (mc && pers && (c.prec == 4 || c.prec == 3)) {   // persistent CTA pairs, every tap pass of a tile inside ONE launch
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    p.n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
+    const int pairs = p.n_items < n_sm / 2 ? p.n_items : n_sm / 2;
+    return c.prec == 4 ? launch_k(umma_conv_lin_pers_kernel<4>, p, 2 * pairs, CLP_SMEM, true, s)
+                       : launch_k(umma_conv_lin_pers_kernel<3>, p, 2 * pairs, CLP_SMEM, true, s);
+  }
+  if (c.tap_span > 0 && c.tap_n > 0 && c.tap_span > c.tap_n) {   // one launch per pass, summed in out[] across launches
+    UmmaConvLin one = c;
+    one.tap_span = 0;
+    for (int t = 0; t < c.tap_span; t += c.tap_n) {
+      one.tap_lo = c.tap_lo + t; one.tap_n = t + c.tap_n <= c.tap_span ? c.tap_n : c.tap_span - t;
+      one.accumulate = (t > 0 || c.accumulate) ? 1 : 0;
+      one.bias = t == 0 ? c.bias : nullptr;
+      one.Mp = t + c.tap_n >= c.tap_span ? c.Mp : 0;
+      const int r = launch_umma_conv_lin(one, s);
+      if (r) return r;
+    }
+    return 0;
+  }
+  if (c.tap_span > 0) p.tap_n = c.tap_span;
   if (c.prec == 4) return mc ? launch_k(umma_gate_kernel<4, true>, p, grid, Cfg<4, false>::kSmemBytes, true, s)
                              : launch_k(umma_gate_kernel<4, false>, p, grid, Cfg<4, false>::kSmemBytes, false, s);
   return mc ? launch_k(umma_gate_kernel<3, true>, p, grid, Cfg<3, false>::kSmemBytes, true, s)

@@ -230,9 +230,12 @@ def test_three_updates_follow_torch_autograd_plus_adam():
 
 
 def test_training_step_ragged_shapes_take_the_fallback_kernels():
-    """3 rolls x 100 frames: an odd tile count (single-CTA tcgen05 kernels instead of CTA pairs), a partial 128-frame tile, and a
-    frame count that is not a multiple of 64 (the conv weight gradient stays on the CUDA-core kernel) -- same parity bar."""
-    frame, audio, t, noise = make_labelled_batch(B=3, T=100, wav_len=65536, seed=21)
+    """3 rolls x 100 frames: an odd tile count (single-CTA tcgen05 kernels instead of CTA pairs, one launch per tap pass), a partial
+    128-frame tile, and a frame count that is not a multiple of 64 (the conv weight gradient stays on the CUDA-core kernel) -- same
+    parity bar.  Seed: with seed 21 one ReLU of the head has its pre-activation within the tensor-core forward's 6e-6 of zero and
+    flips against fp32 autograd (8.4e-3 of input_projection.weight's gradient; the all-fp32 mode DRB_TRAIN_TC=0 gives 2e-6 there);
+    seeds 22 and 23 measure 6e-5 in both modes (profiles/experiments/ragged_probe.py, profiles/r3_ragged_probe.log)."""
+    frame, audio, t, noise = make_labelled_batch(B=3, T=100, wav_len=65536, seed=22)
     hp = _hp("x_0", "huber")
     mask = torch.tensor([1, 0, 0])
     batch = {"frame": frame.cuda(), "audio": audio.cuda()}
@@ -249,7 +252,5 @@ def test_training_step_ragged_shapes_take_the_fallback_kernels():
             worst, worst_name = err, name
     _record(f"train B=3 T=100 (ragged) vs GPU autograd: worst gradient rel. max|delta| = {worst:.3e} ({worst_name}), "
             f"worst rel. L2 error = {worst_l2:.3e}")
-    # 300 rows only: ONE ReLU of the head whose pre-activation sits within the forward's 6e-6 of zero (fp32-vs-fp32 summation
-    # order is enough) switches its whole gradient path and shows as ~1e-2 of a small tensor's max; the L2 error carries the bar
-    assert worst_l2 < TOL and worst < 3e-2
+    assert worst_l2 < TOL and worst < TOL
     m.release_buffers()
