@@ -152,6 +152,7 @@ struct UmmaZGemm {  // A = stored z (groups x C channels of K), B = w maps, fp32
                                     // 2: conditioner tables: A = spectrogram pair (K = nslabs64 * 64), N = 2C gate-interleaved weight
                                     //    rows, plain fp32 result stored in NATURAL channel order [gate 0..C-1 | filter C..2C-1]
   int nslabs64 = 0;                 // mode 2: K-slabs (Mp / 64)
+  int ksplit = 0;                   // mode 4: split-K -- NB = number of K ranges (nslabs64 slabs each); split i writes out32[i][row][n]
                                     // 3: head output projection, see below
                                     // 4: plain GEMM out32[row][n] = sum_k A[row][k] W[n][k] (A = a_h/a_l maps [NB][T rows][K], C = output
                                     //    columns, K = nslabs64 * 64), natural column order, no activation (training: weight gradients)

@@ -386,18 +386,23 @@ struct drb_train {
   // tensor-core path of the two dilated-conv products that carry 2/3 of the step's FLOPs (forward conv, its transposed form):
   // f16e5 operand pairs staged per layer, umma_gate_kernel with the linear epilogue (DRB_TRAIN_TC=0: everything on the CUDA cores)
   bool tc = false;
-  // DRB_TRAIN_TC bits: 1 forward conv, 2 dgrad conv, 4 wgrad conv, 8 the 1x1 output_projection (forward and dgrad) on the tensor cores
-  // (default all).  Products that are linear in a gradient use f16e5 pairs (2 MMA units; their 2^-15 operand rounding stays a ~5e-5
+  // DRB_TRAIN_TC bits: 1 forward conv, 2 dgrad conv, 4 wgrad conv, 8 the 1x1 output_projection (forward and dgrad), 16 the 1x1 weight gradients on the
+  // tensor cores (default all).  Products that are linear in a gradient use f16e5 pairs (2 MMA units; their 2^-15 operand rounding stays a ~5e-5
   // relative error of that gradient).  FORWARD products use f16x3 (fp16 hi + fp16 lo, 3 units, 22 mantissa bits): an f16e5 forward
   // moved the activations by 1e-4 and with them ReLU / gate / L1-loss derivatives (measured worst gradient error 9e-4 .. 1.5e-2
   // instead of 6e-5), so the forward gets fp32-grade operands.
-  int tc_mask = 15;
+  int tc_mask = 31;
   int taps_per_launch = 1;   // DRB_TRAIN_TAPS: taps of the forward conv per tensor-core launch (accumulation chain = taps * C terms)
   size_t uh, ul, gh, gl, sph, spl, wh, wl, wch, wcl, bnat, scal, gth, gtl, uth, utl;
   CUtensorMap m_uh, m_ul, m_gh, m_gl, m_sh, m_sl, m_wfh, m_wfl, m_wgh, m_wgl, m_wch, m_wcl;
   CUtensorMap m_ul5, m_sl5, m_wfl5, m_wcl5, m_woh, m_wol5, m_woTh, m_woTl;   // f16x3 aux views (fp16 lo) and the output_projection weights
   CUtensorMap m_gth, m_gtl, m_uth, m_utl, m_dwt;   // transposed pairs g_y^T [2C][M], im2col(x + d)^T [k*C][M]; tap-major weight gradient [2C][k*C]
   bool tc_wgrad = false;
+  // 1x1 weight gradients (output_projection, conditioner_projection, skip_projection) as split-K tcgen05 GEMMs: few output tiles
+  // (16 / 8 / 8) against K = rolls x frames, so the K range is cut into `splits` launches-worth of tiles that fill the SMs; every
+  // split leaves an fp32 partial [splits][rows][cols] in wtmp and splitk_reduce_kernel adds them into the gradient
+  struct SplitK { int splits = 0, slabs = 0; CUtensorMap out; };
+  SplitK sk_wo, sk_wc, sk_sk;
   template <class Tp> Tp* at(size_t off) const { return reinterpret_cast<Tp*>(ws + off); }
 };
 
@@ -442,6 +447,39 @@ static bool params_ok(const drb_train_params* q, int L) {
 }
 
 #define TR(expr) do { int _r = (expr); if (_r) return _r; } while (0)
+
+// grad[r][c] += scale * sum_s part[s][r][c]   (c < cols_used; part rows have `cols` floats)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t stride, int rows, int cols, int cols_used,
+                                     float* __restrict__ grad, int ld_grad, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols_used) return;
+  const int r = (int)(i / cols_used), c = (int)(i - (size_t)r * cols_used);
+  const float* q = part + (size_t)r * cols + c;
+  float acc = 0.f;
+  for (int sN = 0; sN < splits; ++sN) acc += q[(size_t)sN * stride];
+  grad[(size_t)r * ld_grad + c] += scale * acc;
+}
+
+// dW[rows][cols_used] += out_scale * G^T X over the rolls x frames (G [M][rows] scaled by gscale = {S, 1/S}; X [M][cols]) on the tensor
+// cores: transposed f16e5 operand pairs in the conv weight gradient's buffers, split-K zgemm, fp32 reduction.  g_ready: G^T is in place.
+static int wgrad_splitk(drb_train* p, const drb_train::SplitK& q, const float* G, int ldg, int rows, const float* gscale, bool g_ready,
+                        const float* X, int ldx, int cols, float* dW, int ld_dw, int cols_used, float out_scale, cudaStream_t s) {
+  const int T = p->cfg.frames, M = p->cfg.batch * T;
+  if (!g_ready) TR(launch_split_pair_T(G, ldg, nullptr, 0, T, 1, 1, gscale, p->ws + p->gth, p->ws + p->gtl, M, rows, 0, s));
+  TR(launch_split_pair_T(X, ldx, nullptr, 0, T, 1, 1, nullptr, p->ws + p->uth, p->ws + p->utl, M, cols, 1, s));
+  UmmaZGemm zg;
+  zg.pair = 1; zg.persistent = 0; zg.NB = q.splits; zg.T = rows; zg.C = cols; zg.prec = 3; zg.mode = 4; zg.groups = 1; zg.z_group0 = 0; zg.group_stride = 0;
+  zg.inv_scale = gscale + 1; zg.w_h = &p->m_uth; zg.w_l = &p->m_utl; zg.out32 = &q.out; zg.bias = nullptr; zg.dnext = nullptr;
+  zg.a_h = &p->m_gth; zg.a_l = &p->m_gtl; zg.nslabs64 = q.slabs; zg.ksplit = 1;
+  UmmaMaps dummy;
+  dummy.xh = p->m_gth; dummy.xl = p->m_gtl; dummy.zh = p->m_gth; dummy.zl = p->m_gtl;
+  TR(launch_umma_zgemm(dummy, zg, s));
+  const size_t n = (size_t)rows * cols_used;
+  splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->at<float>(p->wtmp), q.splits, (size_t)rows * cols, rows, cols, cols_used, dW,
+                                                                    ld_dw, out_scale);
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
 
 static inline unsigned nblk(size_t n, int per = 256) { return (unsigned)((n + per - 1) / per); }
 
@@ -500,6 +538,22 @@ int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspa
         if (!r) r = make_tmap_2d(&p->m_uth, p->ws + p->uth, (uint64_t)k * C, Mr, 128, 2);
         if (!r) r = make_tmap_2d(&p->m_utl, p->ws + p->utl, (uint64_t)k * C, 2 * Mr, 128, 3);
         if (!r) r = make_tmap_3d(&p->m_dwt, p->ws + p->wtmp, 1, 2 * C, (uint64_t)k * C, 128, 1);
+      }
+      if (p->tc_wgrad) {
+        int n_sm = 148;
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        size_t cap = (size_t)2 * C * k * C;
+        if (cap < (size_t)2 * C * Mp) cap = (size_t)2 * C * Mp;
+        auto mk_split = [&](drb_train::SplitK& q, int rows, int cols) {
+          const int total = (int)(Mr / 64), tiles = (rows / 128) * (cols / 256);
+          int best = 0;
+          if (rows % 256 == 0 && cols % 256 == 0 && rows <= 2 * C && cols <= k * C)   // even row-tile count (CTA pairs), whole N blocks
+            for (int sn = 1; sn <= total; ++sn)
+              if (total % sn == 0 && sn * tiles <= n_sm && (size_t)sn * rows * cols <= cap) best = sn;
+          q.splits = best; q.slabs = best ? total / best : 0;
+          if (best && !r) r = make_tmap_3d(&q.out, p->ws + p->wtmp, best, rows, cols, 128, 1);
+        };
+        mk_split(p->sk_wo, 2 * C, C); mk_split(p->sk_wc, 2 * C, Mp); mk_split(p->sk_sk, C, C);
       }
       if (r) { delete p; return r; }
     }
@@ -672,10 +726,16 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     TR(launch_simt_gemm(g, s));
     relu_bwd_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gu, h, M * C / 4, 1.f);
     DRB_LAUNCH_CHECK();
+    if (p->tc && (p->tc_mask & 16) && p->sk_sk.splits) {
+      float* sg = p->at<float>(p->scal) + 4;
+      TR(launch_weight_scale(gu, M * C, nullptr, 0, sg, 1.f, s));
+      TR(wgrad_splitk(p, p->sk_sk, gu, C, C, sg, false, p->at<float>(p->skip), C, C, gr->skw, C, C, 1.f / sqrtL, s));
+    } else {
     Wgrad b;
     b.G = gu; b.ldg = C; b.X = p->at<float>(p->skip); b.ldx = C; b.M = (int)M; b.T = T; b.N = C; b.Ck = C; b.dW = gr->skw; b.sn = C;
     b.out_scale = 1.f / sqrtL;
     TR(launch_wgrad(b, s));
+    }
     TR(launch_colsum(gu, C, C, 1, (int)M, gr->skb, C, s));
     TR(launch_transpose(w->skw, wtmp, C, C, s));
     SimtGemm q;                                                     // g_skip = (g_hp . W_sp) / sqrt(L), the same for every layer
@@ -691,14 +751,20 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     const int has_res = l < L - 1;                                   // the last layer's residual output is never used (:676-680)
     make_go_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gx, gskip, go, M, C, has_res);
     DRB_LAUNCH_CHECK();
+    const bool tc_o = p->tc && (p->tc_mask & 8), tc_w1 = p->tc && (p->tc_mask & 16) && p->sk_wo.splits && p->sk_wc.splits;
+    float* so = p->at<float>(p->scal) + 4;                           // {S_o, 1 / S_o}: power-of-two scale that lifts g_o into fp16's range
+    if (tc_o || tc_w1) TR(launch_weight_scale(go, M * 2 * C, nullptr, 0, so, 1.f, s));
+    if (tc_w1) {                                                     // output_projection.weight [2C][C][1]
+      TR(wgrad_splitk(p, p->sk_wo, go, 2 * C, 2 * C, so, false, z_l, C, C, gr->wo[l], C, C, 1.f, s));
+    } else {
     Wgrad a;                                                         // output_projection: weight [2C][C][1], bias
     a.G = go; a.ldg = 2 * C; a.X = z_l; a.ldx = C; a.M = (int)M; a.T = T; a.N = 2 * C; a.Ck = C; a.dW = gr->wo[l]; a.sn = C;
     TR(launch_wgrad(a, s));
+    }
     TR(launch_colsum(go, 2 * C, 2 * C, 1, (int)M, gr->bo[l], 2 * C, s));
     TR(launch_transpose(w->wo[l], wtmp, 2 * C, C, s));               // [2C][C] -> [C][2C]
-    if (p->tc && (p->tc_mask & 8)) {                                 // g_z = g_o . W_o: one-tap conv kernel over scaled f16e5 pairs
-      float* so = p->at<float>(p->scal) + 4; float* sw = p->at<float>(p->scal) + 8; float* sc = p->at<float>(p->scal) + 12;
-      TR(launch_weight_scale(go, M * 2 * C, nullptr, 0, so, 1.f, s));
+    if (tc_o) {                                                      // g_z = g_o . W_o: one-tap conv kernel over scaled f16e5 pairs
+      float* sw = p->at<float>(p->scal) + 8; float* sc = p->at<float>(p->scal) + 12;
       TR(launch_split_pair(go, 2 * C, nullptr, 0, T, so, p->ws + p->gh, p->ws + p->gl, (int)M, 2 * C, s));
       TR(launch_weight_scale(wtmp, (size_t)2 * C * C, nullptr, 0, sw, 1.f, s));
       TR(launch_repack_split(wtmp, p->ws + p->wh, p->ws + p->wl, C, 2 * C, 2 * C, 0, 3, sw, s));
@@ -719,17 +785,21 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     const float* gy = y_l;
     TR(launch_colsum(gy, 2 * C, 2 * C, 1, (int)M, gr->bd[l], 2 * C, s));     // dilated_conv.bias
     TR(launch_colsum(gy, 2 * C, 2 * C, 1, (int)M, gr->bc[l], 2 * C, s));     // conditioner_projection.bias (added to the same y)
+    float* sg = p->at<float>(p->scal) + 4;                           // {S_g, 1 / S_g}: power-of-two scale that lifts g_y into fp16's range
+    const bool tc_w = p->tc && p->tc_wgrad && (p->tc_mask & 4), tc_d = p->tc && (p->tc_mask & 2);
+    if (tc_w || tc_d || tc_w1) TR(launch_weight_scale(gy, M * 2 * C, nullptr, 0, sg, 1.f, s));
+    if (tc_w || tc_w1) TR(launch_split_pair_T(gy, 2 * C, nullptr, 0, T, 1, 1, sg, p->ws + p->gth, p->ws + p->gtl, (int)M, 2 * C, 0, s));
+    if (tc_w1) {                                                     // conditioner_projection.weight [2C][n_mels][1], g_y^T shared with the conv
+      TR(wgrad_splitk(p, p->sk_wc, gy, 2 * C, 2 * C, sg, true, p->at<float>(p->spec), Mp, Mp, gr->wc[l], c.n_mels, c.n_mels, 1.f, s));
+    } else {
     Wgrad cw;                                                        // conditioner_projection.weight [2C][n_mels][1]
     cw.G = gy; cw.ldg = 2 * C; cw.X = p->at<float>(p->spec); cw.ldx = Mp; cw.M = (int)M; cw.T = T; cw.N = 2 * C; cw.Ck = c.n_mels;
     cw.dW = gr->wc[l]; cw.sn = c.n_mels;
     TR(launch_wgrad(cw, s));
-    float* sg = p->at<float>(p->scal) + 4;                           // {S_g, 1 / S_g}: power-of-two scale that lifts g_y into fp16's range
-    const bool tc_w = p->tc && p->tc_wgrad && (p->tc_mask & 4), tc_d = p->tc && (p->tc_mask & 2);
-    if (tc_w || tc_d) TR(launch_weight_scale(gy, M * 2 * C, nullptr, 0, sg, 1.f, s));
+    }
     if (tc_w) {
       // dilated_conv.weight on the tensor cores: one plain GEMM  dW[n][tap*C + c] = sum_m g_y^T[n][m] * im2col(x + d)^T[tap*C + c][m]
       // over transposed f16e5 operand pairs (K = rolls x frames), fp32 result in tap-major order, then added into [2C][C][k]
-      TR(launch_split_pair_T(gy, 2 * C, nullptr, 0, T, 1, 1, sg, p->ws + p->gth, p->ws + p->gtl, (int)M, 2 * C, 0, s));
       TR(launch_split_pair_T(x_l, C, d_l, C, T, k, p->dil[l], nullptr, p->ws + p->uth, p->ws + p->utl, (int)M, C, 1, s));
       UmmaZGemm zg;
       zg.pair = 1; zg.persistent = 0; zg.NB = 1; zg.T = 2 * C; zg.C = k * C; zg.prec = 3; zg.mode = 4; zg.groups = 1; zg.z_group0 = 0; zg.group_stride = 0;

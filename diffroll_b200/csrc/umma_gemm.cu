@@ -120,6 +120,7 @@ struct alignas(64) ZGemmParams {
   uint8_t* xs;             // f16n4: activation scale factors [roll][chunk][frame][8] (xl then maps the 64-byte e2m1 rows)
   // mode 1 with h_pair: relu output as an operand pair through xh / xl.  mode 3: head output projection + guidance + posterior
   int h_pair, dual_B, F;
+  int ksplit;              // mode 4: NB counts K ranges of nslabs slabs each (see the producer)
   drb_update upd;
   const float* x_t; const float* noise; float* x_prev; float* net_out;
 };
@@ -1464,14 +1465,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_zgemm_kernel(const __grid
         uint8_t* st = sv.stage0 + stage * CF::kStageBytes;
         uint64_t* fl = &sv.full[stage];
         const uint32_t fb = PAIR ? mapa_cluster(smem_u32(fl), 0) : 0u;
-        const int grp = s / p.spg, cc = s - grp * p.spg;
-        const int zrow = p.z_group0 + grp * p.group_stride + nb;
+        const int grp = s / p.spg;
+        // split-K (mode 4, training weight gradients): the "roll" index of a tile selects its K range, every split writes its own
+        // partial result [nb][rows][columns] and a reduction kernel adds them up in fp32
+        const int ks = p.ksplit ? nb * p.nslabs : 0;
+        const int cc = s - grp * p.spg + ks;
+        const int zrow = p.ksplit ? 0 : p.z_group0 + grp * p.group_stride + nb;
         prod_expect<PAIR>(fl, fb, CF::kStageBytes);
         load_a<PAIR>(st + CF::kAOff, &p.zh, fl, fb, cc * TILE_K, t0, zrow);
-        load_b<PAIR>(st + CF::kBOff, &p.w_h, fl, fb, s * TILE_K, n_base, rank);
+        load_b<PAIR>(st + CF::kBOff, &p.w_h, fl, fb, (ks + s) * TILE_K, n_base, rank);
         if (CF::kAux) {
           load_a<PAIR>(st + CF::kAAuxOff, &p.zl, fl, fb, AM * cc * TILE_K, t0, zrow);
-          load_b<PAIR>(st + CF::kBAuxOff, &p.w_l, fl, fb, AM * s * TILE_K, n_base, rank);
+          load_b<PAIR>(st + CF::kBAuxOff, &p.w_l, fl, fb, AM * (ks + s) * TILE_K, n_base, rank);
         }
         if (++stage == nst) { stage = 0; phase ^= 1; }
       }
@@ -2351,6 +2356,11 @@ int launch_umma_zgemm(const UmmaMaps& maps, const UmmaZGemm& z, cudaStream_t s) 
   } p.z_group0 = z.z_group0; p.group_stride = z.group_stride;
   p.mode = z.mode; p.bias = z.bias; p.dnext = z.dnext; p.steps = z.steps; p.t_uniform = z.t_uniform; p.bsamp = z.bsamp > 0 ? z.bsamp : 1;
   p.range_max = z.range_max; p.xs = nullptr;
+  p.ksplit = 0;
+  if (z.ksplit) {
+    if (z.mode != 4 || !z.pair || (p.tiles_t & 1)) { set_error("umma_zgemm: split-K needs mode 4 on CTA pairs with an even row-tile count"); return DRB_E_INVALID; }
+    p.ksplit = 1;
+  }
   p.h_pair = 0; p.dual_B = 0; p.F = 0; p.x_t = nullptr; p.noise = nullptr; p.x_prev = nullptr; p.net_out = nullptr;
   p.upd.mode = DRB_UPD_NONE; p.upd.has_noise = 0; p.upd.w = 0.f;
   if (z.mode == 1 && z.hp_h && z.hp_l) { p.h_pair = 1; p.xh = *z.hp_h; p.xl = *z.hp_l; }
