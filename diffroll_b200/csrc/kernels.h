@@ -28,6 +28,7 @@ struct SimtGemm {
   const float* bias = nullptr;
   int act = 0;         // 0 none, 1 relu, 2 silu
   int accumulate = 0;  // C += ...
+  int skinny = 0;      // M <= 32 rows: one warp per output column (training: per-roll projections); summation order differs from the tiled kernel
   float* C = nullptr;
   int ldc = 0;
   int M = 0, N = 0;

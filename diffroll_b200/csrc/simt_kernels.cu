@@ -191,7 +191,57 @@ static void prefer_max_smem_once() {
   cudaGetLastError();
 }
 
+// Skinny form (training: diffusion_projection and the embedding MLP, M = rolls <= 32 rows): the tiled kernel above gives such a
+// product 8 CTAs that walk K serially (63 us for 16 x 512 x 512); here one warp per output column reads its weight row once,
+// coalesced, against the A rows held in shared memory: out[m][n] = act(sum_k A[m][k] W[n][k] + bias[n]) (+ out[m][n]).
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                          const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K,
+                                                          int act, int accumulate) {
+  extern __shared__ float4 sA4[];   // [M][K / 4]
+  const int K4 = K >> 2;
+  for (int i = threadIdx.x; i < M * K4; i += 256) {
+    const int m = i / K4, k4 = i - m * K4;
+    sA4[i] = *reinterpret_cast<const float4*>(A + (size_t)m * lda + 4 * k4);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) acc[m] = 0.f;
+  for (int k4 = lane; k4 < K4; k4 += 32) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * ldw) + k4);
+#pragma unroll
+    for (int m = 0; m < 32; ++m)
+      if (m < M) {
+        const float4 a = sA4[m * K4 + k4];
+        acc[m] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[m]))));
+      }
+  }
+  float mine = 0.f;   // lane m keeps row m
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    float v = acc[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == m) mine = v;
+  }
+  if (lane < M) {
+    float v = mine + (bias ? __ldg(bias + n) : 0.f);
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = v * (1.f / (1.f + expf(-v)));
+    float* dst = C + (size_t)lane * ldc + n;
+    *dst = accumulate ? *dst + v : v;
+  }
+}
+
 int launch_simt_gemm(const SimtGemm& s, cudaStream_t st) {
+  if (s.skinny && s.M <= 32 && s.taps == 1 && !s.A2 && !s.addvec && !s.upd && s.alpha == 1.f && s.a_div == 1.f && (s.Ck % 4) == 0 &&
+      (s.lda % 4) == 0 && (s.ldw % 4) == 0 && (size_t)s.M * s.Ck * 4 <= 48 * 1024 && s.M > 0 && s.N > 0 && s.Ck > 0) {
+    skinny_gemm_kernel<<<(s.N + 7) / 8, 256, (size_t)s.M * s.Ck * 4, st>>>(s.A, s.lda, s.W, s.ldw, s.bias, s.C, s.ldc, s.M, s.N, s.Ck, s.act, s.accumulate);
+    DRB_LAUNCH_CHECK();
+    return 0;
+  }
   prefer_max_smem_once();
   SimtGemmDev g;
   g.A = s.A; g.A2 = s.A2; g.alpha = s.alpha; g.beta = s.beta; g.a_div = s.a_div; g.addvec = s.addvec;

@@ -587,12 +587,12 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
     gather_rows_kernel<<<nblk((size_t)B * 128), 256, 0, s>>>(emb_table, steps, p->at<float>(p->e0), B, 128);
     DRB_LAUNCH_CHECK();
     SimtGemm g;
-    g.A = p->at<float>(p->e0); g.lda = 128; g.T = 1; g.Ck = 128; g.W = w->e1w; g.ldw = 128; g.bias = w->e1b; g.C = p->at<float>(p->p1); g.ldc = 512; g.M = B; g.N = 512;
+    g.A = p->at<float>(p->e0); g.lda = 128; g.T = 1; g.Ck = 128; g.W = w->e1w; g.ldw = 128; g.bias = w->e1b; g.C = p->at<float>(p->p1); g.ldc = 512; g.M = B; g.N = 512; g.skinny = 1;
     TR(launch_simt_gemm(g, s));
     g.act = 2; g.C = p->at<float>(p->s1);
     TR(launch_simt_gemm(g, s));
     SimtGemm h;
-    h.A = p->at<float>(p->s1); h.lda = 512; h.T = 1; h.Ck = 512; h.W = w->e2w; h.ldw = 512; h.bias = w->e2b; h.C = p->at<float>(p->p2); h.ldc = 512; h.M = B; h.N = 512;
+    h.A = p->at<float>(p->s1); h.lda = 512; h.T = 1; h.Ck = 512; h.W = w->e2w; h.ldw = 512; h.bias = w->e2b; h.C = p->at<float>(p->p2); h.ldc = 512; h.M = B; h.N = 512; h.skinny = 1;
     TR(launch_simt_gemm(h, s));
     h.act = 2; h.C = p->at<float>(p->emb);
     TR(launch_simt_gemm(h, s));
@@ -609,7 +609,7 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
     float* z_l = p->at<float>(p->zs) + (size_t)l * M * C;
     float* d_l = p->at<float>(p->dl) + (size_t)l * B * C;
     SimtGemm d;  // diffusion_projection(emb)   model/diffwave.py:137
-    d.A = p->at<float>(p->emb); d.lda = 512; d.T = 1; d.Ck = 512; d.W = w->wdp[l]; d.ldw = 512; d.bias = w->bdp[l]; d.C = d_l; d.ldc = C; d.M = B; d.N = C;
+    d.A = p->at<float>(p->emb); d.lda = 512; d.T = 1; d.Ck = 512; d.W = w->wdp[l]; d.ldw = 512; d.bias = w->bdp[l]; d.C = d_l; d.ldc = C; d.M = B; d.N = C; d.skinny = 1;
     TR(launch_simt_gemm(d, s));
     TR(launch_repack_conv_fp32(w->wd[l], wtmp, 2 * C, C, k, s));   // [2C][C][k] -> tap-major [2C][k*C]
     if (p->tc && (p->tc_mask & 1)) {
@@ -851,7 +851,7 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     TR(launch_colsum(gd, C, C, 1, B, gr->bdp[l], C, s));
     TR(launch_transpose(w->wdp[l], wtmp, C, 512, s));                // [C][512] -> [512][C]
     SimtGemm e;
-    e.A = gd; e.lda = C; e.T = 1; e.Ck = C; e.W = wtmp; e.ldw = C; e.C = gemb; e.ldc = 512; e.M = B; e.N = 512; e.accumulate = l < L - 1;
+    e.A = gd; e.lda = C; e.T = 1; e.Ck = C; e.W = wtmp; e.ldw = C; e.C = gemb; e.ldc = 512; e.M = B; e.N = 512; e.accumulate = l < L - 1; e.skinny = 1;
     TR(launch_simt_gemm(e, s));
     if (has_res) {
       add_res_grad_kernel<<<nblk(M * C / 4), 256, 0, s>>>(gu, gx, M * C / 4);
@@ -885,7 +885,7 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     TR(launch_colsum(gemb, 512, 512, 1, B, gr->e2b, 512, s));
     TR(launch_transpose(w->e2w, wtmp, 512, 512, s));
     SimtGemm g;
-    g.A = gemb; g.lda = 512; g.T = 1; g.Ck = 512; g.W = wtmp; g.ldw = 512; g.C = gs; g.ldc = 512; g.M = B; g.N = 512;
+    g.A = gemb; g.lda = 512; g.T = 1; g.Ck = 512; g.W = wtmp; g.ldw = 512; g.C = gs; g.ldc = 512; g.M = B; g.N = 512; g.skinny = 1;
     TR(launch_simt_gemm(g, s));
     silu_bwd_kernel<<<nblk((size_t)B * 512), 256, 0, s>>>(gs, p->at<float>(p->p1), (size_t)B * 512);
     DRB_LAUNCH_CHECK();
