@@ -49,6 +49,7 @@ if ROOT not in sys.path:
 METRIC = "diffusion sampling steps/sec (B=32, 640x88 roll, 200 steps)"
 UNIT = "steps/s"
 BATCH = 32
+E2E_REPEATS = 3      # end-to-end calls timed per configuration; the median is reported, all are listed
 FRAMES = 640
 WAVE_LEN = 327680
 C, L, KSIZE, PITCHES, NMELS = 512, 15, 9, 88, 229
@@ -321,18 +322,25 @@ def measure(ctx, cfg_id, K, W, precision, want_e2e=True, want_profile=True, samp
         Ke = min(K, TS)
         # warm-up with the same shape: allocates the pinned trajectory buffer the public API keeps per shape
         model.sample_loop(x_host.to(ctx.dev, non_blocking=True), w_host.to(ctx.dev, non_blocking=True), keep_trajectory=True, n_steps=Ke)
-        torch.cuda.synchronize(); ctx.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        xd = x_host.to(ctx.dev, non_blocking=True)
-        wd = w_host.to(ctx.dev, non_blocking=True)
-        x0, _, traj = model.sample_loop(xd, wd, keep_trajectory=True, n_steps=Ke)
-        if ctx.world > 1:   # the path's only collective: one all-gather of the finished rolls over NCCL / NVLink
-            rolls = all_gather_rolls(x0, global_batch)
-            assert rolls.shape[0] == global_batch
-        e1.record()
-        torch.cuda.synchronize(); ctx.barrier()
-        out.update(ms_e2e=ctx.max_over_ranks(e0.elapsed_time(e1)), Ke=Ke,
+        # one chain is one host call: E2E_REPEATS independent calls (new device copies of the host buffers each time, so the mel
+        # front-end and the conditioner tables run again), each timed on the device as the max over ranks; the MEDIAN is reported
+        # and all of them are listed (a single call is exposed to one-off host hiccups)
+        e2e_all = []
+        for _ in range(E2E_REPEATS):
+            torch.cuda.synchronize(); ctx.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            xd = x_host.to(ctx.dev, non_blocking=True)
+            wd = w_host.to(ctx.dev, non_blocking=True)
+            x0, _, traj = model.sample_loop(xd, wd, keep_trajectory=True, n_steps=Ke)
+            if ctx.world > 1:   # the path's only collective: one all-gather of the finished rolls over NCCL / NVLink
+                rolls = all_gather_rolls(x0, global_batch)
+                assert rolls.shape[0] == global_batch
+            e1.record()
+            torch.cuda.synchronize(); ctx.barrier()
+            e2e_all.append(ctx.max_over_ranks(e0.elapsed_time(e1)))
+            del xd, wd
+        out.update(ms_e2e=sorted(e2e_all)[len(e2e_all) // 2], ms_e2e_all=e2e_all, Ke=Ke,
                    h2d=(x_host.numel() + (w_host.numel() if branches != _lib.BRANCH_UNCOND else 0)) * 4 / Ke,
                    d2h=x_host.numel() * 4)
     model.release_buffers()
@@ -618,6 +626,7 @@ def run_b200(args, rank, world, local):
         "clocks": main["clocks"], "gpu_launches": main["launches"],
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
                 "steps": main["Ke"], "ms_per_step": main["ms_e2e"] / main["Ke"], "amortised_over": main["Ke"],
+                "repeats": len(main["ms_e2e_all"]), "ms_per_call_all": [round(v, 3) for v in main["ms_e2e_all"]], "statistic": "median",
                 "note": "per-clip work (H2D of the clip, mel front-end, conditioner tables) is spread over `amortised_over` "
                         "steps; a full chain spreads it over all of its timesteps"},
         "workspace_bytes": main["workspace_bytes"], "activation_operand_max_abs": main["range_max"],

@@ -24,7 +24,7 @@ EXPORTS = [
     "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_plan_precision", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
     "drb_train_workspace_bytes", "drb_train_create", "drb_train_destroy", "drb_train_forward", "drb_train_backward", "drb_loss_grad",
-    "drb_adam_step", "drb_plan_set_step_embeddings",
+    "drb_adam_step", "drb_adam_step_multi", "drb_plan_set_step_embeddings",
 ]
 
 
@@ -141,6 +141,8 @@ def load():
     lib.drb_loss_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int32, C.c_void_p, C.c_void_p]
     lib.drb_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int32, C.c_void_p]
+    lib.drb_adam_step_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_int32, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("drb_version",):

@@ -352,6 +352,30 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+// The same update for a whole parameter list in ONE launch: table[t] = {param, grad, exp_avg, exp_avg_sq, numel} (five 64-bit words, device
+// memory), block_map[b] = {tensor, first element / 4096}: every block owns 4096 consecutive elements of one tensor.
+constexpr int ADAM_CHUNK = 4096;
+__global__ void __launch_bounds__(256) adam_multi_kernel(const unsigned long long* __restrict__ table, const int2* __restrict__ block_map,
+                                                         float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  const int2 bm = block_map[blockIdx.x];
+  const unsigned long long* e = table + (size_t)bm.x * 5;
+  float* __restrict__ p = reinterpret_cast<float*>(e[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
+  float* __restrict__ m = reinterpret_cast<float*>(e[2]);
+  float* __restrict__ v = reinterpret_cast<float*>(e[3]);
+  const size_t n = (size_t)e[4], lo = (size_t)bm.y * ADAM_CHUNK, hi = lo + ADAM_CHUNK < n ? lo + ADAM_CHUNK : n;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
 // d loss / d prediction for the mean l1 / l2 / smooth-l1 losses of p_losses (task/diffusion.py:792-802), times a per-roll factor
 // (training mode 'ex_0': pred_roll = (x_t - s1[t] eps) / sa[t]  ->  d pred_roll / d eps = -s1[t] / sa[t])
 __global__ void loss_grad_kernel(const float* __restrict__ label, const float* __restrict__ pred, float* __restrict__ g, size_t n,
@@ -916,6 +940,18 @@ int drb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<nblk(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
                                                          (float)sqrt(bc2));
+  DRB_LAUNCH_CHECK();
+  return 0;
+}
+
+int drb_adam_step_multi(const void* table, const void* block_map, int32_t n_blocks, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int32_t step, void* stream) {
+  if (!table || !block_map || n_blocks < 0 || step < 1) { set_error("adam_multi: bad argument"); return DRB_E_INVALID; }
+  if (n_blocks == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_multi_kernel<<<(unsigned)n_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(table),
+                                                                           reinterpret_cast<const int2*>(block_map), lr, beta1, beta2, eps,
+                                                                           weight_decay, (float)bc1, (float)sqrt(bc2));
   DRB_LAUNCH_CHECK();
   return 0;
 }

@@ -159,33 +159,64 @@ class Adam:
         self.steps = 0
 
     def zero_grad(self, set_to_none=False):
-        for q in self.params:
-            if q.grad is not None:
-                if set_to_none:
-                    q.grad = None
-                else:
-                    q.grad.zero_()
+        if set_to_none:
+            for q in self.params:
+                q.grad = None
+            return
+        grads = [q.grad for q in self.params if q.grad is not None]
+        if grads:
+            torch._foreach_zero_(grads)      # a few multi-tensor launches instead of one fill per tensor
+
+    ADAM_CHUNK = 4096   # elements per block of drb_adam_step_multi (csrc/train.cu)
+
+    def _tables(self, live):
+        """Device tables of drb_adam_step_multi for the tensors in ``live``; rebuilt when a pointer changes."""
+        key = tuple((q.data_ptr(), q.grad.data_ptr(), q.numel()) for q in live)
+        if getattr(self, "_table_key", None) != key:
+            rows, blocks = [], []
+            for i, q in enumerate(live):
+                st = self.state[id(q)]
+                rows.append([q.data_ptr(), q.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), q.numel()])
+                blocks += [[i, c] for c in range((q.numel() + self.ADAM_CHUNK - 1) // self.ADAM_CHUNK)]
+            dev = live[0].device
+            self._table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            self._block_map = torch.tensor(blocks, dtype=torch.int32).to(dev)
+            self._table_key = key
+        return self._table, self._block_map
 
     @torch.no_grad()
     def step(self):
+        """One update of every tensor that has a gradient, as ONE launch (``drb_adam_step_multi``): torch.optim.Adam steps all of
+        them together too, so they share the step count."""
         lib = _lib.load()
         self.steps += 1
-        for q in self.params:
-            if q.grad is None:
-                continue
+        live = [q for q in self.params if q.grad is not None]
+        if not live:
+            return
+        for q in live:
             if not q.is_cuda or q.dtype != torch.float32 or not q.is_contiguous():
                 raise _lib.DrbError("Adam: parameters must be contiguous fp32 CUDA tensors")
+            if not q.grad.is_contiguous():
+                q.grad = q.grad.contiguous()
             st = self.state.get(id(q))
             if st is None:
                 st = self.state[id(q)] = {"step": 0, "exp_avg": torch.zeros_like(q), "exp_avg_sq": torch.zeros_like(q)}
             st["step"] += 1
-            g = q.grad.contiguous()
-            with torch.cuda.device(q.device):
-                _lib.check(lib.drb_adam_step(_p(q.data), _p(g), _p(st["exp_avg"]), _p(st["exp_avg_sq"]), C.c_size_t(q.numel()),
-                                             C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                                             C.c_float(self.weight_decay), C.c_int32(st["step"]), _stream(q.device)), "drb_adam_step")
+        steps = {self.state[id(q)]["step"] for q in live}
+        dev = live[0].device
+        if len(steps) == 1 and all(q.device == dev for q in live):
+            table, block_map = self._tables(live)
+            with torch.cuda.device(dev):
+                _lib.check(lib.drb_adam_step_multi(_p(table), _p(block_map), C.c_int32(block_map.shape[0]), C.c_float(self.lr),
+                                                   C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                                   C.c_float(self.weight_decay), C.c_int32(steps.pop()), _stream(dev)), "drb_adam_step_multi")
+        else:       # tensors that joined later (a gradient that was None before) carry their own step count: one launch per tensor
+            for q in live:
+                st = self.state[id(q)]
+                with torch.cuda.device(q.device):
+                    _lib.check(lib.drb_adam_step(_p(q.data), _p(q.grad), _p(st["exp_avg"]), _p(st["exp_avg_sq"]), C.c_size_t(q.numel()),
+                                                 C.c_float(self.lr), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                                 C.c_float(self.weight_decay), C.c_int32(st["step"]), _stream(q.device)), "drb_adam_step")
         # the kernels wrote through raw pointers: bump the tensors' version counters so that caches keyed on them (the
         # sampling engine's repacked weights, model._weights_version) see the update
-        touched = [q for q in self.params if q.grad is not None]
-        if touched:
-            torch._foreach_add_(touched, 0.0)
+        torch.autograd.graph.increment_version(live)

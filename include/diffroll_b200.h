@@ -265,6 +265,11 @@ int drb_loss_grad(const float* label, const float* pred, float* g_pred, size_t n
 /* One torch.optim.Adam update of one tensor (amsgrad off); step = 1 for the first update. */
 int drb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, void* stream);
+/* The same update for a list of tensors in one launch (torch's foreach / fused Adam, task/diffusion.py:1057-1059 steps all 130
+ * tensors together).  table: device array of n_tensors x 5 uint64 {param, grad, exp_avg, exp_avg_sq, numel}; block_map: device array
+ * of n_blocks x 2 int32 {tensor index, chunk index}, one entry per 4096-element chunk of every tensor. */
+int drb_adam_step_multi(const void* table, const void* block_map, int32_t n_blocks, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int32_t step, void* stream);
 
 /* Measurement hooks (bench.py): with profiling enabled every step records CUDA events on the launching stream
  * around each kernel class; drb_plan_profile_read synchronises and returns, for class k in
