@@ -74,6 +74,7 @@ def test_mel_frontend_vs_golden():
     t = torch.tensor(37).repeat(2).cuda()
     _, spec = m(x_T.cuda(), wav.cuda(), t)
     assert spec.shape == (2, 229, 640)
+    record(f"mel front-end (fused STFT + mel kernel) max|delta| vs torchaudio golden = {maxabs(spec, g['spec_c']):.3e}")
     assert maxabs(spec, g["spec_c"]) < TOL_SPEC
     _, spec_m = m(x_T.cuda(), wav.cuda(), t, inpainting_t=[100, 420])
     assert maxabs(spec_m[:, :, ::8], g["spec_m"]) < TOL_SPEC
