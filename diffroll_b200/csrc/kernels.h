@@ -185,6 +185,7 @@ struct UmmaConvLin {  // out[roll][t][n] = sum_{tap,c} A[roll][t + (tap - taps/2
   const CUtensorMap *sh = nullptr, *sl = nullptr, *wch = nullptr, *wcl = nullptr;   // optional 1x1 term: [NB][T][Mp] and [Nout][Mp]
   int NB = 0, T = 0, Cin = 0, Nout = 0, taps = 1, dil = 1, Mp = 0, pair = 1;
   int tap_lo = 0, tap_n = 0, accumulate = 0;          // taps [tap_lo, tap_lo + tap_n) only (0: all); out += result
+  float* scratch = nullptr; size_t scratch_bytes = 0; // optional: lets the persistent kernel cut its work between passes of an item (pairs x 256 KB)
   int tap_span = 0;                                  // > 0: taps [tap_lo, tap_lo + tap_span) in passes of tap_n taps, passes summed in out[] in fp32
   int prec = 3;                                      // 3 f16e5 pairs (aux = bytes [.][2C]); 4 f16x3 (aux = fp16 lo [.][C]): fp32-grade
   const float* inv_scale = nullptr;                  // device scalar: 1 / (product of the operand scales)

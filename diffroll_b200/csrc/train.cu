@@ -416,6 +416,8 @@ struct drb_train {
   // moved the activations by 1e-4 and with them ReLU / gate / L1-loss derivatives (measured worst gradient error 9e-4 .. 1.5e-2
   // instead of 6e-5), so the forward gets fp32-grade operands.
   int tc_mask = 31;
+  int dgrad_taps = 1;        // DRB_TRAIN_DGRAD_TAPS: taps per pass of the transposed conv (9: one pass, the round-2 form)
+  size_t wtmp_bytes = 0;
   int taps_per_launch = 1;   // DRB_TRAIN_TAPS: taps of the forward conv per tensor-core launch (accumulation chain = taps * C terms)
   size_t uh, ul, gh, gl, sph, spl, wh, wl, wch, wcl, bnat, scal, gth, gtl, uth, utl;
   CUtensorMap m_uh, m_ul, m_gh, m_gl, m_sh, m_sl, m_wfh, m_wfl, m_wgh, m_wgl, m_wch, m_wcl;
@@ -443,7 +445,7 @@ static size_t train_layout(drb_train& p) {
   p.dl = take(L * B * C * 4); p.iota = take(B * 4);
   size_t wmax = 2 * C * k * C;                       // repacked / transposed weight scratch (largest: the dilated conv)
   if (wmax < 2 * C * (size_t)p.Mp) wmax = 2 * C * (size_t)p.Mp;
-  p.wtmp = take(wmax * 4);
+  p.wtmp = take(wmax * 4); p.wtmp_bytes = wmax * 4;
   p.gskip = take(M * C * 4); p.gx = take(M * C * 4); p.gu = take(M * C * 4); p.gz = take(M * C * 4);
   p.gemb = take(B * 512 * 4); p.gd = take(B * C * 4); p.gsmall = take(B * 512 * 4);
   // operand pairs (2 + 2 bytes per element): x + d [M][C], g_y [M][2C], spectrogram [M][Mp], one layer's conv weights, conditioner weights
@@ -540,6 +542,8 @@ int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspa
     if (env && env[0] >= '1' && env[0] <= '9') p->tc_mask = atoi(env);
     const char* et = getenv("DRB_TRAIN_TAPS");
     if (et && atoi(et) >= 1) p->taps_per_launch = atoi(et);
+    const char* ed = getenv("DRB_TRAIN_DGRAD_TAPS");
+    if (ed && atoi(ed) >= 1) p->dgrad_taps = atoi(ed);
     if (p->tc) {
       int r = 0;
       auto mk3 = [&](CUtensorMap* m, size_t off, int d0, int dtype) { if (!r) r = make_tmap_3d(m, p->ws + off, B, T, d0, 128, dtype); };
@@ -655,6 +659,7 @@ int drb_train_forward(drb_train* p, const drb_train_params* w, const float* x_t,
       // of k*C + Mp terms, summed across launches in exact fp32
       // (one kernel: the persistent linear conv runs the passes of a tile back to back; DRB_LIN_PERS=0 launches once per pass)
       cv.tap_lo = 0; cv.tap_n = p->taps_per_launch < k ? p->taps_per_launch : k; cv.tap_span = k; cv.accumulate = 0;
+      cv.scratch = wtmp; cv.scratch_bytes = p->wtmp_bytes;   // wtmp is free again: the weights were split into wh / wl above
       TR(launch_umma_conv_lin(cv, s));
     } else {
     SimtGemm g;  // dilated_conv(x + d)   :138-139
@@ -858,6 +863,11 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
         cv.ah = &p->m_gh; cv.al = &p->m_gl; cv.wh = &p->m_wgh; cv.wl = &p->m_wgl;
         cv.NB = B; cv.T = T; cv.Cin = 2 * C; cv.Nout = C; cv.taps = k; cv.dil = p->dil[l]; cv.Mp = 0; cv.inv_scale = sc;
         cv.bias = nullptr; cv.out = gu; cv.ldo = C;
+        // one pass per tap, summed in fp32 in g_u (chains of 2C instead of 9 * 2C terms: worst gradient error 6e-5 -> 3.5e-5 at the same
+        // speed).  No scratch, i.e. whole items per pair: cutting the 80 items into balanced pass ranges was measured 2 ms SLOWER per
+        // step -- this product streams ~1.1 GB of operands from L2 per launch, and pairs that no longer walk the same tap in lockstep
+        // lose the sharing of those reads (the forward conv, 160 items, gains 0.5 ms from the same cut)
+        cv.tap_lo = 0; cv.tap_n = p->dgrad_taps < k ? p->dgrad_taps : k; cv.tap_span = k;
         TR(launch_umma_conv_lin(cv, s));
       } else {
       SimtGemm u;

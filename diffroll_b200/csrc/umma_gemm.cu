@@ -105,6 +105,7 @@ struct alignas(64) GateParams {
   // core's fp32 accumulation loses ~1e-8 of the running sum per K-step, which a 4608-long chain turns into 4e-5 -- short chains summed
   // in exact fp32 in global memory keep the training forward at the fp32 floor (csrc/train.cu)
   int tap_lo, tap_n, lin_acc;
+  float* lin_scratch;   // persistent linear kernel: [pairs][2][128][256] fp32 partial tiles, or nullptr (ranges cut at whole items)
   int tap_span;   // persistent linear kernel: taps [tap_lo, tap_lo + tap_span) in passes of tap_n, summed in out[] (0: one pass)
 };
 
@@ -525,6 +526,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
   const int span = p.tap_span > 0 ? p.tap_span : per_pass;
   const int n_pass = (span + per_pass - 1) / per_pass;
   const int cslabs = p.n_cond > 0 ? p.cond_slabs : 0;
+  // This pair's units: the contiguous range [u_lo, u_hi) of u = item * n_pass + pass.  With a scratch buffer the cut may fall
+  // INSIDE an item (n_items * n_pass units over the pairs instead of whole items: 160 items on 74 pairs are 3 rounds of whole
+  // items but 19.5 -> 20 of 27 pass-units): the pair that starts mid-item sums its passes of that item into its own 256 x 256
+  // scratch tile and lin_fixup_kernel adds that tile to out[] afterwards -- the launcher guarantees that a range is at least one
+  // item long, so an item has at most one such partial and the result does not depend on timing.
+  const int gran = p.lin_scratch ? 1 : n_pass;
+  const int n_units = p.n_items * n_pass;
+  const int u_lo = (int)((long long)pair_id * (n_units / gran) / n_pairs) * gran;
+  const int u_hi = (int)((long long)(pair_id + 1) * (n_units / gran) / n_pairs) * gran;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.xh); tma_prefetch_desc(&p.wd_h); tma_prefetch_desc(&p.xl); tma_prefetch_desc(&p.wd_l);
@@ -547,11 +557,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
     if (elect_one()) {
       // ---------------- producer (each CTA: its 128 frames and its half of the weight tile) ----------------
       int stage = 0; uint32_t phase = 0;
-      for (int item = pair_id; item < p.n_items; item += n_pairs) {
+      for (int u = u_lo; u < u_hi; ++u) {
+        const int item = u / n_pass, ps = u - item * n_pass;
         const int nblk = item % p.n_blocks;
         const int mt = (item / p.n_blocks) * 2 + (int)rank;
         const int nb = mt / p.tiles_t, t0 = (mt % p.tiles_t) * TILE_M;
-        for (int ps = 0; ps < n_pass; ++ps) {
+        {
           const int tap0 = p.tap_lo + ps * per_pass;
           const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
           const int conv_slabs = ntap * cpt;
@@ -586,8 +597,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
       // ---------------- MMA issuer (leader CTA) ----------------
       int stage = 0; uint32_t phase = 0;
       int ucnt = 0;
-      for (int item = pair_id; item < p.n_items; item += n_pairs) {
-        for (int ps = 0; ps < n_pass; ++ps, ++ucnt) {
+      for (int u = u_lo; u < u_hi; ++u) {
+        const int ps = u % n_pass;
+        for (int once = 0; once < 1; ++once, ++ucnt) {
           const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
           const int nslabs = ntap * cpt + (ps == n_pass - 1 ? cslabs : 0);
           const int as = ucnt & 1;
@@ -612,17 +624,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
     const float inv_l = __ldg(p.inv_scale);
     const int l8 = lane & 7, lr = lane >> 3;
     int ucnt = 0;
-    for (int item = pair_id; item < p.n_items; item += n_pairs) {
+    for (int u = u_lo; u < u_hi; ++u) {
+      const int item = u / n_pass, ps = u - item * n_pass;
       const int nblk = item % p.n_blocks;
       const int mt = (item / p.n_blocks) * 2 + (int)rank;
       const int nb = mt / p.tiles_t, t0 = (mt % p.tiles_t) * TILE_M;
       const int tq = t0 + q * 32;                                    // first frame of this warp's 32 rows
       const int colb = nblk * TILE_N + grp * 128 + l8 * 4;           // this lane's 4 columns of every 32-column block
-      float* const dst = p.lin_out + ((size_t)nb * p.T + tq) * (size_t)p.ldo + colb;
-      for (int ps = 0; ps < n_pass; ++ps, ++ucnt) {
+      // an item whose first pass belongs to the previous pair: this pair's passes of it are summed in its scratch tile
+      const bool partial = item * n_pass < u_lo;
+      float* const dst = partial ? p.lin_scratch + ((size_t)(2 * pair_id + (int)rank) * TILE_M + q * 32) * TILE_N + grp * 128 + l8 * 4
+                                 : p.lin_out + ((size_t)nb * p.T + tq) * (size_t)p.ldo + colb;
+      const size_t ldd = partial ? (size_t)TILE_N : (size_t)p.ldo;
+      for (int once = 0; once < 1; ++once, ++ucnt) {
         const int as = ucnt & 1;
-        const bool acc = ps > 0 || p.lin_acc != 0;
-        const float* bias = ps == 0 ? p.bias_cond : nullptr;
+        const bool acc = partial ? u > u_lo : (ps > 0 || p.lin_acc != 0);
+        const float* bias = (ps == 0 && !partial) ? p.bias_cond : nullptr;
         mbar_wait(&tfull[as], (ucnt >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u + (uint32_t)grp * 128u;
@@ -649,7 +666,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
             const int r = 4 * k + lr;
             o4[k] = b4;
             if (acc && tq + r < p.T) {
-              const float4 qv = __ldcg(reinterpret_cast<const float4*>(dst + (size_t)r * p.ldo + c4 * 32));
+              const float4 qv = __ldcg(reinterpret_cast<const float4*>(dst + (size_t)r * ldd + c4 * 32));
               o4[k].x += qv.x; o4[k].y += qv.y; o4[k].z += qv.z; o4[k].w += qv.w;
             }
           }
@@ -658,7 +675,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
             const int r = 4 * k + lr;
             const float4 a = lds128(sbuf + (uint32_t)r * 128u + (uint32_t)((l8 ^ (r & 7)) << 4));
             if (tq + r < p.T)
-              *reinterpret_cast<float4*>(dst + (size_t)r * p.ldo + c4 * 32) = make_float4(a.x + o4[k].x, a.y + o4[k].y, a.z + o4[k].z, a.w + o4[k].w);
+              *reinterpret_cast<float4*>(dst + (size_t)r * ldd + c4 * 32) = make_float4(a.x + o4[k].x, a.y + o4[k].y, a.z + o4[k].z, a.w + o4[k].w);
           }
           __syncwarp();
         }
@@ -670,6 +687,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
   if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
+
+// out[] += the partial tile of every pair whose unit range starts inside an item (see umma_conv_lin_pers_kernel).  One block per CTA
+// of the persistent grid; u_lo is recomputed exactly as there.
+__global__ void __launch_bounds__(256) lin_fixup_kernel(const float* __restrict__ scratch, float* __restrict__ out, int ldo, int T, int tiles_t,
+                                                        int n_blocks, int n_items, int n_pass, int n_pairs) {
+  const int pair_id = (int)(blockIdx.x >> 1), rank = (int)(blockIdx.x & 1);
+  const int n_units = n_items * n_pass;
+  const int u_lo = (int)((long long)pair_id * n_units / n_pairs);
+  const int item = u_lo / n_pass;
+  if (item * n_pass == u_lo) return;                       // the range starts at an item boundary: nothing parked
+  const int nblk = item % n_blocks, mt = (item / n_blocks) * 2 + rank;
+  const int nb = mt / tiles_t, t0 = (mt % tiles_t) * TILE_M;
+  const float4* src = reinterpret_cast<const float4*>(scratch + (size_t)(2 * pair_id + rank) * TILE_M * TILE_N);
+  for (int i = threadIdx.x; i < TILE_M * TILE_N / 4; i += 256) {
+    const int r = i / (TILE_N / 4), c = (i - r * (TILE_N / 4)) * 4;
+    if (t0 + r >= T) continue;
+    float4* d = reinterpret_cast<float4*>(out + ((size_t)nb * T + t0 + r) * (size_t)ldo + nblk * TILE_N + c);
+    const float4 a = src[i];
+    float4 o = *d;
+    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    *d = o;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // gate kernel, window variant (CTA pairs, aux operands).  The 9 dilated taps of one 64-channel chunk read the SAME
@@ -2235,7 +2275,7 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
   p.z_group0 = g.z_group0;
   p.bias_cond = g.bias_cond; p.bias_unc = g.bias_unc;
   p.cond = nullptr; p.n_cond_mma = p.n_cond; p.dual_off = 0; p.xs = nullptr; p.lin_out = nullptr; p.ldo = 0;
-  p.tap_lo = 0; p.tap_n = 0; p.lin_acc = 0;
+  p.tap_lo = 0; p.tap_n = 0; p.lin_acc = 0; p.tap_span = 0; p.lin_scratch = nullptr;
   const int grid = p.NB * p.tiles_t * p.n_blocks;
   p.inv_scale = g.inv_scale;
   const bool mc = g.pair && ((p.NB * p.tiles_t) % 2 == 0);
@@ -2321,8 +2361,21 @@ int launch_umma_conv_lin(const UmmaConvLin& c, cudaStream_t s) {
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
     p.n_items = (p.NB * p.tiles_t / 2) * p.n_blocks;
     const int pairs = p.n_items < n_sm / 2 ? p.n_items : n_sm / 2;
-    return c.prec == 4 ? launch_k(umma_conv_lin_pers_kernel<4>, p, 2 * pairs, CLP_SMEM, true, s)
-                       : launch_k(umma_conv_lin_pers_kernel<3>, p, 2 * pairs, CLP_SMEM, true, s);
+    // pass-granular ranges (a pair may start inside an item and park that part in the caller's scratch) when there is more than
+    // one pass, the ranges are at least one item long (at most one partial per item) and the item count does not divide evenly
+    const int per_pass = c.tap_n > 0 ? c.tap_n : c.taps, span = c.tap_span > 0 ? c.tap_span : per_pass;
+    const int n_pass = (span + per_pass - 1) / per_pass;
+    static int bal = -1;   // DRB_LIN_BALANCE=0: whole items per pair (A/B runs)
+    if (bal < 0) { const char* e = getenv("DRB_LIN_BALANCE"); bal = (e && e[0] == '0') ? 0 : 1; }
+    const bool split = bal && c.scratch && n_pass > 1 && (p.n_items % pairs) != 0 && (p.n_items * n_pass) / pairs >= n_pass &&
+                       c.scratch_bytes >= (size_t)pairs * 2 * TILE_M * TILE_N * sizeof(float);
+    p.lin_scratch = split ? c.scratch : nullptr;
+    int r = c.prec == 4 ? launch_k(umma_conv_lin_pers_kernel<4>, p, 2 * pairs, CLP_SMEM, true, s)
+                        : launch_k(umma_conv_lin_pers_kernel<3>, p, 2 * pairs, CLP_SMEM, true, s);
+    if (r || !split) return r;
+    lin_fixup_kernel<<<2 * pairs, 256, 0, s>>>(c.scratch, c.out, c.ldo, c.T, p.tiles_t, p.n_blocks, p.n_items, n_pass, pairs);
+    DRB_LAUNCH_CHECK();
+    return 0;
   }
   if (c.tap_span > 0 && c.tap_n > 0 && c.tap_span > c.tap_n) {   // one launch per pass, summed in out[] across launches
     UmmaConvLin one = c;

@@ -30,7 +30,7 @@ res["ours_ms"] = e0.elapsed_time(e1) / iters
 res["train_workspace_bytes"] = list(m._train_engines.values())[0].workspace_bytes
 m.release_buffers(); del m, opt; torch.cuda.empty_cache()
 
-for name, flag in (("eager_fp32_ms", False), ("eager_tf32_ms", True)):
+for name, flag in (() if "noeager" in sys.argv else (("eager_fp32_ms", False), ("eager_tf32_ms", True))):
     torch.backends.cudnn.allow_tf32 = flag; torch.backends.cuda.matmul.allow_tf32 = flag
     orc = OracleDiffRoll(hp, make_state_dict(hp), device="cuda")
     params = {k: torch.nn.Parameter(v.clone()) for k, v in orc.sd.items() if not k.startswith("mel_layer.")}

@@ -127,6 +127,26 @@ def test_update_structs_reproduce_oracle_samplers(name):
         assert bool(u.has_noise) == (t_index > 0 and name not in ("ddim_x0", "cfdg_ddim_x0", "ddim"))
 
 
+def test_update_structs_are_memoised_and_follow_what_the_samplers_read():
+    """sample_loop asks for the 200 update structs at the head of every call (10 ms of host arithmetic): they are computed once and
+    recomputed when anything a sampler method reads changes -- guidance weight, sampler, mask ranges, the schedule tensors."""
+    m, hp = _model(sampling_type="inpainting_ddpm_x0")
+    ups, branches, masks = m._all_updates()
+    assert m._all_updates()[0] is ups                       # memo hit: the same list object
+    w0 = ups[0].w
+    m.hparams.sampling.w = w0 + 1.5
+    ups2, _, _ = m._all_updates()
+    assert ups2 is not ups and abs(ups2[0].w - (w0 + 1.5)) < 1e-6
+    m.hparams.inpainting_t = [0, 320]
+    assert m._all_updates()[2][0] == [0, 320]
+    m.betas.mul_(1.0)                                       # an in-place edit of a schedule tensor bumps its version
+    ups3, _, _ = m._all_updates()
+    assert ups3 is not ups2
+    m.sqrt_alphas_cumprod = m.sqrt_alphas_cumprod * 0.5     # a replaced schedule tensor
+    ups4, _, _ = m._all_updates()
+    assert abs(ups4[-1].s[0] - 0.5 * ups3[-1].s[0]) < 1e-7  # t = 0: x_0 scaled by sqrt_alphas_cumprod[0]
+
+
 def test_no_cpu_fallback_and_training_mode_guard():
     from diffroll_b200._lib import DrbError
     m, hp = _model()
