@@ -321,7 +321,10 @@ def measure(ctx, cfg_id, K, W, precision, want_e2e=True, want_profile=True, samp
     if want_e2e:
         Ke = min(K, TS)
         # warm-up with the same shape: allocates the pinned trajectory buffer the public API keeps per shape
-        model.sample_loop(x_host.to(ctx.dev, non_blocking=True), w_host.to(ctx.dev, non_blocking=True), keep_trajectory=True, n_steps=Ke)
+        x0w, _, _ = model.sample_loop(x_host.to(ctx.dev, non_blocking=True), w_host.to(ctx.dev, non_blocking=True), keep_trajectory=True, n_steps=Ke)
+        if ctx.world > 1:   # NCCL sets a collective of a new size up lazily (60 ms on the first call): part of the warm-up
+            all_gather_rolls(x0w, global_batch)
+        del x0w
         # one chain is one host call: E2E_REPEATS independent calls (new device copies of the host buffers each time, so the mel
         # front-end and the conditioner tables run again), each timed on the device as the max over ranks; the MEDIAN is reported
         # and all of them are listed (a single call is exposed to one-off host hiccups)
