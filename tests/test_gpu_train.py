@@ -172,6 +172,43 @@ def test_training_step_vs_gpu_autograd_full_frames():
     m.release_buffers()
 
 
+@pytest.mark.parametrize("B", [10, 16])
+def test_training_step_at_batches_whose_tiles_do_not_divide_the_sm_pairs(B):
+    """10 / 16 rolls x 640 frames: 100 / 160 (tile, N block) items on 74 CTA pairs, so the persistent linear conv cuts its unit
+    ranges between the tap passes of an item (parked partial tile + lin_fixup_kernel), the split-K weight gradients pick other
+    split counts, and 16 rolls is the benchmarked training batch -- the same gradient bar against fp32 autograd on the GPU."""
+    frame, audio, _, noise = make_labelled_batch(B=B, T=640, wav_len=327680, seed=9)
+    t = (torch.arange(B) * 37) % 200
+    hp = _hp()
+    mask = (torch.arange(B) % 4 == 1).long()
+    batch = {"frame": frame.cuda(), "audio": audio.cuda()}
+    m = _model(hp)
+    total = m.training_step(batch, 0, t=t.cuda(), noise=noise.cuda(), dropout_mask=mask)
+    losses, grads, _ = _oracle_grads(hp, batch, t, noise.cuda(), mask)
+    assert abs(float(total) - float(losses["diffusion_loss"])) < 2e-5
+    worst, worst_name = 0.0, ""
+    for name, p in m.named_parameters():
+        ref = grads[name]
+        err = float((p.grad - ref).abs().max()) / max(float(ref.abs().max()), 1e-12)
+        if err > worst:
+            worst, worst_name = err, name
+    _record(f"train B={B} T=640 vs GPU autograd (fp32, TF32 off): worst gradient rel. max|delta| = {worst:.3e} ({worst_name})")
+    assert worst < TOL
+    # the forward alone against the all-fp32 CUDA-core mode of this library (same weights, same draws)
+    pred_tc = m.last_step[1]["pred_roll"].clone()
+    m.release_buffers()
+    os.environ["DRB_TRAIN_TC"] = "0"
+    try:
+        m32 = _model(hp)
+        m32.training_step(batch, 0, t=t.cuda(), noise=noise.cuda(), dropout_mask=mask)
+        d = float((m32.last_step[1]["pred_roll"] - pred_tc).abs().max())
+        m32.release_buffers()
+    finally:
+        os.environ.pop("DRB_TRAIN_TC", None)
+    _record(f"train B={B} T=640: network output, tensor-core forward vs fp32 CUDA-core forward max|delta| = {d:.3e}")
+    assert d < 5e-5
+
+
 def test_three_updates_follow_torch_autograd_plus_adam():
     """Three ``training_step`` + Adam updates on one batch against the same loop done with torch autograd over the oracle and
     torch.optim.Adam (fp32, TF32 off): the loss sequences must agree.  Afterwards the SAMPLING engine must see the updated
