@@ -131,15 +131,17 @@ __device__ __forceinline__ float e4m3_to_float(uint32_t b) {
   return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3)));
 }
 // 16 values -> 8 bytes of e2m1 codes (value 2i in the low nibble of byte i) and one ue4m3 scale byte >= max|v| / 6
-__device__ __forceinline__ void n4_block16(const float (&v)[16], uint32_t& c0, uint32_t& c1, uint32_t& sf) {
+// The block is v[i] * mul with mul a power of two (the part multipliers N4_ALO / N4_AHI): folded into the block maximum and into the
+// reciprocal scale instead of 16 multiplies -- both scalings are exact, so the codes are bit-identical to scaling the values first.
+__device__ __forceinline__ void n4_block16(const float (&v)[16], uint32_t& c0, uint32_t& c1, uint32_t& sf, float mul = 1.f) {
   float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
-  const float want = amax * (1.f / 6.f);
+  const float want = (amax * mul) * (1.f / 6.f);
   uint32_t b = (uint32_t)__nv_cvt_float_to_fp8(want, __NV_SATFINITE, __NV_E4M3);
   float q = e4m3_to_float(b);
   if (q < want && b < 0x7eu) { ++b; q = e4m3_to_float(b); }
-  const float inv = q > 0.f ? __frcp_rn(q) : 0.f;
+  const float inv = (q > 0.f ? __frcp_rn(q) : 0.f) * mul;
   uint32_t w[2] = {0u, 0u};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -157,11 +159,11 @@ __device__ __forceinline__ void split_f16n4_x16(const float (&v)[16], uint32_t (
     const __half2 a = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     h[i] = *reinterpret_cast<const uint32_t*>(&a);
     const float2 f = __half22float2(a);
-    l[2 * i] = (v[2 * i] - f.x) * N4_ALO; l[2 * i + 1] = (v[2 * i + 1] - f.y) * N4_ALO;
-    g[2 * i] = f.x * N4_AHI; g[2 * i + 1] = f.y * N4_AHI;
+    l[2 * i] = v[2 * i] - f.x; l[2 * i + 1] = v[2 * i + 1] - f.y;
+    g[2 * i] = f.x; g[2 * i + 1] = f.y;
   }
-  n4_block16(l, lo[0], lo[1], sf_lo);
-  n4_block16(g, hi[0], hi[1], sf_hi);
+  n4_block16(l, lo[0], lo[1], sf_lo, N4_ALO);
+  n4_block16(g, hi[0], hi[1], sf_hi, N4_AHI);
 }
 
 // ---------------------------------------------------------------------------------------------
