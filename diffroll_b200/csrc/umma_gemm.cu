@@ -562,33 +562,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
         const int nblk = item % p.n_blocks;
         const int mt = (item / p.n_blocks) * 2 + (int)rank;
         const int nb = mt / p.tiles_t, t0 = (mt % p.tiles_t) * TILE_M;
-        {
-          const int tap0 = p.tap_lo + ps * per_pass;
-          const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
-          const int conv_slabs = ntap * cpt;
-          const int nslabs = conv_slabs + (ps == n_pass - 1 ? cslabs : 0);
-          for (int sl = 0; sl < nslabs; ++sl) {
-            mbar_wait(&sv.empty[stage], phase ^ 1);
-            uint8_t* st = sv.stage0 + stage * CF::kStageBytes;
-            uint64_t* fl = &sv.full[stage];
-            const uint32_t fb = mapa_cluster(smem_u32(fl), 0);
-            prod_expect<PAIR>(fl, fb, CF::kStageBytes);
-            if (sl < conv_slabs) {
-              const int tap = tap0 + sl / cpt, cc = sl % cpt;
-              const int trow = t0 + (tap - half) * p.dil;
-              load_a<PAIR>(st + CF::kAOff, &p.xh, fl, fb, cc * TILE_K, trow, nb);
-              load_b<PAIR>(st + CF::kBOff, &p.wd_h, fl, fb, tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
-              load_a<PAIR>(st + CF::kAAuxOff, &p.xl, fl, fb, AM * cc * TILE_K, trow, nb);
-              load_b<PAIR>(st + CF::kBAuxOff, &p.wd_l, fl, fb, AM * (tap * p.C + cc * TILE_K), nblk * TILE_N, rank);
-            } else {
-              const int cc = sl - conv_slabs;
-              load_a<PAIR>(st + CF::kAOff, &p.sh, fl, fb, cc * TILE_K, t0, nb);
-              load_b<PAIR>(st + CF::kBOff, &p.wc_h, fl, fb, cc * TILE_K, nblk * TILE_N, rank);
-              load_a<PAIR>(st + CF::kAAuxOff, &p.sl, fl, fb, AM * cc * TILE_K, t0, nb);
-              load_b<PAIR>(st + CF::kBAuxOff, &p.wc_l, fl, fb, AM * cc * TILE_K, nblk * TILE_N, rank);
-            }
-            if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
+        const int tap0 = p.tap_lo + ps * per_pass;
+        const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
+        const int conv_slabs = ntap * cpt;
+        const int nslabs = conv_slabs + (ps == n_pass - 1 ? cslabs : 0);
+        for (int sl = 0; sl < nslabs; ++sl) {
+          mbar_wait(&sv.empty[stage], phase ^ 1);
+          uint8_t* st = sv.stage0 + stage * CF::kStageBytes;
+          uint64_t* fl = &sv.full[stage];
+          const uint32_t fb = mapa_cluster(smem_u32(fl), 0);
+          prod_expect<PAIR>(fl, fb, CF::kStageBytes);
+          if (sl < conv_slabs) {
+            const int tap = tap0 + sl / cpt, cc = sl % cpt;
+            const int trow = t0 + (tap - half) * p.dil;
+            load_a<PAIR>(st + CF::kAOff, &p.xh, fl, fb, cc * TILE_K, trow, nb);
+            load_b<PAIR>(st + CF::kBOff, &p.wd_h, fl, fb, tap * p.C + cc * TILE_K, nblk * TILE_N, rank);
+            load_a<PAIR>(st + CF::kAAuxOff, &p.xl, fl, fb, AM * cc * TILE_K, trow, nb);
+            load_b<PAIR>(st + CF::kBAuxOff, &p.wd_l, fl, fb, AM * (tap * p.C + cc * TILE_K), nblk * TILE_N, rank);
+          } else {
+            const int cc = sl - conv_slabs;
+            load_a<PAIR>(st + CF::kAOff, &p.sh, fl, fb, cc * TILE_K, t0, nb);
+            load_b<PAIR>(st + CF::kBOff, &p.wc_h, fl, fb, cc * TILE_K, nblk * TILE_N, rank);
+            load_a<PAIR>(st + CF::kAAuxOff, &p.sl, fl, fb, AM * cc * TILE_K, t0, nb);
+            load_b<PAIR>(st + CF::kBAuxOff, &p.wc_l, fl, fb, AM * cc * TILE_K, nblk * TILE_N, rank);
           }
+          if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -597,24 +595,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
       // ---------------- MMA issuer (leader CTA) ----------------
       int stage = 0; uint32_t phase = 0;
       int ucnt = 0;
-      for (int u = u_lo; u < u_hi; ++u) {
+      for (int u = u_lo; u < u_hi; ++u, ++ucnt) {
         const int ps = u % n_pass;
-        for (int once = 0; once < 1; ++once, ++ucnt) {
-          const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
-          const int nslabs = ntap * cpt + (ps == n_pass - 1 ? cslabs : 0);
-          const int as = ucnt & 1;
-          mbar_wait(&tempty[as], ((ucnt >> 1) & 1) ^ 1);   // both CTAs' epilogues have read this accumulator stage
+        const int ntap = (ps + 1) * per_pass <= span ? per_pass : span - ps * per_pass;
+        const int nslabs = ntap * cpt + (ps == n_pass - 1 ? cslabs : 0);
+        const int as = ucnt & 1;
+        mbar_wait(&tempty[as], ((ucnt >> 1) & 1) ^ 1);   // both CTAs' epilogues have read this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * 256u;
+        for (int sl = 0; sl < nslabs; ++sl) {
+          mbar_wait(&sv.full[stage], phase);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)as * 256u;
-          for (int sl = 0; sl < nslabs; ++sl) {
-            mbar_wait(&sv.full[stage], phase);
-            tc_fence_after();
-            issue_slab<P, PAIR>(sv.stage0 + stage * CF::kStageBytes, tmem_d, sl == 0);
-            umma_commit_pair(&sv.empty[stage]);
-            if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
-          }
-          umma_commit_pair(&tfull[as]);
+          issue_slab<P, PAIR>(sv.stage0 + stage * CF::kStageBytes, tmem_d, sl == 0);
+          umma_commit_pair(&sv.empty[stage]);
+          if (++stage == CF::kStages) { stage = 0; phase ^= 1; }
         }
+        umma_commit_pair(&tfull[as]);
       }
     }
   } else if (warp >= 4) {
@@ -624,7 +620,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
     const float inv_l = __ldg(p.inv_scale);
     const int l8 = lane & 7, lr = lane >> 3;
     int ucnt = 0;
-    for (int u = u_lo; u < u_hi; ++u) {
+    for (int u = u_lo; u < u_hi; ++u, ++ucnt) {
       const int item = u / n_pass, ps = u - item * n_pass;
       const int nblk = item % p.n_blocks;
       const int mt = (item / p.n_blocks) * 2 + (int)rank;
@@ -636,49 +632,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) umma_conv_lin_pers_kernel(cons
       float* const dst = partial ? p.lin_scratch + ((size_t)(2 * pair_id + (int)rank) * TILE_M + q * 32) * TILE_N + grp * 128 + l8 * 4
                                  : p.lin_out + ((size_t)nb * p.T + tq) * (size_t)p.ldo + colb;
       const size_t ldd = partial ? (size_t)TILE_N : (size_t)p.ldo;
-      for (int once = 0; once < 1; ++once, ++ucnt) {
-        const int as = ucnt & 1;
-        const bool acc = partial ? u > u_lo : (ps > 0 || p.lin_acc != 0);
-        const float* bias = (ps == 0 && !partial) ? p.bias_cond : nullptr;
-        mbar_wait(&tfull[as], (ucnt >> 1) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u + (uint32_t)grp * 128u;
+      const int as = ucnt & 1;
+      const bool acc = partial ? u > u_lo : (ps > 0 || p.lin_acc != 0);
+      const float* bias = (ps == 0 && !partial) ? p.bias_cond : nullptr;
+      mbar_wait(&tfull[as], (ucnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256u + (uint32_t)grp * 128u;
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-          float v[32];
-          load_acc32<P>(taddr + c4 * 32, inv_l, v);
-          if (c4 == 3) {   // this warp's last TMEM read of the stage: hand it back to the MMA issuer (leader CTA)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)   // thread = row: 8 x 16 bytes into the row, 16-byte units XOR-swizzled by the row
-            sts128(sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float v[32];
+        load_acc32<P>(taddr + c4 * 32, inv_l, v);
+        if (c4 == 3) {   // this warp's last TMEM read of the stage: hand it back to the MMA issuer (leader CTA)
+          tc_fence_before();
           __syncwarp();
-          // 8 lanes per row: instruction k moves rows 4k .. 4k+3 as four whole 128-byte lines.  All loads of the block before its
-          // first store (a load queued behind a store to the same row was 9x slower in the one-tile kernel).
-          float4 o4[8];
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias) b4 = *reinterpret_cast<const float4*>(bias + colb + c4 * 32);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int r = 4 * k + lr;
-            o4[k] = b4;
-            if (acc && tq + r < p.T) {
-              const float4 qv = __ldcg(reinterpret_cast<const float4*>(dst + (size_t)r * ldd + c4 * 32));
-              o4[k].x += qv.x; o4[k].y += qv.y; o4[k].z += qv.z; o4[k].w += qv.w;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int r = 4 * k + lr;
-            const float4 a = lds128(sbuf + (uint32_t)r * 128u + (uint32_t)((l8 ^ (r & 7)) << 4));
-            if (tq + r < p.T)
-              *reinterpret_cast<float4*>(dst + (size_t)r * ldd + c4 * 32) = make_float4(a.x + o4[k].x, a.y + o4[k].y, a.z + o4[k].z, a.w + o4[k].w);
-          }
-          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[as]), 0));
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)   // thread = row: 8 x 16 bytes into the row, 16-byte units XOR-swizzled by the row
+          sts128(sbuf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        __syncwarp();
+        // 8 lanes per row: instruction k moves rows 4k .. 4k+3 as four whole 128-byte lines.  All loads of the block before its
+        // first store (a load queued behind a store to the same row was 9x slower in the one-tile kernel).
+        float4 o4[8];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b4 = *reinterpret_cast<const float4*>(bias + colb + c4 * 32);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = 4 * k + lr;
+          o4[k] = b4;
+          if (acc && tq + r < p.T) {
+            const float4 qv = __ldcg(reinterpret_cast<const float4*>(dst + (size_t)r * ldd + c4 * 32));
+            o4[k].x += qv.x; o4[k].y += qv.y; o4[k].z += qv.z; o4[k].w += qv.w;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = 4 * k + lr;
+          const float4 a = lds128(sbuf + (uint32_t)r * 128u + (uint32_t)((l8 ^ (r & 7)) << 4));
+          if (tq + r < p.T)
+            *reinterpret_cast<float4*>(dst + (size_t)r * ldd + c4 * 32) = make_float4(a.x + o4[k].x, a.y + o4[k].y, a.z + o4[k].z, a.w + o4[k].w);
+        }
+        __syncwarp();
       }
     }
   }
