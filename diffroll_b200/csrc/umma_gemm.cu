@@ -30,8 +30,13 @@
 //   umma_gate_win_kernel<P>          + tap window fetched once per 64-channel chunk        (f16f8: needs 512 TMEM columns)
 //   umma_gate_pers_kernel<P, DUAL>   + persistent pairs, two accumulator stages, conditioner term from the per-clip
 //                                      fp32 table in the epilogue; DUAL = layer-0 conv shared by both guidance branches
-//   umma_zgemm_kernel<P, PAIR>       RES / HEAD, one tile per CTA (pair)
-//   umma_res_pers_kernel<P>          RES, persistent pairs, register-prefetched x tile, TMA-staged stores
+//   umma_gate_n4_kernel<DUAL>        the default: f16n4 operands (fp16 product + block-scaled fp4 correction), scale factors in TMEM
+//   umma_conv_lin_pers_kernel<P>     linear fp32 epilogue, persistent pairs over (tile, tap pass) units: training forward / dgrad and
+//                                      the per-clip conditioner tables; lin_fixup_kernel adds the parked partial tiles
+//   umma_zgemm_kernel<P, PAIR>       RES / HEAD, one tile per CTA (pair); mode 3 = output projection + guidance + posterior,
+//                                      mode 4 = plain GEMM with optional split-K (training weight gradients)
+//   umma_res_pers_kernel<P, XF>      RES, persistent pairs, register-prefetched x tile, TMA-staged stores (XF = 4: f16n4 emission)
+//   umma_head_pers_kernel<P>         HEAD (K = L * C), persistent pairs, operand-pair output
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = bias stager /
 // second producer, warps 4-11 = epilogue (TMEM -> registers -> swizzled smem staging -> TMA store).  smem ring:
