@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffroll_b200.so")
 
 PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16F8, PREC_F16E5, PREC_F16N4 = 0, 1, 2, 3, 4, 5
-BRANCH_COND_UNCOND, BRANCH_COND, BRANCH_UNCOND, BRANCH_COND_ZEROSPEC = 0, 1, 2, 3
+BRANCH_COND_UNCOND, BRANCH_COND, BRANCH_UNCOND, BRANCH_COND_ZEROSPEC, BRANCH_COND_LEARNED = 0, 1, 2, 3, 4
 UPD_X0, UPD_X0_FINAL, UPD_EPS_DDPM, UPD_EPS_DDIM, UPD_EPS_FINAL, UPD_NONE = range(6)
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8, "f16e5": PREC_F16E5,
               "f16n4": PREC_F16N4}
@@ -24,7 +24,7 @@ EXPORTS = [
     "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_plan_precision", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
     "drb_train_workspace_bytes", "drb_train_create", "drb_train_destroy", "drb_train_forward", "drb_train_backward", "drb_loss_grad",
-    "drb_adam_step", "drb_adam_step_multi", "drb_plan_set_step_embeddings",
+    "drb_adam_step", "drb_adam_step_multi", "drb_plan_set_step_embeddings", "drb_plan_set_uncond_spec",
 ]
 
 
@@ -122,6 +122,7 @@ def load():
     lib.drb_plan_set_steps.argtypes = [C.c_void_p, C.c_void_p]
     lib.drb_cond_tables.argtypes = [C.c_void_p, C.c_void_p]
     lib.drb_plan_use_cond_tables.argtypes = [C.c_void_p, C.c_int32]
+    lib.drb_plan_set_uncond_spec.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     for fn in (lib.drb_q_sample, lib.drb_extract_x0):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
     lib.drb_p_losses_scratch_bytes.restype = C.c_size_t

@@ -50,6 +50,7 @@ struct Layout {  // byte offsets into the workspace
   size_t wcpad, cond;                                   // fp32 Wc of every layer padded to Mp; conditioner projections of the spectrogram [L][B][T][2C]
   size_t total;
   int NBcap, Mp, KC;
+  int Bs;   // clips held by spec32 / the conditioner tables: batch, or 2 x batch with the learned unconditional spectrogram
 };
 
 static bool cfg_ok(const drb_config& c) {
@@ -57,7 +58,7 @@ static bool cfg_ok(const drb_config& c) {
   if (c.residual_channels <= 0 || c.residual_channels % 256) return false;
   if (c.residual_layers <= 0 || c.kernel_size <= 0 || !(c.kernel_size & 1)) return false;
   if (c.dilation_base <= 0 || c.dilation_bound <= 0 || c.n_mels <= 0 || c.n_fft <= 0 || c.hop_length <= 0) return false;
-  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 5 || c.branches < 0 || c.branches > 3) return false;
+  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 5 || c.branches < 0 || c.branches > 4) return false;
   if (c.wave_len / c.hop_length + 1 < c.frames) return false;
   if (c.wave_len <= c.n_fft / 2) return false;  // reflect padding needs pad < length
   return true;
@@ -82,7 +83,11 @@ static drb_config effective_config(const drb_config& in) {
 static Layout make_layout(const drb_config& c) {
   Layout l; memset(&l, 0, sizeof(l));
   const size_t B = c.batch, T = c.frames, C = c.residual_channels, L = c.residual_layers, k = c.kernel_size;
-  l.NBcap = (c.branches == DRB_BRANCH_COND_UNCOND || c.branches == DRB_BRANCH_COND_ZEROSPEC) ? 2 * c.batch : c.batch;
+  l.NBcap = (c.branches == DRB_BRANCH_COND_UNCOND || c.branches == DRB_BRANCH_COND_ZEROSPEC || c.branches == DRB_BRANCH_COND_LEARNED) ? 2 * c.batch : c.batch;
+  // DRB_BRANCH_COND_LEARNED: the second branch is conditioned on a learned spectrogram (condition='trainable_spec',
+  // model/diffwave.py:657-658).  It is kept as `batch` more clips behind the real ones, so every kernel sees 2 x batch
+  // conditional rolls and nothing in the step changes shape.
+  l.Bs = c.branches == DRB_BRANCH_COND_LEARNED ? 2 * c.batch : c.batch;
   l.Mp = (c.n_mels + 63) / 64 * 64;
   l.KC = (int)(k * C);
   const size_t NB = l.NBcap, Mp = l.Mp, rows = NB * T;
@@ -96,7 +101,7 @@ static Layout make_layout(const drb_config& c) {
   l.x32 = take(rows * C * 4);
   l.skip = take(rows * C * 4);
   l.hbuf = take(rows * C * 4);
-  l.spec32 = take(B * T * Mp * 4);
+  l.spec32 = take((size_t)l.Bs * T * Mp * 4);
   l.bias = take(L * 4 * 2 * C * 4);
   l.wtmp = take(2 * C * k * C * 4);
   l.mel = take(mel_workspace_bytes(c));
@@ -123,7 +128,7 @@ static Layout make_layout(const drb_config& c) {
       l.wsf4 = take(L * (2 * C / 256) * (k * C / 64) * 2048);
     }  // f16f8: {SW, 1/(SA*SW), scratch, -} per gate / out weight set and the head
     if (c.branches != DRB_BRANCH_UNCOND && c.precision != DRB_PREC_F16F8 && c.precision != DRB_PREC_BF16) {
-      l.wcpad = take(L * 2 * C * Mp * 4); l.cond = take(L * B * T * 2 * C * 4);
+      l.wcpad = take(L * 2 * C * Mp * 4); l.cond = take(L * (size_t)l.Bs * T * 2 * C * 4);
       l.sp5h = take(B * T * Mp * 2); l.sp5l = take(B * T * Mp * 2); l.wc5h = take(L * 2 * C * Mp * 2); l.wc5l = take(L * 2 * C * Mp * 2);
     }
   }
@@ -144,6 +149,9 @@ struct drb_plan {
   bool tables_ready, spec_ready;
   bool cond_ready = false;   // cond tables hold the conditioner projections of the CURRENT spectrogram
   bool cond_use = true;      // drb_plan_use_cond_tables: steps read the tables when they are ready
+  bool learned = false;      // DRB_BRANCH_COND_LEARNED is in force: rolls batch..2*batch-1 read the learned clips
+  bool uspec_ready = false;  // drb_plan_set_uncond_spec has filled the learned clips of spec32
+  bool ucond_ready = false;  // ... and their half of the conditioner tables is built
   int pair = 1;        // CTA pairs (cta_group::2); DRB_NO_PAIR=1 selects the single-CTA kernels, for A/B runs
   std::vector<int> dil;
   // weight pointers used in place (caller keeps them alive)
@@ -219,9 +227,14 @@ int drb_plan_set_branches(drb_plan* p, int32_t branches) {
   else if (branches == DRB_BRANCH_COND) { NB = B; nc = B; }
   else if (branches == DRB_BRANCH_UNCOND) { NB = B; nc = 0; }
   else if (branches == DRB_BRANCH_COND_ZEROSPEC) { NB = 2 * B; nc = B; }
+  else if (branches == DRB_BRANCH_COND_LEARNED) {   // every roll reads a conditioner table: its clip's, or the learned one
+    if (p->lay.Bs != 2 * B) { set_error("plan was not created with DRB_BRANCH_COND_LEARNED"); return DRB_E_INVALID; }
+    NB = 2 * B; nc = 2 * B;
+  }
   else { set_error("bad branches %d", branches); return DRB_E_INVALID; }
   if (NB > p->lay.NBcap) { set_error("plan was created for a single branch"); return DRB_E_INVALID; }
   p->NB = NB; p->n_cond = nc; p->zero_spec = branches == DRB_BRANCH_COND_ZEROSPEC;
+  p->learned = branches == DRB_BRANCH_COND_LEARNED;
   return 0;
 }
 
@@ -255,6 +268,10 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
   { const char* e = getenv("DRB_NO_CONDPRE"); p->condpre = (e && e[0] == '1') ? 0 : 1; }
   if (lay.cond == 0 || !p->persistent) p->condpre = 0;   // only the persistent gate kernel (bf16x3 / f16e5) implements it
   if (!p->condpre || lay.NBcap != 2 * cfg->batch) p->share0 = 0;
+  if (lay.Bs != cfg->batch && cfg->precision != DRB_PREC_FP32 && !p->condpre) {
+    set_error("DRB_BRANCH_COND_LEARNED needs the per-clip conditioner tables (precision fp32, bf16x3, f16e5 or f16n4; persistent kernels)");
+    delete p; return DRB_E_INVALID;
+  }
   const int C = cfg->residual_channels, L = cfg->residual_layers, k = cfg->kernel_size, Mp = lay.Mp, T = cfg->frames;
   p->in_w = w->input_projection_w; p->in_b = w->input_projection_b;
   p->e1w = w->emb_projection1_w; p->e1b = w->emb_projection1_b; p->e2w = w->emb_projection2_w; p->e2b = w->emb_projection2_b;
@@ -376,7 +393,7 @@ int drb_plan_create(drb_plan** out, const drb_config* cfg_in, const drb_weights*
     if (lay.cond)   // conditioner tables built on the tensor cores (drb_cond_tables): one fp32 map per layer
       for (int i = 0; i < L; ++i) {
         CUtensorMap mc;
-        PLAN_TRY(make_tmap_3d(&mc, p->at<float>(lay.cond) + (size_t)i * cfg->batch * T * 2 * C, cfg->batch, T, 2 * (uint64_t)C, 128, 1));
+        PLAN_TRY(make_tmap_3d(&mc, p->at<float>(lay.cond) + (size_t)i * lay.Bs * T * 2 * C, cfg->batch, T, 2 * (uint64_t)C, 128, 1));
         p->cond32.push_back(mc);
       }
     PLAN_TRY(make_tmap_3d(&p->maps.x32, p->ws + lay.x32, NBc, T, C, 128, 1));
@@ -490,33 +507,33 @@ int drb_mel_forward(drb_plan* p, const float* waveform, float* spec_out, int32_t
   return r;
 }
 
-int drb_cond_tables(drb_plan* p, void* stream) {
-  if (!p) return DRB_E_INVALID;
-  if (!p->condpre || p->cond_ready) return 0;
-  if (!p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
-  // conditioner_projection_l(spec) (model/diffwave.py:143) does not depend on the timestep: computed once per clip, in
-  // fp32, for every layer; the gate kernel then adds it in its epilogue instead of contracting it every step
+// conditioner_projection_l(spec) (model/diffwave.py:143) does not depend on the timestep: computed once per clip, at fp32
+// grade, for every layer; the gate kernel then adds it in its epilogue instead of contracting it every step.  One call covers
+// `batch` clips starting at clip `clip0` of spec32 (0: the clips of drb_mel_forward; batch: the learned clips of
+// drb_plan_set_uncond_spec) and writes the same clip range of every layer's table -- the launches are the same either way.
+static int build_cond_tables(drb_plan* p, int clip0, void* stream) {
   const drb_config& c = p->cfg;
-  const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)c.batch * c.frames * C2;
+  const size_t C2 = 2 * (size_t)c.residual_channels, per = (size_t)p->lay.Bs * c.frames * C2;
+  const float* spec = p->at<float>(p->lay.spec32) + (size_t)clip0 * c.frames * p->lay.Mp;
+  float* cond = p->at<float>(p->lay.cond) + (size_t)clip0 * c.frames * C2;
   if (p->cond_tc && p->cfg.precision != DRB_PREC_FP32) {
     // default: tcgen05 with f16x3 operands (fp16 hi + fp16 lo) and a single K = Mp chain per output -- fp32-grade, 15 short
     // launches instead of 15 x 0.37 ms of fp32 FMA per clip
-    int r = launch_split_pair(p->at<float>(p->lay.spec32), p->lay.Mp, nullptr, 0, c.frames, nullptr, p->ws + p->lay.sp5h, p->ws + p->lay.sp5l,
+    int r = launch_split_pair(spec, p->lay.Mp, nullptr, 0, c.frames, nullptr, p->ws + p->lay.sp5h, p->ws + p->lay.sp5l,
                               c.batch * c.frames, p->lay.Mp, (cudaStream_t)stream, 5);
     if (r) return r;
     for (int l = 0; l < c.residual_layers; ++l) {
       UmmaConvLin cv;
       cv.ah = &p->sp5h; cv.al = &p->sp5l; cv.wh = &p->wc5h[l]; cv.wl = &p->wc5l[l]; cv.prec = 4; cv.pair = p->pair;
       cv.NB = c.batch; cv.T = c.frames; cv.Cin = p->lay.Mp; cv.Nout = (int)C2; cv.taps = 1; cv.dil = 1; cv.Mp = 0;
-      cv.inv_scale = p->wscale(p->wc5_slot(l)) + 1; cv.bias = nullptr; cv.out = p->at<float>(p->lay.cond) + (size_t)l * per; cv.ldo = (int)C2;
+      cv.inv_scale = p->wscale(p->wc5_slot(l)) + 1; cv.bias = nullptr; cv.out = cond + (size_t)l * per; cv.ldo = (int)C2;
       r = launch_umma_conv_lin(cv, (cudaStream_t)stream); if (r) return r;
     }
-    p->cond_ready = true;
     return 0;
   }
   static int tc_cond = -1;
   if (tc_cond < 0) { const char* e = getenv("DRB_COND_TC"); tc_cond = (e && e[0] == '1') ? 1 : 0; }
-  if (tc_cond && (p->prec() == 1 || p->prec() == 3) && (int)p->cond32.size() == c.residual_layers) {
+  if (tc_cond && clip0 == 0 && p->lay.Bs == c.batch && (p->prec() == 1 || p->prec() == 3) && (int)p->cond32.size() == c.residual_layers) {
     // OPT-IN tensor-core build (DRB_COND_TC=1): the spectrogram operand pair [B][T][Mp] against the conditioner weights in the
     // plan's pair format, K = Mp, plain fp32 result in natural channel order: 15 short tcgen05 launches instead of 15 x 0.37 ms
     // of fp32 FMA per clip.  Measured (B200, configs[1]): per-clip work 5.5 -> 0.9 ms, i.e. +3.6 % on a 20-step e2e run and
@@ -530,17 +547,57 @@ int drb_cond_tables(drb_plan* p, void* stream) {
       uz.a_h = &p->maps.sh; uz.a_l = &p->maps.sl; uz.nslabs64 = p->lay.Mp / 64;
       int r = launch_umma_zgemm(p->maps, uz, (cudaStream_t)stream); if (r) return r;
     }
-    p->cond_ready = true;
     return 0;
   }
   for (int l = 0; l < c.residual_layers; ++l) {
     SimtGemm g;
-    g.A = p->at<float>(p->lay.spec32); g.lda = p->lay.Mp; g.T = c.frames; g.Ck = p->lay.Mp;
+    g.A = spec; g.lda = p->lay.Mp; g.T = c.frames; g.Ck = p->lay.Mp;
     g.W = p->at<float>(p->lay.wcpad) + (size_t)l * C2 * p->lay.Mp; g.ldw = p->lay.Mp;
-    g.C = p->at<float>(p->lay.cond) + (size_t)l * per; g.ldc = (int)C2; g.M = c.batch * c.frames; g.N = (int)C2;
+    g.C = cond + (size_t)l * per; g.ldc = (int)C2; g.M = c.batch * c.frames; g.N = (int)C2;
     int r = launch_simt_gemm(g, (cudaStream_t)stream); if (r) return r;
   }
-  p->cond_ready = true;
+  return 0;
+}
+
+int drb_cond_tables(drb_plan* p, void* stream) {
+  if (!p) return DRB_E_INVALID;
+  if (!p->condpre) return 0;
+  if (!p->cond_ready) {
+    if (!p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
+    int r = build_cond_tables(p, 0, stream); if (r) return r;
+    p->cond_ready = true;
+  }
+  if (p->learned && !p->ucond_ready) {   // the learned clips change with the parameter, not with the audio clip
+    if (!p->uspec_ready) { set_error("drb_plan_set_uncond_spec has not been called"); return DRB_E_STATE; }
+    int r = build_cond_tables(p, p->cfg.batch, stream); if (r) return r;
+    p->ucond_ready = true;
+  }
+  return 0;
+}
+
+namespace {
+// spec32 clip layout [clip][T][Mp] (mel bins fastest, zero beyond n_mels) from the learned table [n_mels][ld], one copy per clip
+__global__ void uncond_spec_kernel(const float* __restrict__ src, int ld, int n_mels, float* __restrict__ dst, int clips, int T, int Mp) {
+  const size_t n = (size_t)clips * T * Mp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i % Mp), t = (int)((i / Mp) % T);
+    dst[i] = m < n_mels ? __ldg(src + (size_t)m * ld + t) : 0.f;
+  }
+}
+}  // namespace
+
+int drb_plan_set_uncond_spec(drb_plan* p, const float* spec, int32_t ld, void* stream) {
+  if (!p || !spec) { set_error("set_uncond_spec: null argument"); return DRB_E_INVALID; }
+  const drb_config& c = p->cfg;
+  if (p->lay.Bs != 2 * c.batch) { set_error("plan was not created with DRB_BRANCH_COND_LEARNED"); return DRB_E_INVALID; }
+  if (ld < c.frames) { set_error("set_uncond_spec: the table holds %d frames, the plan needs %d", ld, c.frames); return DRB_E_INVALID; }
+  float* dst = p->at<float>(p->lay.spec32) + (size_t)c.batch * c.frames * p->lay.Mp;
+  const size_t n = (size_t)c.batch * c.frames * p->lay.Mp;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  uncond_spec_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(spec, ld, c.n_mels, dst, c.batch, c.frames, p->lay.Mp);
+  DRB_CUDA(cudaGetLastError());
+  ++g_launches;
+  p->uspec_ready = true; p->ucond_ready = false;
   return 0;
 }
 
@@ -579,6 +636,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   }
   if (!p->tables_ready) { set_error("drb_time_tables has not been called"); return DRB_E_STATE; }
   if (p->n_cond > 0 && !p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
+  if (p->learned && !p->uspec_ready) { set_error("drb_plan_set_uncond_spec has not been called"); return DRB_E_STATE; }
   NvtxRange nv("drb.resblock l=%d t=%d", layer, t_index);
   cudaStream_t s = (cudaStream_t)stream;
   const drb_config& c = p->cfg;
@@ -616,12 +674,16 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   ug.NB = NB; ug.n_cond = nc; ug.T = T; ug.C = C; ug.taps = k; ug.dil = p->dil[layer]; ug.Mp = Mp;
   ug.pair = p->pair; ug.window = p->window; ug.persistent = p->persistent; ug.xwh = &p->win_h[layer]; ug.xwl = &p->win_l[layer]; ug.prec = p->prec(); ug.z_group0 = layer * p->lay.NBcap; ug.inv_scale = p->wscale(2 * layer) + 1;
   ug.bias_cond = p->bias_ptr(layer, 0); ug.bias_unc = p->bias_ptr(layer, p->zero_spec ? 0 : 1);
-  if (p->n4()) {   // the f16n4 kernel has no conditioner K-slabs: the per-clip tables are always used (built on demand)
-    if (nc > 0 && !p->cond_ready) { r = drb_cond_tables(p, stream); if (r) return r; }
+  // the f16n4 kernel has no conditioner K-slabs, and the learned clips exist only as table rows: there the per-clip tables are
+  // always used (built on demand)
+  const bool need_tables = p->n4() || p->learned;
+  if (need_tables && nc > 0 && !(p->cond_ready && (!p->learned || p->ucond_ready))) { r = drb_cond_tables(p, stream); if (r) return r; }
+  ug.need_tables = p->learned ? 1 : 0;
+  if (p->n4()) {
     ug.n4 = 1; ug.xw4 = &p->win4[layer]; ug.wd4 = &p->wd4[layer]; ug.wsf = &p->wsf4[layer]; ug.xs = p->at<uint8_t>(p->lay.xs);
   }
-  if (p->condpre && p->cond_ready && (p->cond_use || p->n4()) && nc > 0) {
-    ug.cond = p->at<float>(p->lay.cond) + (size_t)layer * B * T * 2 * C;
+  if (p->condpre && p->cond_ready && (p->cond_use || need_tables) && nc > 0) {
+    ug.cond = p->at<float>(p->lay.cond) + (size_t)layer * p->lay.Bs * T * 2 * C;
     if (first && p->share0 && NB == 2 * B && nc == B) ug.dual_B = B;
   }
   const int e0 = p->prof ? p->ev_mark(s) : -1;
@@ -823,7 +885,7 @@ int drb_plan_buffer(drb_plan* p, const char* name, void** ptr, size_t* bytes) {
     off = p->lay.hbuf; sz = rows * C * 4;
   }
   else if (n == "dtab") { off = p->lay.dtab; sz = (size_t)c.residual_layers * c.timesteps * C * 4; }
-  else if (n == "spec32") { off = p->lay.spec32; sz = (size_t)c.batch * c.frames * p->lay.Mp * 4; }
+  else if (n == "spec32") { off = p->lay.spec32; sz = (size_t)p->lay.Bs * c.frames * p->lay.Mp * 4; }
   else if (n == "y" && !tensor) { off = p->lay.ybuf; sz = rows * 2 * C * 4; }
   else if (n == "z32" && !tensor) { off = p->lay.z32; sz = rows * C * 4; }
   else if (n == "xh" && tensor) { off = p->lay.xh; sz = rows * C * 2; }

@@ -142,6 +142,7 @@ struct UmmaGate {  // y = conv(xin) + cond + bias1 ; z = sigmoid(gate)*tanh(filt
   // dual_B > 0 (layer 0, both branches read the same x): conv once over dual_B rolls, two gated outputs per tile.
   const float* cond = nullptr;
   int dual_B = 0;
+  int need_tables = 0;   // the conditioner term exists ONLY as table rows (learned clips): fail instead of contracting K-slabs
   // f16n4 (prec must be 3 for the z output): fp16 main + block-scaled e2m1 correction operands
   int n4 = 0;
   const CUtensorMap *xw4 = nullptr, *wd4 = nullptr, *wsf = nullptr;   // aux window map, aux weight map, weight scale atoms

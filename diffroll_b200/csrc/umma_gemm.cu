@@ -2301,6 +2301,7 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
       int n_sm = 148;
       { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
       if (g.cond) { p.cond = g.cond; p.n_cond_mma = 0; }   // conditioner term added in the epilogue, no cond K-slabs
+      else if (g.need_tables) { set_error("umma_gate: conditioner tables are required but were not given"); return DRB_E_INVALID; }
       // layer-0 branch sharing: conv tiles over the conditional rolls only, two gated outputs per tile
       const bool dual = g.dual_B > 0 && g.cond && g.NB == 2 * g.dual_B && ((g.dual_B * p.tiles_t) % 2 == 0);
       if (dual) {
@@ -2313,11 +2314,13 @@ int launch_umma_gate(const UmmaMaps& maps, const UmmaLayer& L, const UmmaGate& g
       return g.prec == 1 ? launch_k(umma_gate_pers_kernel<1, false>, p, 2 * pairs, PW_SMEM, true, s)
                          : launch_k(umma_gate_pers_kernel<3, false>, p, 2 * pairs, PW_SMEM, true, s);
     }
+    if (g.need_tables) { set_error("umma_gate: conditioner tables are required but this kernel variant contracts the spectrogram"); return DRB_E_INVALID; }
     return g.prec == 1 ? launch_k(umma_gate_win_kernel<1>, p, grid, Cfg<1, true>::kSmemBytes, true, s)
          : g.prec == 2 ? launch_k(umma_gate_win_kernel<2>, p, grid, Cfg<2, true>::kSmemBytes, true, s)
                        : launch_k(umma_gate_win_kernel<3>, p, grid, Cfg<3, true>::kSmemBytes, true, s);
   }
   if (g.n4) { set_error("umma_gate: f16n4 needs CTA pairs (even tile count) and the tap window"); return DRB_E_INVALID; }
+  if (g.need_tables) { set_error("umma_gate: conditioner tables are required but this kernel variant contracts the spectrogram"); return DRB_E_INVALID; }
   p.xwh = maps.xh; p.xwl = maps.xl; p.win_rows = TILE_M; p.n_items = 0;
   if (g.prec == 1) return mc ? launch_k(umma_gate_kernel<1, true>, p, grid, Cfg<1, false>::kSmemBytes, true, s)
                              : launch_k(umma_gate_kernel<1, false>, p, grid, Cfg<1, false>::kSmemBytes, false, s);

@@ -113,6 +113,16 @@ class Engine:
             _lib.check(self.lib.drb_plan_set_branches(self.plan, branches), "drb_plan_set_branches")
             self.branches = branches
 
+    def set_uncond_spec(self, table):
+        """condition='trainable_spec' (model/diffwave.py:601-604,657-658): ``table`` [n_mels, >= frames] is the learned
+        unconditional spectrogram; the plan (created with BRANCH_COND_LEARNED) keeps its own copy."""
+        t = table.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if t.ndim != 2 or t.shape[0] != self.n_mels or t.shape[1] < self.frames:
+            raise ValueError(f"learned spectrogram: expected [{self.n_mels}, >= {self.frames}], got {tuple(t.shape)}")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drb_plan_set_uncond_spec(self.plan, _ptr(t), int(t.shape[1]), _stream(self.device)),
+                       "drb_plan_set_uncond_spec")
+
     def set_step_embeddings(self, emb_rows):
         """Fractional diffusion steps (model/diffwave.py:76-81): ``emb_rows`` [B,128] = the caller's interpolated sinusoid rows, one
         per roll; ``None`` returns to the integer tables."""

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._lib import DrbUpdate
 from .engine import Engine
 from .synthetic import hann_window, melscale_fbanks
 from .task import AttributeDict, SpecRollDiffusion, _upd, to_attr
@@ -127,10 +128,16 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         self.spec_dropout = spec_dropout
         super().__init__(**kwargs)
         del self._pending_hparams
-        if condition == 'trainable_spec' or condition == 'trainable_z':
-            raise NotImplementedError(f"condition '{condition}' is a training-time variant outside the sampling hot path")
-        elif condition != 'fixed':
+        if condition == 'trainable_z':
+            # model/diffwave.py:616 calls ResidualBlockz(n_mels, residual_channels, dilation, kernel_size, uncond=...) but its
+            # __init__ (:154) takes (n_mels, residual_channels, dilation, uncond): the reference cannot construct this variant
+            print(f"================trainable_z layers=================")
+            raise TypeError("ResidualBlockz.__init__() got multiple values for argument 'uncond'")
+        elif condition not in ('fixed', 'trainable_spec'):
             raise ValueError("unrecognized condition '{condition}'")  # sic: model/diffwave.py:610
+        # condition == 'trainable_spec' (model/diffwave.py:600-605): the unconditional branch is conditioned on a learned
+        # spectrogram instead of -1 -- in sampling the whole [n_mels, 641] table (:657-658), in training the dropped rolls (:695-699)
+        self._learned = condition == 'trainable_spec'
         # unconditional=True builds residual blocks without conditioner_projection (model/diffwave.py:125-128), but
         # ClassifierFreeDiffRoll.forward always hands them a spectrogram, which ResidualBlock.forward rejects (:135-136):
         # the reference constructs such a model and fails its first forward with an AssertionError.  Same here.
@@ -138,6 +145,9 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         self.precision = precision
         self.input_projection = Conv1d(88, residual_channels, 1)
         self.diffusion_embedding = DiffusionEmbedding(len(self.betas))
+        if self._learned:
+            self.register_parameter("trainable_parameters", nn.Parameter(torch.full((spec_args["n_mels"], 641), -1.0)))  # :601-604
+            self.uncon_dropout = self.trainable_dropout
         self.residual_layers = nn.ModuleList([
             ResidualBlock(n_mels, residual_channels, dilation_base ** (i % dilation_bound), kernel_size, uncond=unconditional)
             for i in range(residual_layers)])
@@ -161,7 +171,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
     def _engine(self, batch, frames, wave_len, device, any_version=False):
-        key = (batch, frames, wave_len, self.precision, str(device))
+        key = (batch, frames, wave_len, self.precision, str(device))   # one model is either 'fixed' or 'trainable_spec' for life
         ent = self._engines.get(key)
         if ent is not None and any_version:      # mel front-end only (training step): it has no trainable tensors
             return ent[0]
@@ -175,7 +185,10 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         while len(self._engines) >= self.MAX_ENGINES:       # bounded: a workspace is gigabytes; least recently built goes first
             self._engines.pop(next(iter(self._engines)))[0].close()
         eng = Engine(self.state_dict(), self.hparams, batch, frames, wave_len, self.diffusion_embedding.embedding,
-                     precision=self.precision, branches=_lib.BRANCH_COND_UNCOND, device=device)
+                     precision=self.precision, device=device,
+                     branches=_lib.BRANCH_COND_LEARNED if self._learned else _lib.BRANCH_COND_UNCOND)
+        if self._learned:     # a later change of the parameter bumps its version and rebuilds the engine like any weight
+            eng.set_uncond_spec(self.trainable_parameters)
         self._engines[key] = (eng, ver)
         self._mel_key = None
         return eng
@@ -197,7 +210,13 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         if T_min != T:
             xx = xx[:, :, :T_min, :]
         xx = xx.contiguous()
-        if branches == _lib.BRANCH_UNCOND:
+        if self._learned and branches in (_lib.BRANCH_UNCOND, _lib.BRANCH_COND_UNCOND):
+            # the learned table has 641 frames (model/diffwave.py:601) and is trimmed like a spectrogram (:662); the reference's
+            # guidance pair needs both branches to come out equally long, and so does the engine
+            if min(T, self.trainable_parameters.shape[-1]) != T_min:
+                raise RuntimeError(f"trainable_spec: the learned spectrogram trims the roll to "
+                                   f"{min(T, self.trainable_parameters.shape[-1])} frames, the clip to {T_min}")
+        if branches == _lib.BRANCH_UNCOND and not self._learned:
             spec = torch.full((B, sa["n_mels"], T_min), -1.0, device=x.device)   # model/diffwave.py:660
         else:
             wav = waveform.to(device=x.device, dtype=torch.float32).contiguous()
@@ -212,8 +231,24 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
                 self._mel_key = key
                 self._mel_ref = weakref.ref(waveform)
             spec = self._spec
+        if self._learned and branches in (_lib.BRANCH_UNCOND, _lib.BRANCH_COND_UNCOND):
+            # Both of them run as the (clip, learned table) pair.  sampling=True alone (BRANCH_UNCOND: the generation sampler, a plain
+            # forward) is that pair with guidance weight -1, (1 + w) * cond - w * learned = learned exactly: see _learned_upd.  The
+            # clip half then only has to be finite, which the mel front-end above guarantees for any waveform.
+            if branches == _lib.BRANCH_UNCOND:
+                spec = self.trainable_parameters.detach()[..., :T_min]      # 2-D, like the reference's return value (:658,662)
+            branches = _lib.BRANCH_COND_LEARNED
         eng.set_branches(branches)
         return eng, xx, spec
+
+    def _learned_upd(self, upd, branches):
+        """The update struct a step really runs with: under condition='trainable_spec' a sampling=True forward is the learned
+        pair at guidance weight -1 (see _prepare).  Returns ``upd`` itself otherwise."""
+        if not (self._learned and branches == _lib.BRANCH_UNCOND):
+            return upd
+        u = DrbUpdate.from_buffer_copy(upd)
+        u.w = -1.0
+        return u
 
     def _range_guarded(self):
         return self.range_check and self.precision in ("f16n4", "f16e5", "f16f8")
@@ -246,7 +281,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
                 noise = noise.to(device=xx.device, dtype=torch.float32)[:, :, :xx.shape[2], :].contiguous()
         else:
             noise = None
-        out = eng.step(xx, noise, t_index, upd)
+        out = eng.step(xx, noise, t_index, self._learned_upd(upd, branches))
         if not self._range_ok(eng):
             self._range_fallback()
             return self._step(x, waveform, t_index, upd, branches, noise, inpainting_t, inpainting_f)
@@ -275,12 +310,13 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             t0, per_roll = int(diffusion_step), False
         branches = _lib.BRANCH_UNCOND if sampling is True else _lib.BRANCH_COND
         eng, xx, spec = self._prepare(x_t, waveform, branches, inpainting_t, inpainting_f)
+        none = self._learned_upd(_upd(_lib.UPD_NONE), branches)
         if not per_roll:
-            pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
+            pred = eng.step(xx, None, t0, none)
         else:
             eng.set_steps(steps)
             try:
-                pred = eng.step(xx, None, t0, _upd(_lib.UPD_NONE))
+                pred = eng.step(xx, None, t0, none)
             finally:
                 eng.set_steps(None)
         if not self._range_ok(eng):
@@ -304,7 +340,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             raise NotImplementedError("fractional diffusion steps need batch <= timesteps (per-roll table rows)")
         eng.set_step_embeddings(rows)
         try:
-            pred = eng.step(xx, None, 0, _upd(_lib.UPD_NONE))
+            pred = eng.step(xx, None, 0, self._learned_upd(_upd(_lib.UPD_NONE), branches))
         finally:
             eng.set_step_embeddings(None)
         if not self._range_ok(eng):
@@ -325,10 +361,25 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             t0, t1 = (int(inpainting_t[0]), int(inpainting_t[1])) if inpainting_t else (0, spec.shape[2])
             f0, f1 = (int(inpainting_f[0]), int(inpainting_f[1])) if inpainting_f else (0, spec.shape[1])
             spec[:, f0:f1, t0:t1] = -1
-        if sampling is True:
-            spec = torch.full_like(spec, -1.0)
+        if sampling is True:                 # model/diffwave.py:656-660 (the reference hands the 2-D table itself to the blocks)
+            spec = self._uncond_spec_like(spec)
         eng = self._train_engine(x_t.shape[0], x_t.shape[2])
         return eng.forward(x_t, spec, diffusion_step.flatten()), spec
+
+    def _uncond_spec_like(self, spec):
+        """What sampling=True conditions on, in the shape of ``spec`` [B, n_mels, T]: -1, or the learned table."""
+        if self._learned:
+            return self.trainable_parameters.detach()[..., :spec.shape[-1]].expand_as(spec).contiguous()
+        return torch.full_like(spec, -1.0)
+
+    def trainable_dropout(self, x, p, mask=None):
+        """model/diffwave.py:695-699: the dropped rolls are conditioned on the learned spectrogram instead of -1.  Same Bernoulli
+        draw as ``fixed_dropout``; ``x`` is already trimmed to the roll here, so the table is trimmed alike."""
+        if mask is None:
+            mask = torch.bernoulli(torch.full((x.shape[0],), float(p)))
+        drop = mask.to(device=x.device).bool()
+        x[drop] = self.trainable_parameters.detach()[..., :x.shape[-1]]
+        return x
 
     def train(self, mode=True):
         return super().train(mode)

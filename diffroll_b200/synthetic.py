@@ -27,10 +27,10 @@ MEL_ARGS = dict(  # config/spec/mel.yaml:2-10 with sampling_rate/hop_length of c
 
 def default_hparams(timesteps=200, sampling_type="inpainting_ddpm_x0", w=0.5,
                     inpainting_t=None, inpainting_f=None, residual_channels=512,
-                    residual_layers=15, kernel_size=9):
+                    residual_layers=15, kernel_size=9, condition="fixed"):
     """Hyper-parameters of configs[1] (config/model/ClassifierFreeDiffRoll.yaml + config/task/transcription.yaml, k=9)."""
     return dict(
-        residual_channels=residual_channels, unconditional=False, condition="fixed",
+        residual_channels=residual_channels, unconditional=False, condition=condition,
         n_mels=229, norm_args=[0, 1, "imagewise"], residual_layers=residual_layers,
         kernel_size=kernel_size, dilation_base=2, dilation_bound=4,
         spec_args=dict(MEL_ARGS), spec_dropout=0.1,
@@ -81,6 +81,8 @@ def state_dict_shapes(hp):
     s["output_projection.weight"] = (88, C, 1); s["output_projection.bias"] = (88,)
     s["mel_layer.spectrogram.window"] = (n_fft,)
     s["mel_layer.mel_scale.fb"] = (n_fft // 2 + 1, M)
+    if hp.get("condition", "fixed") == "trainable_spec":
+        s["trainable_parameters"] = (hp["spec_args"]["n_mels"], 641)   # model/diffwave.py:601 (641 is hard-coded there)
     return s
 
 
@@ -97,6 +99,8 @@ def make_state_dict(hp, seed=0):
         if key == "mel_layer.mel_scale.fb":
             sa = hp["spec_args"]
             sd[key] = melscale_fbanks(shp[0], float(sa["f_min"]), float(sa["f_max"]), sa["n_mels"], sa["sample_rate"]); continue
+        if key == "trainable_parameters":   # the reference starts it at -1 (= the fixed variant); a trained one is anything in [-1, 1]
+            sd[key] = torch.rand(shp, generator=g) * 1.6 - 1.0; continue
         fan_in = 1
         for d in shp[1:]:
             fan_in *= d

@@ -218,6 +218,8 @@ class SpecRollDiffusion(nn.Module):
                 raise ValueError("n_steps must be in [1, timesteps]")
             ups = ups[:n_steps]
         eng, x, spec = self._prepare(x_T, waveform, branches, *masks)
+        if getattr(self, "_learned", False):      # condition='trainable_spec': see ClassifierFreeDiffRoll._learned_upd
+            ups = [self._learned_upd(u, branches) for u in ups]
         x = x.clone()
         n_total = sum(1 for u in ups if u.has_noise)
         rng_state = None
@@ -459,6 +461,9 @@ class SpecRollDiffusion(nn.Module):
             raise NotImplementedError("debug=True conditions on the label roll (DiffRollDebug); not on this path")
         if mode not in ("epsilon", "x_0", "ex_0"):
             raise ValueError(f"training mode {mode} is not supported. Please either use 'x_0' or 'epsilon'.")
+        if getattr(self, "_learned", False):
+            raise NotImplementedError("training_step with condition='trainable_spec': the backward pass does not produce the gradient "
+                                      "of trainable_parameters (forward, validation step and every sampler are built)")
         from . import _lib
         _, _, spec = self._prepare(x_t, waveform, _lib.BRANCH_COND, self.hparams.inpainting_t, self.hparams.inpainting_f, mel_only=True)
         if spec.shape[-1] != T:
@@ -492,7 +497,7 @@ class SpecRollDiffusion(nn.Module):
         if two and mode == "x_0":                          # second dataset: one more, unconditional, forward (:707-719)
             roll2 = self.normalize(batch[1]["frame"]).unsqueeze(1)
             x_t2 = q_sample(roll2, t, sa, s1, noise)
-            spec2 = torch.full_like(spec, -1.0)            # sampling=True, model/diffwave.py:656-660
+            spec2 = self._uncond_spec_like(spec)           # sampling=True, model/diffwave.py:656-660
             pred_roll2 = eng.forward(x_t2, spec2, t)
             losses["unconditional_diffusion_loss"] = self.p_losses(roll2, pred_roll2, loss_type=self.hparams.loss_type)
             if "unconditional_diffusion_loss" in keys:

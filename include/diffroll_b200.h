@@ -53,6 +53,11 @@ extern "C" {
 #define DRB_BRANCH_UNCOND      2  /* spec == -1 (sampling=True)                    task/diffusion.py:979        */
 #define DRB_BRANCH_COND_ZEROSPEC 3 /* pair: cond + cond on a zero waveform (its normalised spectrogram is all 0)
                                       task/diffusion.py:1038-1040 (cfdg_ddim_x0 omits sampling=True) */
+#define DRB_BRANCH_COND_LEARNED 4  /* pair: cond + cond on the LEARNED unconditional spectrogram of condition='trainable_spec'
+                                      (model/diffwave.py:600-605, 657-658: with sampling=True the spectrogram is the
+                                      [n_mels, 641] parameter instead of -1).  The plan must be CREATED with this value
+                                      (it holds `batch` extra clips and twice the conditioner tables) and given the table
+                                      with drb_plan_set_uncond_spec; it may be switched to the other modes and back. */
 
 /* posterior-update formulas, evaluated in the reference's operation order with fp32 scalars s[0..4] */
 #define DRB_UPD_X0        0  /* s0*net + s1*(x - s2*net)/s3 + s4*noise      task/diffusion.py:1018-1023 */
@@ -158,6 +163,12 @@ int drb_mel_forward(drb_plan* plan, const float* waveform, float* spec_out,
  * without differ by fp32-vs-operand-pair rounding of that term only (~1e-6); drb_plan_use_cond_tables(plan, 0) makes
  * the following steps ignore tables that happen to be ready, so a result never depends on call history. */
 int drb_cond_tables(drb_plan* plan, void* stream);
+
+/* DRB_BRANCH_COND_LEARNED only: the learned unconditional spectrogram `trainable_parameters` (model/diffwave.py:601-604),
+ * fp32 device [n_mels][ld] with ld >= frames (the reference's table has 641 frames and is trimmed to the roll,
+ * model/diffwave.py:30-39,662).  Copied into the plan; call again after the parameter changes.  Its conditioner
+ * projections are (re)built by the next drb_cond_tables / step. */
+int drb_plan_set_uncond_spec(drb_plan* plan, const float* spec, int32_t ld, void* stream);
 int drb_plan_use_cond_tables(drb_plan* plan, int32_t enable);
 
 /* input_projection + ReLU (model/diffwave.py:640,667-668) for timestep t_index. x_t [B,1,T,88]. */

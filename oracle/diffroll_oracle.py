@@ -85,7 +85,8 @@ def normalize_imagewise(x, lo=0.0, hi=1.0):
 
 
 class OracleDiffRoll:
-    """Functional restatement of ClassifierFreeDiffRoll + SpecRollDiffusion (eval mode, condition='fixed')."""
+    """Functional restatement of ClassifierFreeDiffRoll + SpecRollDiffusion, condition='fixed' or 'trainable_spec' (the learned
+    unconditional spectrogram of model/diffwave.py:600-605, 657-658, 695-699)."""
 
     def __init__(self, hp, state_dict, dtype=torch.float32, device=None):
         # device: None/CPU for the checker and the CPU baseline; "cuda" runs the same torch ops eagerly on the GPU
@@ -116,8 +117,12 @@ class OracleDiffRoll:
         sd = self.sd
         x_t = x_t.to(self.dtype).squeeze(1).transpose(1, 2)
         spec = self.spec_frontend(waveform)
+        learned = self.hp.get("condition", "fixed") == "trainable_spec"
         if dropout_mask is not None:
-            spec[dropout_mask.to(spec.device).bool()] = -1
+            if learned:                                                # trainable_dropout, model/diffwave.py:695-699
+                spec[dropout_mask.to(spec.device).bool()] = sd["trainable_parameters"]
+            else:
+                spec[dropout_mask.to(spec.device).bool()] = -1
         if inpainting_t and inpainting_f is None:
             spec[:, :, int(inpainting_t[0]):int(inpainting_t[1])] = -1
         elif inpainting_t is None and inpainting_f:
@@ -125,7 +130,8 @@ class OracleDiffRoll:
         elif inpainting_t and inpainting_f:
             spec[:, int(inpainting_f[0]):int(inpainting_f[1]), int(inpainting_t[0]):int(inpainting_t[1])] = -1
         if sampling is True:
-            spec = torch.full_like(spec, -1)
+            # :657-660; the learned table is 2-D [n_mels, 641]: conv1d treats it as one unbatched clip and the block's sum broadcasts it
+            spec = sd["trainable_parameters"] if learned else torch.full_like(spec, -1)
         T_min = min(x_t.shape[-1], spec.shape[-1])
         x_t = x_t[..., :T_min]
         spectrogram = spec[..., :T_min]

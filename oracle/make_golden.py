@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (container only).
 
-    python oracle/make_golden.py [--only forward,steps,chain,chain_inpaint,chain_gen,valstep]
+    python oracle/make_golden.py [--only forward,steps,chain,chain_inpaint,chain_gen,valstep,learned]
 
 The reference is imported from /root/reference through oracle/ref_shim.py, loaded
 with the seeded weights of diffroll_b200/synthetic.py (strict=True, so the
@@ -157,6 +157,45 @@ def gen_valstep():
     print({k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items()})
 
 
+def gen_learned():
+    """condition='trainable_spec' (model/diffwave.py:600-605, 657-658, 695-699): the 133-key state_dict loads strict=True; one
+    sampling=True forward, single steps of the two samplers that read the learned table, the validation step's second
+    (unconditional) dataset and a whole 200-step guided chain, short clip."""
+    out = {}
+    x_T, wav, noise = make_inputs(2, 200, seed=7, n_noise=1, T=128, wav_len=65536)
+    for name in ("cfdg_ddpm_x0", "generation_ddpm_x0"):
+        hp = default_hparams(sampling_type=name, condition="trainable_spec")
+        m = ref_model(hp)
+        for t_index in (199, 1, 0):
+            with NoiseQueue() as nq, torch.no_grad():
+                nq.q = [noise[0]]
+                x_prev, _ = m.reverse_diffusion(x_T, wav, t_index)
+            out[f"{name}_t{t_index}"] = x_prev.numpy()
+    with torch.no_grad():
+        pred_u, spec_u = m(x_T, wav, torch.tensor([37, 150]), sampling=True)
+    assert spec_u.shape == (229, 128)
+    out["pred_u"] = pred_u.numpy()
+    frame, audio, t, nz = make_labelled_batch(B=2)
+    frame2, audio2, _, _ = make_labelled_batch(B=2, seed=78)
+    orig_randint = torch.randint
+    torch.randint = lambda *a, **k: t.clone()
+    try:
+        with NoiseQueue() as nq, torch.no_grad():
+            nq.q = [nz.clone()]
+            losses, tensors = m.step([{"frame": frame.clone(), "audio": audio.clone()}, {"frame": frame2.clone(), "audio": audio2.clone()}])
+    finally:
+        torch.randint = orig_randint
+    out["two_loss"] = np.float64(losses["diffusion_loss"].item())
+    out["two_uncond_loss"] = np.float64(losses["unconditional_diffusion_loss"].item())
+    out["two_pred_roll2"] = tensors["pred_roll2"].numpy()
+    hp = default_hparams(sampling_type="cfdg_ddpm_x0", condition="trainable_spec")
+    xc, wc, nc = make_inputs(2, 200, seed=13, T=128, wav_len=65536)
+    x0, _, _ = run_chain(ref_model(hp), xc, wc, nc)
+    out["chain_final"] = x0.numpy()
+    np.savez_compressed(os.path.join(GOLD, "learned_T128.npz"), **out)
+    print({k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="forward,steps,chain,chain_inpaint,chain_gen,valstep")
@@ -170,6 +209,8 @@ def main():
         gen_steps(); print("steps done")
     if "valstep" in only:
         gen_valstep(); print("valstep done")
+    if "learned" in only:
+        gen_learned(); print("learned done")
     if "chain" in only:       # configs[0]/[1] shape: transcription, 200 steps, full 640-frame clip
         gen_chain("transcription_b1_200", default_hparams(), 1, seed=123, keep=(150, 100, 50), fp64=True)
     if "chain_inpaint" in only:  # configs[3] shape: 50 % frame mask

@@ -296,3 +296,44 @@ def test_compose_reads_a_reference_style_hydra_tree(tmp_path):
     assert cfg.task.sampling.w == 0.5 and cfg.model.args.kernel_size == 9 and cfg.dataloader.batch_size == 32
     with pytest.raises(KeyError):
         compose(str(tmp_path / "sampling.yaml"), ["task=nope"])
+
+
+def test_trainable_spec_host_side(lib_built):
+    """condition='trainable_spec' (model/diffwave.py:600-605): the extra [n_mels, 641] parameter is part of the state_dict contract
+    (133 tensors incl. the two mel buffers), the learned-capable plan asks for the extra clips and tables, sampling=True steps run
+    as the learned pair at guidance weight -1, and 'trainable_z' fails at construction like the reference (:616 vs :154)."""
+    import diffroll_b200 as M
+    from diffroll_b200 import _lib
+    hp = default_hparams(condition="trainable_spec", sampling_type="generation_ddpm_x0")
+    m = M.ClassifierFreeDiffRoll(**hp)
+    assert m.trainable_parameters.shape == (229, 641) and float(m.trainable_parameters.min()) == -1.0 == float(m.trainable_parameters.max())
+    sd = make_state_dict(hp)
+    assert set(m.state_dict()) == set(sd) and len(sd) == 133
+    m.load_state_dict(sd, strict=True)
+    assert any(q is m.trainable_parameters for q in m.configure_optimizers()[0].params)
+    ups, branches, _ = m._all_updates()
+    assert branches == _lib.BRANCH_UNCOND
+    u = m._learned_upd(ups[0], branches)
+    assert u is not ups[0] and u.w == -1.0 and ups[0].w == 0.0 and list(u.s) == list(ups[0].s) and u.mode == ups[0].mode
+    assert m._learned_upd(ups[0], _lib.BRANCH_COND) is ups[0]
+    fixed = M.ClassifierFreeDiffRoll(**default_hparams(sampling_type="generation_ddpm_x0"))
+    assert fixed._learned_upd(ups[0], _lib.BRANCH_UNCOND) is ups[0]
+    spec = torch.zeros(3, 229, 128)
+    out = m.uncon_dropout(spec.clone(), 0.5, mask=torch.tensor([0, 1, 0]))
+    assert torch.equal(out[1], m.trainable_parameters.detach()[:, :128]) and float(out[0].abs().max()) == 0.0 == float(out[2].abs().max())
+    assert float(fixed.uncon_dropout(spec.clone(), 0.5, mask=torch.tensor([0, 1, 0]))[1].max()) == -1.0
+    with pytest.raises(TypeError, match="multiple values for argument 'uncond'"):
+        M.ClassifierFreeDiffRoll(**default_hparams(condition="trainable_z"))
+    with pytest.raises(ValueError):
+        M.ClassifierFreeDiffRoll(**default_hparams(condition="something"))
+    lib = _lib.load()
+    cfg = _lib.DrbConfig(batch=32, frames=640, pitches=88, wave_len=327680, residual_channels=512, residual_layers=15,
+                         kernel_size=9, dilation_base=2, dilation_bound=4, n_mels=229, n_fft=2048, hop_length=512,
+                         timesteps=200, precision=_lib.PREC_F16N4, branches=_lib.BRANCH_COND_UNCOND, reserved=0)
+    plain = lib.drb_plan_workspace_bytes(C.byref(cfg))
+    cfg.branches = _lib.BRANCH_COND_LEARNED
+    learned = lib.drb_plan_workspace_bytes(C.byref(cfg))
+    extra = 32 * 640 * (256 * 4 + 15 * 1024 * 4)           # 32 more clips of spec32 and of every layer's conditioner table
+    assert learned - plain == extra, (learned - plain, extra)
+    cfg.branches = 5
+    assert lib.drb_plan_workspace_bytes(C.byref(cfg)) == 0

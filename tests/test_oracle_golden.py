@@ -141,3 +141,32 @@ def test_validation_step_two_datasets_vs_reference():
     assert abs(float(losses["diffusion_loss"]) - float(g["two_loss"])) < 1e-5 * max(1.0, float(g["two_loss"]))
     assert abs(float(losses["unconditional_diffusion_loss"]) - float(g["two_uncond_loss"])) < 1e-5 * max(1.0, float(g["two_uncond_loss"]))
     assert _err(tensors["pred_roll2"], g["two_pred_roll2"]) < TOL * max(1.0, float(np.abs(g["two_pred_roll2"]).max()))
+
+
+def test_trainable_spec_vs_golden():
+    """condition='trainable_spec' (model/diffwave.py:600-605, 657-658): the oracle's learned-table branch against the unmodified
+    reference -- single steps of the two samplers that read the table, a sampling=True forward at per-roll steps, the validation
+    step's unconditional second dataset."""
+    g = golden("learned_T128.npz")
+    x_T, wav, noise = make_inputs(2, 200, seed=7, n_noise=1, T=128, wav_len=65536)
+    for name in ("cfdg_ddpm_x0", "generation_ddpm_x0"):
+        o, _ = _oracle(sampling_type=name, condition="trainable_spec")
+        for t_index in (199, 1, 0):
+            with torch.no_grad():
+                x_prev, _ = o.reverse_diffusion(x_T, wav, t_index, noise=noise[0])
+            ref = g[f"{name}_t{t_index}"]
+            assert _err(x_prev, ref) < TOL * max(1.0, float(np.abs(ref).max())), (name, t_index)
+    with torch.no_grad():
+        pu, su = o(x_T, wav, torch.tensor([37, 150]), sampling=True)
+    assert su.shape == (229, 128) and _err(pu, g["pred_u"]) < TOL
+    from diffroll_b200.synthetic import make_labelled_batch
+    frame, audio, t, nz = make_labelled_batch(B=2)
+    frame2, audio2, _, _ = make_labelled_batch(B=2, seed=78)
+    losses, tensors = o.step([{"frame": frame, "audio": audio}, {"frame": frame2, "audio": audio2}], t, nz)
+    assert abs(float(losses["unconditional_diffusion_loss"]) - float(g["two_uncond_loss"])) < 1e-5
+    assert _err(tensors["pred_roll2"], g["two_pred_roll2"]) < TOL
+    # the table matters: the fixed variant's unconditional forward is somewhere else
+    f, _ = _oracle(sampling_type="generation_ddpm_x0")
+    with torch.no_grad():
+        pf, _ = f(x_T, wav, torch.tensor([37, 150]), sampling=True)
+    assert _err(pf, g["pred_u"]) > 1e-3

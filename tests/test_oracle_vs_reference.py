@@ -88,3 +88,46 @@ def test_fractional_diffusion_step_matches_live_reference():
         a, _ = ref(x_T, wav, steps)
         b, _ = orc(x_T, wav, steps)
     assert float((a - b).abs().max()) <= 2e-5
+
+
+def test_trainable_spec_matches_live_reference():
+    """condition='trainable_spec' (model/diffwave.py:600-605): 133-key state_dict, a forward with sampling=True conditions every
+    roll on the learned [n_mels, 641] table (:657-658; returned 2-D and trimmed), the cfdg sampler's second branch reads it, and
+    the training-mode dropout writes it into the dropped rolls (:695-699) -- gradient with respect to the table included."""
+    ref, orc, hp = _pair(sampling_type="cfdg_ddpm_x0", condition="trainable_spec")
+    assert ref.trainable_parameters.shape == (229, 641)
+    x_T, wav, noise = make_inputs(2, 200, seed=4, n_noise=1, T=128, wav_len=65536)
+    steps = torch.tensor([57, 57])
+    with torch.no_grad():
+        a, sa = ref(x_T, wav, steps, sampling=True)
+        b, sb = orc(x_T, wav, steps, sampling=True)
+    assert sa.shape == (229, 128) and torch.equal(sa, sb)
+    assert float((a - b).abs().max()) <= 2e-5
+    orig = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: noise[0].to(x.dtype)
+    try:
+        with torch.no_grad():
+            a, _ = ref.reverse_diffusion(x_T, wav, 120)
+    finally:
+        torch.randn_like = orig
+    with torch.no_grad():
+        b, _ = orc.reverse_diffusion(x_T, wav, 120, noise=noise[0])
+    assert float((a - b).abs().max()) <= 2e-5
+    # the result depends on the table: the fixed variant (spec == -1) gives something else
+    fixed = OracleDiffRoll(default_hparams(sampling_type="cfdg_ddpm_x0"), {k: v for k, v in orc.sd.items() if k != "trainable_parameters"})
+    with torch.no_grad():
+        c, _ = fixed.reverse_diffusion(x_T, wav, 120, noise=noise[0])
+    assert float((b - c).abs().max()) > 1e-3
+
+
+def test_trainable_z_constructor_fails_like_the_live_reference():
+    """condition='trainable_z' builds ResidualBlockz with five arguments where its __init__ takes four (model/diffwave.py:616 vs
+    :154): the reference raises TypeError at construction; so does the product class, with the same message."""
+    hp = default_hparams(condition="trainable_z")
+    with pytest.raises(TypeError) as e_ref:
+        ref_shim.build_reference_model(hp)
+    from diffroll_b200 import ClassifierFreeDiffRoll
+    with pytest.raises(TypeError) as e_own:
+        ClassifierFreeDiffRoll(**hp)
+    assert "multiple values for argument 'uncond'" in str(e_ref.value)
+    assert "multiple values for argument 'uncond'" in str(e_own.value)
