@@ -24,7 +24,7 @@ EXPORTS = [
     "drb_plan_profile", "drb_plan_profile_read", "drb_plan_profile_read2", "drb_plan_range_stats", "drb_plan_precision", "drb_extract_notes_scratch_bytes", "drb_extract_notes",
     "drb_frame_counts", "drb_q_sample", "drb_extract_x0", "drb_p_losses_scratch_bytes", "drb_p_losses", "drb_normalize_imagewise",
     "drb_train_workspace_bytes", "drb_train_create", "drb_train_destroy", "drb_train_forward", "drb_train_backward", "drb_loss_grad",
-    "drb_adam_step", "drb_adam_step_multi", "drb_plan_set_step_embeddings", "drb_plan_set_uncond_spec",
+    "drb_adam_step", "drb_adam_step_multi", "drb_plan_set_step_embeddings", "drb_plan_set_uncond_spec", "drb_train_set_spec_grad",
 ]
 
 
@@ -135,6 +135,7 @@ def load():
     lib.drb_train_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DrbTrainConfig), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.drb_train_destroy.argtypes = [C.c_void_p]
     lib.drb_train_destroy.restype = None
+    lib.drb_train_set_spec_grad.argtypes = [C.c_void_p, C.c_void_p]
     lib.drb_train_forward.argtypes = [C.c_void_p, C.POINTER(DrbTrainParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
     lib.drb_train_backward.argtypes = [C.c_void_p, C.POINTER(DrbTrainParams), C.POINTER(DrbTrainParams), C.c_void_p, C.c_void_p,

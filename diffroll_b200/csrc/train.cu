@@ -322,6 +322,24 @@ __global__ void spec_to_rows_kernel(const float* __restrict__ spec, float* __res
   }
 }
 
+// rows [B*T][Mp] time-major -> spec layout [B][n_mels][T] (the inverse of spec_to_rows_kernel), optionally added to the destination
+__global__ void rows_to_spec_kernel(const float* __restrict__ rows, float* __restrict__ spec, int B, int nm, int T, int Mp, int accumulate) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, m = m0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && m < Mp) ? rows[((size_t)b * T + t) * Mp + m] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int m = m0 + i, t = t0 + threadIdx.x;
+    if (m < nm && t < T) {
+      const size_t j = ((size_t)b * nm + m) * T + t;
+      spec[j] = tile[threadIdx.x][i] + (accumulate ? spec[j] : 0.f);
+    }
+  }
+}
+
 // grad[n][c][tap] += dwt[n][tap * C + c]   (tap-major GEMM result -> PyTorch conv weight layout [out][in][k])
 __global__ void untap_add_kernel(const float* __restrict__ dwt, float* __restrict__ grad, int OC, int C, int k) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,6 +425,10 @@ struct drb_train {
   // workspace offsets (bytes)
   size_t xs, ys, zs, skip, hbuf, obuf, spec, e0, p1, s1, p2, emb, dl, iota, wtmp, gskip, gx, gu, gz, gemb, gd, gsmall, total;
   bool fwd_done = false;
+  // drb_train_set_spec_grad: where the next backward leaves d loss / d spec ([B][n_mels][T]); nullptr = not wanted (the default:
+  // the spectrogram is data).  condition='trainable_spec' needs it for the rolls conditioned on the learned table.
+  float* g_spec_out = nullptr;
+  size_t gspec = 0;          // [B*T][Mp] fp32 accumulator over the layers
   // tensor-core path of the two dilated-conv products that carry 2/3 of the step's FLOPs (forward conv, its transposed form):
   // f16e5 operand pairs staged per layer, umma_gate_kernel with the linear epilogue (DRB_TRAIN_TC=0: everything on the CUDA cores)
   bool tc = false;
@@ -444,7 +466,7 @@ static size_t train_layout(drb_train& p) {
   p.e0 = take(B * 128 * 4); p.p1 = take(B * 512 * 4); p.s1 = take(B * 512 * 4); p.p2 = take(B * 512 * 4); p.emb = take(B * 512 * 4);
   p.dl = take(L * B * C * 4); p.iota = take(B * 4);
   size_t wmax = 2 * C * k * C;                       // repacked / transposed weight scratch (largest: the dilated conv)
-  if (wmax < 2 * C * (size_t)p.Mp) wmax = 2 * C * (size_t)p.Mp;
+  if (wmax < 4 * C * (size_t)p.Mp) wmax = 4 * C * (size_t)p.Mp;   // padded conditioner weights + their transpose (spec gradient)
   p.wtmp = take(wmax * 4); p.wtmp_bytes = wmax * 4;
   p.gskip = take(M * C * 4); p.gx = take(M * C * 4); p.gu = take(M * C * 4); p.gz = take(M * C * 4);
   p.gemb = take(B * 512 * 4); p.gd = take(B * C * 4); p.gsmall = take(B * 512 * 4);
@@ -454,6 +476,7 @@ static size_t train_layout(drb_train& p) {
   p.wh = take(2 * C * k * C * 2); p.wl = take(2 * C * k * C * 2); p.wch = take(2 * C * (size_t)p.Mp * 2); p.wcl = take(2 * C * (size_t)p.Mp * 2);
   p.bnat = take(2 * C * 4); p.scal = take(16 * 4 * 4);
   p.gth = take(2 * C * M * 2); p.gtl = take(2 * C * M * 2); p.uth = take(k * C * M * 2); p.utl = take(k * C * M * 2);
+  p.gspec = take(M * (size_t)p.Mp * 4);
   p.total = off;
   return off;
 }
@@ -591,6 +614,16 @@ int drb_train_create(drb_train** out, const drb_train_config* cfg, void* workspa
 }
 
 void drb_train_destroy(drb_train* p) { delete p; }
+
+// Ask the following drb_train_backward calls for d loss / d spec as well: g_spec [B][n_mels][T] fp32 device, OVERWRITTEN by every
+// backward (the sum over the layers of g_y . W_c, model/diffwave.py:143); NULL switches it off again.  The spectrogram is data
+// for condition='fixed'; condition='trainable_spec' conditions the dropped rolls on a parameter (:695-699) whose gradient is
+// the sum of this tensor over those rolls.
+int drb_train_set_spec_grad(drb_train* p, float* g_spec) {
+  if (!p) return DRB_E_INVALID;
+  p->g_spec_out = g_spec;
+  return 0;
+}
 
 // Forward pass in training form.  x_t [B][T][F]; spec [B][n_mels][T] exactly as the network sees it (normalised log-mel with the
 // spec-dropout rows and masks already set to -1); steps [B] int32; emb_table [timesteps][128].  pred [B][T][F].
@@ -733,6 +766,8 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
       DRB_CUDA(zero(gr->wo[l], (size_t)2 * C * C)); DRB_CUDA(zero(gr->bo[l], 2 * C));
     }
   }
+  float* gspec = p->g_spec_out ? p->at<float>(p->gspec) : nullptr;
+  if (gspec) DRB_CUDA(cudaMemsetAsync(gspec, 0, M * (size_t)Mp * 4, s));
   float* h = p->at<float>(p->hbuf);
   float* gx = p->at<float>(p->gx);        // g_x_{l+1}
   float* gu = p->at<float>(p->gu);        // g_h, then g_u of the current layer
@@ -814,6 +849,14 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
     const float* gy = y_l;
     TR(launch_colsum(gy, 2 * C, 2 * C, 1, (int)M, gr->bd[l], 2 * C, s));     // dilated_conv.bias
     TR(launch_colsum(gy, 2 * C, 2 * C, 1, (int)M, gr->bc[l], 2 * C, s));     // conditioner_projection.bias (added to the same y)
+    if (gspec) {   // d loss / d spec += g_y . W_c (the conditioner is a 1x1 conv, :143); fp32 CUDA cores, wtmp is free between the two products around it
+      float* wcp = wtmp; float* wct = wtmp + (size_t)2 * C * Mp;
+      TR(launch_pad_rows(w->wc[l], wcp, 2 * C, c.n_mels, Mp, s));             // [2C][n_mels] -> [2C][Mp]
+      TR(launch_transpose(wcp, wct, 2 * C, Mp, s));                           // -> [Mp][2C]
+      SimtGemm q;
+      q.A = gy; q.lda = 2 * C; q.T = T; q.Ck = 2 * C; q.W = wct; q.ldw = 2 * C; q.accumulate = 1; q.C = gspec; q.ldc = Mp; q.M = (int)M; q.N = Mp;
+      TR(launch_simt_gemm(q, s));
+    }
     float* sg = p->at<float>(p->scal) + 4;                           // {S_g, 1 / S_g}: power-of-two scale that lifts g_y into fp16's range
     const bool tc_w = p->tc && p->tc_wgrad && (p->tc_mask & 4), tc_d = p->tc && (p->tc_mask & 2);
     if (tc_w || tc_d || tc_w1) TR(launch_weight_scale(gy, M * 2 * C, nullptr, 0, sg, 1.f, s));
@@ -907,6 +950,11 @@ int drb_train_backward(drb_train* p, const drb_train_params* w, const drb_train_
       g.A = gx; g.lda = C; g.T = T; g.Ck = C; g.W = wtmp; g.ldw = C; g.C = g_x_t; g.ldc = F; g.M = (int)M; g.N = F;
       TR(launch_simt_gemm(g, s));
     }
+  }
+  if (gspec) {   // the layers' sum, back in the module's layout
+    dim3 grid((T + 31) / 32, (Mp + 31) / 32, B), block(32, 8);
+    rows_to_spec_kernel<<<grid, block, 0, s>>>(gspec, p->g_spec_out, B, c.n_mels, T, Mp, 0);
+    DRB_LAUNCH_CHECK();
   }
   // ---- diffusion embedding MLP      model/diffwave.py:66-75 ----
   {

@@ -461,16 +461,19 @@ class SpecRollDiffusion(nn.Module):
             raise NotImplementedError("debug=True conditions on the label roll (DiffRollDebug); not on this path")
         if mode not in ("epsilon", "x_0", "ex_0"):
             raise ValueError(f"training mode {mode} is not supported. Please either use 'x_0' or 'epsilon'.")
-        if getattr(self, "_learned", False):
-            raise NotImplementedError("training_step with condition='trainable_spec': the backward pass does not produce the gradient "
-                                      "of trainable_parameters (forward, validation step and every sampler are built)")
+        learned = getattr(self, "_learned", False)      # condition='trainable_spec': the dropped rolls read a parameter
         from . import _lib
         _, _, spec = self._prepare(x_t, waveform, _lib.BRANCH_COND, self.hparams.inpainting_t, self.hparams.inpainting_f, mel_only=True)
         if spec.shape[-1] != T:
             raise NotImplementedError("training step: the clip must cover the whole roll (trim_spec_roll would shorten it)")
         spec = spec.clone()
+        drop = None
         if self.training:                                  # model/diffwave.py:646-647
+            if learned and dropout_mask is None:           # the same draw uncon_dropout would make; kept to route the gradient
+                dropout_mask = torch.bernoulli(torch.full((B,), float(self.hparams.spec_dropout)))
             spec = self.uncon_dropout(spec, self.hparams.spec_dropout, mask=dropout_mask)
+            if learned:
+                drop = dropout_mask.to(device=device).bool()
         eng = self._train_engine(B, T)
         keys = list(self.hparams.loss_keys)
         losses, tensors = {}, {}
@@ -491,8 +494,11 @@ class SpecRollDiffusion(nn.Module):
             g = loss_grad(roll, pred_roll, self.hparams.loss_type, roll_scale=scale)
         gx = None
         if "diffusion_loss" in keys:
-            gx = eng.backward(g, accumulate=acc, want_input_grad=want_input_grad)
+            gx = eng.backward(g, accumulate=acc, want_input_grad=want_input_grad,
+                              want_spec_grad=drop is not None and bool(dropout_mask.bool().any()))
             acc = True
+            if eng.spec_grad is not None:                  # trainable_dropout (:695-699): d loss / d table = sum over the dropped rolls
+                self.trainable_parameters.grad[:, :T].add_(eng.spec_grad[drop].sum(0))
         tensors.update(pred_roll=pred_roll, label_roll=roll, spec=spec)
         if two and mode == "x_0":                          # second dataset: one more, unconditional, forward (:707-719)
             roll2 = self.normalize(batch[1]["frame"]).unsqueeze(1)
@@ -501,7 +507,9 @@ class SpecRollDiffusion(nn.Module):
             pred_roll2 = eng.forward(x_t2, spec2, t)
             losses["unconditional_diffusion_loss"] = self.p_losses(roll2, pred_roll2, loss_type=self.hparams.loss_type)
             if "unconditional_diffusion_loss" in keys:
-                eng.backward(loss_grad(roll2, pred_roll2, self.hparams.loss_type), accumulate=acc)
+                eng.backward(loss_grad(roll2, pred_roll2, self.hparams.loss_type), accumulate=acc, want_spec_grad=learned)
+                if learned:                                # every roll of the second batch is conditioned on the table (:657-658)
+                    self.trainable_parameters.grad[:, :T].add_(eng.spec_grad.sum(0))
             tensors.update(spec2=spec2, label_roll2=roll2, pred_roll2=pred_roll2)
         total_loss = 0
         for k in keys:

@@ -110,8 +110,10 @@ class TrainEngine:
         del keep
         return pred
 
-    def backward(self, g_pred, accumulate=False, want_input_grad=False):
-        """d loss / d pred [B,1,T,88] -> fills (or adds to) ``param.grad`` of every parameter; returns d loss / d x_t if asked."""
+    def backward(self, g_pred, accumulate=False, want_input_grad=False, want_spec_grad=False):
+        """d loss / d pred [B,1,T,88] -> fills (or adds to) ``param.grad`` of every parameter; returns d loss / d x_t if asked.
+        want_spec_grad: also keep d loss / d spec [B,n_mels,T] in ``self.spec_grad`` (condition='trainable_spec': the rolls
+        conditioned on the learned table pass it on to that parameter)."""
         named = self._params()
         for q in named.values():
             if q.grad is None:
@@ -122,7 +124,9 @@ class TrainEngine:
         gs, k2 = _param_struct(lambda n: named[n].grad, self.L)
         g = g_pred.to(torch.float32).reshape(self.batch, self.frames, 88).contiguous()
         gx = torch.empty_like(self._x) if want_input_grad else None
+        self.spec_grad = torch.empty(self.batch, self.cfg.n_mels, self.frames, dtype=torch.float32, device=self.device) if want_spec_grad else None
         with torch.cuda.device(self.device):
+            _lib.check(self.lib.drb_train_set_spec_grad(self.plan, _p(self.spec_grad) if want_spec_grad else None), "drb_train_set_spec_grad")
             _lib.check(self.lib.drb_train_backward(self.plan, C.byref(ps), C.byref(gs), _p(self._x), _p(g), C.c_int32(1 if accumulate else 0),
                                                    _p(gx) if gx is not None else None, _stream(self.device)), "drb_train_backward")
         del k1, k2

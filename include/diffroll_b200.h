@@ -265,6 +265,10 @@ void drb_train_destroy(drb_train* plan);
  * already -1); steps int32[B]; emb_table [timesteps][128] (DiffusionEmbedding._build_embedding); pred [B][T][88]. */
 int drb_train_forward(drb_train* plan, const drb_train_params* params, const float* x_t, const float* spec,
                       const int32_t* steps, const float* emb_table, float* pred, void* stream);
+/* Optional: make the following drb_train_backward calls also leave d loss / d spec in g_spec ([B][n_mels][T] fp32 device,
+ * overwritten by every backward; NULL = off, the default).  condition='trainable_spec' conditions the dropped rolls on the
+ * parameter `trainable_parameters` (model/diffwave.py:695-699): its gradient is this tensor summed over those rolls. */
+int drb_train_set_spec_grad(drb_train* plan, float* g_spec);
 /* Backward of the last drb_train_forward: g_pred = d loss / d pred [B][T][88]; every tensor of grads receives its gradient
  * (accumulate != 0: added to its content); g_x_t (optional) = d loss / d x_t. */
 int drb_train_backward(drb_train* plan, const drb_train_params* params, const drb_train_params* grads, const float* x_t,

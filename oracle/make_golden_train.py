@@ -8,7 +8,8 @@ one of the 130 parameter tensors, the gradient's L2 norm and a strided sample of
 small tensors in full), for three (training mode, loss) settings and the two-dataset batch.  One Adam step of
 ``configure_optimizers`` (:1057-1059) is stored the same way (parameter delta).
 
-    python oracle/make_golden_train.py        ->  tests/golden/trainstep_b2_T128.npz
+    python oracle/make_golden_train.py              ->  tests/golden/trainstep_b2_T128.npz
+    python oracle/make_golden_train.py --learned    ->  tests/golden/trainstep_learned_b2_T640.npz  (condition='trainable_spec')
 """
 from __future__ import annotations
 
@@ -102,5 +103,32 @@ def main():
     print(path, os.path.getsize(path) / 1e6, "MB")
 
 
+def main_learned():
+    """condition='trainable_spec': trainable_dropout (model/diffwave.py:695-699) assigns the [n_mels, 641] table to the dropped
+    rolls, which only broadcasts for clips of exactly 641 spectrogram frames -- so this fixture uses the full 640-frame roll.
+    Two-dataset batch, both losses: the first backward reaches the table through the dropped roll, the second through every roll."""
+    from diffroll_b200.synthetic import make_labelled_batch as mk
+    frame, audio, t, noise = mk(B=2, T=640, wav_len=327680)
+    frame2, audio2, _, _ = mk(B=2, T=640, wav_len=327680, seed=78)
+    mask = torch.tensor([0, 1])
+    store = {"t": t.numpy(), "mask": mask.numpy()}
+    hp = default_hparams(condition="trainable_spec")
+    res = run(hp, {"frame": frame.clone(), "audio": audio.clone()}, t, noise, mask)
+    for k, v in res.items():
+        store[f"one/{k}"] = v
+    print("learned, one dataset: total loss", res["total_loss"], "|g table|", res["norm/trainable_parameters"])
+    hp["loss_keys"] = ["diffusion_loss", "unconditional_diffusion_loss"]
+    res = run(hp, [{"frame": frame.clone(), "audio": audio.clone()}, {"frame": frame2.clone(), "audio": audio2.clone()}], t, noise, mask)
+    for k, v in res.items():
+        store[f"two/{k}"] = v
+    print("learned, two datasets: total loss", res["total_loss"], "|g table|", res["norm/trainable_parameters"])
+    path = os.path.join(GOLD, "trainstep_learned_b2_T640.npz")
+    np.savez_compressed(path, **store)
+    print(path, os.path.getsize(path) / 1e6, "MB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--learned" in sys.argv:
+        main_learned()
+    else:
+        main()

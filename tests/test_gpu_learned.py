@@ -104,10 +104,52 @@ def test_learned_validation_step_chain_and_parameter_update():
     _record(f"trainable_spec[f16n4] after an in-place change of the table, vs the CPU oracle: forward {eu:.3e}, cfdg step {es:.3e}")
     assert eu < TOL_STEP["f16n4"] and es < TOL_STEP["f16n4"]
     assert _err(pred_u, g["pred_u"]) > 1e-3          # and it did move
-    with pytest.raises(NotImplementedError):
-        m.train()
-        m.training_step({"frame": frame.cuda(), "audio": audio.cuda()})
-    m.eval()
+    _close(m)
+
+
+@pytest.mark.parametrize("case", ["one", "two"])
+def test_learned_training_step_gradients_vs_reference_golden(case):
+    """Row f3 under condition='trainable_spec': trainable_dropout (model/diffwave.py:695-699) conditions the dropped roll on the
+    table, so the backward pass also owes d loss / d trainable_parameters (drb_train_set_spec_grad: g_y . W_c summed over the
+    layers, then over the rolls that read the table).  Goldens: the live reference's training_step + backward() on the full
+    640-frame clip (oracle/make_golden_train.py --learned); 'two' adds the unconditional second dataset, every roll on the table.
+    Tolerance as in tests/test_gpu_train.py: every gradient within 1e-3 of its own max |value|."""
+    import diffroll_b200 as M
+    gold = golden("trainstep_learned_b2_T640.npz")
+    frame, audio, t, noise = make_labelled_batch(B=2, T=640, wav_len=327680)
+    hp = default_hparams(condition="trainable_spec")
+    batch = {"frame": frame.cuda(), "audio": audio.cuda()}
+    if case == "two":
+        frame2, audio2, _, _ = make_labelled_batch(B=2, T=640, wav_len=327680, seed=78)
+        hp["loss_keys"] = ["diffusion_loss", "unconditional_diffusion_loss"]
+        batch = [batch, {"frame": frame2.cuda(), "audio": audio2.cuda()}]
+    m = M.ClassifierFreeDiffRoll(**hp)
+    m.load_state_dict(make_state_dict(hp), strict=True)
+    m = m.cuda().train()
+    total = m.training_step(batch, 0, t=t.cuda(), noise=noise.cuda(), dropout_mask=torch.from_numpy(gold["mask"]))
+    torch.cuda.synchronize()
+    assert abs(float(total) - float(gold[f"{case}/total_loss"])) < 2e-5
+
+    def sample_of(g):
+        flat = g.detach().reshape(-1)
+        return flat[::max(1, -(-flat.numel() // 1024))]
+
+    worst, worst_name = 0.0, ""
+    for name, p in m.named_parameters():
+        ref = gold[f"{case}/grad/{name}"]
+        err = float(np.abs(sample_of(p.grad).cpu().numpy() - ref).max()) / max(float(np.abs(ref).max()), 1e-12)
+        if err > worst:
+            worst, worst_name = err, name
+    ref = gold[f"{case}/grad/trainable_parameters"]
+    e_tab = float(np.abs(sample_of(m.trainable_parameters.grad).cpu().numpy() - ref).max()) / float(np.abs(ref).max())
+    n_tab = abs(float(m.trainable_parameters.grad.double().norm()) - float(gold[f"{case}/norm/trainable_parameters"])) / float(gold[f"{case}/norm/trainable_parameters"])
+    _record(f"train[trainable_spec, {case}] B=2 T=640 vs live-reference golden: loss {float(total):.6f}, worst gradient rel. max|delta| = "
+            f"{worst:.3e} ({worst_name}); table gradient {e_tab:.3e}, its norm {n_tab:.3e}")
+    assert worst < 1e-3 and e_tab < 1e-3 and n_tab < 1e-3, (worst, worst_name, e_tab, n_tab)
+    assert float(m.trainable_parameters.grad[:, 640].abs().max()) == 0.0      # the frame trim_spec_roll cuts off
+    before = m.trainable_parameters.detach().clone()
+    m.configure_optimizers()[0].step()
+    assert float((m.trainable_parameters.detach() - before).abs().max()) > 0.0
     _close(m)
 
 
