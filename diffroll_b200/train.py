@@ -72,6 +72,7 @@ class TrainEngine:
                                                  _stream(self.device)), "drb_train_create")
         self.plan = plan
         self.workspace_bytes = need
+        self.spec_grad = None
         self._emb = model.diffusion_embedding.embedding.detach().to(device=self.device, dtype=torch.float32).contiguous()
 
     def close(self):
@@ -129,6 +130,8 @@ class TrainEngine:
             _lib.check(self.lib.drb_train_set_spec_grad(self.plan, _p(self.spec_grad) if want_spec_grad else None), "drb_train_set_spec_grad")
             _lib.check(self.lib.drb_train_backward(self.plan, C.byref(ps), C.byref(gs), _p(self._x), _p(g), C.c_int32(1 if accumulate else 0),
                                                    _p(gx) if gx is not None else None, _stream(self.device)), "drb_train_backward")
+            if want_spec_grad:      # the plan must not keep a pointer into a tensor whose lifetime it does not control
+                _lib.check(self.lib.drb_train_set_spec_grad(self.plan, None), "drb_train_set_spec_grad")
         del k1, k2
         return None if gx is None else gx.reshape(self.batch, 1, self.frames, 88)
 
