@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffroll_b200.so")
 
 PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_F16F8, PREC_F16E5, PREC_F16N4 = 0, 1, 2, 3, 4, 5
-BRANCH_COND_UNCOND, BRANCH_COND, BRANCH_UNCOND, BRANCH_COND_ZEROSPEC, BRANCH_COND_LEARNED = 0, 1, 2, 3, 4
+BRANCH_COND_UNCOND, BRANCH_COND, BRANCH_UNCOND, BRANCH_COND_ZEROSPEC, BRANCH_COND_LEARNED, BRANCH_LEARNED = 0, 1, 2, 3, 4, 5
 UPD_X0, UPD_X0_FINAL, UPD_EPS_DDPM, UPD_EPS_DDIM, UPD_EPS_FINAL, UPD_NONE = range(6)
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "f16f8": PREC_F16F8, "f16e5": PREC_F16E5,
               "f16n4": PREC_F16N4}

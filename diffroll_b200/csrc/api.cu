@@ -58,7 +58,7 @@ static bool cfg_ok(const drb_config& c) {
   if (c.residual_channels <= 0 || c.residual_channels % 256) return false;
   if (c.residual_layers <= 0 || c.kernel_size <= 0 || !(c.kernel_size & 1)) return false;
   if (c.dilation_base <= 0 || c.dilation_bound <= 0 || c.n_mels <= 0 || c.n_fft <= 0 || c.hop_length <= 0) return false;
-  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 5 || c.branches < 0 || c.branches > 4) return false;
+  if (c.timesteps <= 0 || c.precision < 0 || c.precision > 5 || c.branches < 0 || c.branches > 5) return false;
   if (c.wave_len / c.hop_length + 1 < c.frames) return false;
   if (c.wave_len <= c.n_fft / 2) return false;  // reflect padding needs pad < length
   return true;
@@ -87,7 +87,7 @@ static Layout make_layout(const drb_config& c) {
   // DRB_BRANCH_COND_LEARNED: the second branch is conditioned on a learned spectrogram (condition='trainable_spec',
   // model/diffwave.py:657-658).  It is kept as `batch` more clips behind the real ones, so every kernel sees 2 x batch
   // conditional rolls and nothing in the step changes shape.
-  l.Bs = c.branches == DRB_BRANCH_COND_LEARNED ? 2 * c.batch : c.batch;
+  l.Bs = (c.branches == DRB_BRANCH_COND_LEARNED || c.branches == DRB_BRANCH_LEARNED) ? 2 * c.batch : c.batch;
   l.Mp = (c.n_mels + 63) / 64 * 64;
   l.KC = (int)(k * C);
   const size_t NB = l.NBcap, Mp = l.Mp, rows = NB * T;
@@ -149,7 +149,8 @@ struct drb_plan {
   bool tables_ready, spec_ready;
   bool cond_ready = false;   // cond tables hold the conditioner projections of the CURRENT spectrogram
   bool cond_use = true;      // drb_plan_use_cond_tables: steps read the tables when they are ready
-  bool learned = false;      // DRB_BRANCH_COND_LEARNED is in force: rolls batch..2*batch-1 read the learned clips
+  bool learned = false;      // DRB_BRANCH_COND_LEARNED / DRB_BRANCH_LEARNED is in force: rolls read the learned clips
+  int clip0 = 0;             // first clip roll 0 reads: 0, or batch when EVERY roll reads a learned clip (DRB_BRANCH_LEARNED)
   bool uspec_ready = false;  // drb_plan_set_uncond_spec has filled the learned clips of spec32
   bool ucond_ready = false;  // ... and their half of the conditioner tables is built
   int pair = 1;        // CTA pairs (cta_group::2); DRB_NO_PAIR=1 selects the single-CTA kernels, for A/B runs
@@ -231,10 +232,15 @@ int drb_plan_set_branches(drb_plan* p, int32_t branches) {
     if (p->lay.Bs != 2 * B) { set_error("plan was not created with DRB_BRANCH_COND_LEARNED"); return DRB_E_INVALID; }
     NB = 2 * B; nc = 2 * B;
   }
+  else if (branches == DRB_BRANCH_LEARNED) {        // one forward per roll, each conditioned on the learned table
+    if (p->lay.Bs != 2 * B) { set_error("plan was not created with DRB_BRANCH_COND_LEARNED / DRB_BRANCH_LEARNED"); return DRB_E_INVALID; }
+    NB = B; nc = B;
+  }
   else { set_error("bad branches %d", branches); return DRB_E_INVALID; }
   if (NB > p->lay.NBcap) { set_error("plan was created for a single branch"); return DRB_E_INVALID; }
   p->NB = NB; p->n_cond = nc; p->zero_spec = branches == DRB_BRANCH_COND_ZEROSPEC;
-  p->learned = branches == DRB_BRANCH_COND_LEARNED;
+  p->learned = branches == DRB_BRANCH_COND_LEARNED || branches == DRB_BRANCH_LEARNED;
+  p->clip0 = branches == DRB_BRANCH_LEARNED ? B : 0;
   return 0;
 }
 
@@ -562,7 +568,7 @@ static int build_cond_tables(drb_plan* p, int clip0, void* stream) {
 int drb_cond_tables(drb_plan* p, void* stream) {
   if (!p) return DRB_E_INVALID;
   if (!p->condpre) return 0;
-  if (!p->cond_ready) {
+  if (!p->cond_ready && p->clip0 == 0) {   // (DRB_BRANCH_LEARNED never reads the audio clips' rows)
     if (!p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
     int r = build_cond_tables(p, 0, stream); if (r) return r;
     p->cond_ready = true;
@@ -635,7 +641,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
     set_error("resblock: bad argument"); return DRB_E_INVALID;
   }
   if (!p->tables_ready) { set_error("drb_time_tables has not been called"); return DRB_E_STATE; }
-  if (p->n_cond > 0 && !p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
+  if (p->n_cond > 0 && p->clip0 == 0 && !p->spec_ready) { set_error("drb_mel_forward has not been called"); return DRB_E_STATE; }
   if (p->learned && !p->uspec_ready) { set_error("drb_plan_set_uncond_spec has not been called"); return DRB_E_STATE; }
   NvtxRange nv("drb.resblock l=%d t=%d", layer, t_index);
   cudaStream_t s = (cudaStream_t)stream;
@@ -654,7 +660,7 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
       g.A = x32; g.C = y; g.M = nc * T; g.bias = p->bias_ptr(layer, 2);
       r = launch_simt_gemm(g, s); if (r) return r;
       SimtGemm q;  // + conditioner_projection(spec)   model/diffwave.py:143-144
-      q.A = p->at<float>(p->lay.spec32); q.lda = Mp; q.T = T; q.Ck = Mp;
+      q.A = p->at<float>(p->lay.spec32) + (size_t)p->clip0 * T * Mp; q.lda = Mp; q.T = T; q.Ck = Mp;
       q.W = p->at<float>(p->lay.wc32) + (size_t)layer * 2 * C * Mp; q.ldw = Mp; q.accumulate = 1;
       q.C = y; q.ldc = 2 * C; q.M = nc * T; q.N = 2 * C;
       r = launch_simt_gemm(q, s); if (r) return r;
@@ -677,13 +683,14 @@ int drb_resblock_forward(drb_plan* p, int32_t layer, int32_t t_index, void* stre
   // the f16n4 kernel has no conditioner K-slabs, and the learned clips exist only as table rows: there the per-clip tables are
   // always used (built on demand)
   const bool need_tables = p->n4() || p->learned;
-  if (need_tables && nc > 0 && !(p->cond_ready && (!p->learned || p->ucond_ready))) { r = drb_cond_tables(p, stream); if (r) return r; }
+  auto tables_ready = [&]() { return (p->clip0 > 0 || p->cond_ready) && (!p->learned || p->ucond_ready); };
+  if (need_tables && nc > 0 && !tables_ready()) { r = drb_cond_tables(p, stream); if (r) return r; }
   ug.need_tables = p->learned ? 1 : 0;
   if (p->n4()) {
     ug.n4 = 1; ug.xw4 = &p->win4[layer]; ug.wd4 = &p->wd4[layer]; ug.wsf = &p->wsf4[layer]; ug.xs = p->at<uint8_t>(p->lay.xs);
   }
-  if (p->condpre && p->cond_ready && (p->cond_use || need_tables) && nc > 0) {
-    ug.cond = p->at<float>(p->lay.cond) + (size_t)layer * p->lay.Bs * T * 2 * C;
+  if (p->condpre && tables_ready() && (p->cond_use || need_tables) && nc > 0) {
+    ug.cond = p->at<float>(p->lay.cond) + ((size_t)layer * p->lay.Bs + p->clip0) * T * 2 * C;
     if (first && p->share0 && NB == 2 * B && nc == B) ug.dual_B = B;
   }
   const int e0 = p->prof ? p->ev_mark(s) : -1;

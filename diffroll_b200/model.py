@@ -165,6 +165,7 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
         self._mel_key = None
         self._mel_ref = None
         self._spec = None
+        self._learned_pair = False
 
     # ---- engine management ------------------------------------------------------------------------
     def _weights_version(self):
@@ -216,8 +217,19 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
             if min(T, self.trainable_parameters.shape[-1]) != T_min:
                 raise RuntimeError(f"trainable_spec: the learned spectrogram trims the roll to "
                                    f"{min(T, self.trainable_parameters.shape[-1])} frames, the clip to {T_min}")
-        if branches == _lib.BRANCH_UNCOND and not self._learned:
-            spec = torch.full((B, sa["n_mels"], T_min), -1.0, device=x.device)   # model/diffwave.py:660
+        # A sampling=True forward on its own under 'trainable_spec' (the generation sampler, a plain forward): every roll is
+        # conditioned on the table.  DRB_BRANCH_LEARNED does exactly that, but the table exists only as rows of the conditioner
+        # tables, which the CTA-pair kernels read: the tensor-core formats need an even number of 128-frame tiles.  Otherwise the
+        # step runs as the (clip, table) pair at guidance weight -1 -- (1 + w) * cond - w * learned = learned exactly, see
+        # _learned_upd -- whose clip half only has to be finite (the mel front-end guarantees that for any waveform).
+        self._learned_pair = (self._learned and branches == _lib.BRANCH_UNCOND and self.precision != "fp32"
+                              and (B * ((T_min + 127) // 128)) % 2 != 0)
+        if branches == _lib.BRANCH_UNCOND and not self._learned_pair:
+            if self._learned:
+                spec = self.trainable_parameters.detach()[..., :T_min]          # 2-D, like the reference's return value (:658,662)
+                branches = _lib.BRANCH_LEARNED
+            else:
+                spec = torch.full((B, sa["n_mels"], T_min), -1.0, device=x.device)   # model/diffwave.py:660
         else:
             wav = waveform.to(device=x.device, dtype=torch.float32).contiguous()
             it = list(inpainting_t) if inpainting_t else None
@@ -231,20 +243,17 @@ class ClassifierFreeDiffRoll(SpecRollDiffusion):
                 self._mel_key = key
                 self._mel_ref = weakref.ref(waveform)
             spec = self._spec
-        if self._learned and branches in (_lib.BRANCH_UNCOND, _lib.BRANCH_COND_UNCOND):
-            # Both of them run as the (clip, learned table) pair.  sampling=True alone (BRANCH_UNCOND: the generation sampler, a plain
-            # forward) is that pair with guidance weight -1, (1 + w) * cond - w * learned = learned exactly: see _learned_upd.  The
-            # clip half then only has to be finite, which the mel front-end above guarantees for any waveform.
+        if self._learned and branches in (_lib.BRANCH_UNCOND, _lib.BRANCH_COND_UNCOND):   # the (clip, learned table) pair
             if branches == _lib.BRANCH_UNCOND:
-                spec = self.trainable_parameters.detach()[..., :T_min]      # 2-D, like the reference's return value (:658,662)
+                spec = self.trainable_parameters.detach()[..., :T_min]
             branches = _lib.BRANCH_COND_LEARNED
         eng.set_branches(branches)
         return eng, xx, spec
 
     def _learned_upd(self, upd, branches):
-        """The update struct a step really runs with: under condition='trainable_spec' a sampling=True forward is the learned
-        pair at guidance weight -1 (see _prepare).  Returns ``upd`` itself otherwise."""
-        if not (self._learned and branches == _lib.BRANCH_UNCOND):
+        """The update struct a step really runs with, after ``_prepare``: under condition='trainable_spec' a sampling=True forward
+        that had to run as the learned pair takes guidance weight -1 (see _prepare).  Returns ``upd`` itself otherwise."""
+        if not (self._learned and branches == _lib.BRANCH_UNCOND and self._learned_pair):
             return upd
         u = DrbUpdate.from_buffer_copy(upd)
         u.w = -1.0

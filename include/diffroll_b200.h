@@ -58,6 +58,11 @@ extern "C" {
                                       [n_mels, 641] parameter instead of -1).  The plan must be CREATED with this value
                                       (it holds `batch` extra clips and twice the conditioner tables) and given the table
                                       with drb_plan_set_uncond_spec; it may be switched to the other modes and back. */
+#define DRB_BRANCH_LEARNED      5  /* one forward per roll, every roll conditioned on that learned spectrogram: a sampling=True
+                                      forward of condition='trainable_spec' on its own (generation_ddpm_x0,
+                                      task/diffusion.py:979).  Needs a plan created with 4 or 5; the tensor-core precisions
+                                      need an even number of 128-frame tiles (CTA pairs), else the step fails and the caller
+                                      runs mode 4 at guidance weight -1, which gives the same result. */
 
 /* posterior-update formulas, evaluated in the reference's operation order with fp32 scalars s[0..4] */
 #define DRB_UPD_X0        0  /* s0*net + s1*(x - s2*net)/s3 + s4*noise      task/diffusion.py:1018-1023 */

@@ -178,4 +178,26 @@ def test_learned_plan_contract_through_the_c_abi():
     eng.set_uncond_spec(sd["trainable_parameters"])
     out = eng.step(x_T.cuda(), None, 5, _upd(_lib.UPD_NONE, w=-1.0))
     assert torch.isfinite(out).all()
+    # DRB_BRANCH_LEARNED (every roll on the table, one forward) == the pair at guidance weight -1, bit for bit or to the last ulp
+    eng.set_branches(_lib.BRANCH_LEARNED)
+    single = eng.step(x_T.cuda(), None, 5, _upd(_lib.UPD_NONE))
+    assert float((single - out).abs().max()) < 1e-6
     plain.close(); eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16n4"])
+def test_learned_generation_with_an_odd_tile_count(precision):
+    """One roll of 128 frames is a single tile: no CTA pair, so the tensor-core formats run the sampling=True forward as the
+    (clip, table) pair at guidance weight -1 instead of DRB_BRANCH_LEARNED; fp32 takes the single branch.  Same numbers either way."""
+    from oracle.diffroll_oracle import OracleDiffRoll
+    m, hp = _model(precision, "generation_ddpm_x0")
+    x_T, wav, noise = make_inputs(1, 200, seed=21, n_noise=1, T=128, wav_len=65536)
+    orc = OracleDiffRoll(hp, make_state_dict(hp))
+    with torch.no_grad():
+        ref, _ = orc.reverse_diffusion(x_T, wav, 150, noise=noise[0])
+    x_prev, spec = m.reverse_diffusion(x_T.cuda(), wav.cuda(), 150, noise=noise[0].cuda())
+    assert m._learned_pair == (precision != "fp32") and spec.shape == (229, 128)
+    e = _err(x_prev, ref.numpy())
+    _record(f"trainable_spec[{precision}] generation step, 1 roll x 128 frames (odd tile count): max|delta| vs CPU oracle = {e:.3e}")
+    assert e < TOL_STEP[precision]
+    _close(m)

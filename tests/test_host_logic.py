@@ -300,8 +300,9 @@ def test_compose_reads_a_reference_style_hydra_tree(tmp_path):
 
 def test_trainable_spec_host_side(lib_built):
     """condition='trainable_spec' (model/diffwave.py:600-605): the extra [n_mels, 641] parameter is part of the state_dict contract
-    (133 tensors incl. the two mel buffers), the learned-capable plan asks for the extra clips and tables, sampling=True steps run
-    as the learned pair at guidance weight -1, and 'trainable_z' fails at construction like the reference (:616 vs :154)."""
+    (133 tensors incl. the two mel buffers), the learned-capable plan asks for the extra clips and tables, sampling=True steps that
+    cannot run as DRB_BRANCH_LEARNED run as the learned pair at guidance weight -1, and 'trainable_z' fails at construction like
+    the reference (:616 vs :154)."""
     import diffroll_b200 as M
     from diffroll_b200 import _lib
     hp = default_hparams(condition="trainable_spec", sampling_type="generation_ddpm_x0")
@@ -313,6 +314,8 @@ def test_trainable_spec_host_side(lib_built):
     assert any(q is m.trainable_parameters for q in m.configure_optimizers()[0].params)
     ups, branches, _ = m._all_updates()
     assert branches == _lib.BRANCH_UNCOND
+    assert m._learned_upd(ups[0], branches) is ups[0]      # shapes that run as DRB_BRANCH_LEARNED need no guidance trick
+    m._learned_pair = True                                 # what _prepare decides for an odd number of 128-frame tiles
     u = m._learned_upd(ups[0], branches)
     assert u is not ups[0] and u.w == -1.0 and ups[0].w == 0.0 and list(u.s) == list(ups[0].s) and u.mode == ups[0].mode
     assert m._learned_upd(ups[0], _lib.BRANCH_COND) is ups[0]
@@ -335,5 +338,8 @@ def test_trainable_spec_host_side(lib_built):
     learned = lib.drb_plan_workspace_bytes(C.byref(cfg))
     extra = 32 * 640 * (256 * 4 + 15 * 1024 * 4)           # 32 more clips of spec32 and of every layer's conditioner table
     assert learned - plain == extra, (learned - plain, extra)
-    cfg.branches = 5
+    cfg.branches = _lib.BRANCH_LEARNED                     # single-branch capacity, still with the learned clips
+    single = lib.drb_plan_workspace_bytes(C.byref(cfg))
+    assert 0 < single < learned
+    cfg.branches = 6
     assert lib.drb_plan_workspace_bytes(C.byref(cfg)) == 0
